@@ -1,0 +1,250 @@
+// egb_gemm dispatcher + the FP32-FMA GEMM (CUDA cores).
+//
+// Two precision modes share one descriptor and one epilogue:
+//   in_dtype = EGB_BF16 : tcgen05 tensor-core kernel (gemm_tc.cu), fp32 accumulation in TMEM
+//   in_dtype = EGB_F32  : this file's register-tiled FFMA kernel -- the fp32-parity mode whose
+//                         logits must match the reference CPU model to <= 1e-4.
+// bf16 problems the tensor-core kernel cannot tile (N < 16, strides not 16-byte aligned) are
+// also routed here (bf16 in, fp32 math); they are the 3-class heads, a few kFLOP each.
+#include <string.h>
+#include "common.cuh"
+#include "epilogue.cuh"
+
+extern void egb_count_launch(int n);
+int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream);
+
+namespace {
+
+constexpr int FBM = 128, FBN = 128, FBK = 16, FTHREADS = 256;
+
+struct FOperand {
+  const char* ptr;
+  int major;
+  int rpg;
+  long long rs, gs;
+  int vec;  // 4-element vector loads are legal
+};
+
+struct FParams {
+  int M, N, K;
+  FOperand a, b;
+  int split_k, k_per_split;
+  EpiParams epi;
+};
+
+__device__ __forceinline__ long long op_row_offset(const FOperand& o, int row) {
+  const int g = row / o.rpg;
+  return (long long)g * o.gs + (long long)(row - g * o.rpg) * o.rs;
+}
+
+template <typename T>
+__device__ __forceinline__ void load4_guard(const FOperand& o, long long off, int inner0, int inner_extent, bool row_ok,
+                                            float (&v)[4]) {
+  v[0] = v[1] = v[2] = v[3] = 0.f;
+  if (!row_ok) return;
+  const T* p = reinterpret_cast<const T*>(o.ptr) + off + inner0;
+  if (o.vec && inner0 + 3 < inner_extent) {
+    ld4(p, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (inner0 + i < inner_extent) v[i] = to_f(p[i]);
+  }
+}
+
+// Loads this thread's share (2 x 4 elements) of a [128 mn x 16 k] operand tile.
+template <typename T>
+__device__ __forceinline__ void load_tile(const FOperand& o, int mn0, int extent_mn, int k0, int k_end,
+                                          float (&r)[2][4]) {
+  const int t = threadIdx.x;
+  if (o.major == 0) {
+    const int kq = (t & 3) * 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = mn0 + (t >> 2) + 64 * i;
+      const bool ok = row < extent_mn;
+      load4_guard<T>(o, ok ? op_row_offset(o, row) : 0, k0 + kq, k_end, ok, r[i]);
+    }
+  } else {
+    const int mq = (t & 31) * 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = k0 + (t >> 5) + 8 * i;
+      const bool ok = k < k_end;
+      load4_guard<T>(o, ok ? op_row_offset(o, k) : 0, mn0 + mq, extent_mn, ok, r[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_tile(const FOperand& o, float (*s)[FBM + 4], const float (&r)[2][4]) {
+  const int t = threadIdx.x;
+  if (o.major == 0) {
+    const int kq = (t & 3) * 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = (t >> 2) + 64 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[kq + j][row] = r[i][j];
+    }
+  } else {
+    const int mq = (t & 31) * 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = (t >> 5) + 8 * i;
+      *reinterpret_cast<float4*>(&s[k][mq]) = make_float4(r[i][0], r[i][1], r[i][2], r[i][3]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FTHREADS) gemm_fma_kernel(const FParams p) {
+  __shared__ __align__(16) float As[2][FBK][FBM + 4];
+  __shared__ __align__(16) float Bs[2][FBK][FBN + 4];
+  const int m0 = blockIdx.y * FBM;
+  const int n0 = blockIdx.x * FBN;
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kend = min(p.K, kbeg + p.k_per_split);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[2][4], rb[2][4];
+  load_tile<T>(p.a, m0, p.M, kbeg, kend, ra);
+  load_tile<T>(p.b, n0, p.N, kbeg, kend, rb);
+  store_tile(p.a, As[0], ra);
+  store_tile(p.b, Bs[0], rb);
+  __syncthreads();
+
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += FBK) {
+    const bool has_next = k0 + FBK < kend;
+    if (has_next) {
+      load_tile<T>(p.a, m0, p.M, k0 + FBK, kend, ra);
+      load_tile<T>(p.b, n0, p.N, k0 + FBK, kend, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < FBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (has_next) {
+      store_tile(p.a, As[buf ^ 1], ra);
+      store_tile(p.b, Bs[buf ^ 1], rb);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
+      epi_apply_store<4>(p.epi, m, n0 + h * 64 + tx * 4, v);
+    }
+  }
+}
+
+FOperand make_foperand(const egb_operand& o, int extent_mn, int K, int esz) {
+  FOperand f;
+  f.ptr = (const char*)o.ptr;
+  f.major = o.major;
+  const long long total_rows = o.major == 0 ? extent_mn : K;
+  f.rpg = (int)(o.rows_per_group > 0 ? o.rows_per_group : (total_rows > 0 ? total_rows : 1));
+  f.rs = o.row_stride;
+  f.gs = o.group_stride;
+  f.vec = ((uintptr_t)o.ptr % (4 * esz) == 0) && (o.row_stride % 4 == 0) && (o.group_stride % 4 == 0);
+  return f;
+}
+
+bool tc_compatible(const egb_gemm_desc* d) {
+  auto ok = [](const egb_operand& o) {
+    return ((uintptr_t)o.ptr % 16 == 0) && (o.row_stride % 8 == 0) && (o.row_stride > 0) &&
+           (o.rows_per_group <= 0 || o.group_stride % 8 == 0);
+  };
+  return d->N >= 16 && d->M >= 1 && d->K >= 16 && ok(d->a) && ok(d->b);
+}
+
+}  // namespace
+
+int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e) {
+  memset(e, 0, sizeof(*e));
+  e->M = d->M;
+  e->N = d->N;
+  EGB_CHECK(d->c.ptr != nullptr, "gemm: null output");
+  e->c = make_epimat(d->c, d->M);
+  e->c_pre = make_epimat(d->c_pre, d->M);
+  e->res = make_epimat(d->residual, d->M);
+  e->aux = make_epimat(d->aux, d->M);
+  e->bias = d->bias;
+  e->alpha = d->alpha;
+  e->act = d->act;
+  e->act_bwd = d->act_bwd;
+  EGB_CHECK(d->act_bwd == EGB_ACTBWD_NONE || d->aux.ptr != nullptr, "gemm: act_bwd needs aux");
+  e->aux_scale = d->aux_scale;
+  if (d->dropout_p > 0.f) {
+    EGB_CHECK(d->dropout_p < 1.f, "gemm: dropout_p must be < 1");
+    e->drop_thresh = drop_threshold(d->dropout_p);
+    e->drop_scale = 1.f / (1.f - d->dropout_p);
+    e->seed = d->dropout_seed;
+  }
+  e->accumulate = d->accumulate;
+  EGB_CHECK(!d->accumulate || d->c.dtype == EGB_F32, "gemm: accumulate requires fp32 output");
+  EGB_CHECK(!d->accumulate || (d->act == 0 && d->act_bwd == 0 && d->residual.ptr == nullptr && d->bias == nullptr &&
+                               d->c_pre.ptr == nullptr && d->dropout_p == 0.f),
+            "gemm: accumulate mode supports only alpha scaling");
+  return 0;
+}
+
+extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EGB_CHECK(d != nullptr, "gemm: null descriptor");
+  EGB_CHECK(d->M > 0 && d->N > 0 && d->K > 0, "gemm: empty problem %dx%dx%d", d->M, d->N, d->K);
+  EGB_CHECK(d->a.ptr && d->b.ptr, "gemm: null operand");
+  if (d->in_dtype == EGB_BF16 && tc_compatible(d)) return egb_gemm_tc(d, stream);
+
+  FParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  const int esz = d->in_dtype == EGB_BF16 ? 2 : 4;
+  p.a = make_foperand(d->a, d->M, d->K, esz);
+  p.b = make_foperand(d->b, d->N, d->K, esz);
+  if (egb_fill_epilogue(d, &p.epi)) return 1;
+  const int mt = (d->M + FBM - 1) / FBM, nt = (d->N + FBN - 1) / FBN;
+  int split = 1;
+  if (d->accumulate) {
+    split = d->split_k;
+    if (split <= 0) {
+      split = (2 * egb_num_sms() + mt * nt - 1) / (mt * nt);
+      const int max_split = (d->K + 255) / 256;
+      if (split > max_split) split = max_split;
+      if (split < 1) split = 1;
+    }
+  }
+  int kps = (d->K + split - 1) / split;
+  kps = ((kps + FBK - 1) / FBK) * FBK;
+  p.k_per_split = kps;
+  p.split_k = (d->K + kps - 1) / kps;
+  dim3 grid(nt, mt, p.split_k);
+  EGB_CHECK(mt <= 65535 && p.split_k <= 65535, "gemm: grid too large");
+  if (d->in_dtype == EGB_BF16)
+    gemm_fma_kernel<bf16><<<grid, FTHREADS, 0, stream>>>(p);
+  else
+    gemm_fma_kernel<float><<<grid, FTHREADS, 0, stream>>>(p);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,354 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (3-D tensor maps, 128-B swizzle) -> shared memory ->
+// tcgen05.mma (fp32 accumulators in TMEM, double buffered) -> tcgen05.ld epilogue.
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one lane) and
+// TMEM owner, warps 2..5 = epilogue (one TMEM lane quadrant each).  Three mbarrier pipelines:
+// smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+//
+// Operands are 3-level strided views (see include/eyegaze_b200.h) in either K-major or MN-major
+// form, so the same kernel runs y = x.W^T, dx = dy.W, dW = dy^T.x and the Conv1d/Conv2d layers
+// of the reference as implicit GEMMs over overlapping-row views without an im2col buffer.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <string.h>
+#include "common.cuh"
+#include "ptx.cuh"
+#include "epilogue.cuh"
+
+extern void egb_count_launch(int n);
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+  int M, N, K;
+  int a_major, b_major;
+  int a_rpg, b_rpg;
+  int m_tiles, n_tiles, k_blocks, split_k, kb_per_split;
+  EpiParams epi;
+};
+
+template <int BN>
+struct TcConfig {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Cfg = TcConfig<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile % p.split_k;
+        const int mn = tile / p.split_k;
+        const int nt = mn % p.n_tiles;
+        const int mt = mn / p.n_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (p.a_major == 0) {
+            const int row0 = mt * BM;
+            ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, row0 % p.a_rpg, row0 / p.a_rpg);
+          } else {
+            const int red0 = kb * BK;
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              ptx::tma_load_3d(sa + j * (BK * 128), &tmA, &full_bar[stage], mt * BM + j * 64, red0 % p.a_rpg,
+                               red0 / p.a_rpg);
+          }
+          if (p.b_major == 0) {
+            const int row0 = nt * BN;
+            ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, row0 % p.b_rpg, row0 / p.b_rpg);
+          } else {
+            const int red0 = kb * BK;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[stage], nt * BN + j * 64, red0 % p.b_rpg,
+                               red0 / p.b_rpg);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, p.a_major, p.b_major);
+    // per-UMMA_K (16 elements) descriptor advance, in 16-byte units
+    const uint32_t a_adv = p.a_major == 0 ? 2u : (16u * 128u) >> 4;
+    const uint32_t b_adv = p.b_major == 0 ? 2u : (16u * 128u) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ks = tile % p.split_k;
+      const int kb0 = ks * p.kb_per_split;
+      const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = ptx::make_smem_desc(sa, p.a_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
+          const uint64_t bdesc = ptx::make_smem_desc(sb, p.b_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                           (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mn = tile / p.split_k;
+      const int nt = mn % p.n_tiles;
+      const int mt = mn / p.n_tiles;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int m = mt * BM + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld32(taddr + (uint32_t)c0, raw);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        epi_apply_store<32>(p.epi, m, nt * BN + c0, v);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched at run time: no -lcuda link)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long inner, rows, groups, rs, gs;
+  int b0, b1, b2;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+std::mutex g_maps_mu;
+
+// 3-D bf16 tensor map {inner, rows_per_group, groups} with a {64, box_rows, box_groups} box
+int make_map(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long groups, long long rs,
+             long long gs, int box_rows, int box_groups) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = inner; key.rows = rows; key.groups = groups; key.rs = rs; key.gs = gs;
+  key.b0 = 64; key.b1 = box_rows; key.b2 = box_groups;
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  EGB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  EGB_CHECK(((uintptr_t)ptr % 16) == 0, "TMA operand base %p is not 16-byte aligned", ptr);
+  EGB_CHECK((rs % 8) == 0 && rs > 0, "TMA operand row stride %lld must be a positive multiple of 8 bf16", rs);
+  EGB_CHECK(groups == 1 || ((gs % 8) == 0 && gs > 0), "TMA operand group stride %lld must be a multiple of 8", gs);
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)rs * 2, (cuuint64_t)(groups == 1 ? rs : gs) * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, (cuuint32_t)box_groups};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGB_CHECK(r == CUDA_SUCCESS,
+            "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld groups=%lld rs=%lld gs=%lld box=%d,%d", (int)r,
+            inner, rows, groups, rs, gs, box_rows, box_groups);
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    if (g_maps.size() > 8192) g_maps.clear();
+    g_maps[key] = *out;
+  }
+  return 0;
+}
+
+// builds the map of one operand. `tile_rows` = BM or BN; `extent_mn` = M or N; K = reduction length
+int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int K, int tile_rows, int* rpg_out) {
+  const long long total_rows = o.major == 0 ? extent_mn : K;
+  long long rpg = o.rows_per_group > 0 ? o.rows_per_group : total_rows;
+  long long groups = (total_rows + rpg - 1) / rpg;
+  const int span = o.major == 0 ? tile_rows : BK;  // rows of the operand view covered by one tile
+  int box_rows, box_groups;
+  if (rpg >= span || groups == 1) {
+    // single group: rows past the extent are zero-filled by TMA, so the box may overhang
+    EGB_CHECK(groups == 1 || rpg % span == 0, "rows_per_group %lld must be a multiple of the tile span %d", rpg, span);
+    box_rows = span;
+    box_groups = 1;
+  } else {
+    EGB_CHECK(span % rpg == 0, "tile span %d must be a multiple of rows_per_group %lld", span, rpg);
+    box_rows = (int)rpg;
+    box_groups = span / (int)rpg;
+  }
+  const long long inner = o.major == 0 ? K : extent_mn;
+  *rpg_out = (int)rpg;
+  return make_map(out, o.ptr, inner, rpg, groups, o.row_stride, o.group_stride, box_rows, box_groups);
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  using Cfg = TcConfig<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  const int grid = total < egb_num_sms() ? total : egb_num_sms();
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e);
+
+// Called from egb_gemm for in_dtype == EGB_BF16.
+int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
+  EGB_CHECK(d->M > 0 && d->N > 0 && d->K > 0, "gemm: empty problem %dx%dx%d", d->M, d->N, d->K);
+  int BN = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
+  // a 256-wide tile wastes MMA work when N is just above a multiple of 128
+  if (BN == 256 && (d->N % 256) != 0 && (d->N % 256) <= 128 && d->N < 1024) BN = 128;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.a_major = d->a.major; p.b_major = d->b.major;
+  CUtensorMap ma, mb;
+  if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg)) return 1;
+  if (make_operand_map(&mb, d->b, d->N, d->K, BN, &p.b_rpg)) return 1;
+  p.m_tiles = (d->M + BM - 1) / BM;
+  p.n_tiles = (d->N + BN - 1) / BN;
+  p.k_blocks = (d->K + BK - 1) / BK;
+  int split = 1;
+  if (d->accumulate) {
+    EGB_CHECK(d->c.dtype == EGB_F32, "gemm: accumulate requires an fp32 output");
+    split = d->split_k;
+    if (split <= 0) {
+      const int tiles = p.m_tiles * p.n_tiles;
+      split = (2 * egb_num_sms() + tiles - 1) / tiles;
+      const int max_split = (p.k_blocks + 7) / 8;  // keep >= 8 k-blocks per split
+      if (split > max_split) split = max_split;
+      if (split < 1) split = 1;
+    }
+    if (split > p.k_blocks) split = p.k_blocks;
+  }
+  p.kb_per_split = (p.k_blocks + split - 1) / split;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  if (egb_fill_epilogue(d, &p.epi)) return 1;
+  switch (BN) {
+    case 256: return launch_tc<256>(ma, mb, p, stream);
+    case 128: return launch_tc<128>(ma, mb, p, stream);
+    default: return launch_tc<64>(ma, mb, p, stream);
+  }
+}
