@@ -1,0 +1,64 @@
+"""ViT oracle (oracle/vit.py): timm is absent, so the restatement is cross-checked against torchvision's
+VisionTransformer by weight remapping, and against the parameter count the reference documents. CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit as V
+
+
+def _tv_to_timm(tv_sd, depth, pre):
+    sd = {pre + "cls_token": tv_sd["class_token"], pre + "pos_embed": tv_sd["encoder.pos_embedding"],
+          pre + "patch_embed.proj.weight": tv_sd["conv_proj.weight"], pre + "patch_embed.proj.bias": tv_sd["conv_proj.bias"],
+          pre + "norm.weight": tv_sd["encoder.ln.weight"], pre + "norm.bias": tv_sd["encoder.ln.bias"]}
+    for i in range(depth):
+        s, d = f"encoder.layers.encoder_layer_{i}.", f"{pre}blocks.{i}."
+        for a, b in (("ln_1", "norm1"), ("ln_2", "norm2"), ("self_attention.out_proj", "attn.proj"),
+                     ("mlp.0", "mlp.fc1"), ("mlp.3", "mlp.fc2")):
+            sd[d + b + ".weight"], sd[d + b + ".bias"] = tv_sd[s + a + ".weight"], tv_sd[s + a + ".bias"]
+        sd[d + "attn.qkv.weight"], sd[d + "attn.qkv.bias"] = tv_sd[s + "self_attention.in_proj_weight"], tv_sd[s + "self_attention.in_proj_bias"]
+    if "heads.head.weight" in tv_sd:
+        sd[pre + "head.weight"], sd[pre + "head.bias"] = tv_sd["heads.head.weight"], tv_sd["heads.head.bias"]
+    return sd
+
+
+def test_vit_restatement_matches_torchvision():
+    tvm = pytest.importorskip("torchvision.models.vision_transformer")
+    torch.manual_seed(0)
+    m = tvm.VisionTransformer(image_size=32, patch_size=16, num_layers=2, num_heads=4, hidden_dim=64, mlp_dim=256,
+                              num_classes=3).eval()
+    m.conv_proj = torch.nn.Conv2d(6, 64, 16, 16)
+    for p in m.parameters():
+        torch.nn.init.normal_(p, std=0.05)
+    sd = _tv_to_timm({k: v.detach() for k, v in m.state_dict().items()}, 2, "backbone.")
+    a, b = torch.randn(3, 3, 32, 32), torch.randn(3, 3, 32, 32)
+    with torch.no_grad():
+        want = m(torch.cat([a, b], 1))
+    got = V.early_fusion_forward(sd, a, b, heads=4, mode="concat")
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-5, rtol=1e-4)
+
+
+def test_documented_parameter_count():
+    """4_Experiments/experiments_list.md:62 -- EarlyFusionViT ViT-B/16, 6 channels, 3 classes."""
+    sd = V.init_vit_state_dict("vit_base_patch16_224", 6, 3, "backbone.")
+    assert sum(v.numel() for v in sd.values()) == 86_390_787
+
+
+def test_wrapper_logic():
+    a, b = torch.randn(2, 3, 8, 8), torch.randn(2, 3, 8, 8)
+    assert V.fuse_inputs(a, b, "concat").shape == (2, 6, 8, 8)
+    assert torch.allclose(V.fuse_inputs(a, b, "add"), (a + b) / 2)
+    assert torch.allclose(V.fuse_inputs(a, b, "subtract_abs"), (a - b).abs())
+    m = V.fuse_inputs(a, b, "multiply").view(2, 3, -1)
+    assert torch.allclose(m.mean(2), torch.zeros(2, 3), atol=1e-5) and torch.allclose(m.std(2), torch.ones(2, 3), atol=1e-3)
+    with pytest.raises(ValueError):
+        V.fuse_inputs(a, b, "full")
+    c1, c2 = torch.randn(2, 5), torch.randn(2, 5)
+    dims = {"concat": 10, "add": 5, "subtract": 5, "multiply": 5, "full": 20}  # late_fusion_vit.py:304-310
+    for mode, d in dims.items():
+        assert V.fuse_features(c1, c2, mode).shape == (2, d)
+    w3 = torch.randn(4, 3, 16, 16)
+    w6 = V.widen_patch_embed(w3, "duplicate")
+    assert torch.equal(w6[:, :3], w3) and torch.equal(w6[:, 3:], w3)
+    w6 = V.widen_patch_embed(w3, "average")
+    assert torch.allclose(w6[:, 3:], w3.mean(1, keepdim=True).expand_as(w3))
