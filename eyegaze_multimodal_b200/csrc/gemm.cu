@@ -22,6 +22,7 @@ struct FOperand {
   int major;
   int rpg;
   long long rs, gs;
+  int seg, shift;  // inner segmentation (0 = off)
   int vec;  // 4-element vector loads are legal
 };
 
@@ -42,7 +43,13 @@ __device__ __forceinline__ void load4_guard(const FOperand& o, long long off, in
                                             float (&v)[4]) {
   v[0] = v[1] = v[2] = v[3] = 0.f;
   if (!row_ok) return;
-  const T* p = reinterpret_cast<const T*>(o.ptr) + off + inner0;
+  const T* p = reinterpret_cast<const T*>(o.ptr) + off;
+  if (o.seg > 0) {  // segment s of the inner index lives `shift` rows further down
+    const int s = inner0 / o.seg;
+    p += (long long)s * o.shift * o.rs + (inner0 - s * o.seg);
+  } else {
+    p += inner0;
+  }
   if (o.vec && inner0 + 3 < inner_extent) {
     ld4(p, v);
   } else {
@@ -166,16 +173,28 @@ FOperand make_foperand(const egb_operand& o, int extent_mn, int K, int esz) {
   f.rpg = (int)(o.rows_per_group > 0 ? o.rows_per_group : (total_rows > 0 ? total_rows : 1));
   f.rs = o.row_stride;
   f.gs = o.group_stride;
+  f.seg = o.seg_len;
+  f.shift = o.seg_row_shift;
   f.vec = ((uintptr_t)o.ptr % (4 * esz) == 0) && (o.row_stride % 4 == 0) && (o.group_stride % 4 == 0);
   return f;
 }
 
 bool tc_compatible(const egb_gemm_desc* d) {
-  auto ok = [](const egb_operand& o) {
-    return ((uintptr_t)o.ptr % 16 == 0) && (o.row_stride % 8 == 0) && (o.row_stride > 0) &&
-           (o.rows_per_group <= 0 || o.group_stride % 8 == 0);
+  // `span` = rows of the operand view one tile covers; groups must tile evenly into it
+  auto ok = [&](const egb_operand& o, int extent_mn, int tile_rows) {
+    if (((uintptr_t)o.ptr % 16) != 0 || (o.row_stride % 8) != 0 || o.row_stride <= 0) return false;
+    const long long total = o.major == 0 ? extent_mn : d->K;
+    if (o.rows_per_group > 0 && o.rows_per_group < total) {
+      if (o.group_stride % 8 != 0 || o.seg_len > 0) return false;
+      const int span = o.major == 0 ? tile_rows : 64;
+      const int rpg = o.rows_per_group;
+      if (rpg >= span ? (rpg % span != 0) : (span % rpg != 0)) return false;
+    }
+    if (o.seg_len > 0 && o.seg_len % 64 != 0) return false;
+    return true;
   };
-  return d->N >= 16 && d->M >= 1 && d->K >= 16 && ok(d->a) && ok(d->b);
+  return d->N >= 16 && d->K >= 16 && ok(d->a, d->M, 128) && ok(d->b, d->N, 256) && ok(d->b, d->N, 128) &&
+         ok(d->b, d->N, 64);
 }
 
 }  // namespace
@@ -214,6 +233,16 @@ extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
   EGB_CHECK(d != nullptr, "gemm: null descriptor");
   EGB_CHECK(d->M > 0 && d->N > 0 && d->K > 0, "gemm: empty problem %dx%dx%d", d->M, d->N, d->K);
   EGB_CHECK(d->a.ptr && d->b.ptr, "gemm: null operand");
+  if (d->accumulate == 2) {  // zero-initialise the (dense or strided) fp32 output, then split-K accumulate
+    EGB_CHECK(d->c.dtype == EGB_F32 && d->c.ptr, "gemm: accumulate requires an fp32 output");
+    const int rpg = d->c.rows_per_group > 0 ? d->c.rows_per_group : d->M;
+    if (rpg >= d->M && d->c.row_stride == d->N) {
+      EGB_CUDA(cudaMemsetAsync(d->c.ptr, 0, (size_t)d->M * d->N * 4, stream));
+    } else {
+      EGB_CHECK(rpg >= d->M, "gemm: zero-init of grouped outputs is not supported");
+      EGB_CUDA(cudaMemset2DAsync(d->c.ptr, (size_t)d->c.row_stride * 4, 0, (size_t)d->N * 4, (size_t)d->M, stream));
+    }
+  }
   if (d->in_dtype == EGB_BF16 && tc_compatible(d)) return egb_gemm_tc(d, stream);
 
   FParams p;

@@ -29,6 +29,7 @@ struct TcParams {
   int M, N, K;
   int a_major, b_major;
   int a_rpg, b_rpg;
+  int a_seg, a_shift, b_seg, b_shift;  // inner segmentation (0 = off)
   int m_tiles, n_tiles, k_blocks, split_k, kb_per_split;
   EpiParams epi;
 };
@@ -42,6 +43,27 @@ struct TcConfig {
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// Issues the TMA loads of one operand tile: TILE rows of the M/N index x BK of the reduction index.
+//   K-major : one {64 k, TILE rows} box;  MN-major: TILE/64 boxes of {64 mn, BK reduction rows}.
+// `seg`/`shift` implement the inner-index segmentation of egb_operand (single-group operands).
+template <int TILE>
+__device__ __forceinline__ void load_operand_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int major,
+                                                  int rpg, int seg, int shift, int tile, int kb) {
+  if (major == 0) {
+    int inner0 = kb * BK, row0 = tile * TILE;
+    if (seg > 0) { row0 += (inner0 / seg) * shift; inner0 %= seg; }
+    ptx::tma_load_3d(dst, tm, bar, inner0, row0 % rpg, row0 / rpg);
+  } else {
+    const int red0 = kb * BK;
+#pragma unroll
+    for (int j = 0; j < TILE / 64; ++j) {
+      int inner0 = tile * TILE + j * 64, row0 = red0;
+      if (seg > 0) { row0 += (inner0 / seg) * shift; inner0 %= seg; }
+      ptx::tma_load_3d(dst + j * (BK * 128), tm, bar, inner0, row0 % rpg, row0 / rpg);
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -98,26 +120,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          if (p.a_major == 0) {
-            const int row0 = mt * BM;
-            ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, row0 % p.a_rpg, row0 / p.a_rpg);
-          } else {
-            const int red0 = kb * BK;
-#pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              ptx::tma_load_3d(sa + j * (BK * 128), &tmA, &full_bar[stage], mt * BM + j * 64, red0 % p.a_rpg,
-                               red0 / p.a_rpg);
-          }
-          if (p.b_major == 0) {
-            const int row0 = nt * BN;
-            ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, row0 % p.b_rpg, row0 / p.b_rpg);
-          } else {
-            const int red0 = kb * BK;
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              ptx::tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[stage], nt * BN + j * 64, red0 % p.b_rpg,
-                               red0 / p.b_rpg);
-          }
+          load_operand_tile<BM>(sa, &tmA, &full_bar[stage], p.a_major, p.a_rpg, p.a_seg, p.a_shift, mt, kb);
+          load_operand_tile<BN>(sb, &tmB, &full_bar[stage], p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt, kb);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -289,9 +293,17 @@ int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int 
     box_rows = (int)rpg;
     box_groups = span / (int)rpg;
   }
-  const long long inner = o.major == 0 ? K : extent_mn;
+  long long inner = o.major == 0 ? K : extent_mn;
+  long long phys_rows = rpg;
+  if (o.seg_len > 0) {
+    EGB_CHECK(groups == 1 && o.seg_len % 64 == 0, "segmented operands must be single-group with seg_len %% 64 == 0");
+    const long long nseg = (inner + o.seg_len - 1) / o.seg_len;
+    phys_rows = rpg + (nseg - 1) * o.seg_row_shift;
+    inner = o.seg_len;
+    rpg = phys_rows;  // single group: tile coordinates never wrap
+  }
   *rpg_out = (int)rpg;
-  return make_map(out, o.ptr, inner, rpg, groups, o.row_stride, o.group_stride, box_rows, box_groups);
+  return make_map(out, o.ptr, inner, phys_rows, groups, o.row_stride, o.group_stride, box_rows, box_groups);
 }
 
 template <int BN>
@@ -324,6 +336,8 @@ int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.a_major = d->a.major; p.b_major = d->b.major;
+  p.a_seg = d->a.seg_len; p.a_shift = d->a.seg_row_shift;
+  p.b_seg = d->b.seg_len; p.b_shift = d->b.seg_row_shift;
   CUtensorMap ma, mb;
   if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg)) return 1;
   if (make_operand_map(&mb, d->b, d->N, d->K, BN, &p.b_rpg)) return 1;

@@ -1,0 +1,390 @@
+// Inter-brain-synchrony connectivity matrices (dual_eeg_transformer.py:473-819) as two kernels instead of
+// ~2.6e5 per-pair ATen launches:
+//
+//  K1  ibs_analytic_kernel   one CTA per (trial, player, channel): in-shared-memory radix-2 FFT of the
+//      T-sample channel, then per band an inverse FFT of the one-sided masked spectrum (= band-pass +
+//      Hilbert transform in one step, det:545-589) -> band-passed signal xb, instantaneous phase,
+//      per-channel mean / 1/(unbiased std + 1e-8) of xb and xb^2, sum of power, and |X_k|^2 of the
+//      in-band bins for the coherence.
+//  K2  ibs_pairs_kernel      one CTA per (trial, band, tile of player-1 channels): all C x C channel
+//      pairs, streaming the T axis through shared memory; per (i, j, t) it accumulates the seven
+//      features' sums (PLV re/im, sign, weighted sign, |dphi|, two Pearson products) in registers.
+//
+// sign() is taken of the RAW (un-wrapped) fp32 phase difference exactly as the reference does
+// (det:627,655; sign(0) = 0).
+#include "common.cuh"
+#include "../../include/eyegaze_b200.h"
+
+extern void egb_count_launch(int n);
+
+namespace {
+
+struct IbsBands {
+  int lo[8], hi[8];  // inclusive rfft-bin ranges
+  int nb;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// in-place radix-2 DIT on bit-reversed input; tw[k] = exp(-2 pi i k / T); conj -> inverse transform
+template <bool INVERSE>
+__device__ __forceinline__ void fft_inplace(float2* a, const float2* tw, int T, int logT) {
+  for (int s = 1; s <= logT; ++s) {
+    const int half = 1 << (s - 1);
+    const int tstep = T >> s;
+    for (int i = threadIdx.x; i < T / 2; i += blockDim.x) {
+      const int grp = i >> (s - 1), pos = i & (half - 1);
+      const int i0 = (grp << s) + pos, i1 = i0 + half;
+      float2 w = tw[pos * tstep];
+      if (INVERSE) w.y = -w.y;
+      const float2 t = cmul(w, a[i1]);
+      const float2 u = a[i0];
+      a[i0] = make_float2(u.x + t.x, u.y + t.y);
+      a[i1] = make_float2(u.x - t.x, u.y - t.y);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+// scratch layout: phase/xb [B][nb][2][C][T];  stats [B][nb][2][C][8] = {mean_x, rstd_x, mean_p, rstd_p, sum_p};
+// pspec [B][2][C][nbins] with nbins = hi_max - lo_min + 1 (bin k stored at k - lo_min)
+__global__ void __launch_bounds__(256) ibs_analytic_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
+                                                           const float2* __restrict__ twiddle, float* __restrict__ phase,
+                                                           float* __restrict__ xb, float* __restrict__ stats,
+                                                           float* __restrict__ pspec, IbsBands bands, int B, int C, int T,
+                                                           int logT, int lo_min, int nbins) {
+  extern __shared__ float2 sm2[];
+  float2* a = sm2;              // [T]
+  float2* X = a + T;            // [T/2 + 1]
+  float2* tw = X + T / 2 + 1;   // [T/2]
+  __shared__ float red[8];
+  const int c = blockIdx.x, stream = blockIdx.y, b = blockIdx.z;
+  const float* src = (stream == 0 ? e1 : e2) + ((long long)b * C + c) * T;
+  for (int i = threadIdx.x; i < T / 2; i += blockDim.x) tw[i] = twiddle[i];
+  for (int n = threadIdx.x; n < T; n += blockDim.x) a[__brev((unsigned)n) >> (32 - logT)] = make_float2(src[n], 0.f);
+  __syncthreads();
+  fft_inplace<false>(a, tw, T, logT);
+  for (int k = threadIdx.x; k <= T / 2; k += blockDim.x) X[k] = a[k];
+  __syncthreads();
+  float* ps = pspec + (((long long)b * 2 + stream) * C + c) * nbins;
+  for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+    const float2 v = X[lo_min + k];
+    ps[k] = v.x * v.x + v.y * v.y;
+  }
+  const float invT = 1.f / (float)T;
+  for (int bi = 0; bi < bands.nb; ++bi) {
+    const int lo = bands.lo[bi], hi = bands.hi[bi];
+    // one-sided spectrum with the Hilbert weights h_k (1 at DC / Nyquist, 2 elsewhere), scaled by 1/T
+    for (int k = threadIdx.x; k < T; k += blockDim.x) {
+      float2 v = make_float2(0.f, 0.f);
+      if (k >= lo && k <= hi && k <= T / 2) {
+        const float h = (k == 0 || k == T / 2) ? invT : 2.f * invT;
+        v = make_float2(X[k].x * h, X[k].y * h);
+      }
+      a[__brev((unsigned)k) >> (32 - logT)] = v;
+    }
+    __syncthreads();
+    fft_inplace<true>(a, tw, T, logT);
+    // statistics of xb and p = xb^2 (two-pass, unbiased std as torch.std)
+    float sx = 0.f, sp = 0.f;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const float x = a[t].x;
+      sx += x;
+      sp += x * x;
+    }
+    const float sum_p = block_sum(sp, red);
+    const float mean_x = block_sum(sx, red) * invT;
+    const float mean_p = sum_p * invT;
+    float vx = 0.f, vp = 0.f;
+    const long long base = ((((long long)b * bands.nb + bi) * 2 + stream) * C + c) * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const float2 z = a[t];
+      const float dx = z.x - mean_x, dp = z.x * z.x - mean_p;
+      vx += dx * dx;
+      vp += dp * dp;
+      xb[base + t] = z.x;
+      phase[base + t] = atan2f(z.y, z.x);
+    }
+    const float var_x = block_sum(vx, red) / (float)(T - 1);
+    const float var_p = block_sum(vp, red) / (float)(T - 1);
+    if (threadIdx.x == 0) {
+      float* s = stats + ((((long long)b * bands.nb + bi) * 2 + stream) * C + c) * 8;
+      s[0] = mean_x;
+      s[1] = 1.f / (sqrtf(var_x) + 1e-8f);
+      s[2] = mean_p;
+      s[3] = 1.f / (sqrtf(var_p) + 1e-8f);
+      s[4] = sum_p;
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int IBS_TI = 8;    // player-1 channels per CTA
+constexpr int IBS_TC = 64;   // time samples per shared-memory chunk
+constexpr int IBS_NF = 6;    // per-sample derived quantities: phase, cos, sin, p, zx, zp
+
+// feature slots in the output: out[b][band][slot][i][j]; slot_of[f] < 0 drops feature f
+struct IbsSlots { int slot_of[7]; int n_out; };
+
+__global__ void __launch_bounds__(256) ibs_pairs_kernel(const float* __restrict__ phase, const float* __restrict__ xb,
+                                                        const float* __restrict__ stats, const float* __restrict__ pspec,
+                                                        float* __restrict__ out, IbsBands bands, IbsSlots slots, int B,
+                                                        int C, int T, int lo_min, int nbins) {
+  extern __shared__ float sm[];
+  const int ldj = IBS_TC + 1;
+  float* si = sm;                              // [NF][TI][TC]
+  float* sj = si + IBS_NF * IBS_TI * IBS_TC;   // [NF][C][TC+1]
+  const int i0 = blockIdx.x * IBS_TI, bi = blockIdx.y, b = blockIdx.z;
+  const int ti = threadIdx.x >> 5;             // 0..7  -> player-1 channel i0 + ti
+  const int lane = threadIdx.x & 31;           // player-2 channels lane, lane+32, ...
+  const int i = i0 + ti;
+  const long long base1 = ((((long long)b * bands.nb + bi) * 2 + 0) * C) * T;
+  const long long base2 = ((((long long)b * bands.nb + bi) * 2 + 1) * C) * T;
+  const float* st1 = stats + ((((long long)b * bands.nb + bi) * 2 + 0) * C) * 8;
+  const float* st2 = stats + ((((long long)b * bands.nb + bi) * 2 + 1) * C) * 8;
+  constexpr int MAXJ = 4;  // C <= 128
+  float a_re[MAXJ], a_im[MAXJ], a_sg[MAXJ], a_w[MAXJ], a_pd[MAXJ], a_pc[MAXJ], a_tc[MAXJ];
+#pragma unroll
+  for (int q = 0; q < MAXJ; ++q) a_re[q] = a_im[q] = a_sg[q] = a_w[q] = a_pd[q] = a_pc[q] = a_tc[q] = 0.f;
+
+  for (int t0 = 0; t0 < T; t0 += IBS_TC) {
+    __syncthreads();
+    // stage player-1 tile and all player-2 channels for this time chunk, deriving cos/sin/p/z-scores
+    for (int idx = threadIdx.x; idx < (IBS_TI + C) * IBS_TC; idx += blockDim.x) {
+      const int r = idx / IBS_TC, t = idx % IBS_TC;
+      const bool is_i = r < IBS_TI;
+      const int ch = is_i ? i0 + r : r - IBS_TI;
+      float ph = 0.f, x = 0.f, mx = 0.f, rx = 0.f, mp = 0.f, rp = 0.f;
+      if (ch < C && t0 + t < T) {
+        const long long off = (is_i ? base1 : base2) + (long long)ch * T + t0 + t;
+        const float* s = (is_i ? st1 : st2) + ch * 8;
+        ph = phase[off]; x = xb[off];
+        mx = s[0]; rx = s[1]; mp = s[2]; rp = s[3];
+      }
+      float sn, cs;
+      sincosf(ph, &sn, &cs);
+      const float p = x * x;
+      const bool valid = ch < C && t0 + t < T;
+      float vals[IBS_NF] = {ph, cs, sn, p, (x - mx) * rx, (p - mp) * rp};
+      if (!valid) { vals[1] = 0.f; vals[2] = 0.f; }   // padded samples contribute nothing
+#pragma unroll
+      for (int f = 0; f < IBS_NF; ++f) {
+        if (is_i) si[(f * IBS_TI + r) * IBS_TC + t] = vals[f];
+        else sj[(f * C + ch) * ldj + t] = vals[f];
+      }
+    }
+    __syncthreads();
+    if (i < C) {
+      const int tmax = min(IBS_TC, T - t0);
+#pragma unroll
+      for (int q = 0; q < MAXJ; ++q) {
+        const int j = q * 32 + lane;
+        if (j < C) {
+          const float* pi = si + ti * IBS_TC;
+          const float* pj = sj + j * ldj;
+          // chunk-local partial sums, folded into the running totals once per chunk (two-level summation)
+          float l_re = 0.f, l_im = 0.f, l_sg = 0.f, l_w = 0.f, l_pd = 0.f, l_pc = 0.f, l_tc = 0.f;
+          for (int t = 0; t < tmax; ++t) {
+            const float ph1 = pi[t], c1 = pi[(1 * IBS_TI) * IBS_TC + t], s1 = pi[(2 * IBS_TI) * IBS_TC + t];
+            const float p1 = pi[(3 * IBS_TI) * IBS_TC + t], zx1 = pi[(4 * IBS_TI) * IBS_TC + t], zp1 = pi[(5 * IBS_TI) * IBS_TC + t];
+            const float ph2 = pj[t], c2 = pj[(1 * C) * ldj + t], s2 = pj[(2 * C) * ldj + t];
+            const float p2 = pj[(3 * C) * ldj + t], zx2 = pj[(4 * C) * ldj + t], zp2 = pj[(5 * C) * ldj + t];
+            const float d = ph1 - ph2;
+            const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+            l_re += c1 * c2 + s1 * s2;
+            l_im += s1 * c2 - c1 * s2;
+            l_sg += sg;
+            l_w += sg * ((p1 + p2) * 0.5f);
+            l_pd += fabsf(d);
+            l_pc = fmaf(zp1, zp2, l_pc);
+            l_tc = fmaf(zx1, zx2, l_tc);
+          }
+          a_re[q] += l_re; a_im[q] += l_im; a_sg[q] += l_sg; a_w[q] += l_w; a_pd[q] += l_pd; a_pc[q] += l_pc; a_tc[q] += l_tc;
+        }
+      }
+    }
+  }
+  if (i >= C) return;
+  const float invT = 1.f / (float)T;
+  const int klo = bands.lo[bi], khi = bands.hi[bi];
+  const float* ps1 = pspec + (((long long)b * 2 + 0) * C + i) * nbins;
+  const float sum_p1 = st1[i * 8 + 4];
+#pragma unroll
+  for (int q = 0; q < MAXJ; ++q) {
+    const int j = q * 32 + lane;
+    if (j >= C) continue;
+    float feat[7];
+    feat[0] = sqrtf(a_re[q] * a_re[q] + a_im[q] * a_im[q]) * invT;
+    feat[1] = fabsf(a_sg[q] * invT);
+    feat[2] = fabsf(a_w[q] / ((sum_p1 + st2[j * 8 + 4]) * 0.5f + 1e-8f));
+    const float* ps2 = pspec + (((long long)b * 2 + 1) * C + j) * nbins;
+    float coh = 0.f;
+    for (int k = klo; k <= khi; ++k) {
+      const float pp = ps1[k - lo_min] * ps2[k - lo_min];
+      coh += pp / (pp + 1e-8f);
+    }
+    feat[3] = coh / (float)(T / 2 + 1);
+    feat[4] = a_pc[q] * invT;
+    feat[5] = a_pd[q] * invT;
+    feat[6] = a_tc[q] * invT;
+#pragma unroll
+    for (int f = 0; f < 7; ++f) {
+      const int sl = slots.slot_of[f];
+      if (sl >= 0) out[((((long long)b * bands.nb + bi) * slots.n_out + sl) * C + i) * C + j] = feat[f];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ instance norm over tokens
+// x: [B, NT, P] (P = C*C); per (b, p) normalise over the NT tokens (biased variance, eps), affine.
+// (RobustIBSTokenizer, det:893-901).  Coalesced over p.
+template <typename TO>
+__global__ void instnorm_tokens_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, TO* __restrict__ y, int B, int NT, int P,
+                                       float eps, int apply_norm) {
+  const long long total = (long long)B * P;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / P), p = (int)(idx % P);
+    const float* xp = x + (long long)b * NT * P + p;
+    TO* yp = y + (long long)b * NT * P + p;
+    if (!apply_norm) {
+      for (int t = 0; t < NT; ++t) yp[(long long)t * P] = from_f<TO>(xp[(long long)t * P]);
+      continue;
+    }
+    float s = 0.f;
+    for (int t = 0; t < NT; ++t) s += xp[(long long)t * P];
+    const float mean = s / (float)NT;
+    float q = 0.f;
+    for (int t = 0; t < NT; ++t) { const float d = xp[(long long)t * P] - mean; q += d * d; }
+    const float rstd = rsqrtf(q / (float)NT + eps);
+    const float g = gamma[p], be = beta[p];
+    for (int t = 0; t < NT; ++t) yp[(long long)t * P] = from_f<TO>((xp[(long long)t * P] - mean) * rstd * g + be);
+  }
+}
+
+// dgamma[p] += sum_{b,t} dy * xhat ; dbeta[p] += sum_{b,t} dy      (input matrices carry no gradient)
+template <typename TO>
+__global__ void instnorm_tokens_bwd_kernel(const float* __restrict__ x, const TO* __restrict__ dy,
+                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int NT, int P,
+                                           float eps) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float ag = 0.f, ab = 0.f;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const float* xp = x + (long long)b * NT * P + p;
+    const TO* dp = dy + (long long)b * NT * P + p;
+    float s = 0.f;
+    for (int t = 0; t < NT; ++t) s += xp[(long long)t * P];
+    const float mean = s / (float)NT;
+    float q = 0.f;
+    for (int t = 0; t < NT; ++t) { const float d = xp[(long long)t * P] - mean; q += d * d; }
+    const float rstd = rsqrtf(q / (float)NT + eps);
+    for (int t = 0; t < NT; ++t) {
+      const float g = to_f(dp[(long long)t * P]);
+      ag += g * (xp[(long long)t * P] - mean) * rstd;
+      ab += g;
+    }
+  }
+  atomicAdd(dgamma + p, ag);
+  atomicAdd(dbeta + p, ab);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* Scratch sizes (floats): phase, xb: B*nb*2*C*T each; stats: B*nb*2*C*8; pspec: B*2*C*nbins,
+ * nbins = max(hi) - min(lo) + 1.  twiddle: T/2 float2 = exp(-2 pi i k / T) (host-computed in double).
+ * slot_of[7]: output slot of each feature (PLV, PLI, wPLI, Coherence, Power_Corr, Phase_Diff, Time_Corr), -1 = drop. */
+int egb_ibs_connectivity(const float* eeg1, const float* eeg2, const float* twiddle, float* phase, float* xb,
+                         float* stats, float* pspec, float* out, int B, int C, int T, int n_bands, const int32_t* band_lo,
+                         const int32_t* band_hi, const int32_t* slot_of, int n_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGB_CHECK(B > 0 && C > 0 && C <= 128, "ibs: unsupported channel count %d", C);
+  EGB_CHECK(T >= 8 && (T & (T - 1)) == 0 && T <= 8192, "ibs: window length %d must be a power of two in [8, 8192]", T);
+  EGB_CHECK(n_bands >= 1 && n_bands <= 8, "ibs: up to 8 bands");
+  int logT = 0;
+  while ((1 << logT) < T) ++logT;
+  IbsBands bands;
+  bands.nb = n_bands;
+  int lo_min = 1 << 30, hi_max = -1;
+  for (int i = 0; i < n_bands; ++i) {
+    bands.lo[i] = band_lo[i];
+    bands.hi[i] = band_hi[i];
+    EGB_CHECK(band_lo[i] >= 0 && band_hi[i] <= T / 2, "ibs: band %d bins [%d,%d] outside [0,%d]", i, band_lo[i],
+              band_hi[i], T / 2);
+    if (band_lo[i] <= band_hi[i]) {
+      if (band_lo[i] < lo_min) lo_min = band_lo[i];
+      if (band_hi[i] > hi_max) hi_max = band_hi[i];
+    }
+  }
+  if (hi_max < lo_min) { lo_min = 0; hi_max = 0; }
+  const int nbins = hi_max - lo_min + 1;
+  IbsSlots slots;
+  slots.n_out = n_out;
+  for (int f = 0; f < 7; ++f) slots.slot_of[f] = slot_of[f];
+
+  const size_t smem1 = sizeof(float2) * ((size_t)T + T / 2 + 1 + T / 2);
+  static size_t smem1_set = 0;
+  if (smem1 > 48 * 1024 && smem1 > smem1_set) {
+    EGB_CUDA(cudaFuncSetAttribute(ibs_analytic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    smem1_set = smem1;
+  }
+  ibs_analytic_kernel<<<dim3(C, 2, B), 256, smem1, st>>>(eeg1, eeg2, (const float2*)twiddle, phase, xb, stats, pspec,
+                                                         bands, B, C, T, logT, lo_min, nbins);
+  EGB_LAUNCH_CHECK();
+  const size_t smem2 = sizeof(float) * ((size_t)IBS_NF * IBS_TI * IBS_TC + (size_t)IBS_NF * C * (IBS_TC + 1));
+  static size_t smem2_set = 0;
+  if (smem2 > 48 * 1024 && smem2 > smem2_set) {
+    EGB_CUDA(cudaFuncSetAttribute(ibs_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    smem2_set = smem2;
+  }
+  ibs_pairs_kernel<<<dim3((C + IBS_TI - 1) / IBS_TI, n_bands, B), 256, smem2, st>>>(phase, xb, stats, pspec, out, bands,
+                                                                                  slots, B, C, T, lo_min, nbins);
+  egb_count_launch(2);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int egb_instnorm_tokens_fwd(const float* x, const float* gamma, const float* beta, void* y, int dtype, int B, int NT,
+                            int P, float eps, int apply_norm, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * P;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dtype == EGB_BF16)
+    instnorm_tokens_kernel<bf16><<<blocks, 256, 0, st>>>(x, gamma, beta, (bf16*)y, B, NT, P, eps, apply_norm);
+  else
+    instnorm_tokens_kernel<float><<<blocks, 256, 0, st>>>(x, gamma, beta, (float*)y, B, NT, P, eps, apply_norm);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int egb_instnorm_tokens_bwd(const float* x, const void* dy, int dtype, float* dgamma, float* dbeta, int B, int NT, int P,
+                            float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((P + 127) / 128, B < 32 ? B : 32);
+  if (dtype == EGB_BF16)
+    instnorm_tokens_bwd_kernel<bf16><<<grid, 128, 0, st>>>(x, (const bf16*)dy, dgamma, dbeta, B, NT, P, eps);
+  else
+    instnorm_tokens_bwd_kernel<float><<<grid, 128, 0, st>>>(x, (const float*)dy, dgamma, dbeta, B, NT, P, eps);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

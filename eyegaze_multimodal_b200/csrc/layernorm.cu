@@ -1,0 +1,182 @@
+// LayerNorm forward / backward over the last dimension (art.py:283-296,306,328 post-LN blocks, eps 1e-5;
+// timm ViT pre-LN, eps 1e-6).  One warp per row, 128-bit loads, row kept in registers (D <= 1024) so the
+// tensor is read exactly once per pass; mean / rstd are saved in fp32 for the backward.
+#include "common.cuh"
+#include "../../include/eyegaze_b200.h"
+
+extern void egb_count_launch(int n);
+
+namespace {
+
+constexpr int LN_MAX_CHUNKS = 4;  // 4 chunks x 32 lanes x 8 elements = D up to 1024
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int M, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int chunks = (D + 255) / 256;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const T* xr = x + (long long)row * D;
+    float v[LN_MAX_CHUNKS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (c < chunks && d < D) {
+        ld8(xr + d, v[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[c][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+      }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (c < chunks && d < D) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = v[c][j] - mean; q += t * t; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (c < chunks && d < D) {
+        float g[8], b[8], o[8];
+        ld8(gamma + d, g);
+        ld8(beta + d, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
+        st8(y + (long long)row * D + d, o);
+      }
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum dy*xhat; dbeta += sum dy.
+// Optional second output dx2 = dx * dropout-mask (the branch that went through a residual dropout).
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in, T* __restrict__ dx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                                                            int D) {
+  extern __shared__ float red[];  // [2][D]
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int chunks = (D + 255) / 256;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float ag[LN_MAX_CHUNKS][8], ab[LN_MAX_CHUNKS][8];
+#pragma unroll
+  for (int c = 0; c < LN_MAX_CHUNKS; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = 0.f;
+
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[LN_MAX_CHUNKS][8], g[LN_MAX_CHUNKS][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (c < chunks && d < D) {
+        float xv[8], dv[8], gm[8];
+        ld8(x + (long long)row * D + d, xv);
+        ld8(dy + (long long)row * D + d, dv);
+        ld8(gamma + d, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[c][j] = (xv[j] - mean) * rstd;
+          g[c][j] = dv[j] * gm[j];
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+          ag[c][j] += dv[j] * xh[c][j];
+          ab[c][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (c < chunks && d < D) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - s1 - xh[c][j] * s2);
+        st8(dx + (long long)row * D + d, o);
+      }
+    }
+  }
+  // block reduction of the per-warp column partials, then one atomic per column per block
+#pragma unroll
+  for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+    const int d = c * 256 + lane * 8;
+    if (c < chunks && d < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[d + j], ag[c][j]);
+        atomicAdd(&red[D + d + j], ab[c][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[D + i]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int egb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      int dtype, int M, int D, float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGB_CHECK(D % 8 == 0 && D <= 256 * LN_MAX_CHUNKS, "layernorm: D=%d must be a multiple of 8 and <= %d", D,
+            256 * LN_MAX_CHUNKS);
+  EGB_CHECK(M > 0, "layernorm: empty");
+  int blocks = (M + 7) / 8;
+  const int cap = egb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (dtype == EGB_BF16)
+    layernorm_fwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, D, eps);
+  else
+    layernorm_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, D, eps);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* dgamma / dbeta are ACCUMULATED into (caller zeroes them, or passes live .grad buffers). */
+int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                      float* dgamma, float* dbeta, int dtype, int M, int D, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGB_CHECK(D % 8 == 0 && D <= 256 * LN_MAX_CHUNKS, "layernorm_bwd: unsupported D=%d", D);
+  int blocks = (M + 7) / 8;
+  const int cap = egb_num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)2 * D * sizeof(float);
+  if (dtype == EGB_BF16)
+    layernorm_bwd_kernel<bf16><<<blocks, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (bf16*)dx,
+                                                         dgamma, dbeta, M, D);
+  else
+    layernorm_bwd_kernel<float><<<blocks, 256, smem, st>>>((const float*)dy, (const float*)x, gamma, mean, rstd,
+                                                          (float*)dx, dgamma, dbeta, M, D);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// Spectrogram-token prologue (dual_eeg_transformer.py:88-135), memory-bound stages:
+//   1. STFT (n_fft window, hop, centre/reflect padding) -> |.| -> first `bins` bins -> log(.+1e-8)
+//      as a direct windowed DFT from shared memory (frames are 128 samples: a table-driven DFT beats
+//      a library FFT round trip and fuses the magnitude/log).
+//   2. Conv2d(1->32,3x3,pad 1) + ReLU + MaxPool2d(2) fused: the 32-channel full-resolution activation
+//      (4.46 MB per trial and stream in the reference) is never written; output is channels-last with a
+//      zero border, i.e. exactly the operand layout of the implicit-GEMM 3x3 convolution that follows.
+//   3. ReLU + AdaptiveAvgPool2d(4,4) (+ flatten in (c, ph, pw) order) after the tensor-core conv.
+// Backward kernels produce the conv-1 weight gradient (recomputing the pooled arg-max from the stored
+// log-magnitude image) and the pre-activation gradient of conv 2 in the padded layout.
+#include "common.cuh"
+#include "../../include/eyegaze_b200.h"
+
+extern void egb_count_launch(int n);
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ 1. STFT log-magnitude
+// grid = (signals), block = 256.  Signal (T samples) is staged in smem with reflect padding.
+__global__ void __launch_bounds__(256) stft_logmag_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
+                                                          const float* __restrict__ window, float* __restrict__ out,
+                                                          int n_sig_per_stream, int T, int n_fft, int hop, int bins,
+                                                          int frames) {
+  extern __shared__ float sm[];
+  float* xs = sm;                       // [T + n_fft]  reflect padded
+  float* ct = xs + T + n_fft;           // [n_fft] cos table
+  float* st = ct + n_fft;               // [n_fft] sin table
+  float* ws = st + n_fft;               // [n_fft] window
+  const int sig = blockIdx.x;
+  const float* src = sig < n_sig_per_stream ? e1 + (long long)sig * T : e2 + (long long)(sig - n_sig_per_stream) * T;
+  const int half = n_fft / 2;
+  for (int i = threadIdx.x; i < T + n_fft; i += blockDim.x) {
+    int t = i - half;                   // torch.stft(center=True, pad_mode='reflect')
+    if (t < 0) t = -t;
+    if (t >= T) t = 2 * (T - 1) - t;
+    xs[i] = src[t];
+  }
+  for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
+    float s, c;
+    sincospif(2.0f * (float)i / (float)n_fft, &s, &c);
+    ct[i] = c;
+    st[i] = s;
+    ws[i] = window[i];
+  }
+  __syncthreads();
+  float* o = out + (long long)sig * bins * frames;
+  for (int idx = threadIdx.x; idx < bins * frames; idx += blockDim.x) {
+    const int k = idx / frames, f = idx % frames;
+    const float* x = xs + f * hop;
+    float re = 0.f, im = 0.f;
+    int ph = 0;                          // (k * n) mod n_fft
+    for (int n = 0; n < n_fft; ++n) {
+      const float v = x[n] * ws[n];
+      re = fmaf(v, ct[ph], re);
+      im = fmaf(-v, st[ph], im);
+      ph += k;
+      if (ph >= n_fft) ph -= n_fft;
+    }
+    o[idx] = logf(sqrtf(re * re + im * im) + 1e-8f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 2. conv1 + relu + maxpool
+// img: [N, Hh, Ww] fp32.  out: [N, Hh/2 + 2, Wp, 32] channels-last, Wp = Ww/2 + 2, zero border.
+// One thread per (pooled position, channel quad); the 4x4 input patch feeding a 2x2 pool window is held
+// in registers and reused across the 4 conv outputs.
+template <typename T>
+__global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, T* __restrict__ out, int Hh,
+                                                              int Ww, int H1, int W1, int Wp, long long out_img_stride) {
+  extern __shared__ float sm[];
+  float* im = sm;                    // [(Hh+2)][(Ww+2)] zero padded
+  float* wsm = im + (Hh + 2) * (Ww + 2);  // [32][9] + [32]
+  const int n = blockIdx.x;
+  const int ldw = Ww + 2;
+  for (int i = threadIdx.x; i < (Hh + 2) * ldw; i += blockDim.x) {
+    const int y = i / ldw - 1, x = i % ldw - 1;
+    im[i] = (y >= 0 && y < Hh && x >= 0 && x < Ww) ? img[(long long)n * Hh * Ww + y * Ww + x] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 32 * 9 + 32; i += blockDim.x) wsm[i] = i < 288 ? w[i] : bias[i - 288];
+  __syncthreads();
+  T* o = out + (long long)n * out_img_stride;
+  for (int idx = threadIdx.x; idx < H1 * W1 * 8; idx += blockDim.x) {
+    const int cq = idx & 7, pos = idx >> 3;
+    const int ph = pos / W1, pw = pos % W1;
+    float patch[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) patch[a][b] = im[(2 * ph + a) * ldw + 2 * pw + b];
+    float res[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = cq * 4 + cc;
+      const float* wc = wsm + c * 9;
+      float best = 0.f;  // relu(max(.)) == max(0, .)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float a = wsm[288 + c];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) a = fmaf(wc[kh * 3 + kw], patch[dy + kh][dx + kw], a);
+          best = fmaxf(best, a);
+        }
+      res[cc] = best;
+    }
+    st4(o + ((long long)(ph + 1) * Wp + (pw + 1)) * 32 + cq * 4, res);
+  }
+}
+
+// dW1[c,kh,kw] += sum dP1 * img(arg-max patch); db1[c] += sum dP1 (only where the pooled relu is active).
+// dP1: [N, H1+2, Wp, 32] padded layout (values at (h+1, w+1)).  Per-block partial sums -> global atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) spec_conv1_pool_bwd_kernel(const float* __restrict__ img,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ bias,
+                                                                  const T* __restrict__ dout, float* __restrict__ dw,
+                                                                  float* __restrict__ db, int N, int Hh, int Ww, int H1,
+                                                                  int W1, int Wp, long long out_img_stride) {
+  extern __shared__ float sm[];
+  const int ldw = Ww + 2;
+  float* im = sm;
+  float* wsm = im + (Hh + 2) * ldw;   // 288 + 32
+  float* acc = wsm + 320;             // 288 + 32 block accumulators
+  for (int i = threadIdx.x; i < 320; i += blockDim.x) {
+    wsm[i] = i < 288 ? w[i] : bias[i - 288];
+    acc[i] = 0.f;
+  }
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (Hh + 2) * ldw; i += blockDim.x) {
+      const int y = i / ldw - 1, x = i % ldw - 1;
+      im[i] = (y >= 0 && y < Hh && x >= 0 && x < Ww) ? img[(long long)n * Hh * Ww + y * Ww + x] : 0.f;
+    }
+    __syncthreads();
+    const T* g = dout + (long long)n * out_img_stride;
+    // thread -> channel c = tid & 31 (so the 32 lanes of a warp hit 32 different accumulators)
+    const int c = threadIdx.x & 31;
+    const float* wc = wsm + c * 9;
+    float lw[9], lb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) lw[i] = 0.f;
+    for (int pos = threadIdx.x >> 5; pos < H1 * W1; pos += blockDim.x >> 5) {
+      const int ph = pos / W1, pw = pos % W1;
+      const float go = to_f(g[((long long)(ph + 1) * Wp + (pw + 1)) * 32 + c]);
+      if (go == 0.f) continue;
+      float best = 0.f;
+      int by = -1, bx = 0;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float a = wsm[288 + c];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) a = fmaf(wc[kh * 3 + kw], im[(2 * ph + dy + kh) * ldw + 2 * pw + dx + kw], a);
+          if (a > best) { best = a; by = dy; bx = dx; }   // first maximum wins, as in max_pool2d
+        }
+      if (by < 0) continue;  // relu inactive
+      lb += go;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) lw[kh * 3 + kw] = fmaf(go, im[(2 * ph + by + kh) * ldw + 2 * pw + bx + kw], lw[kh * 3 + kw]);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) atomicAdd(&acc[c * 9 + i], lw[i]);
+    atomicAdd(&acc[288 + c], lb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 320; i += blockDim.x) {
+    if (i < 288) atomicAdd(dw + i, acc[i]);
+    else atomicAdd(db + (i - 288), acc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 3. relu + adaptive avgpool
+// y: conv-2 pre-activation in the padded layout [N, H1+2, Wp, 64] (value of (h,w) at (h+1,w+1)).
+// out: [N, 64*16] with index c*16 + ph*4 + pw  (== flatten of (64,4,4)).
+template <typename T>
+__global__ void __launch_bounds__(256) relu_avgpool_kernel(const T* __restrict__ y, T* __restrict__ out, int H1, int W1,
+                                                           int Wp, long long img_stride) {
+  const int n = blockIdx.x;
+  const T* yi = y + (long long)n * img_stride;
+  for (int idx = threadIdx.x; idx < 16 * 64; idx += blockDim.x) {
+    const int c = idx & 63, bin = idx >> 6;
+    const int ph = bin >> 2, pw = bin & 3;
+    const int h0 = (ph * H1) / 4, h1 = ((ph + 1) * H1 + 3) / 4;
+    const int w0 = (pw * W1) / 4, w1 = ((pw + 1) * W1 + 3) / 4;
+    float a = 0.f;
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w) a += fmaxf(to_f(yi[((long long)(h + 1) * Wp + (w + 1)) * 64 + c]), 0.f);
+    out[(long long)n * 1024 + c * 16 + bin] = from_f<T>(a / (float)((h1 - h0) * (w1 - w0)));
+  }
+}
+
+// dy (padded layout, zero on the border and where relu is inactive) from dpooled [N, 1024].
+template <typename T>
+__global__ void __launch_bounds__(256) relu_avgpool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dpool,
+                                                               T* __restrict__ dy, int H1, int W1, int Wp, int Hp,
+                                                               long long img_stride) {
+  const int n = blockIdx.x;
+  const T* yi = y + (long long)n * img_stride;
+  T* di = dy + (long long)n * img_stride;
+  for (int idx = threadIdx.x; idx < Hp * Wp * 64; idx += blockDim.x) {
+    const int c = idx & 63, pos = idx >> 6;
+    const int h = pos / Wp - 1, w = pos % Wp - 1;
+    float g = 0.f;
+    if (h >= 0 && h < H1 && w >= 0 && w < W1 && to_f(yi[idx]) > 0.f) {
+      // adaptive bins may overlap when H1 % 4 != 0: sum over every bin containing (h, w)
+      for (int ph = 0; ph < 4; ++ph) {
+        const int h0 = (ph * H1) / 4, h1 = ((ph + 1) * H1 + 3) / 4;
+        if (h < h0 || h >= h1) continue;
+        for (int pw = 0; pw < 4; ++pw) {
+          const int w0 = (pw * W1) / 4, w1 = ((pw + 1) * W1 + 3) / 4;
+          if (w < w0 || w >= w1) continue;
+          g += to_f(dpool[(long long)n * 1024 + c * 16 + ph * 4 + pw]) / (float)((h1 - h0) * (w1 - w0));
+        }
+      }
+    }
+    di[idx] = from_f<T>(g);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int egb_stft_logmag(const float* eeg1, const float* eeg2, const float* window, float* out, int n_sig_per_stream, int T,
+                    int n_fft, int hop, int bins, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGB_CHECK(n_fft >= 2 && n_fft % 2 == 0 && bins <= n_fft / 2 + 1 && hop > 0 && T > n_fft / 2,
+            "stft: unsupported configuration n_fft=%d hop=%d bins=%d T=%d", n_fft, hop, bins, T);
+  const int frames = 1 + T / hop;
+  const size_t smem = sizeof(float) * ((size_t)T + 4 * n_fft);
+  EGB_CHECK(smem <= 200 * 1024, "stft: window too long for shared memory");
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    EGB_CUDA(cudaFuncSetAttribute(stft_logmag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  stft_logmag_kernel<<<2 * n_sig_per_stream, 256, smem, st>>>(eeg1, eeg2, window, out, n_sig_per_stream, T, n_fft, hop,
+                                                              bins, frames);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* out must hold N * (H1+2) * Wp * 32 elements (+ slack rows for the implicit-GEMM over-read); this call zeroes it. */
+int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias, void* out, int dtype, int N, int Hh,
+                            int Ww, int64_t out_elems, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H1 = Hh / 2, W1 = Ww / 2, Wp = W1 + 2;
+  EGB_CHECK(H1 > 0 && W1 > 0, "spec_conv1: image too small");
+  const size_t esz = dtype == EGB_BF16 ? 2 : 4;
+  EGB_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * esz, st));
+  const size_t smem = sizeof(float) * ((size_t)(Hh + 2) * (Ww + 2) + 320);
+  const long long istr = (long long)(H1 + 2) * Wp * 32;
+  if (dtype == EGB_BF16)
+    spec_conv1_pool_kernel<bf16><<<N, 256, smem, st>>>(img, w, bias, (bf16*)out, Hh, Ww, H1, W1, Wp, istr);
+  else
+    spec_conv1_pool_kernel<float><<<N, 256, smem, st>>>(img, w, bias, (float*)out, Hh, Ww, H1, W1, Wp, istr);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* dw (288) and db (32) are accumulated into. */
+int egb_spec_conv1_pool_bwd(const float* img, const float* w, const float* bias, const void* dout, int dtype, float* dw,
+                            float* db, int N, int Hh, int Ww, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H1 = Hh / 2, W1 = Ww / 2, Wp = W1 + 2;
+  const size_t smem = sizeof(float) * ((size_t)(Hh + 2) * (Ww + 2) + 640);
+  const long long istr = (long long)(H1 + 2) * Wp * 32;
+  int blocks = N < 4 * egb_num_sms() ? N : 4 * egb_num_sms();
+  if (dtype == EGB_BF16)
+    spec_conv1_pool_bwd_kernel<bf16><<<blocks, 256, smem, st>>>(img, w, bias, (const bf16*)dout, dw, db, N, Hh, Ww, H1,
+                                                               W1, Wp, istr);
+  else
+    spec_conv1_pool_bwd_kernel<float><<<blocks, 256, smem, st>>>(img, w, bias, (const float*)dout, dw, db, N, Hh, Ww, H1,
+                                                                W1, Wp, istr);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int W1, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Wp = W1 + 2;
+  const long long istr = (long long)(H1 + 2) * Wp * 64;
+  if (dtype == EGB_BF16)
+    relu_avgpool_kernel<bf16><<<N, 256, 0, st>>>((const bf16*)y, (bf16*)out, H1, W1, Wp, istr);
+  else
+    relu_avgpool_kernel<float><<<N, 256, 0, st>>>((const float*)y, (float*)out, H1, W1, Wp, istr);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Wp = W1 + 2, Hp = H1 + 2;
+  const long long istr = (long long)Hp * Wp * 64;
+  if (dtype == EGB_BF16)
+    relu_avgpool_bwd_kernel<bf16><<<N, 256, 0, st>>>((const bf16*)y, (const bf16*)dpool, (bf16*)dy, H1, W1, Wp, Hp, istr);
+  else
+    relu_avgpool_bwd_kernel<float><<<N, 256, 0, st>>>((const float*)y, (const float*)dpool, (float*)dy, H1, W1, Wp, Hp,
+                                                      istr);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+"""DualEEGTransformer -- drop-in for ``3_Models/backbones/dual_eeg_transformer.py`` of the reference.
+
+Same class names, constructor signatures (incl. defaults), sub-module names, ``state_dict`` keys and output
+dictionary (cited below as ``det:<line>``).  The forward/backward pass runs on this package's sm_100a kernels:
+
+  * both players are stacked into one 2B batch (every per-player module is batch-independent and shares
+    weights, det:1127-1128/1148-1149/1182-1183), halving launches and doubling GEMM M;
+  * Conv1d frontend = implicit GEMMs over an overlapping-row channels-last view (no im2col);
+  * IBS connectivity = 2 kernels instead of ~2.6e5 ATen launches (det:593-758);
+  * spectrogram CNN: STFT-log kernel, fused conv+ReLU+maxpool, tensor-core 3x3 conv, fused ReLU+avgpool;
+  * sequence assembly + positional embedding in one kernel; pooling tail in one kernel; fused cross-entropy.
+
+Hooks the reference's analysis code attaches (5_Metrics/eeg_metrics.py) keep working: ``ibs_matrix_generator`` and
+``ibs_tokenizer`` are called as modules; ``cross_attn.cross_attn.dropout`` receives the exported probabilities;
+hooks on ``spectrogram_generator.spec_conv`` switch that sub-module to a reference-structured path.
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+from .art import (LayerNorm, MultiHeadAttention, PositionalEmbedding, TransformerEncoder,  # noqa: F401
+                  TransformerEncoderBlock, _has_hooks)
+from .precision import compute_code
+
+IBS_BANDS = [(0.5, 45.0), (0.5, 4.0), (4.0, 8.0), (8.0, 13.0), (13.0, 30.0), (30.0, 45.0)]   # det:500-507
+SCALAR_BANDS = [(4.0, 8.0), (8.0, 13.0), (13.0, 30.0), (30.0, 45.0)]                            # det:201-206
+
+
+class SpectrogramTokenGenerator(nn.Module):
+    """det:40-135."""
+
+    def __init__(self, in_channels: int, d_model: int, n_fft: int = 128, hop_length: int = 64, sampling_rate: int = 256,
+                 freq_bins: int = 64, use_log_magnitude: bool = True):
+        super().__init__()
+        self.d_model = d_model
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.sampling_rate = sampling_rate
+        self.freq_bins = freq_bins
+        self.use_log_magnitude = use_log_magnitude
+        self.register_buffer('window', torch.hann_window(n_fft))
+        self.spec_conv = nn.Sequential(
+            nn.Conv2d(1, 32, kernel_size=(3, 3), padding=1), nn.ReLU(), nn.MaxPool2d(kernel_size=(2, 2)),
+            nn.Conv2d(32, 64, kernel_size=(3, 3), padding=1), nn.ReLU(), nn.AdaptiveAvgPool2d((4, 4)))
+        self.proj = nn.Sequential(nn.Linear(64 * 4 * 4, d_model * 2), nn.ReLU(), nn.Dropout(0.1),
+                                  nn.Linear(d_model * 2, d_model))
+
+    def _hooked(self) -> bool:
+        return _has_hooks(self.spec_conv, *self.spec_conv, self.proj, *self.proj)
+
+    def forward_pair(self, eeg1: torch.Tensor, eeg2: torch.Tensor) -> torch.Tensor:
+        """Both players at once -> (2B, C, d_model)."""
+        if not self.use_log_magnitude:
+            raise NotImplementedError("use_log_magnitude=False is never constructed by the reference (det:1052-1055)")
+        B, C, _ = eeg1.shape
+        code = compute_code()
+        if self._hooked():
+            return torch.cat([self._reference_structured(eeg1), self._reference_structured(eeg2)], 0)
+        c1, c2 = self.spec_conv[0], self.spec_conv[3]
+        feat = ops.spectrogram_cnn(eeg1, eeg2, self.window, c1.weight, c1.bias, c2.weight, c2.bias, code, self.n_fft,
+                                   self.hop_length, self.freq_bins)                       # [2B*C, 1024]
+        p = self.proj[2].p if self.training else 0.0
+        tok = ops.mlp2(feat, self.proj[0].weight, self.proj[0].bias, self.proj[3].weight, self.proj[3].bias, L.ACT_RELU,
+                       p_mid=p)
+        return tok.view(2 * B, C, self.d_model)
+
+    def _reference_structured(self, x: torch.Tensor) -> torch.Tensor:
+        """Module-by-module path (ATen ops on the device) used only while analysis hooks are attached to
+        ``spec_conv`` / ``proj`` (Grad-CAM on spec_conv[3], 5_Metrics/eeg_metrics.py:841)."""
+        B, C, T = x.shape
+        st = torch.stft(x.reshape(B * C, T).float(), n_fft=self.n_fft, hop_length=self.hop_length, window=self.window,
+                        return_complex=True, center=True)
+        mag = torch.log(torch.abs(st)[:, :self.freq_bins, :] + 1e-8).unsqueeze(1)
+        f = self.spec_conv(mag).flatten(start_dim=1)
+        return ops.cast(self.proj(f).reshape(B, C, self.d_model).contiguous(), compute_code())
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward_pair(x, x)[:x.shape[0]]
+
+
+class TemporalConvFrontend(nn.Module):
+    """det:138-175."""
+
+    def __init__(self, in_channels: int, d_model: int, kernel_size: int = 25, stride: int = 4, num_layers: int = 2):
+        super().__init__()
+        self.convs = nn.ModuleList()
+        self.convs.append(nn.Conv1d(in_channels, d_model, kernel_size, stride, padding=kernel_size // 2))
+        for _ in range(num_layers - 1):
+            self.convs.append(nn.Conv1d(d_model, d_model, kernel_size, stride, padding=kernel_size // 2))
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(0.1)
+
+    def forward_pair(self, eeg1: torch.Tensor, eeg2: torch.Tensor) -> torch.Tensor:
+        """Both players at once -> (2B, T~, d)."""
+        p = self.dropout.p if self.training else 0.0
+        return ops.temporal_conv(eeg1, eeg2, [c.weight for c in self.convs], [c.bias for c in self.convs],
+                                 compute_code(), self.convs[0].stride[0], p)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward_pair(x, x)[:x.shape[0]]
+
+
+class IBSTokenGenerator(nn.Module):
+    """Legacy scalar IBS token (det:178-470): 4 bands x 7 global features -> MLP."""
+
+    def __init__(self, in_channels: int, d_model: int, sampling_rate: int = 256, use_layernorm: bool = False):
+        super().__init__()
+        self.sampling_rate = sampling_rate
+        self.use_layernorm = use_layernorm
+        self.freq_bands = {'theta': (4, 8), 'alpha': (8, 13), 'beta': (13, 30), 'gamma': (30, 45)}
+        feature_dim = len(self.freq_bands) * 7
+        self.proj = nn.Sequential(nn.Linear(feature_dim, d_model * 2), nn.ReLU(), nn.Dropout(0.1),
+                                  nn.Linear(d_model * 2, d_model))
+        if self.use_layernorm:
+            self.norm = LayerNorm(d_model)
+
+    def forward(self, eeg1: torch.Tensor, eeg2: torch.Tensor) -> torch.Tensor:
+        feats = ops.ibs_scalar_features(eeg1, eeg2, float(self.sampling_rate), SCALAR_BANDS)      # (B, 28) fp32
+        p = self.proj[2].p if self.training else 0.0
+        tok = ops.mlp2(ops.cast(feats, compute_code()), self.proj[0].weight, self.proj[0].bias, self.proj[3].weight,
+                       self.proj[3].bias, L.ACT_RELU, p_mid=p)
+        if self.use_layernorm:
+            tok = self.norm(tok)
+        return tok
+
+
+class IBSConnectivityMatrixGenerator(nn.Module):
+    """det:473-819 -- parameter-free; output (B, 6, num_features, C, C) fp32."""
+
+    def __init__(self, in_channels: int, sampling_rate: int = 256, feature_type: str = "all"):
+        super().__init__()
+        self.in_channels = in_channels
+        self.sampling_rate = sampling_rate
+        self.feature_type = feature_type
+        self.freq_bands = {'broadband': (0.5, 45), 'delta': (0.5, 4), 'theta': (4, 8), 'alpha': (8, 13),
+                           'beta': (13, 30), 'gamma': (30, 45)}
+        self.band_names = ['broadband', 'delta', 'theta', 'alpha', 'beta', 'gamma']
+        self.feature_names = ['PLV', 'PLI', 'wPLI', 'Coherence', 'Power_Corr', 'Phase_Diff', 'Time_Corr']
+        if feature_type == "phase":
+            self.feature_indices = [0, 1, 2, 5]
+            self.num_features = 4
+        elif feature_type == "amplitude":
+            self.feature_indices = [3, 4, 6]
+            self.num_features = 3
+        else:  # "all" (unknown strings fall through to "all", det:523-525)
+            self.feature_indices = list(range(7))
+            self.num_features = 7
+
+    def forward(self, eeg1: torch.Tensor, eeg2: torch.Tensor) -> torch.Tensor:
+        bands = [tuple(float(v) for v in self.freq_bands[n]) for n in self.band_names]
+        return ops.ibs_connectivity(eeg1, eeg2, float(self.sampling_rate), bands, self.feature_indices)
+
+
+class RobustIBSTokenizer(nn.Module):
+    """det:822-911."""
+
+    def __init__(self, in_channels: int, d_model: int, use_instance_norm: bool = True, num_features: int = 7,
+                 num_bands: int = 6):
+        super().__init__()
+        self.in_channels = in_channels
+        self.d_model = d_model
+        self.use_instance_norm = use_instance_norm
+        self.num_features = num_features
+        self.num_bands = num_bands
+        self.num_tokens = num_bands * num_features
+        matrix_dim = in_channels * in_channels
+        if use_instance_norm:
+            self.instance_norm = nn.InstanceNorm1d(matrix_dim, affine=True)
+        self.bottleneck = nn.Sequential(nn.Linear(matrix_dim, 64), nn.GELU(), nn.Dropout(0.1), nn.Linear(64, d_model))
+        self.type_embedding = nn.Parameter(torch.randn(1, self.num_tokens, d_model))
+        nn.init.normal_(self.type_embedding, std=0.02)
+
+    def forward(self, connectivity_matrices: torch.Tensor) -> torch.Tensor:
+        B, num_bands, num_features, C1, C2 = connectivity_matrices.shape
+        assert C1 == C2 == self.in_channels, "Channel dimension mismatch"
+        assert num_bands == self.num_bands, f"Expected {self.num_bands} bands, got {num_bands}"
+        assert num_features == self.num_features, f"Expected {self.num_features} features, got {num_features}"
+        code = compute_code()
+        x = connectivity_matrices.reshape(B, num_bands * num_features, C1 * C2)
+        if self.use_instance_norm:
+            x = ops.instnorm_tokens(x, self.instance_norm.weight, self.instance_norm.bias, code, True)
+        else:
+            x = ops.instnorm_tokens(x, None, None, code, False)       # dtype conversion only
+        p = self.bottleneck[2].p if self.training else 0.0
+        x = ops.mlp2(x, self.bottleneck[0].weight, self.bottleneck[0].bias, self.bottleneck[3].weight,
+                     self.bottleneck[3].bias, L.ACT_GELU, p_mid=p,
+                     residual=None)
+        return ops.add_broadcast_rows(x, self.type_embedding)
+
+
+class SymmetricFusion(nn.Module):
+    """det:914-941: proj(cat[z1+z2, z1*z2, |z1-z2|])."""
+
+    def __init__(self, d_model: int):
+        super().__init__()
+        self.proj = nn.Linear(d_model * 3, d_model)
+
+    def forward(self, z1: torch.Tensor, z2: torch.Tensor) -> torch.Tensor:
+        z1, z2 = z1.float(), z2.float()
+        combined = torch.cat([z1 + z2, z1 * z2, torch.abs(z1 - z2)], dim=-1)   # standalone use; fused in the model tail
+        return ops.linear(combined, self.proj.weight, self.proj.bias, out_f32=True)
+
+
+class CrossBrainAttention(nn.Module):
+    """det:944-974: one MHA and one LayerNorm shared by both directions; direction 2 uses the ORIGINAL z1."""
+
+    def __init__(self, d_model: int, num_heads: int, dropout: float = 0.1):
+        super().__init__()
+        self.cross_attn = MultiHeadAttention(d_model, num_heads, dropout)
+        self.norm = LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward_stacked(self, z: torch.Tensor) -> torch.Tensor:
+        """z = [z1; z2] stacked along the batch (2B, L, d): both directions in one pass (kv_shift = B)."""
+        B = z.shape[0] // 2
+        ctx = self.cross_attn.context_packed(z, kv_shift=B, hook_split=B)
+        p = self.dropout.p if self.training else 0.0
+        y = ops.linear(ctx, self.cross_attn.out_proj.weight, self.cross_attn.out_proj.bias, residual=z, p=p)
+        return self.norm(y)
+
+    def forward(self, z1: torch.Tensor, z2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        code = compute_code()
+        if z1.shape == z2.shape:
+            out = self.forward_stacked(torch.cat([ops.cast(z1, code), ops.cast(z2, code)], 0))
+            return out[:z1.shape[0]], out[z1.shape[0]:]
+        z1c = self.cross_attn(z1, z2, z2)                     # unequal lengths (BASELINE config 3)
+        z2c = self.cross_attn(z2, z1, z1)
+        z1, z2 = ops.cast(z1, code), ops.cast(z2, code)
+        return self.norm(z1 + self.dropout(z1c)), self.norm(z2 + self.dropout(z2c))
+
+
+class DualEEGTransformer(nn.Module):
+    """det:977-1371."""
+
+    def __init__(self, in_channels: int = 62, num_classes: int = 3, d_model: int = 256, num_layers: int = 6,
+                 num_heads: int = 8, d_ff: int = 1024, dropout: float = 0.1, max_len: int = 2048,
+                 conv_kernel_size: int = 25, conv_stride: int = 4, conv_layers: int = 2, sampling_rate: int = 256,
+                 use_spectrogram: bool = True, spec_n_fft: int = 128, spec_hop_length: int = 64,
+                 spec_freq_bins: int = 64, use_robust_ibs: bool = True, use_ibs: bool = True,
+                 use_cross_attention: bool = True, ibs_instance_norm: bool = True, ibs_feature_type: str = "all"):
+        super().__init__()
+        self.d_model = d_model
+        self.in_channels = in_channels
+        self.use_spectrogram = use_spectrogram
+        self.use_robust_ibs = use_robust_ibs
+        self.use_ibs = use_ibs
+        self.use_cross_attention = use_cross_attention
+        self.ibs_feature_type = ibs_feature_type
+        feature_counts = {"all": 7, "phase": 4, "amplitude": 3}
+        self.num_ibs_features = feature_counts.get(ibs_feature_type, 7)
+        if use_ibs:
+            self.num_ibs_tokens = 6 * self.num_ibs_features if use_robust_ibs else 1
+        else:
+            self.num_ibs_tokens = 0
+        self.temporal_conv = TemporalConvFrontend(in_channels, d_model, conv_kernel_size, conv_stride, conv_layers)
+        if use_spectrogram:
+            self.spectrogram_generator = SpectrogramTokenGenerator(in_channels, d_model, spec_n_fft, spec_hop_length,
+                                                                   sampling_rate, spec_freq_bins)
+        if use_ibs:
+            if use_robust_ibs:
+                self.ibs_matrix_generator = IBSConnectivityMatrixGenerator(in_channels, sampling_rate,
+                                                                           feature_type=ibs_feature_type)
+                self.ibs_tokenizer = RobustIBSTokenizer(in_channels, d_model, use_instance_norm=ibs_instance_norm,
+                                                        num_features=self.num_ibs_features)
+            else:
+                self.ibs_generator = IBSTokenGenerator(in_channels, d_model, sampling_rate, use_layernorm=False)
+            self.ibs_classifier = nn.Sequential(nn.Linear(d_model, d_model // 2), nn.ReLU(), nn.Dropout(0.3),
+                                                nn.Linear(d_model // 2, num_classes))
+        self.cls_token = nn.Parameter(torch.randn(1, 1, d_model))
+        self.pos_embed = PositionalEmbedding(max_len, d_model, mode='learned')
+        self.encoder = TransformerEncoder(d_model, num_layers, num_heads, d_ff, dropout, dropout)
+        if use_cross_attention:
+            self.cross_attn = CrossBrainAttention(d_model, num_heads, dropout)
+        self.symmetric_fusion = SymmetricFusion(d_model)
+        self.classifier = nn.Sequential(nn.Linear(d_model * 3, d_model), nn.ReLU(), nn.Dropout(dropout),
+                                        nn.Linear(d_model, num_classes))
+        self.dropout = nn.Dropout(dropout)
+        self.num_classes = num_classes
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, eeg1: torch.Tensor, eeg2: torch.Tensor, labels: Optional[torch.Tensor] = None) -> dict:
+        if not eeg1.is_cuda:
+            raise RuntimeError("DualEEGTransformer (B200 build) needs CUDA inputs; there is no CPU path")
+        code = compute_code()
+        training = self.training
+        # 1. temporal conv frontend, both players stacked along the batch: (2B, T~, d)
+        h = self.temporal_conv.forward_pair(eeg1, eeg2)
+        # 2. IBS tokens (module calls: hooks on ibs_matrix_generator may observe / replace the matrices)
+        ibs_tokens = None
+        if self.use_ibs:
+            if self.use_robust_ibs:
+                connectivity_matrices = self.ibs_matrix_generator(eeg1, eeg2)
+                ibs_tokens = self.ibs_tokenizer(connectivity_matrices)
+            else:
+                ibs_tokens = self.ibs_generator(eeg1, eeg2).unsqueeze(1)
+        # 2.5 spectrogram tokens (2B, C, d)
+        spec = self.spectrogram_generator.forward_pair(eeg1, eeg2) if self.use_spectrogram else None
+        # 3. [CLS | IBS | Spec | H] + positional embedding, one kernel
+        seq = ops.seq_assemble(self.cls_token, self.pos_embed.table(), ibs_tokens, spec, h, code)
+        # 4. shared (Siamese) encoder on the stacked batch; 5. both cross-attention directions in one pass
+        z = self.encoder(seq)
+        if self.use_cross_attention:
+            z = self.cross_attn.forward_stacked(z)
+        # 6-8. CLS / mean-pool / symmetric features -> heads (fp32 tail)
+        offset = 1 + (self.num_ibs_tokens if self.use_ibs else 0) + (self.in_channels if self.use_spectrogram else 0)
+        pooled = ops.tail_pool(z, self.num_ibs_tokens, offset, self.use_ibs and not self.use_robust_ibs)
+        cls1, cls2, sym, mp = pooled[:4]
+        f_pair = ops.linear(sym, self.symmetric_fusion.proj.weight, self.symmetric_fusion.proj.bias, out_f32=True)
+        z_fuse = ops.concat2(f_pair, mp)
+        logits = ops.mlp2(z_fuse, self.classifier[0].weight, self.classifier[0].bias, self.classifier[3].weight,
+                          self.classifier[3].bias, L.ACT_RELU, p_mid=self.classifier[2].p if training else 0.0,
+                          out_f32=True)
+        output = {'logits': logits, 'cls1': cls1, 'cls2': cls2}
+        ibs_logits = None
+        if self.use_ibs:
+            ibs_pool = pooled[4]
+            ibs_logits = ops.mlp2(ibs_pool, self.ibs_classifier[0].weight, self.ibs_classifier[0].bias,
+                                  self.ibs_classifier[3].weight, self.ibs_classifier[3].bias, L.ACT_RELU,
+                                  p_mid=self.ibs_classifier[2].p if training else 0.0, out_f32=True)
+            output['ibs_logits'] = ibs_logits
+            output['ibs_token'] = ibs_pool
+        if labels is not None:
+            loss_ce = ops.cross_entropy(logits, labels)
+            output['loss'] = loss_ce
+            output['loss_ce'] = loss_ce
+            if self.use_ibs and ibs_logits is not None:
+                output['loss_ibs_cls'] = ops.cross_entropy(ibs_logits, labels)
+        return output
+
+    # ------------------------------------------------------------------------------------------ aux losses (det:1255-1371)
+    # Optional, off by default (dual_eeg_transformer.yaml:98-106); batch-level ATen ops on (B, d) tensors.
+    def compute_symmetry_loss(self, cls1: torch.Tensor, cls2: torch.Tensor) -> torch.Tensor:
+        return F.mse_loss(cls1, cls2)
+
+    def compute_ibs_alignment_loss(self, ibs_token: torch.Tensor, cls1: torch.Tensor, cls2: torch.Tensor,
+                                   temperature: float = 0.07) -> torch.Tensor:
+        B = ibs_token.shape[0]
+        ibs_norm = F.normalize(ibs_token, dim=-1)
+        all_cls = torch.cat([F.normalize(cls1, dim=-1), F.normalize(cls2, dim=-1)], dim=0)
+        sim = torch.matmul(ibs_norm, all_cls.T) / temperature
+        return F.cross_entropy(sim, torch.arange(B, device=ibs_token.device))
+
+    def compute_ibs_contrastive_loss(self, ibs_tokens: torch.Tensor, labels: torch.Tensor,
+                                     temperature: float = 0.07) -> torch.Tensor:
+        B = ibs_tokens.shape[0]
+        t = F.normalize(ibs_tokens, p=2, dim=1)
+        sim = torch.matmul(t, t.t()) / temperature
+        eye = torch.eye(B, device=t.device).bool()
+        pos = (labels.unsqueeze(1) == labels.unsqueeze(0)).float().masked_fill(eye, 0)
+        has_pos = pos.sum(dim=1) > 0
+        if has_pos.sum() == 0:
+            return torch.tensor(0.0, device=t.device)
+        e = torch.exp(sim)
+        loss = -torch.log((e * pos).sum(dim=1) / (e.masked_fill(eye, 0).sum(dim=1) + 1e-8) + 1e-8)
+        return loss[has_pos].mean()

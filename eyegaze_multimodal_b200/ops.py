@@ -1,0 +1,1165 @@
+"""Host side of the hot path: autograd Functions that launch the sm_100a kernels through the C ABI.
+
+Every Function here enqueues kernels of libeyegaze_b200.so on the current CUDA stream via ctypes
+(raw device pointers + sizes, see include/eyegaze_b200.h); PyTorch only provides device memory, streams and
+the autograd graph between the fused ops.  Activations are stored in the *compute dtype* (fp32 for the
+parity mode, bf16 for the throughput mode); parameters stay fp32 ``nn.Parameter``s and are re-cast once
+per parameter version.  Nothing in this file has a CPU or eager fallback.
+"""
+import ctypes as C
+import math
+import threading
+
+import torch
+
+from . import _lib as L
+
+F32, BF16 = L.F32, L.BF16
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+
+
+# ------------------------------------------------------------------------------------------------------
+# small helpers
+# ------------------------------------------------------------------------------------------------------
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("unsupported dtype %s (fp32 / bf16 only)" % t.dtype)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("eyegaze_multimodal_b200 runs on CUDA tensors only (got a %s tensor); "
+                               "there is no CPU path" % t.device)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: torch.Tensor):
+    """(tensor, total_rows, rows_per_group, row_stride, group_stride) of a [.., K] view whose last dim is contiguous."""
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        t = t.contiguous()
+    if t.dim() > 3:
+        t = t.reshape(-1, t.shape[-2], t.shape[-1]) if t.is_contiguous() else t.contiguous().view(-1, t.shape[-2], t.shape[-1])
+    if t.dim() == 2:
+        return t, t.shape[0], 0, t.stride(0), 0
+    G, R = t.shape[0], t.shape[1]
+    if G == 1 or t.stride(0) == R * t.stride(1):
+        return t, G * R, 0, t.stride(1), 0
+    return t, G * R, R, t.stride(1), t.stride(0)
+
+
+def _operand(t, major):
+    t, rows, rpg, rs, gs = _rows(t)
+    return L.Operand(t.data_ptr(), major, rpg, rs, gs, 0, 0), t
+
+
+def _matrix(t):
+    if t is None:
+        return L.Matrix(None, 0, 0, 0, 0), None
+    t, rows, rpg, rs, gs = _rows(t)
+    return L.Matrix(t.data_ptr(), _code(t), rpg, rs, gs), t
+
+
+def _dense_matrix(ptr, code, ld):
+    return L.Matrix(ptr, code, 0, ld, 0)
+
+
+def zeros(shape, dtype, device):
+    t = torch.empty(shape, dtype=dtype, device=device)
+    L.call("egb_zero", t.data_ptr(), t.numel() * t.element_size(), _stream())
+    return t
+
+
+def gemm(M, N, K, in_code, a: L.Operand, b: L.Operand, c: L.Matrix, *, bias=None, c_pre=None, residual=None, aux=None,
+         alpha=1.0, act=0, act_bwd=0, aux_scale=1.0, dropout_p=0.0, seed=0, accumulate=0, split_k=0):
+    empty = L.Matrix(None, 0, 0, 0, 0)
+    d = L.GemmDesc(M, N, K, in_code, a, b, c, c_pre or empty, residual or empty, aux or empty, _p(bias), alpha, act,
+                   act_bwd, aux_scale, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, accumulate, split_k)
+    L.call("egb_gemm", C.byref(d), _stream())
+
+
+def cast(x: torch.Tensor, code: int) -> torch.Tensor:
+    """dtype conversion through the library's cast kernels (fp32 <-> bf16)."""
+    if _code(x) == code:
+        return x
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=_TORCH_DT[code], device=x.device)
+    if code == F32:
+        L.call("egb_cast_to_f32", x.data_ptr(), _code(x), out.data_ptr(), x.numel(), _stream())
+    else:
+        L.call("egb_cast_from_f32", x.data_ptr(), out.data_ptr(), code, x.numel(), _stream())
+    return out
+
+
+def copy_strided4(src, dst, sizes, src_strides, dst_strides, src_offset=0, dst_offset=0):
+    sz = (L.i32 * 4)(*sizes)
+    ss = (L.i64 * 4)(*src_strides)
+    ds = (L.i64 * 4)(*dst_strides)
+    L.call("egb_copy_strided4", src.data_ptr() + src_offset * src.element_size(), _code(src),
+           dst.data_ptr() + dst_offset * dst.element_size(), _code(dst), sz, ss, ds, _stream())
+
+
+def colsum(x: torch.Tensor, N: int) -> torch.Tensor:
+    m, xt = _matrix(x)
+    rows = _rows(xt)[1]
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    L.call("egb_colsum", C.byref(m), rows, N, out.data_ptr(), 1, _stream())
+    return out
+
+
+# dropout seeds: one fresh 64-bit value per op instance, derived from torch's seed so runs are reproducible
+_seed_lock = threading.Lock()
+_seed_state = {"base": None, "ctr": 0}
+
+
+def next_seed() -> int:
+    with _seed_lock:
+        base = torch.initial_seed()
+        if _seed_state["base"] != base:
+            _seed_state["base"], _seed_state["ctr"] = base, 0
+        _seed_state["ctr"] += 1
+        x = (base * 0x9E3779B97F4A7C15 + _seed_state["ctr"] * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 31
+        return x
+
+
+# ------------------------------------------------------------------------------------------------------
+# per-version cache of re-laid-out / re-cast parameter copies
+# ------------------------------------------------------------------------------------------------------
+class _WeightCache:
+    def __init__(self):
+        self._d = {}
+
+    def get(self, params, code, tag, builder):
+        # keyed by storage address (stable for parameters; saved_tensors hands back new Python objects)
+        key = (tuple((p.data_ptr(), tuple(p.shape)) for p in params), code, tag)
+        ver = tuple(p._version for p in params)
+        hit = self._d.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = builder()
+        self._d[key] = (ver, val)
+        if len(self._d) > 4096:
+            self._d.clear()
+        return val
+
+
+wcache = _WeightCache()
+
+
+def weight_plain(w: torch.Tensor, code: int) -> torch.Tensor:
+    """[N, K...] parameter flattened to [N, K] in the compute dtype (no copy in fp32 mode)."""
+    w2 = w.detach().reshape(w.shape[0], -1)
+    if code == F32:
+        return w2
+    return wcache.get((w,), code, "plain", lambda: cast(w2, code))
+
+
+def weight_packed(ws, code):
+    """Row-concatenation of several [N_i, K] parameters (QKV packing) in the compute dtype."""
+    def build():
+        n = sum(w.shape[0] for w in ws)
+        out = torch.empty(n, ws[0].shape[1], dtype=_TORCH_DT[code], device=ws[0].device)
+        r = 0
+        for w in ws:
+            copy_strided4(w.detach(), out, (1, 1, w.shape[0], w.shape[1]), (0, 0, w.shape[1], 1), (0, 0, w.shape[1], 1),
+                          dst_offset=r * w.shape[1])
+            r += w.shape[0]
+        return out
+    return wcache.get(tuple(ws), code, "packed", build)
+
+
+def bias_packed(bs):
+    def build():
+        n = sum(b.shape[0] for b in bs)
+        out = torch.empty(n, dtype=torch.float32, device=bs[0].device)
+        r = 0
+        for b in bs:
+            copy_strided4(b.detach(), out, (1, 1, 1, b.shape[0]), (0, 0, 0, 1), (0, 0, 0, 1), dst_offset=r)
+            r += b.shape[0]
+        return out
+    return wcache.get(tuple(bs), F32, "bias_packed", build)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Linear (+bias +relu +dropout +residual)
+# ------------------------------------------------------------------------------------------------------
+def _linear_forward(x, w2, bias, residual, act, p, seed, out_code, c_pre=None):
+    """x: [.., K] (compute dtype), w2: [N, K] same dtype.  Returns y [.., N]."""
+    a, xt = _operand(x, 0)
+    rows = _rows(xt)[1]
+    N, K = w2.shape
+    y = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=_TORCH_DT[out_code], device=x.device)
+    cm = _dense_matrix(y.data_ptr(), out_code, N)
+    rm, rt = _matrix(residual)
+    pm = _dense_matrix(c_pre.data_ptr(), _code(c_pre), N) if c_pre is not None else None
+    gemm(rows, N, K, _code(xt), a, L.Operand(w2.data_ptr(), 0, 0, w2.stride(0), 0, 0, 0), cm, bias=bias, residual=rm if rt is not None else None,
+         c_pre=pm, act=act, dropout_p=p, seed=seed)
+    return y
+
+
+def _grad_input(dpre, w2, x_shape, out_code, act_bwd=0, aux=None, aux_scale=1.0, dropout_p=0.0, seed=0):
+    """dx[.., K] = dpre[.., N] . W[N, K]  (W consumed as an MN-major operand, no transposed copy)."""
+    a, dt = _operand(dpre, 0)
+    rows = _rows(dt)[1]
+    N, K = w2.shape
+    dx = torch.empty(tuple(x_shape), dtype=_TORCH_DT[out_code], device=dpre.device)
+    am = _dense_matrix(aux.data_ptr(), _code(aux), K) if aux is not None else None
+    gemm(rows, K, N, _code(dt), a, L.Operand(w2.data_ptr(), 1, 0, w2.stride(0), 0, 0, 0),
+         _dense_matrix(dx.data_ptr(), out_code, K), act_bwd=act_bwd, aux=am, aux_scale=aux_scale, dropout_p=dropout_p,
+         seed=seed)
+    return dx
+
+
+def _grad_weight(dpre, x, N, K):
+    """dW[N, K] (fp32) = dpre^T . x, split-K accumulation; both operands MN-major views (no transposes)."""
+    a, dt = _operand(dpre, 1)
+    b, xt = _operand(x, 1)
+    rows = _rows(dt)[1]
+    dw = torch.empty(N, K, dtype=torch.float32, device=dpre.device)
+    gemm(N, K, rows, _code(dt), a, b, _dense_matrix(dw.data_ptr(), F32, K), accumulate=2)
+    return dw
+
+
+def _act_bwd(dy, aux, mode, scale):
+    """dense dpre = dy * act'(aux); dy may be a strided view."""
+    dm, dt = _matrix(dy)
+    rows = _rows(dt)[1]
+    N = dt.shape[-1]
+    out = torch.empty(tuple(dy.shape), dtype=dt.dtype, device=dy.device)
+    om = _dense_matrix(out.data_ptr(), _code(out), N)
+    L.call("egb_act_bwd", C.byref(dm), aux.data_ptr(), C.byref(om), rows, N, mode, float(scale), _stream())
+    return out
+
+
+def _dropout_bwd(dy, p, seed):
+    dy = dy.contiguous()
+    out = torch.empty_like(dy)
+    L.call("egb_dropout_bwd", dy.data_ptr(), out.data_ptr(), _code(dy), dy.numel(), float(p), int(seed), _stream())
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = [residual +] dropout(act(x W^T + b)).  `weights`/`biases`: 1 parameter, or several packed along N."""
+
+    @staticmethod
+    def forward(ctx, x, residual, n_w, act, p, out_f32, *wb):
+        weights, biases = wb[:n_w], wb[n_w:]
+        code = _code(x)
+        _require_cuda(x, *weights)
+        w2 = weight_plain(weights[0], code) if n_w == 1 else weight_packed(weights, code)
+        has_bias = len(biases) > 0 and biases[0] is not None
+        bias = None
+        if has_bias:
+            bias = biases[0].detach() if n_w == 1 else bias_packed([b.detach() for b in biases])
+        seed = next_seed() if p > 0 else 0
+        out_code = F32 if out_f32 else code
+        y = _linear_forward(x, w2, bias, residual, act, p, seed, out_code)
+        ctx.save_for_backward(x, y if act == L.ACT_RELU else None, *weights)
+        ctx.meta = (n_w, act, p, seed, has_bias, residual is not None, code)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n_w, act, p, seed, has_bias, has_res, code = ctx.meta
+        saved = ctx.saved_tensors
+        x, y, weights = saved[0], saved[1], saved[2:]
+        w2 = weight_plain(weights[0], code) if n_w == 1 else weight_packed(weights, code)
+        N, K = w2.shape
+        if _code(dy) != code:
+            dy = cast(dy, code)
+        if act == L.ACT_RELU:
+            dpre = _act_bwd(dy, y, 1, 1.0 / (1.0 - p) if p > 0 else 1.0)
+        elif p > 0:
+            dpre = _dropout_bwd(dy, p, seed)
+        else:
+            dpre = dy
+        dx = _grad_input(dpre, w2, x.shape, code) if ctx.needs_input_grad[0] else None
+        dres = dy if has_res else None
+        need_w = any(ctx.needs_input_grad[6 + i] for i in range(n_w))
+        dws = [None] * n_w
+        dbs = [None] * (len(ctx.needs_input_grad) - 6 - n_w)
+        if need_w:
+            dw = _grad_weight(dpre, x, N, K)
+            r = 0
+            for i, w in enumerate(weights):
+                dws[i] = dw[r:r + w.shape[0]].view(w.shape)
+                r += w.shape[0]
+        if has_bias and any(ctx.needs_input_grad[6 + n_w:]):
+            db = colsum(dpre, N)
+            r = 0
+            for i, w in enumerate(weights):
+                dbs[i] = db[r:r + w.shape[0]]
+                r += w.shape[0]
+        return (dx, dres, None, None, None, None) + tuple(dws) + tuple(dbs)
+
+
+def linear(x, weight, bias=None, residual=None, act=0, p=0.0, out_f32=False):
+    return LinearFn.apply(x, residual, 1, act, float(p), out_f32, weight, bias)
+
+
+def linear_packed(x, weights, biases, out_f32=False):
+    return LinearFn.apply(x, None, len(weights), 0, 0.0, out_f32, *weights, *biases)
+
+
+# ------------------------------------------------------------------------------------------------------
+# two-layer MLP:  y = [residual +] drop_out(act(drop_mid(x W1^T + b1)) W2^T + b2)     (fused backward)
+# ------------------------------------------------------------------------------------------------------
+class Mlp2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, w1, b1, w2, b2, act, p_mid, p_out, out_f32):
+        code = _code(x)
+        _require_cuda(x, w1, w2)
+        w1c, w2c = weight_plain(w1, code), weight_plain(w2, code)
+        s_mid = next_seed() if p_mid > 0 else 0
+        s_out = next_seed() if p_out > 0 else 0
+        pre = None
+        if act == L.ACT_GELU:
+            pre = torch.empty(tuple(x.shape[:-1]) + (w1.shape[0],), dtype=x.dtype, device=x.device)
+        h = _linear_forward(x, w1c, b1.detach(), None, act, p_mid, s_mid, code, c_pre=pre)
+        y = _linear_forward(h, w2c, b2.detach(), residual, 0, p_out, s_out, F32 if out_f32 else code)
+        ctx.save_for_backward(x, h, pre, w1, w2)
+        ctx.meta = (act, p_mid, p_out, s_mid, s_out, residual is not None, code)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        act, p_mid, p_out, s_mid, s_out, has_res, code = ctx.meta
+        x, h, pre, w1, w2 = ctx.saved_tensors
+        w1c, w2c = weight_plain(w1, code), weight_plain(w2, code)
+        if _code(dy) != code:
+            dy = cast(dy, code)
+        dyd = _dropout_bwd(dy, p_out, s_out) if p_out > 0 else dy
+        need = ctx.needs_input_grad
+        dw2 = _grad_weight(dyd, h, w2.shape[0], w2.shape[1]) if need[4] else None
+        db2 = colsum(dyd, w2.shape[0]) if need[5] else None
+        # dpre1 = (dyd . W2) * act'(.)   -- activation derivative and mid-dropout mask fused in the GEMM epilogue
+        if act == L.ACT_RELU:
+            dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_RELU_MASK, aux=h,
+                                aux_scale=1.0 / (1.0 - p_mid) if p_mid > 0 else 1.0)
+        elif act == L.ACT_GELU:
+            dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_GELU, aux=pre, dropout_p=p_mid, seed=s_mid)
+        else:
+            dpre1 = _grad_input(dyd, w2c, h.shape, code, dropout_p=p_mid, seed=s_mid)
+        dw1 = _grad_weight(dpre1, x, w1.shape[0], w1.shape[1]) if need[2] else None
+        db1 = colsum(dpre1, w1.shape[0]) if need[3] else None
+        dx = _grad_input(dpre1, w1c, x.shape, code) if need[0] else None
+        return dx, (dy if has_res else None), dw1, db1, dw2, db2, None, None, None, None
+
+
+def mlp2(x, w1, b1, w2, b2, act, p_mid=0.0, p_out=0.0, residual=None, out_f32=False):
+    return Mlp2Fn.apply(x, residual, w1, b1, w2, b2, act, float(p_mid), float(p_out), out_f32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _require_cuda(x, gamma)
+        x = x.contiguous()
+        D = x.shape[-1]
+        M = x.numel() // D
+        y = torch.empty_like(x)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+        L.call("egb_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+               rstd.data_ptr(), _code(x), M, D, float(eps), _stream())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        D = x.shape[-1]
+        M = x.numel() // D
+        dy = dy.contiguous()
+        if _code(dy) != _code(x):
+            dy = cast(dy, _code(x))
+        dx = torch.empty_like(x)
+        dgb = zeros((2, D), torch.float32, x.device)
+        L.call("egb_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+               dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), _code(x), M, D, _stream())
+        return dx, dgb[0], dgb[1], None
+
+
+def layernorm(x, gamma, beta, eps):
+    return LayerNormFn.apply(x, gamma, beta, float(eps))
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused attention
+# ------------------------------------------------------------------------------------------------------
+def _att_strides(t):
+    """(batch_stride, row_stride) of a [S, L, H*dk] view with contiguous last dim."""
+    return t.stride(0), t.stride(1)
+
+
+class AttentionFn(torch.autograd.Function):
+    """ctx = softmax(q k^T * scale) [dropout] v over heads.  q: [S, Lq, D], k/v: [S, Lk, D] (views allowed).
+
+    With ``packed=True`` the single input is the packed projection [S, L, 3D] (q | k | v) and a single packed
+    gradient is returned.  kv_shift pairs query batch s with key/value batch (s + kv_shift) % S.
+    """
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, kv_shift, p, scale, packed, want_probs):
+        _require_cuda(q)
+        if packed:
+            qkv = q.contiguous()
+            D = qkv.shape[-1] // 3
+            q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+        else:
+            q = q if q.stride(-1) == 1 else q.contiguous()
+            k = k if k.stride(-1) == 1 else k.contiguous()
+            v = v if v.stride(-1) == 1 else v.contiguous()
+            D = q.shape[-1]
+        S, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+        dk = D // heads
+        code = _code(q)
+        o = torch.empty(S, Lq, D, dtype=q.dtype, device=q.device)
+        lse = torch.empty(S, heads, Lq, dtype=torch.float32, device=q.device)
+        probs = torch.empty(S, heads, Lq, Lk, dtype=torch.float32, device=q.device) if want_probs else None
+        seed = next_seed() if p > 0 else 0
+        d = L.AttentionDesc()
+        d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+        d.q_bs, d.q_rs = _att_strides(q)
+        d.k_bs, d.k_rs = _att_strides(k)
+        d.v_bs, d.v_rs = _att_strides(v)
+        d.o_bs, d.o_rs = _att_strides(o)
+        d.lse, d.probs = lse.data_ptr(), _p(probs)
+        d.dtype, d.S, d.H, d.Lq, d.Lk, d.head_dim, d.kv_shift = code, S, heads, Lq, Lk, dk, kv_shift
+        d.scale, d.dropout_p, d.seed = float(scale), float(p), seed
+        L.call("egb_attention_fwd", C.byref(d), _stream())
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.meta = (heads, kv_shift, p, scale, seed, packed)
+        if want_probs:
+            ctx.mark_non_differentiable(probs)
+            return o, probs
+        return o
+
+    @staticmethod
+    def backward(ctx, do, *unused):
+        heads, kv_shift, p, scale, seed, packed = ctx.meta
+        q, k, v, o, lse = ctx.saved_tensors
+        S, Lq, D = o.shape
+        Lk = k.shape[1]
+        code = _code(q)
+        do = do if do.stride(-1) == 1 else do.contiguous()
+        if _code(do) != code:
+            do = cast(do, code)
+        if packed:
+            dqkv = torch.empty(S, Lq, 3 * D, dtype=q.dtype, device=q.device)
+            dq, dk_, dv = dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:]
+        else:
+            dq = torch.empty(S, Lq, D, dtype=q.dtype, device=q.device)
+            dk_ = torch.empty(S, Lk, D, dtype=q.dtype, device=q.device)
+            dv = torch.empty(S, Lk, D, dtype=q.dtype, device=q.device)
+        delta = torch.empty(S, heads, Lq, dtype=torch.float32, device=q.device)
+        d = L.AttentionDesc()
+        d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+        d.q_bs, d.q_rs = _att_strides(q)
+        d.k_bs, d.k_rs = _att_strides(k)
+        d.v_bs, d.v_rs = _att_strides(v)
+        d.o_bs, d.o_rs = _att_strides(o)
+        d.d_o = do.data_ptr()
+        d.do_bs, d.do_rs = _att_strides(do)
+        d.dq, d.dk, d.dv = dq.data_ptr(), dk_.data_ptr(), dv.data_ptr()
+        d.dq_bs, d.dq_rs = _att_strides(dq)
+        d.dk_bs, d.dk_rs = _att_strides(dk_)
+        d.dv_bs, d.dv_rs = _att_strides(dv)
+        d.lse, d.delta, d.probs = lse.data_ptr(), delta.data_ptr(), None
+        d.dtype, d.S, d.H, d.Lq, d.Lk, d.head_dim, d.kv_shift = code, S, heads, Lq, Lk, D // heads, kv_shift
+        d.scale, d.dropout_p, d.seed = float(scale), float(p), seed
+        L.call("egb_attention_bwd", C.byref(d), _stream())
+        if packed:
+            return dqkv, None, None, None, None, None, None, None, None
+        return dq, dk_, dv, None, None, None, None, None, None
+
+
+def attention_packed(qkv, heads, kv_shift=0, p=0.0, scale=None, want_probs=False):
+    D = qkv.shape[-1] // 3
+    scale = scale if scale is not None else 1.0 / math.sqrt(D // heads)
+    return AttentionFn.apply(qkv, None, None, heads, kv_shift, float(p), scale, True, want_probs)
+
+
+def attention(q, k, v, heads, p=0.0, scale=None, want_probs=False):
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1] // heads)
+    return AttentionFn.apply(q, k, v, heads, 0, float(p), scale, False, want_probs)
+
+
+# ------------------------------------------------------------------------------------------------------
+# temporal-conv frontend: [Conv1d(k, stride, pad=k//2) -> ReLU -> Dropout] x n as implicit GEMMs
+# ------------------------------------------------------------------------------------------------------
+def _conv_weight(w, code):
+    """(O, C, K) parameter -> [O, K*C] (tap-major, channel-minor: matches the channels-last operand view)."""
+    O, Cc, K = w.shape
+
+    def build():
+        out = torch.empty(O, K * Cc, dtype=_TORCH_DT[code], device=w.device)
+        copy_strided4(w.detach(), out, (1, O, K, Cc), (0, Cc * K, 1, K), (0, K * Cc, Cc, 1))
+        return out
+    return wcache.get((w,), code, "conv1d", build)
+
+
+def _conv_weight_phase(w, code, stride, J):
+    """Transposed-conv operand: Bp[p][c, (jj, o)] = W[o, c, p + stride*(J-1-jj)] (0 where the tap does not exist)."""
+    O, Cc, K = w.shape
+
+    def build():
+        out = zeros((stride, Cc, J * O), _TORCH_DT[code], w.device)
+        for ph in range(stride):
+            for jj in range(J):
+                tap = ph + stride * (J - 1 - jj)
+                if tap < K:
+                    copy_strided4(w.detach(), out, (1, 1, Cc, O), (0, 0, K, Cc * K), (0, 0, J * O, 1), src_offset=tap,
+                                  dst_offset=ph * Cc * J * O + jj * O)
+        return out
+    return wcache.get((w,), code, "conv1d_phase", build)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class TemporalConvFn(torch.autograd.Function):
+    """eeg1, eeg2 (B,C,T) fp32 -> h [2B, T~, d] (players stacked along the batch).  dual_eeg_transformer.py:163-175."""
+
+    @staticmethod
+    def forward(ctx, eeg1, eeg2, code, stride, p, *wb):
+        n = len(wb) // 2
+        ws, bs = wb[:n], wb[n:]
+        _require_cuda(eeg1, eeg2, *ws)
+        eeg1 = eeg1.contiguous().float()
+        eeg2 = eeg2.contiguous().float()
+        B, Cin, T = eeg1.shape
+        S = 2 * B
+        dev = eeg1.device
+        tdt = _TORCH_DT[code]
+        ksz = ws[0].shape[2]
+        pad = ksz // 2
+        # channels-last, zero-padded input; group stride kept a multiple of 8 elements for TMA
+        Tp = T + 2 * pad
+        while (Tp * Cin) % 8:
+            Tp += 1
+        xp = torch.empty(S, Tp, Cin, dtype=tdt, device=dev)
+        L.call("egb_eeg_pack", eeg1.data_ptr(), eeg2.data_ptr(), xp.data_ptr(), code, B, Cin, T, pad, Tp, _stream())
+        bufs, geo, seeds = [xp], [(T, Tp, Cin)], []
+        cur, t_in, tp_in, c_in = xp, T, Tp, Cin
+        for i in range(n):
+            O = ws[i].shape[0]
+            t_out = (t_in + 2 * pad - ksz) // stride + 1
+            last = i == n - 1
+            tp_out = t_out if last else t_out + 2 * pad
+            out = torch.empty(S, tp_out, O, dtype=tdt, device=dev) if last else zeros((S, tp_out, O), tdt, dev)
+            wr = _conv_weight(ws[i], code)
+            seed = next_seed() if p > 0 else 0
+            seeds.append(seed)
+            a = L.Operand(cur.data_ptr(), 0, t_out, stride * c_in, tp_in * c_in, 0, 0)
+            off = 0 if last else pad * O
+            cm = L.Matrix(out.data_ptr() + off * out.element_size(), code, t_out, O, tp_out * O)
+            gemm(S * t_out, O, ksz * c_in, code, a, L.Operand(wr.data_ptr(), 0, 0, wr.stride(0), 0, 0, 0), cm,
+                 bias=bs[i].detach(), act=L.ACT_RELU, dropout_p=p, seed=seed)
+            bufs.append(out)
+            geo.append((t_out, tp_out, O))
+            cur, t_in, tp_in, c_in = out, t_out, tp_out, O
+        ctx.save_for_backward(*bufs, *ws)
+        ctx.meta = (n, code, stride, p, ksz, pad, S, geo)
+        return cur
+
+    @staticmethod
+    def backward(ctx, dh):
+        n, code, stride, p, ksz, pad, S, geo = ctx.meta
+        saved = ctx.saved_tensors
+        bufs, ws = saved[:n + 1], saved[n + 1:]
+        tdt = _TORCH_DT[code]
+        dev = dh.device
+        scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+        if _code(dh) != code:
+            dh = cast(dh, code)
+        J = (ksz + stride - 1) // stride
+        if n > 1 and (pad % stride != 0 or stride < 2):
+            raise NotImplementedError("temporal conv backward needs stride >= 2 and (kernel//2) %% stride == 0")
+        dws, dbs = [None] * n, [None] * n
+        # gradient of the last layer's pre-activation, written with J-1-s0 zero rows in front (slab view below)
+        s0 = pad // stride
+        front = max(J - 1 - s0, 0)
+        t_out, _, O = geo[n]
+        rp = front + t_out + J
+        g = zeros((S, rp, O), tdt, dev)
+        dm, dht = _matrix(dh)
+        gm = L.Matrix(g.data_ptr() + front * O * g.element_size(), code, t_out, O, rp * O)
+        L.call("egb_act_bwd", C.byref(dm), bufs[n].data_ptr(), C.byref(gm), S * t_out, O, 1, float(scale), _stream())
+        g_front, g_rp = front, rp
+        for i in range(n - 1, -1, -1):
+            t_out, _, O = geo[i + 1]
+            t_in, tp_in, c_in = geo[i]
+            src = bufs[i]
+            g_ptr = g.data_ptr() + g_front * O * g.element_size()
+            # dW[O, K*C] = dpre^T . (overlapping-row view of the layer input); db = column sums
+            if ctx.needs_input_grad[5 + i]:
+                dw = torch.empty(O, ksz * c_in, dtype=torch.float32, device=dev)
+                gemm(O, ksz * c_in, S * t_out, code, L.Operand(g_ptr, 1, t_out, O, g_rp * O, 0, 0),
+                     L.Operand(src.data_ptr(), 1, t_out, stride * c_in, tp_in * c_in, 0, 0),
+                     _dense_matrix(dw.data_ptr(), F32, ksz * c_in), accumulate=2)
+                dws[i] = dw.view(O, ksz, c_in).permute(0, 2, 1)
+            if ctx.needs_input_grad[5 + n + i]:
+                db = torch.empty(O, dtype=torch.float32, device=dev)
+                gmat = L.Matrix(g_ptr, code, t_out, O, g_rp * O)
+                L.call("egb_colsum", C.byref(gmat), S * t_out, O, db.data_ptr(), 1, _stream())
+                dbs[i] = db
+            if i == 0:
+                break
+            # d(input) via `stride` phase GEMMs (transposed convolution), fused with the previous ReLU(+dropout) mask
+            assert t_in % stride == 0
+            wp = _conv_weight_phase(ws[i], code, stride, J)
+            g_prev = zeros((S, tp_in, c_in), tdt, dev)   # same padded geometry as bufs[i]
+            rows = t_in // stride
+            slab0 = g_front - (J - 1 - s0)
+            for ph in range(stride):
+                a = L.Operand(g.data_ptr() + slab0 * O * g.element_size(), 0, rows, O, g_rp * O, 0, 0)
+                bop = L.Operand(wp.data_ptr() + ph * c_in * J * O * wp.element_size(), 0, 0, J * O, 0, 0, 0)
+                off = (pad + ph) * c_in
+                cm = L.Matrix(g_prev.data_ptr() + off * g_prev.element_size(), code, rows, stride * c_in, tp_in * c_in)
+                am = L.Matrix(src.data_ptr() + off * src.element_size(), code, rows, stride * c_in, tp_in * c_in)
+                gemm(S * rows, c_in, J * O, code, a, bop, cm, act_bwd=L.ACTBWD_RELU_MASK, aux=am, aux_scale=scale)
+            g, g_front, g_rp = g_prev, pad, tp_in
+        return (None, None, None, None, None) + tuple(dws) + tuple(dbs)
+
+
+def temporal_conv(eeg1, eeg2, weights, biases, code, stride, p):
+    return TemporalConvFn.apply(eeg1, eeg2, code, stride, float(p), *weights, *biases)
+
+
+# ------------------------------------------------------------------------------------------------------
+# spectrogram CNN:  STFT-log -> conv(1->32)+relu+maxpool -> conv(32->64) [tensor-core implicit GEMM] -> relu+avgpool
+# ------------------------------------------------------------------------------------------------------
+def _spec_w2_seg(w, code):
+    """(64, 32, 3, 3) -> [64, 3 segs x (4 kw x 32 c)] with a zero kw=3 slot (128-element K segments)."""
+    def build():
+        O, Cc = w.shape[0], w.shape[1]
+        out = zeros((O, 3 * 4 * Cc), _TORCH_DT[code], w.device)
+        for kh in range(3):
+            copy_strided4(w.detach(), out, (1, O, 3, Cc), (0, Cc * 9, 1, 9), (0, 12 * Cc, Cc, 1), src_offset=kh * 3,
+                          dst_offset=kh * 4 * Cc)
+        return out
+    return wcache.get((w,), code, "spec_w2_seg", build)
+
+
+def _spec_w2_flip(w, code):
+    """dX operand: [32 c, 3 segs(a) x (4 b x 64 o)] = W[o, c, 2-a, 2-b], zero for b = 3."""
+    def build():
+        O, Cc = w.shape[0], w.shape[1]
+        out = zeros((Cc, 3 * 4 * O), _TORCH_DT[code], w.device)
+        for a in range(3):
+            for b in range(3):
+                copy_strided4(w.detach(), out, (1, 1, Cc, O), (0, 0, 9, Cc * 9), (0, 0, 12 * O, 1),
+                              src_offset=(2 - a) * 3 + (2 - b), dst_offset=a * 4 * O + b * O)
+        return out
+    return wcache.get((w,), code, "spec_w2_flip", build)
+
+
+class SpectrogramCNNFn(torch.autograd.Function):
+    """(B,C,T) x2 -> pooled features [2B*C, 1024] (dual_eeg_transformer.py:98-127).  `want_pre` also returns the
+    conv-2 pre-activation in NCHW (what a hook on spec_conv[3] observes)."""
+
+    @staticmethod
+    def forward(ctx, eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
+        _require_cuda(eeg1, eeg2, w1, w2)
+        eeg1 = eeg1.contiguous().float()
+        eeg2 = eeg2.contiguous().float()
+        B, Cc, T = eeg1.shape
+        N = 2 * B * Cc
+        dev = eeg1.device
+        tdt = _TORCH_DT[code]
+        frames = 1 + T // hop
+        img = torch.empty(N, bins, frames, dtype=torch.float32, device=dev)
+        L.call("egb_stft_logmag", eeg1.data_ptr(), eeg2.data_ptr(), window.data_ptr(), img.data_ptr(), B * Cc, T, n_fft,
+               hop, bins, _stream())
+        H1, W1 = bins // 2, frames // 2
+        Wp, Hp = W1 + 2, H1 + 2
+        RP = Hp * Wp
+        slack = 2 * Wp + 8
+        p1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
+        L.call("egb_spec_conv1_pool_fwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), p1.data_ptr(), code, N, bins,
+               frames, p1.numel(), _stream())
+        y2 = zeros(((N * RP + slack) * 64,), tdt, dev)
+        w2s = _spec_w2_seg(w2, code)
+        a = L.Operand(p1.data_ptr(), 0, 0, 32, 0, 128, Wp)
+        cm = _dense_matrix(y2.data_ptr() + (Wp + 1) * 64 * y2.element_size(), code, 64)
+        gemm(N * RP, 64, 384, code, a, L.Operand(w2s.data_ptr(), 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
+        pooled = torch.empty(N, 1024, dtype=tdt, device=dev)
+        L.call("egb_relu_avgpool_fwd", y2.data_ptr(), pooled.data_ptr(), code, N, H1, W1, _stream())
+        ctx.save_for_backward(img, p1, y2, w1, b1, w2)
+        ctx.meta = (code, N, bins, frames, H1, W1, Wp, RP, slack)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpool):
+        code, N, bins, frames, H1, W1, Wp, RP, slack = ctx.meta
+        img, p1, y2, w1, b1, w2 = ctx.saved_tensors
+        dev, tdt = dpool.device, _TORCH_DT[code]
+        dpool = dpool.contiguous()
+        if _code(dpool) != code:
+            dpool = cast(dpool, code)
+        dy2 = zeros(((N * RP + slack) * 64,), tdt, dev)
+        L.call("egb_relu_avgpool_bwd", y2.data_ptr(), dpool.data_ptr(), dy2.data_ptr(), code, N, H1, W1, _stream())
+        need = ctx.needs_input_grad
+        dw1 = db1 = dw2 = db2 = None
+        if need[6]:
+            db2 = torch.empty(64, dtype=torch.float32, device=dev)
+            m = _dense_matrix(dy2.data_ptr(), code, 64)
+            L.call("egb_colsum", C.byref(m), N * RP, 64, db2.data_ptr(), 1, _stream())
+        esz = dy2.element_size()
+        if need[5]:
+            # dW2[o, (kh, kw4, c)] = sum over flat padded positions of dY[m + Wp + 1, o] * P1[m + kh*Wp, kw4*32 + c]
+            dw = torch.empty(64, 384, dtype=torch.float32, device=dev)
+            gemm(64, 384, N * RP, code, L.Operand(dy2.data_ptr() + (Wp + 1) * 64 * esz, 1, 0, 64, 0, 0, 0),
+                 L.Operand(p1.data_ptr(), 1, 0, 32, 0, 128, Wp), _dense_matrix(dw.data_ptr(), F32, 384), accumulate=2)
+            dw2 = dw.view(64, 3, 4, 32)[:, :, :3, :].permute(0, 3, 1, 2)
+        if need[3] or need[4]:
+            # dP1 (padded layout) = full correlation of dY with the flipped kernel: same implicit GEMM, K = 3 x 256
+            w2f = _spec_w2_flip(w2, code)
+            dp1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
+            a = L.Operand(dy2.data_ptr(), 0, 0, 64, 0, 256, Wp)
+            cm = _dense_matrix(dp1.data_ptr() + (Wp + 1) * 32 * esz, code, 32)
+            gemm(N * RP, 32, 768, code, a, L.Operand(w2f.data_ptr(), 0, 0, 768, 0, 0, 0), cm)
+            dwb = zeros((320,), torch.float32, dev)
+            L.call("egb_spec_conv1_pool_bwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), dp1.data_ptr(), code,
+                   dwb.data_ptr(), dwb.data_ptr() + 288 * 4, N, bins, frames, _stream())
+            dw1 = dwb[:288].view(32, 1, 3, 3)
+            db1 = dwb[288:]
+        return None, None, None, dw1, db1, dw2, db2, None, None, None, None
+
+
+def spectrogram_cnn(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
+    return SpectrogramCNNFn.apply(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
+
+
+def spectrogram_conv2_nchw(eeg1, eeg2, window, w1, b1, w2, b2, n_fft, hop, bins):
+    """Analysis helper: the spec_conv[3] output (N, 64, H1, W1) in fp32, recomputed with the same kernels."""
+    code = F32
+    with torch.no_grad():
+        B, Cc, T = eeg1.shape
+        N = 2 * B * Cc
+        frames = 1 + T // hop
+        H1, W1 = bins // 2, frames // 2
+        Wp, RP = W1 + 2, (H1 + 2) * (W1 + 2)
+        fn_ctx = type("Ctx", (), {"save_for_backward": lambda self, *a: setattr(self, "saved", a),
+                                  "needs_input_grad": (False,) * 11})()
+        SpectrogramCNNFn.forward(fn_ctx, eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
+        y2 = fn_ctx.saved[2][:N * RP * 64].view(N, H1 + 2, Wp, 64)
+        return y2[:, 1:H1 + 1, 1:W1 + 1, :].permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# IBS connectivity (parameter-free, no gradient) and the token-axis instance norm
+# ------------------------------------------------------------------------------------------------------
+_twiddles = {}
+
+
+def _twiddle(T, device):
+    key = (T, str(device))
+    if key not in _twiddles:
+        k = torch.arange(T // 2, dtype=torch.float64)
+        ang = -2.0 * math.pi * k / T
+        _twiddles[key] = torch.stack([torch.cos(ang), torch.sin(ang)], dim=1).to(torch.float32).to(device).contiguous()
+    return _twiddles[key]
+
+
+def band_bins(T, fs, bands):
+    """Inclusive rfft-bin range of each band under the reference's mask (freqs >= lo) & (freqs <= hi)
+    (dual_eeg_transformer.py:548-551), evaluated in fp32 like torch.fft.rfftfreq."""
+    freqs = torch.fft.rfftfreq(T, d=1.0 / fs)
+    lo_hi = []
+    for lo, hi in bands:
+        idx = torch.nonzero((freqs >= lo) & (freqs <= hi)).flatten()
+        lo_hi.append((int(idx[0]), int(idx[-1])) if idx.numel() else (1, 0))
+    return lo_hi
+
+
+def ibs_connectivity(eeg1, eeg2, fs, bands, feature_indices, chunk=64):
+    """(B,C,T) x2 fp32 -> (B, n_bands, len(feature_indices), C, C) fp32.  Batch is processed in chunks so the
+    phase / band-passed scratch stays bounded."""
+    _require_cuda(eeg1, eeg2)
+    with torch.no_grad():
+        eeg1 = eeg1.detach().contiguous().float()
+        eeg2 = eeg2.detach().contiguous().float()
+        B, Cc, T = eeg1.shape
+        dev = eeg1.device
+        nb, nf = len(bands), len(feature_indices)
+        bins = band_bins(T, fs, bands)
+        lo = (L.i32 * nb)(*[b[0] for b in bins])
+        hi = (L.i32 * nb)(*[b[1] for b in bins])
+        slot = [-1] * 7
+        for s, f in enumerate(feature_indices):
+            slot[f] = s
+        slot_c = (L.i32 * 7)(*slot)
+        valid = [b for b in bins if b[0] <= b[1]]
+        nbins = (max(b[1] for b in valid) - min(b[0] for b in valid) + 1) if valid else 1
+        out = torch.empty(B, nb, nf, Cc, Cc, dtype=torch.float32, device=dev)
+        tw = _twiddle(T, dev)
+        cb = min(B, chunk)
+        phase = torch.empty(cb * nb * 2 * Cc * T, dtype=torch.float32, device=dev)
+        xb = torch.empty_like(phase)
+        stats = torch.empty(cb * nb * 2 * Cc * 8, dtype=torch.float32, device=dev)
+        pspec = torch.empty(cb * 2 * Cc * nbins, dtype=torch.float32, device=dev)
+        for b0 in range(0, B, cb):
+            n = min(cb, B - b0)
+            L.call("egb_ibs_connectivity", eeg1[b0:].data_ptr(), eeg2[b0:].data_ptr(), tw.data_ptr(), phase.data_ptr(),
+                   xb.data_ptr(), stats.data_ptr(), pspec.data_ptr(), out[b0:].data_ptr(), n, Cc, T, nb, lo, hi, slot_c,
+                   nf, _stream())
+        return out
+
+
+class InstNormTokensFn(torch.autograd.Function):
+    """x (B, NT, P) fp32 -> y (compute dtype): per (b, p) normalisation over the NT tokens + affine (det:893-901)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, code, apply_norm):
+        _require_cuda(x)
+        x = x.contiguous().float()
+        B, NT, P = x.shape
+        y = torch.empty(B, NT, P, dtype=_TORCH_DT[code], device=x.device)
+        L.call("egb_instnorm_tokens_fwd", x.data_ptr(), _p(gamma), _p(beta), y.data_ptr(), code, B, NT, P, 1e-5,
+               1 if apply_norm else 0, _stream())
+        ctx.save_for_backward(x)
+        ctx.meta = (code, apply_norm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        code, apply_norm = ctx.meta
+        if not apply_norm:
+            return None, None, None, None, None
+        (x,) = ctx.saved_tensors
+        B, NT, P = x.shape
+        dy = dy.contiguous()
+        if _code(dy) != code:
+            dy = cast(dy, code)
+        dgb = zeros((2, P), torch.float32, x.device)
+        L.call("egb_instnorm_tokens_bwd", x.data_ptr(), dy.data_ptr(), code, dgb[0].data_ptr(), dgb[1].data_ptr(), B, NT,
+               P, 1e-5, _stream())
+        return None, dgb[0], dgb[1], None, None
+
+
+def instnorm_tokens(x, gamma, beta, code, apply_norm=True):
+    return InstNormTokensFn.apply(x, gamma, beta, code, apply_norm)
+
+
+# ------------------------------------------------------------------------------------------------------
+# sequence assembly, pooling tail, concat
+# ------------------------------------------------------------------------------------------------------
+class SeqAssembleFn(torch.autograd.Function):
+    """[cls | ibs | spec | h] + pos_embed[:L]  ->  X [2B, L, D]   (dual_eeg_transformer.py:1157-1179)."""
+
+    @staticmethod
+    def forward(ctx, cls, pos, ibs, spec, h, code):
+        _require_cuda(h, cls, pos)
+        S, n_h, D = h.shape
+        B = S // 2
+        n_ibs = ibs.shape[1] if ibs is not None else 0
+        n_spec = spec.shape[1] if spec is not None else 0
+        Lq = 1 + n_ibs + n_spec + n_h
+        if Lq > pos.shape[0]:
+            raise IndexError("index out of range in self: sequence length %d exceeds max_len %d" % (Lq, pos.shape[0]))
+        ibs = cast(ibs.contiguous(), code) if ibs is not None else None
+        spec = cast(spec.contiguous(), code) if spec is not None else None
+        h = cast(h.contiguous(), code)
+        out = torch.empty(S, Lq, D, dtype=_TORCH_DT[code], device=h.device)
+        L.call("egb_seq_assemble_fwd", cls.data_ptr(), pos.data_ptr(), _p(ibs), _p(spec), h.data_ptr(), out.data_ptr(),
+               code, S, B, Lq, D, n_ibs, n_spec, n_h, _stream())
+        ctx.meta = (code, S, B, Lq, D, n_ibs, n_spec, n_h, pos.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        code, S, B, Lq, D, n_ibs, n_spec, n_h, max_len = ctx.meta
+        dx = dx.contiguous()
+        if _code(dx) != code:
+            dx = cast(dx, code)
+        dpos = zeros((max_len, D), torch.float32, dx.device)
+        dibs = torch.empty(B, n_ibs, D, dtype=dx.dtype, device=dx.device) if n_ibs else None
+        L.call("egb_seq_assemble_bwd", dx.data_ptr(), dpos.data_ptr(), _p(dibs), code, S, B, Lq, D, n_ibs, _stream())
+        dcls = dpos[0].view(1, 1, D)
+        dspec = dx[:, 1 + n_ibs:1 + n_ibs + n_spec] if n_spec else None
+        dh = dx[:, 1 + n_ibs + n_spec:]
+        # cls also collects pos row 0's sum; both parameters receive the same batch-summed row
+        return dcls, dpos, dibs, dspec, dh, None
+
+
+def seq_assemble(cls, pos, ibs, spec, h, code):
+    return SeqAssembleFn.apply(cls, pos, ibs, spec, h, code)
+
+
+class AddRowsBroadcastFn(torch.autograd.Function):
+    """x [B, NT, D] + e [1, NT, D] (fp32 parameter) -- the IBS type embedding (det:909)."""
+
+    @staticmethod
+    def forward(ctx, x, e):
+        x = x.contiguous()
+        B, NT, D = x.shape
+        out = torch.empty_like(x)
+        L.call("egb_add_rows_broadcast", x.data_ptr(), e.data_ptr(), out.data_ptr(), _code(x), B * NT, NT, D, _stream())
+        ctx.meta = (B, NT, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, NT, D = ctx.meta
+        de = None
+        if ctx.needs_input_grad[1]:
+            dyc = dy.contiguous()
+            de = zeros((NT, D), torch.float32, dy.device)
+            L.call("egb_seq_assemble_bwd", dyc.data_ptr(), de.data_ptr(), None, _code(dyc), B, B, NT, D, 0, _stream())
+            de = de.view(1, NT, D)
+        return dy, de
+
+
+def add_broadcast_rows(x, e):
+    return AddRowsBroadcastFn.apply(x, e)
+
+
+def ibs_scalar_features(eeg1, eeg2, fs, bands):
+    raise NotImplementedError("legacy scalar IBS mode (ibs_mode: scalar) kernel not built yet")
+
+
+class TailPoolFn(torch.autograd.Function):
+    """Z [2B, L, D] -> cls1, cls2 (B,D), sym (B,3D), mp (B,2D), ibs_pool (B,D); all fp32 (det:1193-1225)."""
+
+    @staticmethod
+    def forward(ctx, z, n_ibs, offset, ibs_single):
+        _require_cuda(z)
+        z = z.contiguous()
+        S, Lq, D = z.shape
+        B = S // 2
+        dev = z.device
+        f = torch.float32
+        cls1 = torch.empty(B, D, dtype=f, device=dev)
+        cls2 = torch.empty(B, D, dtype=f, device=dev)
+        sym = torch.empty(B, 3 * D, dtype=f, device=dev)
+        zf = torch.empty(B, 3 * D, dtype=f, device=dev)
+        ibs_pool = torch.empty(B, D, dtype=f, device=dev) if n_ibs > 0 else None
+        L.call("egb_tail_pool_fwd", z.data_ptr(), _code(z), cls1.data_ptr(), cls2.data_ptr(), sym.data_ptr(), zf.data_ptr(),
+               _p(ibs_pool), B, Lq, D, n_ibs, offset, 1 if ibs_single else 0, _stream())
+        ctx.save_for_backward(z)
+        ctx.meta = (n_ibs, offset, ibs_single)
+        mp = zf[:, D:]
+        if ibs_pool is None:
+            return cls1, cls2, sym, mp
+        return cls1, cls2, sym, mp, ibs_pool
+
+    @staticmethod
+    def backward(ctx, dcls1, dcls2, dsym, dmp, dibs=None):
+        (z,) = ctx.saved_tensors
+        n_ibs, offset, ibs_single = ctx.meta
+        S, Lq, D = z.shape
+        B = S // 2
+        dev = z.device
+
+        def f32c(t):
+            return None if t is None else t.contiguous().float()
+        dcls1, dcls2, dibs = f32c(dcls1), f32c(dcls2), f32c(dibs)
+        dsym = f32c(dsym) if dsym is not None else zeros((B, 3 * D), torch.float32, dev)
+        dzf = zeros((B, 3 * D), torch.float32, dev)
+        if dmp is not None:
+            copy_strided4(dmp.contiguous().float(), dzf, (1, 1, B, 2 * D), (0, 0, 2 * D, 1), (0, 0, 3 * D, 1), dst_offset=D)
+        dz = torch.empty_like(z)
+        L.call("egb_tail_pool_bwd", z.data_ptr(), _code(z), _p(dcls1), _p(dcls2), dsym.data_ptr(), dzf.data_ptr(), _p(dibs),
+               dz.data_ptr(), B, Lq, D, n_ibs, offset, 1 if ibs_single else 0, _stream())
+        return dz, None, None, None
+
+
+def tail_pool(z, n_ibs, offset, ibs_single):
+    return TailPoolFn.apply(z, n_ibs, offset, ibs_single)
+
+
+class Concat2Fn(torch.autograd.Function):
+    """[a | b] along the last dim of 2-D fp32 tensors (classifier input [f_pair, mp1, mp2], det:1212)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        B, Da = a.shape
+        Db = b.shape[1]
+        out = torch.empty(B, Da + Db, dtype=torch.float32, device=a.device)
+        copy_strided4(a, out, (1, 1, B, Da), (0, 0, a.stride(0), a.stride(1)), (0, 0, Da + Db, 1))
+        copy_strided4(b, out, (1, 1, B, Db), (0, 0, b.stride(0), b.stride(1)), (0, 0, Da + Db, 1), dst_offset=Da)
+        ctx.meta = (Da, Db)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        Da, Db = ctx.meta
+        return d[:, :Da], d[:, Da:]
+
+
+def concat2(a, b):
+    return Concat2Fn.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------------
+# losses / fusion head
+# ------------------------------------------------------------------------------------------------------
+class CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        _require_cuda(logits, labels)
+        logits = logits.contiguous().float()
+        labels = labels.contiguous().long()
+        B, Cn = logits.shape
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        dl = torch.empty_like(logits)
+        L.call("egb_cross_entropy", logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), dl.data_ptr(), B, Cn, _stream())
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        out = torch.empty_like(dl)
+        L.call("egb_scale_by_device_scalar", dl.data_ptr(), g.data_ptr(), out.data_ptr(), dl.numel(), _stream())
+        return out, None
+
+
+def cross_entropy(logits, labels):
+    return CrossEntropyFn.apply(logits, labels)
+
+
+FUZZY_MODES = {"full": 0, "no_temperature": 1, "no_fuzzification": 2, "fixed_weights": 3}
+
+
+def _fuzzy_desc(params, mode, B, Cn, eps_temp, eps_log, eps_div):
+    d = L.FuzzyDesc()
+    (d.tau_img, d.tau_eeg, d.c_reliable, d.c_unreliable_img, d.c_unreliable_eeg, d.log_sigma_reliable_img,
+     d.log_sigma_reliable_eeg, d.log_sigma_unreliable_img, d.log_sigma_unreliable_eeg, d.beta) = [t.data_ptr() for t in params]
+    d.mode, d.B, d.num_classes = mode, B, Cn
+    d.eps_temp, d.eps_log, d.eps_div = eps_temp, eps_log, eps_div
+    return d
+
+
+class FuzzyGatingFn(torch.autograd.Function):
+    """params order: tau_img, tau_eeg, c_reliable(buffer), c_unreliable_img, c_unreliable_eeg, log_sigma_reliable_img,
+    log_sigma_reliable_eeg, log_sigma_unreliable_img, log_sigma_unreliable_eeg, beta."""
+
+    @staticmethod
+    def forward(ctx, img, eeg, mode, eps_temp, eps_log, eps_div, *params):
+        _require_cuda(img, eeg, *params)
+        img = img.contiguous().float()
+        eeg = eeg.contiguous().float()
+        B, Cn = img.shape
+        dev = img.device
+        fused = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+        alpha = torch.empty(B, dtype=torch.float32, device=dev)
+        aux = torch.empty(B, 16, dtype=torch.float32, device=dev)
+        d = _fuzzy_desc(params, mode, B, Cn, eps_temp, eps_log, eps_div)
+        L.call("egb_fuzzy_fwd", C.byref(d), img.data_ptr(), eeg.data_ptr(), fused.data_ptr(), alpha.data_ptr(),
+               aux.data_ptr(), _stream())
+        ctx.save_for_backward(img, eeg, *params)
+        ctx.meta = (mode, eps_temp, eps_log, eps_div)
+        ctx.mark_non_differentiable(aux)
+        return fused, alpha, aux
+
+    @staticmethod
+    def backward(ctx, g_fused, g_alpha, _g_aux):
+        mode, eps_temp, eps_log, eps_div = ctx.meta
+        saved = ctx.saved_tensors
+        img, eeg, params = saved[0], saved[1], saved[2:]
+        B, Cn = img.shape
+        dev = img.device
+        g_fused = g_fused.contiguous().float() if g_fused is not None else zeros((B, Cn), torch.float32, dev)
+        g_alpha = g_alpha.contiguous().float() if g_alpha is not None else None
+        d_img = torch.empty_like(img)
+        d_eeg = torch.empty_like(eeg)
+        dp = zeros((12,), torch.float32, dev)
+        d = _fuzzy_desc(params, mode, B, Cn, eps_temp, eps_log, eps_div)
+        L.call("egb_fuzzy_bwd", C.byref(d), img.data_ptr(), eeg.data_ptr(), g_fused.data_ptr(), _p(g_alpha), d_img.data_ptr(),
+               d_eeg.data_ptr(), dp.data_ptr(), _stream())
+        grads = (dp[0], dp[1], None, dp[2], dp[3], dp[4], dp[5], dp[6], dp[7], dp[8:12])
+        return (d_img, d_eeg, None, None, None, None) + grads
+
+
+def fuzzy_gating(img, eeg, mode, eps_temp, eps_log, eps_div, params):
+    return FuzzyGatingFn.apply(img, eeg, mode, float(eps_temp), float(eps_log), float(eps_div), *params)
+
+
+# ------------------------------------------------------------------------------------------------------
+# ViT patch embedding (+ input fusion + cls + pos)
+# ------------------------------------------------------------------------------------------------------
+PATCH_MODES = {"concat": 0, "add": 1, "subtract": 2, "subtract_abs": 3, "multiply": 4, "single": 5}
+
+
+class VitEmbedFn(torch.autograd.Function):
+    """img_a, img_b (B,3,H,W) fp32 -> tokens [B, 1+n, D]: fuse -> patchify -> patch GEMM (+bias +pos) -> cls row."""
+
+    @staticmethod
+    def forward(ctx, img_a, img_b, w, b, cls, pos, mode, code, ps):
+        _require_cuda(img_a, w)
+        img_a = img_a.contiguous().float()
+        img_b = img_b.contiguous().float() if img_b is not None else img_a
+        B, _, H, W = img_a.shape
+        D = w.shape[0]
+        n = (H // ps) * (W // ps)
+        cin = 6 if mode == 0 else 3
+        K = cin * ps * ps
+        if w.shape[1] != cin:
+            raise RuntimeError("patch embedding expects %d input channels, weight has %d" % (cin, w.shape[1]))
+        if pos.shape[1] != n + 1:
+            raise RuntimeError("pos_embed has %d tokens, image gives %d" % (pos.shape[1], n + 1))
+        dev, tdt = img_a.device, _TORCH_DT[code]
+        patches = torch.empty(B * n, K, dtype=tdt, device=dev)
+        stats = torch.empty(B * 6, dtype=torch.float32, device=dev) if mode == 4 else None
+        L.call("egb_vit_patchify", img_a.data_ptr(), img_b.data_ptr(), patches.data_ptr(), _p(stats), code, B, H, W, ps,
+               mode, _stream())
+        w2 = weight_plain(w, code)
+        out = torch.empty(B, n + 1, D, dtype=tdt, device=dev)
+        pos2 = pos.detach().reshape(n + 1, D)
+        cm = L.Matrix(out.data_ptr() + D * out.element_size(), code, n, D, (n + 1) * D)
+        rm = L.Matrix(pos2.data_ptr() + D * 4, F32, n, D, 0)
+        gemm(B * n, D, K, code, L.Operand(patches.data_ptr(), 0, 0, K, 0, 0, 0), L.Operand(w2.data_ptr(), 0, 0, K, 0, 0, 0),
+             cm, bias=b.detach() if b is not None else None, residual=rm)
+        L.call("egb_fill_row0", cls.data_ptr(), pos2.data_ptr(), out.data_ptr(), code, B, n + 1, D, _stream())
+        ctx.save_for_backward(patches, w)
+        ctx.meta = (code, B, n, D, K, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        code, B, n, D, K, has_bias = ctx.meta
+        patches, w = ctx.saved_tensors
+        dev = dx.device
+        dx = dx.contiguous()
+        if _code(dx) != code:
+            dx = cast(dx, code)
+        need = ctx.needs_input_grad
+        dw = db = dcls = dpos = None
+        if need[2] or need[3]:
+            dtok = torch.empty(B * n, D, dtype=dx.dtype, device=dev)   # dense copy of dx[:, 1:, :]
+            copy_strided4(dx, dtok, (1, B, n, D), (0, (n + 1) * D, D, 1), (0, n * D, D, 1), src_offset=D)
+            if need[2]:
+                dw = _grad_weight(dtok, patches, D, K).view(w.shape)
+            if need[3] and has_bias:
+                db = colsum(dtok, D)
+        if need[4] or need[5]:
+            dp = zeros((n + 1, D), torch.float32, dev)
+            L.call("egb_seq_assemble_bwd", dx.data_ptr(), dp.data_ptr(), None, code, B, B, n + 1, D, 0, _stream())
+            dpos = dp.view(1, n + 1, D)
+            dcls = dp[0].view(1, 1, D)
+        return None, None, dw, db, dcls, dpos, None, None, None
+
+
+def vit_embed(img_a, img_b, w, b, cls, pos, mode, code, ps=16):
+    return VitEmbedFn.apply(img_a, img_b, w, b, cls, pos, mode, code, ps)

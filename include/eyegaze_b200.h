@@ -43,6 +43,8 @@ int64_t egb_launch_count(void);
  * `major` = 0: rows are the M (or N) index and the inner index is K (reduction)   ("K-major")
  * `major` = 1: rows are the K (reduction) index and the inner index is M (or N)   ("MN-major")
  * Overlapping rows (row_stride < inner extent) are legal: that is the conv-as-GEMM view.
+ * The 3x3 Conv2d of the spectrogram CNN uses inner segmentation (one segment per kernel row) over a
+ * zero-padded channels-last image, so it also runs without an im2col buffer.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* ptr;
@@ -50,6 +52,11 @@ typedef struct {
   int32_t rows_per_group; /* <= 0: a single group holding all rows */
   int64_t row_stride;     /* elements */
   int64_t group_stride;   /* elements */
+  /* Optional inner-index segmentation (2-D convolutions): inner index i is split as
+   * seg = i / seg_len, i' = i % seg_len and addresses row (row + seg * seg_row_shift), inner i'.
+   * seg_len = 0 disables it; seg_len must be a multiple of 64.  Single-group operands only. */
+  int32_t seg_len;
+  int32_t seg_row_shift;
 } egb_operand;
 
 typedef struct {
@@ -83,11 +90,142 @@ typedef struct {
   float aux_scale;
   float dropout_p;     /* applied after activation; 0 disables */
   uint64_t dropout_seed;
-  int32_t accumulate;  /* 1: C += result (C must be fp32); enables split-K with red.global.add */
+  int32_t accumulate;  /* 1: C += result (C must be fp32, split-K with red.global.add); 2: zero C first, then accumulate */
   int32_t split_k;     /* 0 = auto */
 } egb_gemm_desc;
 
 int egb_gemm(const egb_gemm_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * dtype casts / weight re-layout (per-step bf16 copies of the fp32 master parameters)
+ * ------------------------------------------------------------------------------------------- */
+int egb_cast_from_f32(const float* src, void* dst, int dtype, int64_t n, void* stream);
+int egb_cast_to_f32(const void* src, int dtype, float* dst, int64_t n, void* stream);
+/* dst[i0*d0+i1*d1+i2*d2+i3*d3] = src[i0*s0+i1*s1+i2*s2+i3*s3], any dtype pair */
+int egb_copy_strided4(const void* src, int src_dtype, void* dst, int dst_dtype, const int32_t* sizes,
+                      const int64_t* src_strides, const int64_t* dst_strides, void* stream);
+int egb_zero(void* ptr, int64_t nbytes, void* stream); /* cudaMemsetAsync */
+
+/* (B,C,T) fp32 x2 -> [2B, Tp, C] channels-last, `pad` zero rows in front (the Conv1d padding,
+ * dual_eeg_transformer.py:154), zero rows behind up to Tp.  Operand layout of the implicit-GEMM conv. */
+int egb_eeg_pack(const float* eeg1, const float* eeg2, void* out, int dtype, int B, int C, int T, int pad, int Tp,
+                 void* stream);
+
+/* Token sequence [cls | ibs tokens (shared by both players) | spectrogram tokens | temporal tokens] + learned
+ * positional embedding (dual_eeg_transformer.py:1157-1179, art.py:120-126).  S = 2B stacked players. */
+int egb_seq_assemble_fwd(const float* cls, const float* pos, const void* ibs, const void* spec, const void* h, void* out,
+                         int dtype, int S, int B, int L, int D, int n_ibs, int n_spec, int n_h, void* stream);
+/* dpos[L,D] (+=) = sum_s dx[s]; dibs[B,n_ibs,D] = dx[b,1+t] + dx[B+b,1+t] (may be NULL) */
+int egb_seq_assemble_bwd(const void* dx, float* dpos, void* dibs, int dtype, int S, int B, int L, int D, int n_ibs,
+                         void* stream);
+
+/* out[b,t,:] = x[b,t,:] + e[t,:] (IBS type embedding, dual_eeg_transformer.py:909) */
+int egb_add_rows_broadcast(const void* x, const float* e, void* out, int dtype, int64_t rows, int NT, int D, void* stream);
+
+/* CLS slice, temporal mean-pool, IBS-token mean-pool, symmetric features (dual_eeg_transformer.py:1193-1225,933-938).
+ * zf is the (B,3D) classifier input; columns [0,D) are filled later by the SymmetricFusion GEMM. */
+int egb_tail_pool_fwd(const void* z, int dtype, float* cls1, float* cls2, float* sym, float* zf, float* ibs_pool, int B,
+                      int L, int D, int n_ibs, int offset, int ibs_single, void* stream);
+int egb_tail_pool_bwd(const void* z, int dtype, const float* dcls1, const float* dcls2, const float* dsym,
+                      const float* dzf, const float* dibs_pool, void* dz, int B, int L, int D, int n_ibs, int offset,
+                      int ibs_single, void* stream);
+
+/* out[n] (+)= sum_m x[m,n]  -- bias gradients */
+int egb_colsum(const egb_matrix* x, int M, int N, float* out, int zero_first, void* stream);
+/* out = dy * act'(aux) (mode 1: aux = relu output, factor (aux!=0)*scale; mode 2: aux = pre-activation, gelu') */
+int egb_act_bwd(const egb_matrix* dy, const void* aux, const egb_matrix* out, int M, int N, int mode, float scale,
+                void* stream);
+/* out = dy * mask(seed) / (1-p): regenerates the mask a GEMM epilogue applied (index m*N+n) */
+int egb_dropout_bwd(const void* dy, void* out, int dtype, int64_t n_elems, float p, uint64_t seed, void* stream);
+/* mean cross entropy (F.cross_entropy) and d(loss)/d(logits) in one pass; labels are int64 */
+int egb_cross_entropy(const float* logits, const int64_t* labels, float* loss, float* dlogits, int B, int C, void* stream);
+int egb_scale_by_device_scalar(const float* x, const float* g, float* out, int64_t n, void* stream);
+
+/* LayerNorm over the last dim (art.py:283-296,306; timm eps 1e-6).  bwd ACCUMULATES into dgamma/dbeta. */
+int egb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int dtype,
+                      int M, int D, float eps, void* stream);
+int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                      float* dgamma, float* dbeta, int dtype, int M, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-head attention (art.py:203-213; timm Attention): softmax(QK^T*scale) [dropout] V without
+ * materialising the probabilities.  Tensors are addressed base[b*bs + row*rs + head*head_dim + d].
+ * kv_shift: query batch s uses keys/values of batch (s+kv_shift)%S  (CrossBrainAttention, both directions
+ * in one launch).  `probs` (optional, fp32 [S,H,Lq,Lk]) exports the softmax for the analysis hooks.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void *q, *k, *v;
+  void* o;
+  int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
+  const void* d_o;
+  int64_t do_bs, do_rs;
+  void *dq, *dk, *dv;
+  int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  float* lse;   /* [S,H,Lq] saved by fwd */
+  float* delta; /* [S,H,Lq] scratch of bwd */
+  float* probs;
+  int32_t dtype, S, H, Lq, Lk, head_dim, kv_shift;
+  float scale, dropout_p;
+  uint64_t seed;
+} egb_attention_desc;
+int egb_attention_fwd(const egb_attention_desc* d, void* stream);
+int egb_attention_bwd(const egb_attention_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spectrogram tokens (dual_eeg_transformer.py:88-135)
+ * ------------------------------------------------------------------------------------------- */
+/* STFT(n_fft, hop, hann window, centre/reflect) -> |.| -> first `bins` -> log(+1e-8); out fp32 [2*n_sig, bins, 1+T/hop] */
+int egb_stft_logmag(const float* eeg1, const float* eeg2, const float* window, float* out, int n_sig_per_stream, int T,
+                    int n_fft, int hop, int bins, void* stream);
+/* Conv2d(1->32,3x3,p1)+ReLU+MaxPool2 fused; out = zero-bordered channels-last [N, Hh/2+2, Ww/2+2, 32] */
+int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias, void* out, int dtype, int N, int Hh,
+                            int Ww, int64_t out_elems, void* stream);
+int egb_spec_conv1_pool_bwd(const float* img, const float* w, const float* bias, const void* dout, int dtype, float* dw,
+                            float* db, int N, int Hh, int Ww, void* stream);
+/* ReLU + AdaptiveAvgPool2d(4,4) + flatten over the padded conv-2 output [N, H1+2, W1+2, 64] */
+int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int W1, void* stream);
+int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Inter-brain-synchrony connectivity (dual_eeg_transformer.py:473-819), parameter-free, forward only.
+ * out fp32 [B, n_bands, n_out, C, C].  Scratch (floats): phase, xb: B*n_bands*2*C*T each; stats:
+ * B*n_bands*2*C*8; pspec: B*2*C*(max(hi)-min(lo)+1).  twiddle: T/2 complex exp(-2 pi i k/T).
+ * ------------------------------------------------------------------------------------------- */
+int egb_ibs_connectivity(const float* eeg1, const float* eeg2, const float* twiddle, float* phase, float* xb,
+                         float* stats, float* pspec, float* out, int B, int C, int T, int n_bands, const int32_t* band_lo,
+                         const int32_t* band_hi, const int32_t* slot_of, int n_out, void* stream);
+/* InstanceNorm1d over the token axis per (trial, matrix cell) (dual_eeg_transformer.py:893-901) */
+int egb_instnorm_tokens_fwd(const float* x, const float* gamma, const float* beta, void* y, int dtype, int B, int NT,
+                            int P, float eps, int apply_norm, void* stream);
+int egb_instnorm_tokens_bwd(const float* x, const void* dy, int dtype, float* dgamma, float* dbeta, int B, int NT, int P,
+                            float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FuzzyGatingFusion (fuzzy_gating_fusion.py:297-390).  mode: 0 full, 1 no_temperature,
+ * 2 no_fuzzification, 3 fixed_weights.  aux: 16 floats per trial {H_img,H_eeg,mu[4],w[4],alpha,T_img,T_eeg}.
+ * dparams (12 floats, accumulated): tau_img, tau_eeg, c_unrel_img, c_unrel_eeg, ls_rel_img, ls_rel_eeg,
+ * ls_unrel_img, ls_unrel_eeg, beta[4].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *tau_img, *tau_eeg, *c_reliable, *c_unreliable_img, *c_unreliable_eeg;
+  const float *log_sigma_reliable_img, *log_sigma_reliable_eeg, *log_sigma_unreliable_img, *log_sigma_unreliable_eeg;
+  const float* beta;
+  int32_t mode, B, num_classes;
+  float eps_temp, eps_log, eps_div;
+} egb_fuzzy_desc;
+int egb_fuzzy_fwd(const egb_fuzzy_desc* d, const float* img, const float* eeg, float* fused, float* alpha, float* aux,
+                  void* stream);
+int egb_fuzzy_bwd(const egb_fuzzy_desc* d, const float* img, const float* eeg, const float* g_fused,
+                  const float* g_alpha, float* d_img, float* d_eeg, float* dparams, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gaze branch prologue (early_fusion_vit.py:149-196 + timm PatchEmbed): fuse the two heat-maps and emit
+ * the [B*n_patches, C*ps*ps] patch matrix.  mode: 0 concat 1 add 2 subtract 3 subtract_abs 4 multiply
+ * 5 single image.  egb_fill_row0: out[s,0,:] = cls + pos[0,:].
+ * ------------------------------------------------------------------------------------------- */
+int egb_vit_patchify(const float* img_a, const float* img_b, void* out, float* stats_scratch, int dtype, int B, int H,
+                     int W, int ps, int mode, void* stream);
+int egb_fill_row0(const float* cls, const float* pos, void* out, int dtype, int S, int L, int D, void* stream);
 
 #ifdef __cplusplus
 }

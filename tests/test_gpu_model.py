@@ -1,0 +1,156 @@
+"""GPU parity of the drop-in DualEEGTransformer against (a) golden vectors from the UNMODIFIED reference and
+(b) the CPU oracle at BASELINE sizes.  Tolerances are the north-star ones: fp32 logits max-abs-err <= 1e-4,
+bf16 <= 2e-2 relative, identical argmax.  Run on the B200 box:  pytest -m gpu"""
+import ast
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state_dict, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from eyegaze_multimodal_b200.dual_eeg_transformer import CrossBrainAttention, DualEEGTransformer
+    from eyegaze_multimodal_b200.precision import precision
+from eyegaze_multimodal_b200.synth import eeg_pair_batch
+from oracle import eeg as O
+
+DEV = "cuda:0"
+
+
+def _build(g):
+    kw = ast.literal_eval(str(g["kwargs_repr"]))
+    m = DualEEGTransformer(**kw)
+    missing = m.load_state_dict(golden_state_dict(g), strict=True)      # reference checkpoints load unchanged
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.to(DEV).eval(), kw
+
+
+@pytest.mark.parametrize("name", ["full", "a1_baseline", "phase_noin_nocross"])
+def test_golden_forward_backward_fp32(cuda_device, name):
+    g = load_golden(f"eeg_model_{name}.npz")
+    m, kw = _build(g)
+    e1, e2 = torch.from_numpy(g["eeg1"]).to(DEV), torch.from_numpy(g["eeg2"]).to(DEV)
+    labels = torch.from_numpy(g["labels"]).to(DEV)
+    with precision("fp32"):
+        out = m(e1, e2, labels)
+        loss = out["loss"] + (out["loss_ibs_cls"] if "loss_ibs_cls" in out else 0.0)
+        loss.backward()
+    for k in ("logits", "cls1", "cls2", "ibs_logits", "ibs_token", "loss", "loss_ibs_cls"):
+        if "out::" + k in g:
+            err = np.abs(out[k].detach().float().cpu().numpy() - g["out::" + k]).max()
+            assert err <= 1e-4, f"{k}: max abs err {err:.3e}"
+    assert (out["logits"].argmax(-1).cpu().numpy() == g["out::logits"].argmax(-1)).all()
+    params = dict(m.named_parameters())
+    checked = 0
+    for k, v in g.items():
+        if k.startswith("grad::"):
+            gr = params[k[6:]].grad
+            assert gr is not None, k
+            err = np.abs(gr.float().cpu().numpy() - v).max()
+            assert err <= 2e-5 + 2e-3 * np.abs(v).max(), f"{k}: grad max abs err {err:.3e} (ref max {np.abs(v).max():.3e})"
+            checked += 1
+    assert checked >= 5
+
+
+@pytest.mark.parametrize("name", ["full", "a1_baseline"])
+def test_golden_forward_bf16(cuda_device, name):
+    g = load_golden(f"eeg_model_{name}.npz")
+    m, kw = _build(g)
+    e1, e2 = torch.from_numpy(g["eeg1"]).to(DEV), torch.from_numpy(g["eeg2"]).to(DEV)
+    with precision("bf16"), torch.no_grad():
+        out = m(e1, e2)
+    ref = g["out::logits"]
+    rel = np.abs(out["logits"].float().cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert rel <= 2e-2, f"bf16 logits relative error {rel:.3e}"
+
+
+def test_cross_attention_golden(cuda_device):
+    g = load_golden("cross_attention.npz")
+    m = CrossBrainAttention(64, 4, dropout=0.1)
+    m.load_state_dict(golden_state_dict(g), strict=True)
+    m = m.to(DEV).eval()
+    z1 = torch.from_numpy(g["z1"]).to(DEV).requires_grad_(True)
+    z2 = torch.from_numpy(g["z2"]).to(DEV).requires_grad_(True)
+    with precision("fp32"):
+        o = m.cross_attn(z1, z2, z2)            # Lq = 16 != Lk = 24
+        (o ** 2).sum().backward()
+        a, b = torch.from_numpy(g["a"]).to(DEV), torch.from_numpy(g["b"]).to(DEV)
+        o1, o2 = m(a, b)
+    assert np.abs(o.detach().cpu().numpy() - g["out"]).max() < 2e-5
+    assert np.abs(z1.grad.cpu().numpy() - g["grad_z1"]).max() < 5e-5
+    assert np.abs(z2.grad.cpu().numpy() - g["grad_z2"]).max() < 5e-5
+    for k, p in m.named_parameters():
+        if "grad::" + k in g:
+            assert np.abs(p.grad.cpu().numpy() - g["grad::" + k]).max() < 1e-4, k
+    assert np.abs(o1.detach().cpu().numpy() - g["cross1"]).max() < 2e-5
+    assert np.abs(o2.detach().cpu().numpy() - g["cross2"]).max() < 2e-5
+
+
+def _oracle_vs_cuda(cfg, B, T, seed, grads=True):
+    sd = O.init_state_dict(cfg, seed)
+    m = DualEEGTransformer(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    e1, e2 = eeg_pair_batch(B, cfg.in_channels, T, seed=seed, coupled=True)
+    labels = torch.arange(B) % 3
+    sdr = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    ref = O.dual_eeg_forward(sdr, e1, e2, cfg, labels)
+    with precision("fp32"):
+        out = m(e1.to(DEV), e2.to(DEV), labels.to(DEV))
+    err = (out["logits"].detach().cpu() - ref["logits"].detach()).abs().max().item()
+    assert err <= 1e-4, f"fp32 logits max abs err {err:.3e}"
+    assert torch.equal(out["logits"].argmax(-1).cpu(), ref["logits"].argmax(-1))
+    if grads:
+        (ref["loss"] + ref.get("loss_ibs_cls", 0.0)).backward()
+        with precision("fp32"):
+            (out["loss"] + out.get("loss_ibs_cls", 0.0)).backward()
+        worst = 0.0
+        for k, p in m.named_parameters():
+            if sdr[k].grad is None:
+                continue
+            r = sdr[k].grad
+            e = (p.grad.cpu() - r).abs().max().item() / (r.abs().max().item() + 1e-8)
+            worst = max(worst, e)
+            assert e <= 5e-3, f"grad {k}: relative max err {e:.3e}"
+    with precision("bf16"), torch.no_grad():
+        ob = m(e1.to(DEV), e2.to(DEV))
+    rel = (ob["logits"].float().cpu() - ref["logits"].detach()).abs().max().item() / ref["logits"].abs().max().item()
+    assert rel <= 2e-2, f"bf16 logits relative err {rel:.3e}"
+
+
+def test_cfg1_eeg_only_conv_encoder(cuda_device):
+    """BASELINE config 1: A1 baseline (no spectrogram, no IBS), 32 ch x 512 samples."""
+    cfg = O.EEGConfig(in_channels=32, max_len=128, use_spectrogram=False, use_ibs=False)
+    _oracle_vs_cuda(cfg, B=8, T=512, seed=1)
+
+
+def test_default_full_model_32x1024(cuda_device):
+    """Full EEG encoder of BASELINE configs 2/4 (32 ch x 1024, L = 139)."""
+    cfg = O.EEGConfig(in_channels=32, max_len=256)
+    _oracle_vs_cuda(cfg, B=4, T=1024, seed=2)
+
+
+def test_train_mode_runs_and_is_stochastic(cuda_device):
+    cfg = O.EEGConfig(in_channels=8, d_model=64, num_layers=2, num_heads=4, d_ff=128, max_len=96)
+    m = DualEEGTransformer(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__}).to(DEV).train()
+    e1, e2 = eeg_pair_batch(4, 8, 256, seed=3)
+    labels = torch.tensor([0, 1, 2, 0], device=DEV)
+    for mode in ("fp32", "bf16"):
+        with precision(mode):
+            o1 = m(e1.to(DEV), e2.to(DEV), labels)
+            o2 = m(e1.to(DEV), e2.to(DEV), labels)
+            (o1["loss"] + o1["loss_ibs_cls"]).backward()
+        assert torch.isfinite(o1["logits"]).all() and (o1["logits"] - o2["logits"]).abs().max() > 0
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+        m.zero_grad()
+
+
+def test_sequence_longer_than_max_len_raises(cuda_device):
+    cfg = O.EEGConfig(in_channels=8, d_model=32, num_layers=1, num_heads=4, d_ff=64, max_len=16)
+    m = DualEEGTransformer(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__}).to(DEV).eval()
+    e1, e2 = eeg_pair_batch(2, 8, 256, seed=4)
+    with pytest.raises(IndexError):
+        m(e1.to(DEV), e2.to(DEV))
