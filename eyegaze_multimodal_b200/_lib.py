@@ -54,6 +54,8 @@ class FuzzyDesc(C.Structure):
 # name -> argtypes (all return int except where noted); mirrors include/eyegaze_b200.h one to one
 _SIGNATURES = {
     "egb_gemm": [C.POINTER(GemmDesc), vp],
+    "egb_prof_enable": [i32],
+    "egb_prof_read": [i32, C.POINTER(C.c_double), i32],
     "egb_cast_from_f32": [vp, vp, i32, i64, vp],
     "egb_cast_to_f32": [vp, i32, vp, i64, vp],
     "egb_copy_strided4": [vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), vp],
@@ -84,7 +86,7 @@ _SIGNATURES = {
     "egb_instnorm_tokens_bwd": [vp, vp, i32, vp, vp, i32, i32, i32, f32, vp],
     "egb_fuzzy_fwd": [C.POINTER(FuzzyDesc), vp, vp, vp, vp, vp, vp],
     "egb_fuzzy_bwd": [C.POINTER(FuzzyDesc), vp, vp, vp, vp, vp, vp, vp, vp],
-    "egb_vit_patchify": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "egb_vit_patchify": [vp, vp, i64, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "egb_fill_row0": [vp, vp, vp, i32, i32, i32, i32, vp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["egb_last_error", "egb_version", "egb_launch_count"])
@@ -122,3 +124,13 @@ def call(name, *args):
 
 def launch_count() -> int:
     return int(load().egb_launch_count())
+
+
+def prof_enable(on: bool) -> None:
+    call("egb_prof_enable", 1 if on else 0)
+
+
+def prof_read(kind: int = 0, reset: bool = True) -> dict:
+    out = (C.c_double * 4)()
+    call("egb_prof_read", kind, out, 1 if reset else 0)
+    return {"launches": int(out[0]), "ms": out[1], "flops": out[2], "bytes": out[3]}

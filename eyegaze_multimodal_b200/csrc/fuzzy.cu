@@ -91,6 +91,12 @@ __global__ void fuzzy_fwd_kernel(const FuzzyParams P, const float* __restrict__ 
   a[0] = r.H_i; a[1] = r.H_e;
   for (int k = 0; k < 4; ++k) { a[2 + k] = (P.mode < 2) ? r.mu[k] : 0.f; a[6 + k] = (P.mode < 2) ? r.w[k] : 0.f; }
   a[10] = r.alpha; a[11] = r.T_i; a[12] = r.T_e;
+  if (b == 0) {  // parameter-derived analysis values (aux_info['fuzz_params'] / ['consequents']), once per call
+    float* q = aux + (long long)P.B * 16;
+    q[0] = expf(*P.ls_rel_img); q[1] = expf(*P.ls_rel_eeg); q[2] = expf(*P.ls_unrel_img); q[3] = expf(*P.ls_unrel_eeg);
+    for (int k = 0; k < 4; ++k) q[4 + k] = 1.f / (1.f + expf(-P.beta[k]));
+    q[8] = r.T_i; q[9] = r.T_e;
+  }
 }
 
 // dparams (16 floats, accumulated): tau_img, tau_eeg, c_unrel_img, c_unrel_eeg, ls_rel_img, ls_rel_eeg,

@@ -18,6 +18,9 @@
 #include "epilogue.cuh"
 
 extern void egb_count_launch(int n);
+int egb_prof_enabled();
+void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind);
+void egb_prof_end(cudaStream_t st);
 
 namespace {
 
@@ -316,7 +319,13 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, c
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = total < egb_num_sms() ? total : egb_num_sms();
+  const bool prof = egb_prof_enabled() != 0;
+  if (prof) {
+    const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
+    egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
+  }
   gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  if (prof) egb_prof_end(stream);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;

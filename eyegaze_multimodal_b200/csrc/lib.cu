@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include "common.cuh"
 #include "../../include/eyegaze_b200.h"
 
@@ -26,7 +27,58 @@ int egb_num_sms() {
   return sms;
 }
 
+// ---------------------------------------------------------------------------------------------
+// optional per-launch timing of the dominant (GEMM) kernel with CUDA events on the launching stream
+// (bench.py's roofline block).  Disabled by default: zero overhead on the normal path.
+// ---------------------------------------------------------------------------------------------
+#include <vector>
+struct ProfRec { cudaEvent_t e0, e1; double flops; double bytes; int kind; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mu;
+static int g_prof_on = 0;
+
+int egb_prof_enabled() { return g_prof_on; }
+
+static cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+// called by the GEMM launcher right before / after its kernel launch
+void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.e0 = prof_event(); r.e1 = prof_event(); r.flops = flops; r.bytes = bytes; r.kind = kind;
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+}
+void egb_prof_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, st);
+}
+
 extern "C" {
+/* kind: 0 = tcgen05 GEMM, 1 = FFMA GEMM.  out[0..3] = launches, total ms, total flops, total algorithmic bytes */
+int egb_prof_enable(int on) { g_prof_on = on; return 0; }
+int egb_prof_read(int kind, double* out, int reset) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double n = 0, ms = 0, fl = 0, by = 0;
+  for (auto& r : g_prof) {
+    if (r.kind != kind) continue;
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      n += 1; ms += t; fl += r.flops; by += r.bytes;
+    }
+  }
+  out[0] = n; out[1] = ms; out[2] = fl; out[3] = by;
+  if (reset) {
+    for (auto& r : g_prof) { g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1); }
+    g_prof.clear();
+  }
+  return 0;
+}
 const char* egb_last_error(void) { return g_err; }
 int egb_version(void) { return 1; }
 int64_t egb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,43 @@
+"""MultimodalFusionModel + its loss -- the glue module the reference defines inside its training script
+(4_Experiments/scripts/train_multimodal_fuzzy_fusion.py:106-179, loss at :436-460)."""
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class MultimodalFusionModel(nn.Module):
+    def __init__(self, gaze_encoder: nn.Module, eeg_encoder: nn.Module, fusion_module: nn.Module,
+                 freeze_gaze: bool = False, freeze_eeg: bool = False):
+        super().__init__()
+        self.gaze_encoder = gaze_encoder
+        self.eeg_encoder = eeg_encoder
+        self.fusion = fusion_module
+        if freeze_gaze:
+            for p in self.gaze_encoder.parameters():
+                p.requires_grad = False
+        if freeze_eeg:
+            for p in self.eeg_encoder.parameters():
+                p.requires_grad = False
+
+    def forward(self, img1: torch.Tensor, img2: torch.Tensor, eeg1: torch.Tensor, eeg2: torch.Tensor,
+                labels: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        img_logits = self.gaze_encoder(img1, img2)
+        eeg_logits = self.eeg_encoder(eeg1, eeg2, labels)['logits']
+        fused_logits, alpha, aux_info = self.fusion(img_logits, eeg_logits)
+        return {'fused_logits': fused_logits, 'img_logits': img_logits, 'eeg_logits': eeg_logits, 'alpha': alpha,
+                'aux_info': aux_info}
+
+
+def multimodal_loss(model: MultimodalFusionModel, outputs: Dict, labels: torch.Tensor, lambda_aux_img: float = 0.3,
+                    lambda_aux_eeg: float = 0.3, lambda_reg: float = 0.1, t_min: float = 0.5,
+                    t_max: float = 5.0) -> torch.Tensor:
+    """CE(fused) + 0.3 CE(img/T_img) + 0.3 CE(eeg/T_eeg) + 0.1 temperature hinge; temperatures are the detached
+    copies from aux_info (train_multimodal_fuzzy_fusion.py:440-460)."""
+    t = outputs['aux_info']['temperatures']
+    loss = ops.cross_entropy(outputs['fused_logits'], labels)
+    loss = loss + lambda_aux_img * ops.cross_entropy(outputs['img_logits'] / t['img'], labels)
+    loss = loss + lambda_aux_eeg * ops.cross_entropy(outputs['eeg_logits'] / t['eeg'], labels)
+    return loss + lambda_reg * model.fusion.compute_temperature_regularization(t_min, t_max).squeeze()

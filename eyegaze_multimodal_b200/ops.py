@@ -1079,7 +1079,7 @@ class FuzzyGatingFn(torch.autograd.Function):
         dev = img.device
         fused = torch.empty(B, Cn, dtype=torch.float32, device=dev)
         alpha = torch.empty(B, dtype=torch.float32, device=dev)
-        aux = torch.empty(B, 16, dtype=torch.float32, device=dev)
+        aux = torch.empty(B + 1, 16, dtype=torch.float32, device=dev)
         d = _fuzzy_desc(params, mode, B, Cn, eps_temp, eps_log, eps_div)
         L.call("egb_fuzzy_fwd", C.byref(d), img.data_ptr(), eeg.data_ptr(), fused.data_ptr(), alpha.data_ptr(),
                aux.data_ptr(), _stream())
@@ -1114,18 +1114,32 @@ def fuzzy_gating(img, eeg, mode, eps_temp, eps_log, eps_div, params):
 # ------------------------------------------------------------------------------------------------------
 # ViT patch embedding (+ input fusion + cls + pos)
 # ------------------------------------------------------------------------------------------------------
-PATCH_MODES = {"concat": 0, "add": 1, "subtract": 2, "subtract_abs": 3, "multiply": 4, "single": 5}
+PATCH_MODES = {"concat": 0, "add": 1, "subtract": 2, "subtract_abs": 3, "multiply": 4, "single": 5, "single_pair": 6}
+
+
+def _img_view(t):
+    """(tensor, batch_stride) of a (B,3,H,W) fp32 image batch; channel-sliced views of a wider tensor are legal."""
+    t = t.float()
+    B, Cc, H, W = t.shape
+    if not (t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W and t.stride(0) % 4 == 0):
+        t = t.contiguous()
+    return t, t.stride(0)
 
 
 class VitEmbedFn(torch.autograd.Function):
-    """img_a, img_b (B,3,H,W) fp32 -> tokens [B, 1+n, D]: fuse -> patchify -> patch GEMM (+bias +pos) -> cls row."""
+    """Fuse -> patchify -> patch GEMM (+bias +pos) -> cls row.  img_a, img_b: (B,3,H,W) fp32.
+    mode 0..4: EarlyFusionViT input fusion (one token sequence per trial);
+    mode 5   : single image (img_b None) ;  mode 6: two single images stacked along the batch (LateFusionViT)."""
 
     @staticmethod
     def forward(ctx, img_a, img_b, w, b, cls, pos, mode, code, ps):
         _require_cuda(img_a, w)
-        img_a = img_a.contiguous().float()
-        img_b = img_b.contiguous().float() if img_b is not None else img_a
-        B, _, H, W = img_a.shape
+        img_a, a_bs = _img_view(img_a)
+        if img_b is not None:
+            img_b, b_bs = _img_view(img_b)
+        else:
+            img_b, b_bs = img_a, a_bs
+        Bi, _, H, W = img_a.shape
         D = w.shape[0]
         n = (H // ps) * (W // ps)
         cin = 6 if mode == 0 else 3
@@ -1135,10 +1149,17 @@ class VitEmbedFn(torch.autograd.Function):
         if pos.shape[1] != n + 1:
             raise RuntimeError("pos_embed has %d tokens, image gives %d" % (pos.shape[1], n + 1))
         dev, tdt = img_a.device, _TORCH_DT[code]
+        B = 2 * Bi if mode == 6 else Bi
         patches = torch.empty(B * n, K, dtype=tdt, device=dev)
-        stats = torch.empty(B * 6, dtype=torch.float32, device=dev) if mode == 4 else None
-        L.call("egb_vit_patchify", img_a.data_ptr(), img_b.data_ptr(), patches.data_ptr(), _p(stats), code, B, H, W, ps,
-               mode, _stream())
+        stats = torch.empty(Bi * 6, dtype=torch.float32, device=dev) if mode == 4 else None
+        if mode == 6:
+            L.call("egb_vit_patchify", img_a.data_ptr(), img_a.data_ptr(), a_bs, a_bs, patches.data_ptr(), None, code, Bi,
+                   H, W, ps, 5, _stream())
+            L.call("egb_vit_patchify", img_b.data_ptr(), img_b.data_ptr(), b_bs, b_bs,
+                   patches.data_ptr() + Bi * n * K * patches.element_size(), None, code, Bi, H, W, ps, 5, _stream())
+        else:
+            L.call("egb_vit_patchify", img_a.data_ptr(), img_b.data_ptr(), a_bs, b_bs, patches.data_ptr(), _p(stats), code,
+                   Bi, H, W, ps, mode, _stream())
         w2 = weight_plain(w, code)
         out = torch.empty(B, n + 1, D, dtype=tdt, device=dev)
         pos2 = pos.detach().reshape(n + 1, D)

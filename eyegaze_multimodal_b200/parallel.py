@@ -1,0 +1,132 @@
+"""Trial-wise data parallelism for the drop-in models: one process per GPU, replicated parameters, the batch of
+trials split across ranks, and ONE real exchange step per training step -- the gradient all-reduce.
+
+The reference is single-process (no torch.distributed anywhere); trials are independent in
+forward and backward (LayerNorm per token, InstanceNorm per trial, no BatchNorm), so the path shards with no
+data-path collective.  Gradients are reduced in flat fp32 buckets:
+
+  * every trainable parameter's ``.grad`` is a *view* into a flat bucket buffer (no gather / scatter copies);
+  * a post-accumulate-grad hook counts a bucket's parameters down during backward; when the last one lands, the
+    bucket's all-reduce (NCCL over NVLink / NVSwitch, average) is enqueued asynchronously, so it overlaps the rest
+    of the backward pass (buckets are filled in reverse registration order ~ backward execution order);
+  * ``finish()`` flushes buckets whose parameters received no gradient this step and makes the compute stream wait
+    for the communication.
+
+``backend='gloo'`` (CPU tests, world_size 2) takes the same code path with SUM + scale instead of NCCL's AVG.
+"""
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+class _Bucket:
+    __slots__ = ("flat", "params", "pending", "work", "launched")
+
+    def __init__(self, flat, params):
+        self.flat = flat
+        self.params = params
+        self.pending = len(params)
+        self.work = None
+        self.launched = False
+
+
+class TrialParallel(nn.Module):
+    """Wraps a model; ``forward`` is the model's.  Call ``zero_grad()`` before and ``finish()`` after ``backward()``."""
+
+    def __init__(self, module: nn.Module, bucket_mb: float = 32.0, process_group=None, broadcast: bool = True):
+        super().__init__()
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self._avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        if broadcast and self.world > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t, src=0, group=process_group)
+        self.buckets: List[_Bucket] = []
+        self._build_buckets(int(bucket_mb * (1 << 20)))
+
+    # ------------------------------------------------------------------------------------------------
+    def _build_buckets(self, bucket_bytes: int) -> None:
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        params.reverse()                       # heads first: the order in which backward produces gradients
+        groups, cur, cur_bytes = [], [], 0
+        for p in params:
+            nb = p.numel() * 4
+            if cur and (cur_bytes + nb > bucket_bytes or cur[0].device != p.device):
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nb
+        if cur:
+            groups.append(cur)
+        for g in groups:
+            # 16-byte aligned slices keep the kernels' vectorised access to parameter gradients legal
+            offs, n = [], 0
+            for p in g:
+                offs.append(n)
+                n += (p.numel() + 3) // 4 * 4
+            flat = torch.zeros(n, dtype=torch.float32, device=g[0].device)
+            b = _Bucket(flat, g)
+            for p, o in zip(g, offs):
+                if p.dtype != torch.float32:
+                    raise TypeError("TrialParallel expects fp32 master parameters")
+                p.grad = flat[o:o + p.numel()].view(p.shape)
+                p.register_post_accumulate_grad_hook(self._make_hook(b))
+            self.buckets.append(b)
+
+    def _make_hook(self, b: _Bucket):
+        def hook(_p):
+            b.pending -= 1
+            if b.pending == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: _Bucket) -> None:
+        b.launched = True
+        if self.world == 1:
+            return
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:   # noqa: D401 (views must survive: never set to None)
+        for b in self.buckets:
+            b.flat.zero_()
+            b.pending = len(b.params)
+            b.work = None
+            b.launched = False
+
+    def finish(self) -> None:
+        """Reduce whatever has not been reduced yet and order the compute stream after all communication."""
+        for b in self.buckets:
+            if not b.launched:
+                self._launch(b)
+        for b in self.buckets:
+            if b.work is not None:
+                b.work.wait()
+                if not self._avg:
+                    b.flat.div_(self.world)
+                b.work = None
+
+    def grad_bytes(self) -> int:
+        return sum(b.flat.numel() * 4 for b in self.buckets)
+
+    def flat_grads(self) -> Iterable[torch.Tensor]:
+        return [b.flat for b in self.buckets]
+
+
+def shard_trials(n_trials: int, rank: Optional[int] = None, world: Optional[int] = None) -> range:
+    """Contiguous shard of trial indices owned by ``rank`` (ragged tails go to the low ranks)."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    base, rem = divmod(n_trials, world)
+    lo = rank * base + min(rank, rem)
+    return range(lo, lo + base + (1 if rank < rem else 0))

@@ -29,6 +29,10 @@ const char* egb_last_error(void);
 int egb_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t egb_launch_count(void);
+/* optional CUDA-event timing of every tensor-core GEMM launch (bench.py roofline): enable, run, read.
+ * egb_prof_read: kind 0 = tcgen05 GEMM; out[4] = {launches, total ms, total FLOPs, total algorithmic bytes} */
+int egb_prof_enable(int on);
+int egb_prof_read(int kind, double* out, int reset);
 
 /* ---------------------------------------------------------------------------------------------
  * Generalised GEMM   C[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )
@@ -202,7 +206,8 @@ int egb_instnorm_tokens_bwd(const float* x, const void* dy, int dtype, float* dg
 
 /* ---------------------------------------------------------------------------------------------
  * FuzzyGatingFusion (fuzzy_gating_fusion.py:297-390).  mode: 0 full, 1 no_temperature,
- * 2 no_fuzzification, 3 fixed_weights.  aux: 16 floats per trial {H_img,H_eeg,mu[4],w[4],alpha,T_img,T_eeg}.
+ * 2 no_fuzzification, 3 fixed_weights.  aux: (B+1) rows of 16 floats; row b = {H_img,H_eeg,mu[4],w[4],alpha,T_img,T_eeg},
+ * row B = {sigma_rel_img, sigma_rel_eeg, sigma_unrel_img, sigma_unrel_eeg, theta[4], T_img, T_eeg}.
  * dparams (12 floats, accumulated): tau_img, tau_eeg, c_unrel_img, c_unrel_eeg, ls_rel_img, ls_rel_eeg,
  * ls_unrel_img, ls_unrel_eeg, beta[4].
  * ------------------------------------------------------------------------------------------- */
@@ -221,10 +226,11 @@ int egb_fuzzy_bwd(const egb_fuzzy_desc* d, const float* img, const float* eeg, c
 /* ---------------------------------------------------------------------------------------------
  * Gaze branch prologue (early_fusion_vit.py:149-196 + timm PatchEmbed): fuse the two heat-maps and emit
  * the [B*n_patches, C*ps*ps] patch matrix.  mode: 0 concat 1 add 2 subtract 3 subtract_abs 4 multiply
- * 5 single image.  egb_fill_row0: out[s,0,:] = cls + pos[0,:].
+ * 5 single image.  Images are (B,3,H,W) fp32 with an explicit batch stride (channel-sliced views are legal).
+ * egb_fill_row0: out[s,0,:] = cls + pos[0,:].
  * ------------------------------------------------------------------------------------------- */
-int egb_vit_patchify(const float* img_a, const float* img_b, void* out, float* stats_scratch, int dtype, int B, int H,
-                     int W, int ps, int mode, void* stream);
+int egb_vit_patchify(const float* img_a, const float* img_b, int64_t a_batch_stride, int64_t b_batch_stride, void* out,
+                     float* stats_scratch, int dtype, int B, int H, int W, int ps, int mode, void* stream);
 int egb_fill_row0(const float* cls, const float* pos, void* out, int dtype, int S, int L, int D, void* stream);
 
 #ifdef __cplusplus
