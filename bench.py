@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- train trials/sec (forward + backward) of the gaze+EEG fusion classifier on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl b200|reference]
+
+One *step* = one pass of the hot path (MultimodalFusionModel forward, the 4-term loss of
+train_multimodal_fuzzy_fusion.py:440-460, backward, and for N > 1 the gradient all-reduce) over one batch of
+synthetic trials per GPU.  Rank 0 prints ONE JSON line (see the contract in the task description):
+
+  value     whole-job trials/s with the inputs already resident in HBM (device-timed with CUDA events,
+            max over ranks);
+  e2e       the same metric through the public nn.Module API with HOST inputs: every step copies its batch from
+            pinned host memory to the device and reads the loss back, all inside the timed region;
+  roofline  the dominant kernel (the tcgen05 bf16 GEMM): algorithmic FLOPs of its launches / their CUDA-event
+            durations, against the measured sustained bf16 peak in MEASURED_PEAKS.json;
+  cpu_baseline  the CPU oracle port (oracle/: the reference's algorithm restated in fp32 PyTorch-CPU) timed on this
+            box's host cores on a bounded sample of the same workload (N = 1, rank 0 only).
+
+``--impl reference`` times that CPU port alone, with all host threads, on the same workload / metric / unit
+(the reference itself is pure Python + PyTorch and /root/reference does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train trials/sec (fwd+bwd)"
+UNIT = "trials/s"
+
+# name -> workload (BASELINE.json configs; SURVEY.md section 8d maps them to reference objects)
+WORKLOADS = {
+    # configs[1]: full gaze+EEG classifier as 4_Experiments/configs/multimodal_fuzzy_fusion.yaml builds it
+    "cfg2": dict(desc="gaze+EEG fusion classifier (EarlyFusionViT vit_base_patch16_224 concat + DualEEGTransformer "
+                      "32ch x 1024 + FuzzyGatingFusion full), batch 256 per GPU, fwd+bwd",
+                 vit="vit_base_patch16_224", C=32, T=1024, batch=256, eeg_kwargs={}),
+    # configs[3]: same with a ViT-S gaze backbone (data-parallel at 2/4/8 GPUs)
+    "cfg4": dict(desc="cross-attention fusion with a ViT-S gaze-heatmap backbone, batch 256 per GPU, fwd+bwd",
+                 vit="vit_small_patch16_224", C=32, T=1024, batch=256, eeg_kwargs={}),
+    # configs[0]: EEG-only conv encoder + head (ablation A1: no spectrogram, no IBS), 32ch x 512, batch 64
+    "cfg1": dict(desc="EEG-only temporal-conv encoder + head (A1_baseline_temporal_only), 32ch x 512, batch 64",
+                 vit=None, C=32, T=512, batch=64, eeg_kwargs=dict(use_spectrogram=False, use_ibs=False)),
+    # configs[4]: large sweep, 64ch x 2048, 4096 trials per step over 8 GPUs = 512 per GPU
+    "cfg5": dict(desc="large sweep: 64ch x 2048 EEG, full fusion model (ViT-B), 512 trials per GPU",
+                 vit="vit_base_patch16_224", C=64, T=2048, batch=512, eeg_kwargs={}),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="trials per GPU (default: the workload's)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=2, help="trials per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (fp32 PyTorch-CPU restatement of the reference), forward + backward
+# ------------------------------------------------------------------------------------------------------
+def _cpu_step_fn(wl, B, seed=0):
+    """Returns (step, n_threads): step() runs one fwd+bwd of the workload on B synthetic trials on the CPU."""
+    import torch
+    from oracle import eeg as O
+    from oracle import fuzzy as FZ
+    from oracle import vit as V
+    from eyegaze_multimodal_b200.synth import gaze_pair_batch, labels_batch, randn_eeg_pair
+
+    n_threads = os.cpu_count() or 1
+    torch.set_num_threads(n_threads)
+    cfg = O.EEGConfig(in_channels=wl["C"], max_len=wl["T"] // 4, **wl["eeg_kwargs"])
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and k != "spectrogram_generator.window")
+          for k, v in O.init_state_dict(cfg, seed=seed).items()}
+    e1, e2 = randn_eeg_pair(B, wl["C"], wl["T"], seed=seed)
+    labels = labels_batch(B, seed=seed)
+    if wl["vit"] is None:
+        def step():
+            out = O.dual_eeg_forward(sd, e1, e2, cfg, labels)
+            out["loss"].backward()
+            return float(out["loss"].detach())
+        return step, n_threads
+    heads = V.VIT_VARIANTS[wl["vit"]][2]
+    vsd = {k: v.clone().requires_grad_(True) for k, v in V.init_vit_state_dict(wl["vit"], 6, 3, "backbone.", seed=seed).items()}
+    fz = {k: v.clone().requires_grad_(k != "c_reliable") for k, v in FZ.init_params().items()}
+    a, b = gaze_pair_batch(B, seed=seed)
+
+    def step():
+        img_logits = V.early_fusion_forward(vsd, a, b, heads, "concat")
+        eeg_logits = O.dual_eeg_forward(sd, e1, e2, cfg, labels)["logits"]
+        fused, _alpha, aux = FZ.fuzzy_forward(fz, img_logits, eeg_logits, "full")
+        loss = FZ.multimodal_loss(fused, img_logits, eeg_logits, aux, FZ.temperature_regularization(fz), labels)
+        loss.backward()
+        return float(loss.detach())
+    return step, n_threads
+
+
+def time_cpu(wl, B, steps, warmup):
+    step, n_threads = _cpu_step_fn(wl, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps, n_threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0                      # the CPU arm does not shard: rank 0 alone runs it
+    wl = WORKLOADS[args.workload]
+    B = args.cpu_sample
+    tps, s_per_step, n_threads = time_cpu(wl, B, args.steps, args.warmup)
+    sample = "%d trials per step of workload %s (fp32, eval-mode fwd+bwd, vectorised IBS restatement)" % (B, args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "sample_batch": B},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": n_threads, "kind": "port", "sample": sample},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(self.NAMES, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def build_model(wl, device):
+    import warnings
+
+    import torch
+    from eyegaze_multimodal_b200.dual_eeg_transformer import DualEEGTransformer
+    from eyegaze_multimodal_b200.early_fusion_vit import EarlyFusionViT
+    from eyegaze_multimodal_b200.fuzzy_gating_fusion import FuzzyGatingFusion
+    from eyegaze_multimodal_b200.multimodal import MultimodalFusionModel
+
+    torch.manual_seed(0)
+    # constructor calls of train_multimodal_fuzzy_fusion.py:653-700 / train_art.py:360-385
+    eeg = DualEEGTransformer(in_channels=wl["C"], num_classes=3, d_model=256, num_layers=6, num_heads=8, d_ff=1024,
+                             dropout=0.1, max_len=wl["T"] // 4, conv_kernel_size=25, conv_stride=4, conv_layers=2,
+                             sampling_rate=256, **wl["eeg_kwargs"])
+    if wl["vit"] is None:
+        return eeg.to(device)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gaze = EarlyFusionViT(model_name=wl["vit"], num_classes=3, pretrained=False, img_size=224, fusion_mode="concat",
+                              weight_init_strategy="duplicate")
+    return MultimodalFusionModel(gaze, eeg, FuzzyGatingFusion(num_classes=3, mode="full", eps_temp=0.1)).to(device)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from eyegaze_multimodal_b200 import _lib as L
+    from eyegaze_multimodal_b200.multimodal import multimodal_loss
+    from eyegaze_multimodal_b200.parallel import TrialParallel
+    from eyegaze_multimodal_b200.precision import set_precision
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback")
+    L.load()                                            # fails loudly if libeyegaze_b200.so is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise RuntimeError("--gpus %d needs a torchrun launch (one rank per GPU); WORLD_SIZE is 1" % args.gpus)
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    set_precision(args.precision)
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    multimodal = wl["vit"] is not None
+
+    model = build_model(wl, dev)
+    model.train()
+    tp = TrialParallel(model, bucket_mb=32.0)
+    n_params = sum(p.numel() for p in model.parameters())
+
+    # ---- synthetic inputs (seeded per rank: every rank owns different trials) --------------------------------
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 2                                          # distinct pinned host batches cycled by the e2e leg
+    host = []
+    for _ in range(n_host):
+        hb = {"eeg1": torch.randn(B, wl["C"], wl["T"], generator=g).pin_memory(),
+              "eeg2": torch.randn(B, wl["C"], wl["T"], generator=g).pin_memory(),
+              "labels": torch.randint(0, 3, (B,), generator=g).pin_memory()}
+        if multimodal:
+            hb["img1"] = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+            hb["img2"] = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+        host.append(hb)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0].values())
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+
+    def fwd_bwd(batch):
+        tp.zero_grad()
+        if multimodal:
+            out = tp(batch["img1"], batch["img2"], batch["eeg1"], batch["eeg2"], batch["labels"])
+            loss = multimodal_loss(model, out, batch["labels"])
+        else:
+            out = tp(batch["eeg1"], batch["eeg2"], batch["labels"])
+            loss = out["loss"] + out["loss_ibs_cls"] if "loss_ibs_cls" in out else out["loss"]
+        loss.backward()
+        tp.finish()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident throughput ---------------------------------------------------------------------
+    for i in range(args.warmup):
+        fwd_bwd(resident[i % n_host])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = fwd_bwd(resident[i % n_host])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = L.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(loss.item())
+    ms_per_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- (2) end to end: pinned host inputs -> H2D -> fwd+bwd -> loss D2H, every step, double-buffered ------
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        slots = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+        def stage(i):
+            s = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s])           # slot free once step i-2 has finished with it
+                for k, v in host[i % n_host].items():
+                    slots[s][k].copy_(v, non_blocking=True)
+                ready[s].record(copy_stream)
+
+        def e2e_loop(n):
+            for s in range(2):
+                consumed[s].record()
+            stage(0)
+            for i in range(n):
+                if i + 1 < n:
+                    stage(i + 1)                             # overlaps the previous step's compute
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                ls = fwd_bwd(slots[i % 2])
+                consumed[i % 2].record()
+                loss_host.copy_(ls.detach().reshape(1), non_blocking=True)
+            torch.cuda.synchronize()                          # the last loss has reached the host
+            return float(loss_host[0])
+
+        e2e_loop(2)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        e2e_loop(args.steps)
+        t1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        e2e_ms = max_over_ranks(max(t0.elapsed_time(t1), wall_ms))
+        e2e = {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps,
+               "api": "MultimodalFusionModel.forward + multimodal_loss + backward, pinned host batches, "
+                      "double-buffered H2D on a copy stream"}
+
+    # ---- (3) roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch ---------------
+    roofline = None
+    if not args.no_roofline and rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(pk):
+            with open(pk) as f:
+                peaks = json.load(f)
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF sustained (of fallback)"
+        torch.cuda.synchronize()
+        L.prof_read(0, reset=True)
+        L.prof_enable(True)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        n_prof = 2
+        for i in range(n_prof):
+            fwd_bwd(resident[i % n_host])
+        pe1.record()
+        torch.cuda.synchronize()
+        L.prof_enable(False)
+        pr = L.prof_read(0, reset=True)
+        step_ms = pe0.elapsed_time(pe1) / n_prof
+        if pr["launches"] > 0 and pr["ms"] > 0:
+            ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma bf16, TMA operands, TMEM accumulators)",
+                        "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                        "peak_source": peak_src, "launches_per_step": pr["launches"] / n_prof,
+                        "avg_launch_us": pr["ms"] * 1e3 / pr["launches"],
+                        "flops_per_launch": pr["flops"] / pr["launches"],
+                        "share_of_step": pr["ms"] / n_prof / step_ms,
+                        "model_flops_per_step": pr["flops"] / n_prof}
+    if world > 1:
+        dist.barrier()
+
+    # ---- (4) CPU baseline: the oracle port on this box's host cores, bounded sample --------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        tps, s_step, n_threads = time_cpu(wl, args.cpu_sample, steps=2, warmup=1)
+        cpu = {"value": tps, "unit": UNIT, "cores": n_threads, "kind": "port",
+               "sample": "%d trials per step x 2 timed steps (1 warm-up) of workload %s, fp32 eval-mode fwd+bwd, %.2f s/step"
+                         % (args.cpu_sample, args.workload, s_step)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "trials_per_gpu": B, "global_batch": B * world,
+                       "parallelism": "dp%d (trial-wise, bucketed gradient all-reduce overlapped with backward)" % world,
+                       "mode": "train (dropout on), random-init weights, %d parameters" % n_params,
+                       "l2": "inputs larger than L2: %.0f MB of fresh activations/inputs per step" % (h2d_bytes / 1e6),
+                       "loss": loss_val},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -11,6 +11,10 @@
 #include "../../include/eyegaze_b200.h"
 
 extern void egb_count_launch(int n);
+// tensor-core (tcgen05) path, attention_tc.cu
+bool egb_attention_tc_supported(const egb_attention_desc* d, bool backward);
+int egb_attention_tc_fwd(const egb_attention_desc* d, cudaStream_t st);
+int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st);
 
 namespace {
 
@@ -278,6 +282,7 @@ static int fill_att(const egb_attention_desc* d, AttParams* p) {
 
 int egb_attention_fwd(const egb_attention_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (egb_attention_tc_supported(d, false)) return egb_attention_tc_fwd(d, st);
   AttParams p;
   if (fill_att(d, &p)) return 1;
   const int dk = d->head_dim;
@@ -297,6 +302,7 @@ int egb_attention_fwd(const egb_attention_desc* d, void* stream) {
 
 int egb_attention_bwd(const egb_attention_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (egb_attention_tc_supported(d, true)) return egb_attention_tc_bwd(d, st);
   AttParams p;
   if (fill_att(d, &p)) return 1;
   EGB_CHECK(d->lse && d->delta && d->d_o && d->dq && d->dk && d->dv, "attention_bwd: missing buffers");

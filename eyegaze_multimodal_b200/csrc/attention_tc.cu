@@ -1,0 +1,518 @@
+// Fused multi-head attention on the 5th-generation tensor cores (tcgen05 + TMEM), bf16 operands, fp32 softmax.
+//   forward : S = Q K^T (TMEM) -> row softmax in registers -> P (bf16) written back to TMEM ->
+//             O = P V with the A operand read from TMEM (no shared-memory round trip for P)
+//   backward: dQ kernel  (one CTA per 128 query rows): S and dP = dO V^T in TMEM -> dS -> dQ = dS K
+//             dKV kernel (one CTA per 128 key rows)  : S^T = K Q^T and dP^T = V dO^T in TMEM ->
+//                                                      P~^T, dS^T (bf16, TMEM) -> dV = P~^T dO, dK = dS^T Q
+// Sequence lengths on this path are <= 256 (L = 33 / 139 / 235 for the EEG encoder, 197 for the ViT), so the
+// whole key axis is ONE tcgen05 N tile (N <= 256) and no online-softmax rescaling across tiles is needed.
+// One thread owns one TMEM lane = one query (or key) row, so row statistics need no shuffles at all.
+//
+// Operand tiles are staged by the CTA's threads (128-bit loads of the strided per-head slices of the packed
+// [S, L, 3D] projection) directly into the 128-byte-swizzled UMMA layout; the same physical tile serves as a
+// K-major operand (Q K^T, dO V^T) and as an MN-major operand (P V, dS K, dS^T Q, P^T dO).
+// art.py:203-213 / timm Attention; cross-brain attention (dual_eeg_transformer.py:966-974) via kv_shift.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/eyegaze_b200.h"
+
+extern void egb_count_launch(int n);
+int egb_prof_enabled();
+void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind);
+void egb_prof_end(cudaStream_t st);
+
+namespace {
+
+constexpr int TC_THREADS = 128;
+constexpr int TILE_ROWS = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint32_t ACC_COL = 128;  // accumulator columns of the second-stage MMAs (above the packed bf16 A operand)
+constexpr uint32_t HALF_COL = 256; // second score matrix (dP) of the backward kernels
+
+struct AttTcParams {
+  const bf16 *q, *k, *v, *o, *d_o;
+  bf16 *out, *dq, *dk, *dv;
+  float* lse;    // [S,H,Lq]
+  float* delta;  // [S,H,Lq]
+  float* probs;  // optional [S,H,Lq,Lk]
+  long long q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
+  long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, do_bs, do_rs;
+  int S, H, Lq, Lk, d, kv_shift, Lq_pad, Lk_pad;
+  float scale;
+  unsigned drop_thresh;
+  float drop_scale;
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// rows [0, rows_total) of a [rows][d] bf16 slice (row stride rs elements) -> 128-B pitched, 128-B swizzled tile.
+// Rows >= rows_valid are zero-filled.  16-byte chunk c of row r lands at chunk (c ^ (r & 7)) of its 128-B line.
+__device__ __forceinline__ void load_rows_sw128(uint8_t* dst, const bf16* src, long long rs, int rows_valid,
+                                                int rows_total, int d) {
+  const int cpr = d >> 3;
+  for (int idx = threadIdx.x; idx < rows_total * cpr; idx += TC_THREADS) {
+    const int r = idx / cpr, c = idx - r * cpr;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * rs + c * 8));
+    *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+}
+
+// D[tmem] (+)= A[tmem, bf16 packed 2 per column] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// acc[tmem_d] = A_tile[128 x d] . B_tile[n x d]^T : both operands K-major in shared memory (K step = 32 B)
+__device__ __forceinline__ void mma_ss_kk(uint32_t tmem_d, const uint8_t* a, const uint8_t* b, int n, int d) {
+  const uint32_t idesc = ptx::make_idesc_bf16(TILE_ROWS, n, 0, 0);
+  const uint64_t ad = ptx::make_smem_desc(ptx::smem_u32(a), 16u, 1024u);
+  const uint64_t bd = ptx::make_smem_desc(ptx::smem_u32(b), 16u, 1024u);
+  for (int k = 0; k < d / 16; ++k)
+    ptx::umma_bf16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+}
+// acc[tmem_d] = A[tmem: 128 x kdim, packed bf16] . B_tile[kdim rows][d] : B MN-major in shared memory
+// (K step = 16 rows = 2048 B; the packed A operand advances 8 columns per step)
+__device__ __forceinline__ void mma_ts_mn(uint32_t tmem_d, uint32_t tmem_a, const uint8_t* b, int kdim, int d) {
+  const uint32_t idesc = ptx::make_idesc_bf16(TILE_ROWS, d, 0, 1);
+  const uint64_t bd = ptx::make_smem_desc(ptx::smem_u32(b), (uint32_t)kdim * 128u, 1024u);
+  for (int ks = 0; ks < kdim / 16; ++ks)
+    umma_bf16_ts(tmem_d, tmem_a + (uint32_t)(8 * ks), bd + (uint64_t)(128 * ks), idesc, ks > 0 ? 1u : 0u);
+}
+
+// 32 accumulator columns of this thread's row -> scaled bf16 -> global (row pointer may be null for padded rows)
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, int d, float mul, bf16* row) {
+  for (int c0 = 0; c0 < d; c0 += 32) {
+    uint32_t raw[32];
+    ptx::tmem_ld32(taddr + (uint32_t)c0, raw);
+    ptx::tmem_ld_wait();
+    if (row != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]) * mul;
+        st8(row + c0 + g * 8, v);
+      }
+    }
+  }
+}
+
+struct TcSetup {
+  uint32_t tmem;
+  uint64_t* bars;
+};
+
+// barrier init + TMEM allocation; must be followed by the tile loads and ONE tc-fenced __syncthreads
+template <int COLS>
+__device__ __forceinline__ void cta_prologue(uint64_t* bars, uint32_t* slot) {
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if ((threadIdx.x >> 5) == 0) ptx::tmem_alloc<COLS>(slot);
+}
+template <int COLS>
+__device__ __forceinline__ void cta_epilogue(uint32_t tmem) {
+  ptx::tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<COLS>(tmem);
+  }
+}
+
+// ======================================================================================= forward
+__global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sQ = align1024(smem_raw);
+  uint8_t* sK = sQ + TILE_ROWS * 128;
+  uint8_t* sV = sK + p.Lk_pad * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.Lk_pad * 128);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int q0 = blockIdx.x * TILE_ROWS, h = blockIdx.y, s = blockIdx.z;
+  const int skv = (s + p.kv_shift) % p.S;
+  const int warp = threadIdx.x >> 5;
+  const int d = p.d;
+
+  cta_prologue<256>(bars, slot);
+  load_rows_sw128(sQ, p.q + s * p.q_bs + (long long)q0 * p.q_rs + h * d, p.q_rs, min(TILE_ROWS, p.Lq - q0), TILE_ROWS, d);
+  load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
+  load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (threadIdx.x == 0) {
+    mma_ss_kk(tmem, sQ, sK, p.Lk_pad, d);
+    ptx::umma_commit(&bars[0]);
+  }
+  const int i = q0 + threadIdx.x;
+  const bool valid = i < p.Lq;
+  const long long row_id = ((long long)s * p.H + h) * p.Lq + (valid ? i : 0);
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int nchunk = (p.Lk_pad + 31) / 32;
+  ptx::mbar_wait(&bars[0], 0);
+  ptx::tc_fence_after();
+
+  // pass 1: row maximum of the raw scores
+  float mx = -INFINITY;
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t raw[32];
+    ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c * 32 + j < p.Lk) mx = fmaxf(mx, __uint_as_float(raw[j]));
+  }
+  const float sl2 = p.scale * LOG2E;
+  const float mb = mx * sl2;
+  if (p.probs != nullptr) {  // analysis hooks: export the normalised probabilities (extra passes, rare path)
+    float sum0 = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t raw[32];
+      ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c * 32 + j < p.Lk) sum0 += exp2f(__uint_as_float(raw[j]) * sl2 - mb);
+    }
+    const float inv0 = 1.f / sum0;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t raw[32];
+      ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < p.Lk) p.probs[row_id * p.Lk + c * 32 + j] = exp2f(__uint_as_float(raw[j]) * sl2 - mb) * inv0;
+      }
+    }
+  }
+  // pass 2: exponentials, row sum, (dropout), bf16 probabilities written back to TMEM in place
+  float sum = 0.f;
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t raw[32];
+    ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
+    ptx::tmem_ld_wait();
+    float pv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      float e = col < p.Lk ? exp2f(__uint_as_float(raw[j]) * sl2 - mb) : 0.f;
+      sum += e;
+      if (p.drop_thresh != 0u)
+        e = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? e * p.drop_scale : 0.f;
+      pv[j] = e;
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(pv[2 * j], pv[2 * j + 1]);
+    tmem_st16(trow + (uint32_t)(c * 16), pk);
+  }
+  ptx::tmem_st_wait();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::tc_fence_after();
+    mma_ts_mn(tmem + ACC_COL, tmem, sV, p.Lk_pad, d);
+    ptx::umma_commit(&bars[1]);
+  }
+  if (valid && p.lse != nullptr) p.lse[row_id] = mx * p.scale + __logf(sum);
+  ptx::mbar_wait(&bars[1], 0);
+  ptx::tc_fence_after();
+  store_acc_row(trow + ACC_COL, d, 1.f / sum, valid ? p.out + s * p.o_bs + (long long)i * p.o_rs + h * d : nullptr);
+  cta_epilogue<256>(tmem);
+}
+
+// ======================================================================================= backward: dQ (+ delta)
+__global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sQ = align1024(smem_raw);
+  uint8_t* sG = sQ + TILE_ROWS * 128;  // dO tile
+  uint8_t* sK = sG + TILE_ROWS * 128;
+  uint8_t* sV = sK + p.Lk_pad * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.Lk_pad * 128);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int q0 = blockIdx.x * TILE_ROWS, h = blockIdx.y, s = blockIdx.z;
+  const int skv = (s + p.kv_shift) % p.S;
+  const int warp = threadIdx.x >> 5;
+  const int d = p.d;
+  const int rows = min(TILE_ROWS, p.Lq - q0);
+
+  cta_prologue<512>(bars, slot);
+  load_rows_sw128(sQ, p.q + s * p.q_bs + (long long)q0 * p.q_rs + h * d, p.q_rs, rows, TILE_ROWS, d);
+  load_rows_sw128(sG, p.d_o + s * p.do_bs + (long long)q0 * p.do_rs + h * d, p.do_rs, rows, TILE_ROWS, d);
+  load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
+  load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (threadIdx.x == 0) {
+    mma_ss_kk(tmem, sQ, sK, p.Lk_pad, d);             // S  = Q K^T
+    mma_ss_kk(tmem + HALF_COL, sG, sV, p.Lk_pad, d);  // dP = dO V^T
+    ptx::umma_commit(&bars[0]);
+  }
+  const int i = q0 + threadIdx.x;
+  const bool valid = i < p.Lq;
+  const long long row_id = ((long long)s * p.H + h) * p.Lq + (valid ? i : 0);
+  // delta_i = dO_i . O_i (overlaps the MMAs)
+  float dl = 0.f, lse2 = 0.f;
+  if (valid) {
+    const bf16* orow = p.o + s * p.o_bs + (long long)i * p.o_rs + h * d;
+    const bf16* grow = p.d_o + s * p.do_bs + (long long)i * p.do_rs + h * d;
+    for (int c = 0; c < d; c += 8) {
+      float a[8], b[8];
+      ld8(orow + c, a);
+      ld8(grow + c, b);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) dl = fmaf(a[t], b[t], dl);
+    }
+    p.delta[row_id] = dl;
+    lse2 = p.lse[row_id] * LOG2E;
+  }
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int nchunk = (p.Lk_pad + 31) / 32;
+  const float sl2 = p.scale * LOG2E;
+  ptx::mbar_wait(&bars[0], 0);
+  ptx::tc_fence_after();
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t rs[32], rp[32];
+    ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
+    ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
+    ptx::tmem_ld_wait();
+    float ds[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float pr = col < p.Lk ? exp2f(__uint_as_float(rs[j]) * sl2 - lse2) : 0.f;
+      float dp = __uint_as_float(rp[j]);
+      if (p.drop_thresh != 0u)
+        dp = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? dp * p.drop_scale : 0.f;
+      ds[j] = col < p.Lk ? pr * (dp - dl) : 0.f;
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(ds[2 * j], ds[2 * j + 1]);
+    tmem_st16(trow + (uint32_t)(c * 16), pk);
+  }
+  ptx::tmem_st_wait();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::tc_fence_after();
+    mma_ts_mn(tmem + ACC_COL, tmem, sK, p.Lk_pad, d);  // dQ = dS K
+    ptx::umma_commit(&bars[1]);
+  }
+  ptx::mbar_wait(&bars[1], 0);
+  ptx::tc_fence_after();
+  store_acc_row(trow + ACC_COL, d, p.scale, valid ? p.dq + s * p.dq_bs + (long long)i * p.dq_rs + h * d : nullptr);
+  cta_epilogue<512>(tmem);
+}
+
+// ======================================================================================= backward: dK, dV
+__global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sK = align1024(smem_raw);   // 128 key rows of this tile
+  uint8_t* sV = sK + TILE_ROWS * 128;
+  uint8_t* sQ = sV + TILE_ROWS * 128;  // all query rows
+  uint8_t* sG = sQ + p.Lq_pad * 128;   // dO, all query rows
+  float* s_lse = reinterpret_cast<float*>(sG + p.Lq_pad * 128);
+  float* s_del = s_lse + p.Lq_pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_del + p.Lq_pad);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int k0 = blockIdx.x * TILE_ROWS, h = blockIdx.y, s = blockIdx.z;
+  const int skv = (s + p.kv_shift) % p.S;
+  const int warp = threadIdx.x >> 5;
+  const int d = p.d;
+  const int rows = min(TILE_ROWS, p.Lk - k0);
+  const long long row_base = ((long long)s * p.H + h) * p.Lq;
+
+  cta_prologue<512>(bars, slot);
+  load_rows_sw128(sK, p.k + skv * p.k_bs + (long long)k0 * p.k_rs + h * d, p.k_rs, rows, TILE_ROWS, d);
+  load_rows_sw128(sV, p.v + skv * p.v_bs + (long long)k0 * p.v_rs + h * d, p.v_rs, rows, TILE_ROWS, d);
+  load_rows_sw128(sQ, p.q + s * p.q_bs + h * d, p.q_rs, p.Lq, p.Lq_pad, d);
+  load_rows_sw128(sG, p.d_o + s * p.do_bs + h * d, p.do_rs, p.Lq, p.Lq_pad, d);
+  for (int t = threadIdx.x; t < p.Lq_pad; t += TC_THREADS) {
+    s_lse[t] = t < p.Lq ? p.lse[row_base + t] * LOG2E : 0.f;
+    s_del[t] = t < p.Lq ? p.delta[row_base + t] : 0.f;
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (threadIdx.x == 0) {
+    mma_ss_kk(tmem, sK, sQ, p.Lq_pad, d);             // S^T  = K Q^T
+    mma_ss_kk(tmem + HALF_COL, sV, sG, p.Lq_pad, d);  // dP^T = V dO^T
+    ptx::umma_commit(&bars[0]);
+  }
+  const int j = k0 + threadIdx.x;
+  const bool valid = j < p.Lk;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int nchunk = (p.Lq_pad + 31) / 32;
+  const float sl2 = p.scale * LOG2E;
+  ptx::mbar_wait(&bars[0], 0);
+  ptx::tc_fence_after();
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t rs[32], rp[32];
+    ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
+    ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
+    ptx::tmem_ld_wait();
+    uint32_t pkp[16], pks[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      float pt2[2], ds2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int col = c * 32 + 2 * t + u;  // query index
+        const bool in = col < p.Lq && valid;
+        const float pr = in ? exp2f(__uint_as_float(rs[2 * t + u]) * sl2 - s_lse[min(col, p.Lq_pad - 1)]) : 0.f;
+        float dp = __uint_as_float(rp[2 * t + u]);
+        float pt = pr;
+        if (p.drop_thresh != 0u) {
+          const bool keep = drop_keep(p.seed, (unsigned long long)((row_base + col) * p.Lk + j), p.drop_thresh);
+          pt = keep ? pr * p.drop_scale : 0.f;
+          dp = keep ? dp * p.drop_scale : 0.f;
+        }
+        pt2[u] = pt;
+        ds2[u] = in ? pr * (dp - s_del[min(col, p.Lq_pad - 1)]) : 0.f;
+      }
+      pkp[t] = pack_bf16(pt2[0], pt2[1]);
+      pks[t] = pack_bf16(ds2[0], ds2[1]);
+    }
+    tmem_st16(trow + (uint32_t)(c * 16), pkp);
+    tmem_st16(trow + HALF_COL + (uint32_t)(c * 16), pks);
+  }
+  ptx::tmem_st_wait();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::tc_fence_after();
+    mma_ts_mn(tmem + ACC_COL, tmem, sG, p.Lq_pad, d);                        // dV = P~^T dO
+    mma_ts_mn(tmem + HALF_COL + ACC_COL, tmem + HALF_COL, sQ, p.Lq_pad, d);  // dK = dS^T Q
+    ptx::umma_commit(&bars[1]);
+  }
+  ptx::mbar_wait(&bars[1], 0);
+  ptx::tc_fence_after();
+  store_acc_row(trow + ACC_COL, d, 1.f, valid ? p.dv + skv * p.dv_bs + (long long)j * p.dv_rs + h * d : nullptr);
+  store_acc_row(trow + HALF_COL + ACC_COL, d, p.scale, valid ? p.dk + skv * p.dk_bs + (long long)j * p.dk_rs + h * d : nullptr);
+  cta_epilogue<512>(tmem);
+}
+
+template <typename K>
+int set_smem_tc(K kernel, size_t bytes) {
+  EGB_CHECK(bytes <= 227 * 1024, "attention_tc: needs %zu bytes of shared memory (> 227 KB)", bytes);
+  EGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int fill_tc(const egb_attention_desc* d, AttTcParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->q = (const bf16*)d->q; p->k = (const bf16*)d->k; p->v = (const bf16*)d->v; p->o = (const bf16*)d->o;
+  p->out = (bf16*)d->o; p->d_o = (const bf16*)d->d_o;
+  p->dq = (bf16*)d->dq; p->dk = (bf16*)d->dk; p->dv = (bf16*)d->dv;
+  p->lse = d->lse; p->delta = d->delta; p->probs = d->probs;
+  p->q_bs = d->q_bs; p->q_rs = d->q_rs; p->k_bs = d->k_bs; p->k_rs = d->k_rs; p->v_bs = d->v_bs; p->v_rs = d->v_rs;
+  p->o_bs = d->o_bs; p->o_rs = d->o_rs; p->do_bs = d->do_bs; p->do_rs = d->do_rs;
+  p->dq_bs = d->dq_bs; p->dq_rs = d->dq_rs; p->dk_bs = d->dk_bs; p->dk_rs = d->dk_rs; p->dv_bs = d->dv_bs; p->dv_rs = d->dv_rs;
+  p->S = d->S; p->H = d->H; p->Lq = d->Lq; p->Lk = d->Lk; p->d = d->head_dim; p->kv_shift = d->kv_shift;
+  p->Lq_pad = (d->Lq + 15) / 16 * 16;
+  p->Lk_pad = (d->Lk + 15) / 16 * 16;
+  p->scale = d->scale;
+  if (d->dropout_p > 0.f) {
+    p->drop_thresh = drop_threshold(d->dropout_p);
+    p->drop_scale = 1.f / (1.f - d->dropout_p);
+    p->seed = d->seed;
+  }
+  return 0;
+}
+
+bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
+
+}  // namespace
+
+// The tensor-core path covers bf16 tensors with head_dim 32 or 64, sequence lengths <= 256 and 16-byte aligned
+// rows; everything else (fp32 parity mode, other shapes) runs the CUDA-core kernels of attention.cu.
+bool egb_attention_tc_supported(const egb_attention_desc* d, bool backward) {
+  if (d->dtype != EGB_BF16) return false;
+  if (d->head_dim != 32 && d->head_dim != 64) return false;
+  if (d->Lq < 1 || d->Lk < 1 || d->Lq > 256 || d->Lk > 256) return false;
+  const long long strides[] = {d->q_bs, d->q_rs, d->k_bs, d->k_rs, d->v_bs, d->v_rs, d->o_bs, d->o_rs};
+  for (long long st : strides)
+    if (st % 8 != 0) return false;
+  if (!aligned16(d->q) || !aligned16(d->k) || !aligned16(d->v) || !aligned16(d->o)) return false;
+  if (backward) {
+    const long long bs[] = {d->do_bs, d->do_rs, d->dq_bs, d->dq_rs, d->dk_bs, d->dk_rs, d->dv_bs, d->dv_rs};
+    for (long long st : bs)
+      if (st % 8 != 0) return false;
+    if (!aligned16(d->d_o) || !aligned16(d->dq) || !aligned16(d->dk) || !aligned16(d->dv)) return false;
+  }
+  return true;
+}
+
+int egb_attention_tc_fwd(const egb_attention_desc* d, cudaStream_t st) {
+  AttTcParams p;
+  if (fill_tc(d, &p)) return 1;
+  const size_t smem = (size_t)(TILE_ROWS + 2 * p.Lk_pad) * 128 + 1024 + 64;
+  if (set_smem_tc(att_tc_fwd_kernel, smem)) return 1;
+  dim3 grid((d->Lq + TILE_ROWS - 1) / TILE_ROWS, d->H, d->S);
+  const bool prof = egb_prof_enabled() != 0;
+  if (prof) egb_prof_begin(st, 4.0 * d->S * d->H * (double)d->Lq * d->Lk * d->head_dim,
+                           2.0 * d->S * d->H * (double)d->head_dim * (2.0 * d->Lq + 2.0 * d->Lk), 2);
+  att_tc_fwd_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  if (prof) egb_prof_end(st);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
+  AttTcParams p;
+  if (fill_tc(d, &p)) return 1;
+  EGB_CHECK(d->lse && d->delta && d->d_o && d->dq && d->dk && d->dv, "attention_bwd: missing buffers");
+  const size_t smem_a = (size_t)(2 * TILE_ROWS + 2 * p.Lk_pad) * 128 + 1024 + 64;
+  const size_t smem_b = (size_t)(2 * TILE_ROWS + 2 * p.Lq_pad) * 128 + (size_t)p.Lq_pad * 8 + 1024 + 64;
+  if (set_smem_tc(att_tc_bwd_dq_kernel, smem_a) || set_smem_tc(att_tc_bwd_dkv_kernel, smem_b)) return 1;
+  dim3 grid_a((d->Lq + TILE_ROWS - 1) / TILE_ROWS, d->H, d->S);
+  dim3 grid_b((d->Lk + TILE_ROWS - 1) / TILE_ROWS, d->H, d->S);
+  const bool prof = egb_prof_enabled() != 0;
+  if (prof) egb_prof_begin(st, 10.0 * d->S * d->H * (double)d->Lq * d->Lk * d->head_dim,
+                           2.0 * d->S * d->H * (double)d->head_dim * (4.0 * d->Lq + 4.0 * d->Lk), 3);
+  att_tc_bwd_dq_kernel<<<grid_a, TC_THREADS, smem_a, st>>>(p);
+  att_tc_bwd_dkv_kernel<<<grid_b, TC_THREADS, smem_b, st>>>(p);
+  if (prof) egb_prof_end(st);
+  egb_count_launch(2);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}

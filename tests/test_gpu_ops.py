@@ -185,6 +185,31 @@ def test_attention_dropout_statistics(cuda_device):
     assert (outs.mean(0) - base).abs().mean() < 0.05       # inverted dropout is unbiased
 
 
+@pytest.mark.parametrize("cfg", [(6, 139, 139, 256, 8, 3), (2, 197, 197, 384, 6, 0), (2, 235, 235, 256, 8, 1),
+                                 (3, 256, 256, 128, 2, 0), (2, 17, 40, 64, 2, 0)])
+def test_attention_tensor_core_vs_fp32_kernel_same_dropout_mask(cuda_device, cfg):
+    """The tcgen05 kernels (bf16) and the CUDA-core kernels (fp32) draw the same counter-based dropout mask for the
+    same seed, so outputs and gradients must agree to bf16 accuracy -- forward, dQ, dK, dV, with kv_shift."""
+    S, Lq, Lk, D, H, shift = cfg
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(S, Lq, D, generator=g) * 0.8).to(DEV)
+    k = (torch.randn(S, Lk, D, generator=g) * 0.8).to(DEV)
+    v = torch.randn(S, Lk, D, generator=g).to(DEV)
+    go = torch.randn(S, Lq, D, generator=g).to(DEV)
+    res = {}
+    for mode in ("fp32", "bf16"):
+        torch.manual_seed(1000 + len(res))      # changing the base seed ...
+        ops.next_seed()
+        torch.manual_seed(77)                   # ... and restoring it restarts the op-seed sequence
+        ts = [t.detach().clone().to(_dt(mode)).requires_grad_(True) for t in (q, k, v)]
+        o = ops.AttentionFn.apply(*ts, H, shift, 0.25, 1.0 / math.sqrt(D // H), False, False)
+        o.backward(go.to(_dt(mode)))
+        res[mode] = [o.detach().float()] + [t.grad.float() for t in ts]
+    for a, b, nm in zip(res["bf16"], res["fp32"], ["o", "dq", "dk", "dv"]):
+        err = (a - b).abs().max().item()
+        assert err <= 3e-2 * b.abs().max().item() + 1e-3, f"{nm}: {err:.3e} vs max {b.abs().max().item():.3e}"
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("cfg", [(3, 8, 256, 32), (2, 32, 1024, 256), (2, 62, 512, 64)])
 def test_temporal_conv(cuda_device, mode, cfg):
