@@ -50,16 +50,22 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // rows [0, rows_total) of a [rows][d] bf16 slice (row stride rs elements) -> 128-B pitched, 128-B swizzled tile.
 // Rows >= rows_valid are zero-filled.  16-byte chunk c of row r lands at chunk (c ^ (r & 7)) of its 128-B line.
+// The copies are asynchronous (cp.async / LDGSTS, zero-fill for the padding rows): a thread issues all of its
+// chunks back to back; cp_async_wait_all() + a proxy fence + __syncthreads() publish the tiles to the tensor core.
 __device__ __forceinline__ void load_rows_sw128(uint8_t* dst, const bf16* src, long long rs, int rows_valid,
                                                 int rows_total, int d) {
   const int cpr = d >> 3;
+  const uint32_t dst0 = ptx::smem_u32(dst);
   for (int idx = threadIdx.x; idx < rows_total * cpr; idx += TC_THREADS) {
     const int r = idx / cpr, c = idx - r * cpr;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * rs + c * 8));
-    *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+    const bool in = r < rows_valid;
+    const bf16* g = src + (in ? (long long)r * rs + c * 8 : 0);
+    const uint32_t sa = dst0 + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+    const uint32_t nbytes = in ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(nbytes) : "memory");
   }
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem, bf16 packed 2 per column] * B[smem desc]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
   load_rows_sw128(sQ, p.q + s * p.q_bs + (long long)q0 * p.q_rs + h * d, p.q_rs, min(TILE_ROWS, p.Lq - q0), TILE_ROWS, d);
   load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
   load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+  cp_async_wait_all();
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
@@ -271,6 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
   load_rows_sw128(sG, p.d_o + s * p.do_bs + (long long)q0 * p.do_rs + h * d, p.do_rs, rows, TILE_ROWS, d);
   load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
   load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+  cp_async_wait_all();
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
@@ -366,6 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
     s_lse[t] = t < p.Lq ? p.lse[row_base + t] * LOG2E : 0.f;
     s_del[t] = t < p.Lq ? p.delta[row_base + t] : 0.f;
   }
+  cp_async_wait_all();
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();

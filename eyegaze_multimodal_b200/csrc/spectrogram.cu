@@ -16,7 +16,13 @@ extern void egb_count_launch(int n);
 namespace {
 
 // ------------------------------------------------------------------------------------------ 1. STFT log-magnitude
-// grid = (signals), block = 256.  Signal (T samples) is staged in smem with reflect padding.
+// grid = (signals), block = 256.  The signal (T samples) is staged in smem with reflect padding.
+// Thread (k, g): frequency bin k = tid % bins, frame group g = tid / bins; the thread accumulates up to STFT_FPT
+// frames (g, g + G, g + 2G, ...) of bin k in registers.  Within a warp all lanes share the frames (sample loads are
+// smem broadcasts) and differ in k (twiddle loads spread over the banks); the window is folded into the twiddle
+// once per sample and reused by all frames of the thread.
+constexpr int STFT_FPT = 5;
+
 __global__ void __launch_bounds__(256) stft_logmag_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
                                                           const float* __restrict__ window, float* __restrict__ out,
                                                           int n_sig_per_stream, int T, int n_fft, int hop, int bins,
@@ -44,19 +50,38 @@ __global__ void __launch_bounds__(256) stft_logmag_kernel(const float* __restric
   }
   __syncthreads();
   float* o = out + (long long)sig * bins * frames;
-  for (int idx = threadIdx.x; idx < bins * frames; idx += blockDim.x) {
-    const int k = idx / frames, f = idx % frames;
-    const float* x = xs + f * hop;
-    float re = 0.f, im = 0.f;
-    int ph = 0;                          // (k * n) mod n_fft
+  const int groups = blockDim.x / bins;          // frame groups (4 for 64 bins)
+  const int k = threadIdx.x % bins, g = threadIdx.x / bins;
+  if (g >= groups) return;
+  for (int f0 = g; f0 < frames; f0 += groups * STFT_FPT) {
+    float re[STFT_FPT], im[STFT_FPT];
+    const float* xf[STFT_FPT];
+#pragma unroll
+    for (int j = 0; j < STFT_FPT; ++j) {
+      re[j] = 0.f;
+      im[j] = 0.f;
+      const int f = f0 + j * groups;
+      xf[j] = xs + (f < frames ? f : f0) * hop;   // out-of-range slots recompute frame f0 and are not stored
+    }
+    int ph = 0;                                   // (k * n) mod n_fft
+#pragma unroll 4
     for (int n = 0; n < n_fft; ++n) {
-      const float v = x[n] * ws[n];
-      re = fmaf(v, ct[ph], re);
-      im = fmaf(-v, st[ph], im);
+      const float w = ws[n];
+      const float cw = ct[ph] * w, sw = st[ph] * w;
+#pragma unroll
+      for (int j = 0; j < STFT_FPT; ++j) {
+        const float v = xf[j][n];
+        re[j] = fmaf(v, cw, re[j]);
+        im[j] = fmaf(-v, sw, im[j]);
+      }
       ph += k;
       if (ph >= n_fft) ph -= n_fft;
     }
-    o[idx] = logf(sqrtf(re * re + im * im) + 1e-8f);
+#pragma unroll
+    for (int j = 0; j < STFT_FPT; ++j) {
+      const int f = f0 + j * groups;
+      if (f < frames) o[k * frames + f] = logf(sqrtf(re[j] * re[j] + im[j] * im[j]) + 1e-8f);
+    }
   }
 }
 
@@ -238,6 +263,7 @@ int egb_stft_logmag(const float* eeg1, const float* eeg2, const float* window, f
   const int frames = 1 + T / hop;
   const size_t smem = sizeof(float) * ((size_t)T + 4 * n_fft);
   EGB_CHECK(smem <= 200 * 1024, "stft: window too long for shared memory");
+  EGB_CHECK(bins <= 256, "stft: at most 256 frequency bins");
   static size_t smem_set = 0;
   if (smem > smem_set) {
     EGB_CUDA(cudaFuncSetAttribute(stft_logmag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

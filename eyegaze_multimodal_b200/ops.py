@@ -91,10 +91,7 @@ def gemm(M, N, K, in_code, a: L.Operand, b: L.Operand, c: L.Matrix, *, bias=None
     L.call("egb_gemm", C.byref(d), _stream())
 
 
-def cast(x: torch.Tensor, code: int) -> torch.Tensor:
-    """dtype conversion through the library's cast kernels (fp32 <-> bf16)."""
-    if _code(x) == code:
-        return x
+def _cast_raw(x: torch.Tensor, code: int) -> torch.Tensor:
     x = x.contiguous()
     out = torch.empty(x.shape, dtype=_TORCH_DT[code], device=x.device)
     if code == F32:
@@ -102,6 +99,28 @@ def cast(x: torch.Tensor, code: int) -> torch.Tensor:
     else:
         L.call("egb_cast_from_f32", x.data_ptr(), out.data_ptr(), code, x.numel(), _stream())
     return out
+
+
+class CastFn(torch.autograd.Function):
+    """dtype conversion that stays on the autograd graph (the gradient is converted back)."""
+
+    @staticmethod
+    def forward(ctx, x, code):
+        ctx.src_code = _code(x)
+        return _cast_raw(x, code)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g if _code(g) == ctx.src_code else _cast_raw(g, ctx.src_code)), None
+
+
+def cast(x: torch.Tensor, code: int) -> torch.Tensor:
+    """dtype conversion through the library's cast kernels (fp32 <-> bf16); differentiable."""
+    if _code(x) == code:
+        return x
+    if torch.is_grad_enabled() and x.requires_grad:
+        return CastFn.apply(x, code)
+    return _cast_raw(x, code)
 
 
 def copy_strided4(src, dst, sizes, src_strides, dst_strides, src_offset=0, dst_offset=0):

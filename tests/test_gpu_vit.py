@@ -63,6 +63,23 @@ def test_early_fusion_backward_fp32(cuda_device):
         assert e <= 5e-3 * r.abs().max().item() + 2e-6, f"{k}: {e:.3e} vs max {r.abs().max().item():.3e}"
 
 
+def test_early_fusion_backward_bf16(cuda_device):
+    """bf16 mode: EVERY backbone parameter must receive a gradient (the dtype conversions stay on the autograd
+    graph) and it must agree with the fp32 CPU oracle to bf16 accuracy (relative to the tensor's max)."""
+    m, sd = _early("concat", seed=3)
+    a, b = gaze_pair_batch(2, seed=2)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    labels = torch.tensor([0, 2])
+    F.cross_entropy(V.early_fusion_forward(sdr, a, b, HEADS, "concat"), labels).backward()
+    with precision("bf16"):
+        F.cross_entropy(m(a.to(DEV), b.to(DEV)), labels.to(DEV)).backward()
+    for k, p in m.named_parameters():
+        assert p.grad is not None, f"{k} received no gradient in bf16 mode"
+        r = sdr[k].grad
+        e = (p.grad.cpu() - r).abs().max().item()
+        assert e <= 8e-2 * r.abs().max().item() + 1e-5, f"{k}: {e:.3e} vs max {r.abs().max().item():.3e}"
+
+
 def test_patch_embed_surgery(cuda_device):
     warnings.simplefilter("ignore")
     torch.manual_seed(0)
@@ -142,6 +159,19 @@ def test_multimodal_end_to_end(cuda_device):
     for k in ("classifier.3.weight", "temporal_conv.convs.0.weight", "encoder.layers.1.ffn.linear1.weight"):
         gp = dict(model.eeg_encoder.named_parameters())[k].grad.cpu()
         assert (gp - er[k].grad).abs().max() <= 5e-3 * er[k].grad.abs().max() + 1e-6, k
+    # bf16 mode: the whole model still trains (all parameters that feed the loss get finite gradients)
+    model.zero_grad(set_to_none=True)
+    with precision("bf16"):
+        o16 = model(a.to(DEV), b.to(DEV), e1.to(DEV), e2.to(DEV), labels.to(DEV))
+        multimodal_loss(model, o16, labels.to(DEV)).backward()
+    for k, p in model.named_parameters():
+        if "ibs_classifier" in k:
+            continue                      # auxiliary head: not part of the multimodal loss
+        assert p.grad is not None and torch.isfinite(p.grad).all(), f"{k}: no / non-finite gradient in bf16 mode"
+    for k in ("backbone.blocks.0.attn.qkv.weight", "backbone.patch_embed.proj.weight"):
+        gp = dict(model.gaze_encoder.named_parameters())[k].grad.cpu()
+        assert (gp - vr[k].grad).abs().max() <= 0.15 * vr[k].grad.abs().max() + 1e-4, k
+    model.zero_grad(set_to_none=True)
     # frozen encoders receive no gradient (train_multimodal_fuzzy_fusion.py:129-137)
     frozen = MultimodalFusionModel(gaze, eeg, FuzzyGatingFusion(3, "full"), freeze_gaze=True, freeze_eeg=True).to(DEV)
     frozen.zero_grad()
