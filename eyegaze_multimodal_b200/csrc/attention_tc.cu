@@ -23,7 +23,7 @@ void egb_prof_end(cudaStream_t st);
 
 namespace {
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;   // 8 warps: warp w owns TMEM lanes 32*(w%4).., column chunks of parity w/4
 constexpr int TILE_ROWS = 128;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint32_t ACC_COL = 128;  // accumulator columns of the second-stage MMAs (above the packed bf16 A operand)
@@ -42,7 +42,15 @@ struct AttTcParams {
   unsigned drop_thresh;
   float drop_scale;
   unsigned long long seed;
+  long long* dbg;  // optional: phase timestamps (clock64) of CTA (0, 0, S/2), see egb_debug_attention_timing
 };
+
+#define ATT_STAMP(slot)                                                                       \
+  do {                                                                                        \
+    if (p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 &&         \
+        blockIdx.z == gridDim.z / 2)                                                          \
+      p.dbg[slot] = clock64();                                                                \
+  } while (0)
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
@@ -91,6 +99,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 2^x for x <= 0 (one MUFU; results below the normal range flush to zero, which is what a softmax wants)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // acc[tmem_d] = A_tile[128 x d] . B_tile[n x d]^T : both operands K-major in shared memory (K step = 32 B)
 __device__ __forceinline__ void mma_ss_kk(uint32_t tmem_d, const uint8_t* a, const uint8_t* b, int n, int d) {
@@ -109,9 +123,9 @@ __device__ __forceinline__ void mma_ts_mn(uint32_t tmem_d, uint32_t tmem_a, cons
     umma_bf16_ts(tmem_d, tmem_a + (uint32_t)(8 * ks), bd + (uint64_t)(128 * ks), idesc, ks > 0 ? 1u : 0u);
 }
 
-// 32 accumulator columns of this thread's row -> scaled bf16 -> global (row pointer may be null for padded rows)
-__device__ __forceinline__ void store_acc_row(uint32_t taddr, int d, float mul, bf16* row) {
-  for (int c0 = 0; c0 < d; c0 += 32) {
+// accumulator columns [c_begin, c_end) (multiples of 32) of this thread's row -> scaled bf16 -> global
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, int c_begin, int c_end, float mul, bf16* row) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
     uint32_t raw[32];
     ptx::tmem_ld32(taddr + (uint32_t)c0, raw);
     ptx::tmem_ld_wait();
@@ -127,20 +141,14 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, int d, float mul, 
   }
 }
 
-struct TcSetup {
-  uint32_t tmem;
-  uint64_t* bars;
-};
-
-// barrier init + TMEM allocation; must be followed by the tile loads and ONE tc-fenced __syncthreads
-template <int COLS>
-__device__ __forceinline__ void cta_prologue(uint64_t* bars, uint32_t* slot) {
+// barrier init (thread 0) -- TMEM is allocated AFTER the tile copies have been issued, so a CTA that has to wait
+// for the previous CTA's tensor memory stages its operands meanwhile
+__device__ __forceinline__ void init_bars(uint64_t* bars) {
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bars[0], 1);
     ptx::mbar_init(&bars[1], 1);
     ptx::fence_barrier_init();
   }
-  if ((threadIdx.x >> 5) == 0) ptx::tmem_alloc<COLS>(slot);
 }
 template <int COLS>
 __device__ __forceinline__ void cta_epilogue(uint32_t tmem) {
@@ -153,44 +161,52 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem) {
 }
 
 // ======================================================================================= forward
+template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
   uint8_t* sK = sQ + TILE_ROWS * 128;
   uint8_t* sV = sK + p.Lk_pad * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.Lk_pad * 128);
+  float* s_red = reinterpret_cast<float*>(sV + p.Lk_pad * 128);  // [2][128] cross-half row statistics
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 2 * TILE_ROWS);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int q0 = blockIdx.x * TILE_ROWS, h = blockIdx.y, s = blockIdx.z;
   const int skv = (s + p.kv_shift) % p.S;
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = warp >> 2, row = (warp & 3) * 32 + lane;
   const int d = p.d;
 
-  cta_prologue<256>(bars, slot);
+  ATT_STAMP(0);
+  init_bars(bars);
   load_rows_sw128(sQ, p.q + s * p.q_bs + (long long)q0 * p.q_rs + h * d, p.q_rs, min(TILE_ROWS, p.Lq - q0), TILE_ROWS, d);
   load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
   load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+  if (warp == 0) ptx::tmem_alloc<256>(slot);
+  ATT_STAMP(1);
   cp_async_wait_all();
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *slot;
+  ATT_STAMP(2);
 
   if (threadIdx.x == 0) {
     mma_ss_kk(tmem, sQ, sK, p.Lk_pad, d);
     ptx::umma_commit(&bars[0]);
   }
-  const int i = q0 + threadIdx.x;
+  const int i = q0 + row;
   const bool valid = i < p.Lq;
   const long long row_id = ((long long)s * p.H + h) * p.Lq + (valid ? i : 0);
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int nchunk = (p.Lk_pad + 31) / 32;
   ptx::mbar_wait(&bars[0], 0);
   ptx::tc_fence_after();
+  ATT_STAMP(3);
 
-  // pass 1: row maximum of the raw scores
+  // pass 1: row maximum of the raw scores (this half's column chunks), combined across the two halves
   float mx = -INFINITY;
-  for (int c = 0; c < nchunk; ++c) {
+  for (int c = half; c < nchunk; c += 2) {
     uint32_t raw[32];
     ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
     ptx::tmem_ld_wait();
@@ -198,52 +214,71 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
     for (int j = 0; j < 32; ++j)
       if (c * 32 + j < p.Lk) mx = fmaxf(mx, __uint_as_float(raw[j]));
   }
+  s_red[half * TILE_ROWS + row] = mx;
+  __syncthreads();
+  mx = fmaxf(s_red[row], s_red[TILE_ROWS + row]);
   const float sl2 = p.scale * LOG2E;
   const float mb = mx * sl2;
   if (p.probs != nullptr) {  // analysis hooks: export the normalised probabilities (extra passes, rare path)
     float sum0 = 0.f;
-    for (int c = 0; c < nchunk; ++c) {
+    for (int c = half; c < nchunk; c += 2) {
       uint32_t raw[32];
       ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < p.Lk) sum0 += exp2f(__uint_as_float(raw[j]) * sl2 - mb);
+        if (c * 32 + j < p.Lk) sum0 += fast_exp2(__uint_as_float(raw[j]) * sl2 - mb);
     }
-    const float inv0 = 1.f / sum0;
-    for (int c = 0; c < nchunk; ++c) {
+    __syncthreads();                      // everyone has consumed the maxima
+    s_red[half * TILE_ROWS + row] = sum0;
+    __syncthreads();
+    const float inv0 = 1.f / (s_red[row] + s_red[TILE_ROWS + row]);
+    for (int c = half; c < nchunk; c += 2) {
       uint32_t raw[32];
       ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
       ptx::tmem_ld_wait();
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < p.Lk) p.probs[row_id * p.Lk + c * 32 + j] = exp2f(__uint_as_float(raw[j]) * sl2 - mb) * inv0;
+          if (c * 32 + j < p.Lk) p.probs[row_id * p.Lk + c * 32 + j] = fast_exp2(__uint_as_float(raw[j]) * sl2 - mb) * inv0;
       }
     }
   }
-  // pass 2: exponentials, row sum, (dropout), bf16 probabilities written back to TMEM in place
+  __syncthreads();                        // s_red is rewritten below
+  // pass 2: exponentials, row sum, (dropout), bf16 probabilities written back to TMEM in place.  Round t handles
+  // chunks 2t (half 0) and 2t+1 (half 1): their packed forms go to columns [32t, 32t+32) = chunk t, which both
+  // halves have consumed once the round's barrier is passed (t = 0: this round; t >= 1: an earlier round).
   float sum = 0.f;
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t raw[32];
-    ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
-    ptx::tmem_ld_wait();
-    float pv[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      float e = col < p.Lk ? exp2f(__uint_as_float(raw[j]) * sl2 - mb) : 0.f;
-      sum += e;
-      if (p.drop_thresh != 0u)
-        e = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? e * p.drop_scale : 0.f;
-      pv[j] = e;
-    }
+  const int nround = (nchunk + 1) / 2;
+  for (int t = 0; t < nround; ++t) {
+    const int c = 2 * t + half;
     uint32_t pk[16];
+    if (c < nchunk) {
+      uint32_t raw[32];
+      ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
+      ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(pv[2 * j], pv[2 * j + 1]);
-    tmem_st16(trow + (uint32_t)(c * 16), pk);
+      for (int j = 0; j < 16; ++j) {
+        float e2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int col = c * 32 + 2 * j + u;
+          float e = col < p.Lk ? fast_exp2(__uint_as_float(raw[2 * j + u]) * sl2 - mb) : 0.f;
+          sum += e;
+          if (DROP) e = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? e * p.drop_scale : 0.f;
+          e2[u] = e;
+        }
+        pk[j] = pack_bf16(e2[0], e2[1]);
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (c < nchunk) tmem_st16(trow + (uint32_t)(c * 16), pk);
   }
+  s_red[half * TILE_ROWS + row] = sum;
   ptx::tmem_st_wait();
+  ATT_STAMP(4);
   ptx::tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -251,14 +286,23 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
     mma_ts_mn(tmem + ACC_COL, tmem, sV, p.Lk_pad, d);
     ptx::umma_commit(&bars[1]);
   }
-  if (valid && p.lse != nullptr) p.lse[row_id] = mx * p.scale + __logf(sum);
+  sum = s_red[row] + s_red[TILE_ROWS + row];
+  if (half == 0 && valid && p.lse != nullptr) p.lse[row_id] = mx * p.scale + __logf(sum);
   ptx::mbar_wait(&bars[1], 0);
   ptx::tc_fence_after();
-  store_acc_row(trow + ACC_COL, d, 1.f / sum, valid ? p.out + s * p.o_bs + (long long)i * p.o_rs + h * d : nullptr);
+  ATT_STAMP(5);
+  {
+    bf16* orow = valid ? p.out + s * p.o_bs + (long long)i * p.o_rs + h * d : nullptr;
+    const int per = d >= 64 ? d / 2 : d;  // d = 64: one 32-column chunk per half; d = 32: half 0 stores
+    if (half == 0 || d >= 64) store_acc_row(trow + ACC_COL, half * (d >= 64 ? per : 0), half * (d >= 64 ? per : 0) + per, 1.f / sum, orow);
+  }
+  ATT_STAMP(6);
   cta_epilogue<256>(tmem);
+  ATT_STAMP(7);
 }
 
 // ======================================================================================= backward: dQ (+ delta)
+template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
@@ -269,31 +313,21 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
   uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int q0 = blockIdx.x * TILE_ROWS, h = blockIdx.y, s = blockIdx.z;
   const int skv = (s + p.kv_shift) % p.S;
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = warp >> 2, row = (warp & 3) * 32 + lane;
   const int d = p.d;
   const int rows = min(TILE_ROWS, p.Lq - q0);
 
-  cta_prologue<512>(bars, slot);
+  ATT_STAMP(0);
+  init_bars(bars);
   load_rows_sw128(sQ, p.q + s * p.q_bs + (long long)q0 * p.q_rs + h * d, p.q_rs, rows, TILE_ROWS, d);
   load_rows_sw128(sG, p.d_o + s * p.do_bs + (long long)q0 * p.do_rs + h * d, p.do_rs, rows, TILE_ROWS, d);
   load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
   load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
-  cp_async_wait_all();
-  ptx::fence_proxy_async_smem();
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *slot;
-
-  if (threadIdx.x == 0) {
-    mma_ss_kk(tmem, sQ, sK, p.Lk_pad, d);             // S  = Q K^T
-    mma_ss_kk(tmem + HALF_COL, sG, sV, p.Lk_pad, d);  // dP = dO V^T
-    ptx::umma_commit(&bars[0]);
-  }
-  const int i = q0 + threadIdx.x;
+  // delta_i = dO_i . O_i (both halves compute it; overlaps the copies and the TMEM wait)
+  const int i = q0 + row;
   const bool valid = i < p.Lq;
   const long long row_id = ((long long)s * p.H + h) * p.Lq + (valid ? i : 0);
-  // delta_i = dO_i . O_i (overlaps the MMAs)
   float dl = 0.f, lse2 = 0.f;
   if (valid) {
     const bf16* orow = p.o + s * p.o_bs + (long long)i * p.o_rs + h * d;
@@ -305,35 +339,60 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
 #pragma unroll
       for (int t = 0; t < 8; ++t) dl = fmaf(a[t], b[t], dl);
     }
-    p.delta[row_id] = dl;
+    if (half == 0) p.delta[row_id] = dl;
     lse2 = p.lse[row_id] * LOG2E;
   }
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  if (warp == 0) ptx::tmem_alloc<512>(slot);
+  ATT_STAMP(1);
+  cp_async_wait_all();
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+  ATT_STAMP(2);
+
+  if (threadIdx.x == 0) {
+    mma_ss_kk(tmem, sQ, sK, p.Lk_pad, d);             // S  = Q K^T
+    mma_ss_kk(tmem + HALF_COL, sG, sV, p.Lk_pad, d);  // dP = dO V^T
+    ptx::umma_commit(&bars[0]);
+  }
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int nchunk = (p.Lk_pad + 31) / 32;
   const float sl2 = p.scale * LOG2E;
   ptx::mbar_wait(&bars[0], 0);
   ptx::tc_fence_after();
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t rs[32], rp[32];
-    ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
-    ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
-    ptx::tmem_ld_wait();
-    float ds[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      const float pr = col < p.Lk ? exp2f(__uint_as_float(rs[j]) * sl2 - lse2) : 0.f;
-      float dp = __uint_as_float(rp[j]);
-      if (p.drop_thresh != 0u)
-        dp = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? dp * p.drop_scale : 0.f;
-      ds[j] = col < p.Lk ? pr * (dp - dl) : 0.f;
-    }
+  ATT_STAMP(3);
+  const int nround = (nchunk + 1) / 2;
+  for (int t = 0; t < nround; ++t) {     // see the forward kernel for the in-place write-back schedule
+    const int c = 2 * t + half;
     uint32_t pk[16];
+    if (c < nchunk) {
+      uint32_t rs[32], rp[32];
+      ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
+      ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
+      ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(ds[2 * j], ds[2 * j + 1]);
-    tmem_st16(trow + (uint32_t)(c * 16), pk);
+      for (int j = 0; j < 16; ++j) {
+        float ds2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int col = c * 32 + 2 * j + u;
+          const float pr = fast_exp2(__uint_as_float(rs[2 * j + u]) * sl2 - lse2);
+          float dp = __uint_as_float(rp[2 * j + u]);
+          if (DROP) dp = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? dp * p.drop_scale : 0.f;
+          ds2[u] = col < p.Lk ? pr * (dp - dl) : 0.f;
+        }
+        pk[j] = pack_bf16(ds2[0], ds2[1]);
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (c < nchunk) tmem_st16(trow + (uint32_t)(c * 16), pk);
   }
   ptx::tmem_st_wait();
+  ATT_STAMP(4);
   ptx::tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -343,11 +402,19 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
   }
   ptx::mbar_wait(&bars[1], 0);
   ptx::tc_fence_after();
-  store_acc_row(trow + ACC_COL, d, p.scale, valid ? p.dq + s * p.dq_bs + (long long)i * p.dq_rs + h * d : nullptr);
+  ATT_STAMP(5);
+  {
+    bf16* drow = valid ? p.dq + s * p.dq_bs + (long long)i * p.dq_rs + h * d : nullptr;
+    if (d >= 64) store_acc_row(trow + ACC_COL, half * (d / 2), half * (d / 2) + d / 2, p.scale, drow);
+    else if (half == 0) store_acc_row(trow + ACC_COL, 0, d, p.scale, drow);
+  }
+  ATT_STAMP(6);
   cta_epilogue<512>(tmem);
+  ATT_STAMP(7);
 }
 
 // ======================================================================================= backward: dK, dV
+template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sK = align1024(smem_raw);   // 128 key rows of this tile
@@ -360,12 +427,14 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
   uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int k0 = blockIdx.x * TILE_ROWS, h = blockIdx.y, s = blockIdx.z;
   const int skv = (s + p.kv_shift) % p.S;
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = warp >> 2, row = (warp & 3) * 32 + lane;
   const int d = p.d;
   const int rows = min(TILE_ROWS, p.Lk - k0);
   const long long row_base = ((long long)s * p.H + h) * p.Lq;
 
-  cta_prologue<512>(bars, slot);
+  ATT_STAMP(0);
+  init_bars(bars);
   load_rows_sw128(sK, p.k + skv * p.k_bs + (long long)k0 * p.k_rs + h * d, p.k_rs, rows, TILE_ROWS, d);
   load_rows_sw128(sV, p.v + skv * p.v_bs + (long long)k0 * p.v_rs + h * d, p.v_rs, rows, TILE_ROWS, d);
   load_rows_sw128(sQ, p.q + s * p.q_bs + h * d, p.q_rs, p.Lq, p.Lq_pad, d);
@@ -374,56 +443,71 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
     s_lse[t] = t < p.Lq ? p.lse[row_base + t] * LOG2E : 0.f;
     s_del[t] = t < p.Lq ? p.delta[row_base + t] : 0.f;
   }
+  if (warp == 0) ptx::tmem_alloc<512>(slot);
+  ATT_STAMP(1);
   cp_async_wait_all();
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *slot;
+  ATT_STAMP(2);
 
   if (threadIdx.x == 0) {
     mma_ss_kk(tmem, sK, sQ, p.Lq_pad, d);             // S^T  = K Q^T
     mma_ss_kk(tmem + HALF_COL, sV, sG, p.Lq_pad, d);  // dP^T = V dO^T
     ptx::umma_commit(&bars[0]);
   }
-  const int j = k0 + threadIdx.x;
+  const int j = k0 + row;
   const bool valid = j < p.Lk;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int nchunk = (p.Lq_pad + 31) / 32;
   const float sl2 = p.scale * LOG2E;
   ptx::mbar_wait(&bars[0], 0);
   ptx::tc_fence_after();
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t rs[32], rp[32];
-    ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
-    ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
-    ptx::tmem_ld_wait();
+  ATT_STAMP(3);
+  const int nround = (nchunk + 1) / 2;
+  for (int t = 0; t < nround; ++t) {     // see the forward kernel for the in-place write-back schedule
+    const int c = 2 * t + half;
     uint32_t pkp[16], pks[16];
+    if (c < nchunk) {
+      uint32_t rs[32], rp[32];
+      ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
+      ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
+      ptx::tmem_ld_wait();
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      float pt2[2], ds2[2];
+      for (int jj = 0; jj < 16; ++jj) {
+        float pt2[2], ds2[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int col = c * 32 + 2 * t + u;  // query index
-        const bool in = col < p.Lq && valid;
-        const float pr = in ? exp2f(__uint_as_float(rs[2 * t + u]) * sl2 - s_lse[min(col, p.Lq_pad - 1)]) : 0.f;
-        float dp = __uint_as_float(rp[2 * t + u]);
-        float pt = pr;
-        if (p.drop_thresh != 0u) {
-          const bool keep = drop_keep(p.seed, (unsigned long long)((row_base + col) * p.Lk + j), p.drop_thresh);
-          pt = keep ? pr * p.drop_scale : 0.f;
-          dp = keep ? dp * p.drop_scale : 0.f;
+        for (int u = 0; u < 2; ++u) {
+          const int col = c * 32 + 2 * jj + u;    // query index
+          const int ci = min(col, p.Lq_pad - 1);  // columns past Lq_pad are masked; keep their smem index in range
+          const bool in = col < p.Lq && valid;
+          const float pr = in ? fast_exp2(__uint_as_float(rs[2 * jj + u]) * sl2 - s_lse[ci]) : 0.f;
+          float dp = __uint_as_float(rp[2 * jj + u]);
+          float pt = pr;
+          if (DROP) {
+            const bool keep = drop_keep(p.seed, (unsigned long long)((row_base + col) * p.Lk + j), p.drop_thresh);
+            pt = keep ? pr * p.drop_scale : 0.f;
+            dp = keep ? dp * p.drop_scale : 0.f;
+          }
+          pt2[u] = pt;
+          ds2[u] = in ? pr * (dp - s_del[ci]) : 0.f;
         }
-        pt2[u] = pt;
-        ds2[u] = in ? pr * (dp - s_del[min(col, p.Lq_pad - 1)]) : 0.f;
+        pkp[jj] = pack_bf16(pt2[0], pt2[1]);
+        pks[jj] = pack_bf16(ds2[0], ds2[1]);
       }
-      pkp[t] = pack_bf16(pt2[0], pt2[1]);
-      pks[t] = pack_bf16(ds2[0], ds2[1]);
     }
-    tmem_st16(trow + (uint32_t)(c * 16), pkp);
-    tmem_st16(trow + HALF_COL + (uint32_t)(c * 16), pks);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (c < nchunk) {
+      tmem_st16(trow + (uint32_t)(c * 16), pkp);
+      tmem_st16(trow + HALF_COL + (uint32_t)(c * 16), pks);
+    }
   }
   ptx::tmem_st_wait();
+  ATT_STAMP(4);
   ptx::tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -434,9 +518,14 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
   }
   ptx::mbar_wait(&bars[1], 0);
   ptx::tc_fence_after();
-  store_acc_row(trow + ACC_COL, d, 1.f, valid ? p.dv + skv * p.dv_bs + (long long)j * p.dv_rs + h * d : nullptr);
-  store_acc_row(trow + HALF_COL + ACC_COL, d, p.scale, valid ? p.dk + skv * p.dk_bs + (long long)j * p.dk_rs + h * d : nullptr);
+  ATT_STAMP(5);
+  if (half == 0)
+    store_acc_row(trow + ACC_COL, 0, d, 1.f, valid ? p.dv + skv * p.dv_bs + (long long)j * p.dv_rs + h * d : nullptr);
+  else
+    store_acc_row(trow + HALF_COL + ACC_COL, 0, d, p.scale, valid ? p.dk + skv * p.dk_bs + (long long)j * p.dk_rs + h * d : nullptr);
+  ATT_STAMP(6);
   cta_epilogue<512>(tmem);
+  ATT_STAMP(7);
 }
 
 template <typename K>
@@ -445,6 +534,8 @@ int set_smem_tc(K kernel, size_t bytes) {
   EGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
+
+long long* g_att_dbg = nullptr;
 
 int fill_tc(const egb_attention_desc* d, AttTcParams* p) {
   memset(p, 0, sizeof(*p));
@@ -464,12 +555,21 @@ int fill_tc(const egb_attention_desc* d, AttTcParams* p) {
     p->drop_scale = 1.f / (1.f - d->dropout_p);
     p->seed = d->seed;
   }
+  p->dbg = g_att_dbg;
   return 0;
 }
 
 bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
 
 }  // namespace
+
+// Debug aid: device buffer of 8 int64 receiving the clock64() phase stamps of one CTA of the next attention launches
+// (0 start, 1 after TMEM alloc, 2 tiles staged, 3 first MMAs done, 4 softmax / dS written, 5 second MMAs done,
+//  6 results stored, 7 TMEM released).  NULL disables.
+extern "C" int egb_debug_attention_timing(long long* device_buf) {
+  g_att_dbg = device_buf;
+  return 0;
+}
 
 // The tensor-core path covers bf16 tensors with head_dim 32 or 64, sequence lengths <= 256 and 16-byte aligned
 // rows; everything else (fp32 parity mode, other shapes) runs the CUDA-core kernels of attention.cu.
@@ -493,13 +593,15 @@ bool egb_attention_tc_supported(const egb_attention_desc* d, bool backward) {
 int egb_attention_tc_fwd(const egb_attention_desc* d, cudaStream_t st) {
   AttTcParams p;
   if (fill_tc(d, &p)) return 1;
-  const size_t smem = (size_t)(TILE_ROWS + 2 * p.Lk_pad) * 128 + 1024 + 64;
-  if (set_smem_tc(att_tc_fwd_kernel, smem)) return 1;
+  const size_t smem = (size_t)(TILE_ROWS + 2 * p.Lk_pad) * 128 + 2 * TILE_ROWS * sizeof(float) + 1024 + 64;
+  const bool drop = p.drop_thresh != 0u;
+  if (set_smem_tc(att_tc_fwd_kernel<true>, smem) || set_smem_tc(att_tc_fwd_kernel<false>, smem)) return 1;
   dim3 grid((d->Lq + TILE_ROWS - 1) / TILE_ROWS, d->H, d->S);
   const bool prof = egb_prof_enabled() != 0;
   if (prof) egb_prof_begin(st, 4.0 * d->S * d->H * (double)d->Lq * d->Lk * d->head_dim,
                            2.0 * d->S * d->H * (double)d->head_dim * (2.0 * d->Lq + 2.0 * d->Lk), 2);
-  att_tc_fwd_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  if (drop) att_tc_fwd_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
+  else att_tc_fwd_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
   if (prof) egb_prof_end(st);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
@@ -512,14 +614,22 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
   EGB_CHECK(d->lse && d->delta && d->d_o && d->dq && d->dk && d->dv, "attention_bwd: missing buffers");
   const size_t smem_a = (size_t)(2 * TILE_ROWS + 2 * p.Lk_pad) * 128 + 1024 + 64;
   const size_t smem_b = (size_t)(2 * TILE_ROWS + 2 * p.Lq_pad) * 128 + (size_t)p.Lq_pad * 8 + 1024 + 64;
-  if (set_smem_tc(att_tc_bwd_dq_kernel, smem_a) || set_smem_tc(att_tc_bwd_dkv_kernel, smem_b)) return 1;
+  const bool drop = p.drop_thresh != 0u;
+  if (set_smem_tc(att_tc_bwd_dq_kernel<true>, smem_a) || set_smem_tc(att_tc_bwd_dkv_kernel<true>, smem_b) ||
+      set_smem_tc(att_tc_bwd_dq_kernel<false>, smem_a) || set_smem_tc(att_tc_bwd_dkv_kernel<false>, smem_b))
+    return 1;
   dim3 grid_a((d->Lq + TILE_ROWS - 1) / TILE_ROWS, d->H, d->S);
   dim3 grid_b((d->Lk + TILE_ROWS - 1) / TILE_ROWS, d->H, d->S);
   const bool prof = egb_prof_enabled() != 0;
   if (prof) egb_prof_begin(st, 10.0 * d->S * d->H * (double)d->Lq * d->Lk * d->head_dim,
                            2.0 * d->S * d->H * (double)d->head_dim * (4.0 * d->Lq + 4.0 * d->Lk), 3);
-  att_tc_bwd_dq_kernel<<<grid_a, TC_THREADS, smem_a, st>>>(p);
-  att_tc_bwd_dkv_kernel<<<grid_b, TC_THREADS, smem_b, st>>>(p);
+  if (drop) {
+    att_tc_bwd_dq_kernel<true><<<grid_a, TC_THREADS, smem_a, st>>>(p);
+    att_tc_bwd_dkv_kernel<true><<<grid_b, TC_THREADS, smem_b, st>>>(p);
+  } else {
+    att_tc_bwd_dq_kernel<false><<<grid_a, TC_THREADS, smem_a, st>>>(p);
+    att_tc_bwd_dkv_kernel<false><<<grid_b, TC_THREADS, smem_b, st>>>(p);
+  }
   if (prof) egb_prof_end(st);
   egb_count_launch(2);
   EGB_LAUNCH_CHECK();

@@ -65,15 +65,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 
 // Counter-based dropout mask: keep iff hash(seed, idx) >= p * 2^32. Stateless so the backward
 // pass regenerates the mask from (seed, idx) instead of storing it.
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
-  return x;
+__device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint64_t idx) {
+  uint32_t h = ((uint32_t)idx ^ (uint32_t)seed) * 0x9E3779B1u + ((uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32)) * 0x85EBCA77u;
+  h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;   // 2-round multiply-xorshift finaliser
+  return h;
 }
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
-  uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
-  uint32_t h = mix32(lo * 0x9E3779B1u + (uint32_t)seed);
-  h = mix32(h ^ (hi * 0x85ebca77u + (uint32_t)(seed >> 32)));
-  return h >= thresh;
+  return drop_hash(seed, idx) >= thresh;
 }
 static inline uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;

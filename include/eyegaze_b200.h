@@ -173,6 +173,9 @@ typedef struct {
   uint64_t seed;
 } egb_attention_desc;
 int egb_attention_fwd(const egb_attention_desc* d, void* stream);
+/* debug aid: 8 x int64 device buffer receiving clock64() phase stamps of one CTA of the following tensor-core
+ * attention launches (NULL disables) */
+int egb_debug_attention_timing(long long* device_buf);
 int egb_attention_bwd(const egb_attention_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
