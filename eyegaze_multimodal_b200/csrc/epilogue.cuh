@@ -42,6 +42,7 @@ static inline EpiMat make_epimat(const egb_matrix& m, int total_rows) {
 }
 
 __device__ __forceinline__ long long epi_row_offset(const EpiMat& m, int row) {
+  if (row < m.rpg) return (long long)row * m.rs;   // single group (the common case): no division
   const int g = row / m.rpg;
   const int r = row - g * m.rpg;
   return (long long)g * m.gs + (long long)r * m.rs;
@@ -159,5 +160,186 @@ __device__ __forceinline__ void epi_apply_store(const EpiParams& p, int m, int n
       if (i < ncols) atomicAdd(c + i, v[i]);
   } else {
     epi_store<W>(p.c, off, n, ncols, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-hoisted variant for the tensor-core kernels: the per-row work (bounds, group/row offsets of every
+// operand matrix -- integer divisions) is done once per tile row, not once per 32-column chunk.
+// ---------------------------------------------------------------------------------------------
+struct EpiRow {
+  long long c, c_pre, res, aux;
+  bool ok;
+};
+
+__device__ __forceinline__ EpiRow epi_row_setup(const EpiParams& p, int m) {
+  EpiRow r;
+  r.ok = m < p.M;
+  r.c = r.c_pre = r.res = r.aux = 0;
+  if (r.ok) {
+    r.c = epi_row_offset(p.c, m);
+    if (p.c_pre.ptr != nullptr) r.c_pre = epi_row_offset(p.c_pre, m);
+    if (p.res.ptr != nullptr) r.res = epi_row_offset(p.res, m);
+    if (p.act_bwd != EGB_ACTBWD_NONE) r.aux = epi_row_offset(p.aux, m);
+  }
+  return r;
+}
+
+template <int W>
+__device__ __forceinline__ void epi_apply_store_row(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[W]) {
+  if (!row.ok || n >= p.N) return;
+  const int ncols = min(W, p.N - n);
+  if (p.alpha != 1.f) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] *= p.alpha;
+  }
+  if (p.bias != nullptr) {
+    if (ncols == W && ((reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0) && (n & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < W; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        if (i < ncols) v[i] += __ldg(p.bias + n + i);
+    }
+  }
+  if (p.c_pre.ptr != nullptr) epi_store<W>(p.c_pre, row.c_pre, n, ncols, v);
+  if (p.act == EGB_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (p.act == EGB_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.drop_thresh != 0u) {
+    const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = drop_keep(p.seed, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+  }
+  if (p.act_bwd != EGB_ACTBWD_NONE) {
+    float a[W];
+    epi_load<W>(p.aux, row.aux, n, ncols, a);
+    if (p.act_bwd == EGB_ACTBWD_RELU_MASK) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[i] = (a[i] != 0.f) ? v[i] * p.aux_scale : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[i] *= gelu_erf_grad(a[i]);
+    }
+  }
+  if (p.res.ptr != nullptr) {
+    float r[W];
+    epi_load<W>(p.res, row.res, n, ncols, r);
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] += r[i];
+  }
+  if (p.accumulate) {
+    float* c = reinterpret_cast<float*>(p.c.ptr) + row.c + n;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+      if (i < ncols) atomicAdd(c + i, v[i]);
+  } else {
+    epi_store<W>(p.c, row.c, n, ncols, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compile-time specialised epilogue for the tensor-core kernels.  The generic function above decides everything
+// at run time (per call: ~10 parameter loads and branches); in the transposed 8-column layout it is invoked four
+// times per 32x32 chunk, and ncu shows the warps stalled on exactly those dependent branch chains.  The fast
+// variants fix the operation list in a template mask; they require bf16 16-byte-aligned matrices (fp32 for the
+// split-K accumulate), N % 8 == 0 and alpha == 1 (egb_epi_fast_mask() checks this and otherwise returns GENERIC).
+// Dropout stays a (warp-uniform) run-time switch.
+// ---------------------------------------------------------------------------------------------
+enum : int {
+  EF_BIAS = 1, EF_RELU = 2, EF_GELU = 4, EF_RES = 8, EF_PRE = 16, EF_ABWD_RELU = 32, EF_ABWD_GELU = 64, EF_ACC = 128,
+  EF_GENERIC = 1 << 20
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int F>
+__device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8]) {
+  if (!row.ok || n >= p.N) return;
+  if (F & EF_ACC) {
+    float* c = reinterpret_cast<float*>(p.c.ptr) + row.c + n;
+    red_add_v4(c, v[0], v[1], v[2], v[3]);
+    red_add_v4(c + 4, v[4], v[5], v[6], v[7]);
+    return;
+  }
+  if (F & EF_BIAS) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (F & EF_PRE) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, v);
+  if (F & EF_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (F & EF_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.drop_thresh != 0u) {
+    const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = drop_keep(p.seed, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+  }
+  if (F & (EF_ABWD_RELU | EF_ABWD_GELU)) {
+    float a[8];
+    ld8(reinterpret_cast<const bf16*>(p.aux.ptr) + row.aux + n, a);
+    if (F & EF_ABWD_RELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (a[i] != 0.f) ? v[i] * p.aux_scale : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(a[i]);
+    }
+  }
+  if (F & EF_RES) {
+    float r[8];
+    ld8(reinterpret_cast<const bf16*>(p.res.ptr) + row.res + n, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+  }
+  st8(reinterpret_cast<bf16*>(p.c.ptr) + row.c + n, v);
+}
+
+template <int F>
+__device__ __forceinline__ void epi_dispatch8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8]) {
+  if (F == EF_GENERIC) epi_apply_store_row<8>(p, row, m, n, v);
+  else epi_fast8<F>(p, row, m, n, v);
+}
+
+// host: the specialisation that implements this call exactly, or EF_GENERIC
+static inline int egb_epi_fast_mask(const EpiParams& e) {
+  auto bf16_vec = [](const EpiMat& m) { return m.ptr != nullptr && !m.f32 && m.vec_ok; };
+  if ((e.N % 8) != 0 || e.alpha != 1.f) return EF_GENERIC;
+  if (e.bias != nullptr && ((uintptr_t)e.bias % 16) != 0) return EF_GENERIC;
+  if (e.accumulate) return (e.c.f32 && e.c.vec_ok) ? EF_ACC : EF_GENERIC;
+  if (!bf16_vec(e.c)) return EF_GENERIC;
+  int f = 0;
+  if (e.bias != nullptr) f |= EF_BIAS;
+  if (e.act == EGB_ACT_RELU) f |= EF_RELU;
+  if (e.act == EGB_ACT_GELU) f |= EF_GELU;
+  if (e.c_pre.ptr != nullptr) { if (!bf16_vec(e.c_pre)) return EF_GENERIC; f |= EF_PRE; }
+  if (e.res.ptr != nullptr) { if (!bf16_vec(e.res)) return EF_GENERIC; f |= EF_RES; }
+  if (e.act_bwd != EGB_ACTBWD_NONE) {
+    if (!bf16_vec(e.aux)) return EF_GENERIC;
+    f |= (e.act_bwd == EGB_ACTBWD_RELU_MASK) ? EF_ABWD_RELU : EF_ABWD_GELU;
+  }
+  switch (f) {   // the instantiated set (everything else runs the generic epilogue)
+    case 0: case EF_BIAS: case EF_BIAS | EF_RES: case EF_BIAS | EF_RELU: case EF_BIAS | EF_GELU | EF_PRE:
+    case EF_ABWD_RELU: case EF_ABWD_GELU:
+      return f;
+    default:
+      return EF_GENERIC;
   }
 }

@@ -13,6 +13,7 @@
 #include <unordered_map>
 #include <string>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "epilogue.cuh"
@@ -21,12 +22,16 @@ extern void egb_count_launch(int n);
 int egb_prof_enabled();
 void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind);
 void egb_prof_end(cudaStream_t st);
+int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e);
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int STG_PITCH = 36;  // floats per staged epilogue row (32 + 4: conflict-free 16-byte access)
+constexpr int STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;
 
 struct TcParams {
   int M, N, K;
@@ -42,9 +47,9 @@ struct TcConfig {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // Issues the TMA loads of one operand tile: TILE rows of the M/N index x BK of the reduction index.
@@ -68,14 +73,85 @@ __device__ __forceinline__ void load_operand_tile(uint8_t* dst, const CUtensorMa
   }
 }
 
-template <int BN>
+
+// same as load_operand_tile, for a CTA pair: the bytes are signalled on the leader CTA's barrier
+template <int TILE>
+__device__ __forceinline__ void load_operand_tile_2sm(uint8_t* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
+                                                      int major, int rpg, int seg, int shift, int tile, int kb) {
+  if (major == 0) {
+    int inner0 = kb * BK, row0 = tile * TILE;
+    if (seg > 0) { row0 += (inner0 / seg) * shift; inner0 %= seg; }
+    ptx::tma_load_3d_2sm(dst, tm, bar_cluster_addr, inner0, row0 % rpg, row0 / rpg);
+  } else {
+    const int red0 = kb * BK;
+#pragma unroll
+    for (int j = 0; j < TILE / 64; ++j) {
+      int inner0 = tile * TILE + j * 64, row0 = red0;
+      if (seg > 0) { row0 += (inner0 / seg) * shift; inner0 %= seg; }
+      ptx::tma_load_3d_2sm(dst + j * (BK * 128), tm, bar_cluster_addr, inner0, row0 % rpg, row0 / rpg);
+    }
+  }
+}
+
+
+// Epilogue of one accumulator tile for one warp: TMEM lane quadrant (32 rows m_base..m_base+31), columns
+// [col0, col0 + ncol).  A tcgen05.ld gives every lane ONE ROW (32 consecutive columns); storing from that layout
+// would scatter each warp-wide store over 32 different 128-byte lines.  Each 32x32 fp32 chunk is therefore
+// transposed through a warp-private shared-memory tile so that a lane owns 8 consecutive columns of a row and
+// 4 lanes cover a 64-byte row segment: every global access of the epilogue (output, pre-activation copy, residual,
+// activation-backward operand, split-K atomics) becomes sector-exact and 4x denser per instruction.
+// TMEM loads are double buffered: chunk i+1 is in flight while chunk i goes through the math and stores.
+
+template <int EF>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRow (&rows)[4], int m_base, int n,
+                                               const uint32_t (&r)[32], float* stage, int lane) {
+  __syncwarp();                                                 // previous chunk's readers are done
+  float4* mine = reinterpret_cast<float4*>(stage + lane * STG_PITCH);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    mine[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                          __uint_as_float(r[4 * i + 3]));
+  __syncwarp();
+  const int sub = lane >> 2, cg = (lane & 3) * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const float4* src = reinterpret_cast<const float4*>(stage + (it * 8 + sub) * STG_PITCH + cg);
+    const float4 x = src[0], y = src[1];
+    float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    epi_dispatch8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v);
+  }
+}
+
+template <int EF>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& epi, uint32_t taddr, int m_base, int n0, int col0, int ncol,
+                                              float* stage, int lane) {
+  EpiRow rows[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) rows[it] = epi_row_setup(epi, m_base + it * 8 + (lane >> 2));
+  uint32_t ra[32], rb[32];
+  ptx::tmem_ld32(taddr + (uint32_t)col0, ra);
+#pragma unroll 1
+  for (int c = 0; c < ncol; c += 64) {
+    ptx::tmem_ld_wait();
+    if (c + 32 < ncol) ptx::tmem_ld32(taddr + (uint32_t)(col0 + c + 32), rb);
+    epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c, ra, stage, lane);
+    if (c + 32 < ncol) {
+      ptx::tmem_ld_wait();
+      if (c + 64 < ncol) ptx::tmem_ld32(taddr + (uint32_t)(col0 + c + 64), ra);
+      epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c + 32, rb, stage, lane);
+    }
+  }
+}
+
+template <int BN, int EF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   using Cfg = TcConfig<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  float* stage_all = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
@@ -94,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], 4);
+      ptx::mbar_init(&tempty_bar[s], EPI_WARPS);
     }
     ptx::fence_barrier_init();
   }
@@ -170,7 +246,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;     // which half of the tile's columns this warp drains
+    constexpr int NCOL = BN >= 64 ? BN / 2 : BN;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -179,18 +257,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = mn / p.n_tiles;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int m = mt * BM + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        ptx::tmem_ld32(taddr + (uint32_t)c0, raw);
-        ptx::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        epi_apply_store<32>(p.epi, m, nt * BN + c0, v);
-      }
+      epilogue_tile<EF>(p.epi, taddr, mt * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
+                    stage_all + (warp - 2) * (32 * STG_PITCH), lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
@@ -204,6 +273,166 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ================================================================================================
+// CTA-pair variant (cta_group::2): one 256 x BN output tile per pair of CTAs on neighbouring SMs.  Each CTA stages
+// its own 128 rows of A and only HALF of the B tile (BN/2 rows); the pair's tensor cores read both halves, so the
+// L2 -> SM operand traffic per FLOP drops by a third against the single-CTA 128 x 256 tile (32 KB instead of 48 KB
+// per 128x256x64 step) -- the single-CTA kernel is bound by exactly that traffic on the big projection GEMMs.
+// Only the leader CTA (cluster rank 0) issues MMAs; TMA completions of both CTAs land on the leader's "full"
+// barrier; MMA completion is multicast to both CTAs' "empty" / "accumulator full" barriers; the epilogue warps of
+// both CTAs release the accumulator on the leader's barrier.
+// ================================================================================================
+template <int BN>
+struct Tc2Config {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 5 : 7;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Cfg = Tc2Config<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* stage_all = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 2 * EPI_WARPS);  // epilogue warps of both CTAs (used in the leader only)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;  // m_tiles counts 256-row pair tiles here
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int ks = tile % p.split_k;
+        const int mn = tile / p.split_k;
+        const int nt = mn % p.n_tiles;
+        const int mt = mn / p.n_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          load_operand_tile_2sm<BM>(sa, &tmA, lead_bar, p.a_major, p.a_rpg, p.a_seg, p.a_shift, mt * 2 + (int)rank, kb);
+          load_operand_tile_2sm<BN / 2>(sb, &tmB, lead_bar, p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt * 2 + (int)rank, kb);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN, p.a_major, p.b_major);
+      const uint32_t a_adv = p.a_major == 0 ? 2u : (16u * 128u) >> 4;
+      const uint32_t b_adv = p.b_major == 0 ? 2u : (16u * 128u) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int ks = tile % p.split_k;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
+            const uint64_t adesc = ptx::make_smem_desc(sa, p.a_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
+            const uint64_t bdesc = ptx::make_smem_desc(sb, p.b_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              ptx::umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                                 (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit_2sm(&empty_bar[stage], 3);  // both CTAs' smem slots reusable once these MMAs retire
+            if (kb == kb1 - 1) ptx::umma_commit_2sm(&tfull_bar[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    constexpr int NCOL = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t lead_tempty0 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0);
+    const uint32_t lead_tempty1 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[1]), 0);
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int mn = tile / p.split_k;
+      const int nt = mn % p.n_tiles;
+      const int mt = mn / p.n_tiles;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      epilogue_tile<EF>(p.epi, taddr, (mt * 2 + (int)rank) * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
+                    stage_all + (warp - 2) * (32 * STG_PITCH), lane);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(acc == 0 ? lead_tempty0 : lead_tempty1);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -309,12 +538,12 @@ int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int 
   return make_map(out, o.ptr, inner, phys_rows, groups, o.row_stride, o.group_stride, box_rows, box_groups);
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+template <int BN, int EF>
+int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
   using Cfg = TcConfig<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    EGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    EGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
@@ -324,20 +553,111 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, c
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
   }
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  gemm_tc_kernel<BN, EF><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
   if (prof) egb_prof_end(stream);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;
 }
 
+// run-time epilogue mask -> compile-time instantiation (FAST = the specialised set is built for this tile shape)
+#define EGB_EF_SWITCH(FN, BN_, FAST)                                                                            \
+  if (FAST) {                                                                                                   \
+    switch (egb_epi_fast_mask(p.epi)) {                                                                         \
+      case 0: return FN<BN_, 0>(ma, mb, p, stream);                                                             \
+      case EF_BIAS: return FN<BN_, EF_BIAS>(ma, mb, p, stream);                                                 \
+      case EF_BIAS | EF_RES: return FN<BN_, EF_BIAS | EF_RES>(ma, mb, p, stream);                               \
+      case EF_BIAS | EF_RELU: return FN<BN_, EF_BIAS | EF_RELU>(ma, mb, p, stream);                             \
+      case EF_BIAS | EF_GELU | EF_PRE: return FN<BN_, EF_BIAS | EF_GELU | EF_PRE>(ma, mb, p, stream);           \
+      case EF_ABWD_RELU: return FN<BN_, EF_ABWD_RELU>(ma, mb, p, stream);                                       \
+      case EF_ABWD_GELU: return FN<BN_, EF_ABWD_GELU>(ma, mb, p, stream);                                       \
+      case EF_ACC: return FN<BN_, EF_ACC>(ma, mb, p, stream);                                                   \
+      default: break;                                                                                           \
+    }                                                                                                           \
+  }                                                                                                             \
+  return FN<BN_, EF_GENERIC>(ma, mb, p, stream);
+
+template <int BN>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  EGB_EF_SWITCH(launch_tc_ef, BN, BN == 256)
+}
+
+template <int BN, int EF>
+int launch_tc2_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  using Cfg = Tc2Config<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  const int pairs = egb_num_sms() / 2;
+  const int grid = 2 * (total < pairs ? total : pairs);
+  const bool prof = egb_prof_enabled() != 0;
+  if (prof) {
+    const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
+    egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
+  }
+  gemm_tc2_kernel<BN, EF><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  if (prof) egb_prof_end(stream);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  EGB_EF_SWITCH(launch_tc2_ef, BN, true)
+}
+
+// CTA-pair path: 256 x BN tiles.  Chosen for problems with at least one full wave of pair tiles.
+int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.a_major = d->a.major; p.b_major = d->b.major;
+  p.a_seg = d->a.seg_len; p.a_shift = d->a.seg_row_shift;
+  p.b_seg = d->b.seg_len; p.b_shift = d->b.seg_row_shift;
+  CUtensorMap ma, mb;
+  if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg)) return 1;
+  if (make_operand_map(&mb, d->b, d->N, d->K, BN / 2, &p.b_rpg)) return 1;
+  p.m_tiles = (d->M + 2 * BM - 1) / (2 * BM);
+  p.n_tiles = (d->N + BN - 1) / BN;
+  p.k_blocks = (d->K + BK - 1) / BK;
+  int split = 1;
+  if (d->accumulate) {
+    split = d->split_k;
+    if (split <= 0) {
+      const int tiles = p.m_tiles * p.n_tiles;
+      split = (egb_num_sms() + tiles - 1) / tiles;  // ~2 waves of pair tiles
+      const int max_split = (p.k_blocks + 7) / 8;
+      if (split > max_split) split = max_split;
+      if (split < 1) split = 1;
+    }
+    if (split > p.k_blocks) split = p.k_blocks;
+  }
+  p.kb_per_split = (p.k_blocks + split - 1) / split;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  if (egb_fill_epilogue(d, &p.epi)) return 1;
+  return BN == 256 ? launch_tc2<256>(ma, mb, p, stream) : launch_tc2<128>(ma, mb, p, stream);
+}
+
 }  // namespace
 
-int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e);
 
 // Called from egb_gemm for in_dtype == EGB_BF16.
 int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
   EGB_CHECK(d->M > 0 && d->N > 0 && d->K > 0, "gemm: empty problem %dx%dx%d", d->M, d->N, d->K);
+  {
+    // CTA pairs when the problem offers enough 256-row tiles and N fills a 256- or 128-wide pair tile
+    // (EGB_GEMM_PAIR=0 disables the path, =2 forces it for every eligible shape: used by the device tests)
+    static const int pair_mode = getenv("EGB_GEMM_PAIR") ? atoi(getenv("EGB_GEMM_PAIR")) : 1;
+    const int bn2 = (d->N % 256 == 0 || d->N >= 1024) ? 256 : ((d->N % 128 == 0) ? 128 : 0);
+    if (pair_mode && bn2 != 0 && d->M >= 256) {
+      const long long tiles = (long long)((d->M + 255) / 256) * ((d->N + bn2 - 1) / bn2);
+      if (pair_mode == 2 || tiles >= egb_num_sms() / 2 || d->accumulate) return gemm_tc_pair(d, stream, bn2);
+    }
+  }
   int BN = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
   // a 256-wide tile wastes MMA work when N is just above a multiple of 128
   if (BN == 256 && (d->N % 256) != 0 && (d->N % 256) <= 128 && d->N < 1024) BN = 128;
