@@ -55,12 +55,32 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// exact (erf) GELU and its derivative: the reference uses nn.GELU() default
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact (erf) GELU and its derivative: the reference uses nn.GELU() default.  erf through the Abramowitz-Stegun
+// 7.1.26 rational form (|error| <= 1.5e-7, i.e. below fp32 rounding of erff itself for this use): one reciprocal,
+// one exponential and five FMAs, no branches -- and the derivative reuses the same exponential, since with
+// u = x / sqrt(2) the Gaussian factor exp(-u^2) IS the normal pdf's exp(-x^2 / 2).
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+  gauss = __expf(-u * u);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, gauss, 1.0f);
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, g;
+  gelu_parts(x, cdf, g);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, g;
+  gelu_parts(x, cdf, g);
+  return fmaf(x * 0.3989422804014327f, g, cdf);
 }
 
 // Counter-based dropout mask: keep iff hash(seed, idx) >= p * 2^32. Stateless so the backward

@@ -254,6 +254,60 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
   if (ry == 0 && n < N) atomicAdd(out + n, part[0][threadIdx.x] + part[1][threadIdx.x]);
 }
 
+
+// Vectorised variant (rows 16-byte aligned): a thread owns V = 16/sizeof(T) consecutive columns, a warp spans 32*V
+// columns of one row (512 contiguous bytes), the 8 warps of a CTA take every 8th row and keep 4 row loads in flight.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N,
+                                                         int rpg, long long rs, long long gs, int rows_per_block) {
+  constexpr int V = 16 / (int)sizeof(T);
+  __shared__ float part[8][32 * V];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + cg) * V;
+  const int m0 = blockIdx.y * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  if (n < N) {
+    auto row_ptr = [&](int m) -> const T* {
+      if (m < rpg) return x + (long long)m * rs + n;
+      const int g = m / rpg;
+      return x + (long long)g * gs + (long long)(m - g * rpg) * rs + n;
+    };
+    int m = m0 + rl;
+    for (; m + 24 < m1; m += 32) {
+      uint4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const uint4*>(row_ptr(m + 8 * u)));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const T* e = reinterpret_cast<const T*>(&t[u]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += to_f(e[i]);
+      }
+    }
+    for (; m < m1; m += 8) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(row_ptr(m)));
+      const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += to_f(e[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) part[rl][cg * V + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * V; c += 256) {
+    const int col = blockIdx.x * 32 * V + c;
+    if (col < N) {
+      float sum = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sum += part[r][c];
+      atomicAdd(out + col, sum);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- dropout backward
 // out[m,n] = dy[m,n] * keep(seed, m*N+n) / (1-p): regenerates the mask the GEMM epilogue applied.
 template <typename T>
@@ -475,6 +529,26 @@ int egb_colsum(const egb_matrix* x, int M, int N, float* out, int zero_first, vo
   EGB_CHECK(M > 0 && N > 0, "colsum: empty");
   if (zero_first) EGB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 4, st));
   const int rpg = x->rows_per_group > 0 ? x->rows_per_group : M;
+  {
+    const int V = x->dtype == EGB_BF16 ? 8 : 4;
+    const bool vec = (N % V) == 0 && ((uintptr_t)x->ptr % 16) == 0 && (x->row_stride % V) == 0 &&
+                     (rpg >= M || (x->group_stride % V) == 0);
+    if (vec) {
+      const int cb = (N + 32 * V - 1) / (32 * V);
+      int rb = (6 * egb_num_sms() + cb - 1) / cb;
+      if (rb > (M + 63) / 64) rb = (M + 63) / 64;
+      if (rb < 1) rb = 1;
+      const int rpb = ((M + rb - 1) / rb + 7) / 8 * 8;
+      dim3 grid(cb, (M + rpb - 1) / rpb);
+      if (x->dtype == EGB_BF16)
+        colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x->ptr, out, M, N, rpg, x->row_stride, x->group_stride, rpb);
+      else
+        colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x->ptr, out, M, N, rpg, x->row_stride, x->group_stride, rpb);
+      egb_count_launch(1);
+      EGB_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const int col_blocks = (N + 127) / 128;
   int row_blocks = (4 * egb_num_sms() + col_blocks - 1) / col_blocks;
   if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;

@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum dy*xhat; dbeta += sum dy.
 // Optional second output dx2 = dx * dropout-mask (the branch that went through a residual dropout).
-template <typename T>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, int C>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, T* __restrict__ dx,
@@ -73,21 +73,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   extern __shared__ float red[];  // [2][D]
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  const int chunks = (D + 255) / 256;
+  constexpr int chunks = C;
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  float ag[LN_MAX_CHUNKS][8], ab[LN_MAX_CHUNKS][8];
+  float ag[C][8], ab[C][8];
 #pragma unroll
-  for (int c = 0; c < LN_MAX_CHUNKS; ++c)
+  for (int c = 0; c < C; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = 0.f;
 
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[LN_MAX_CHUNKS][8], g[LN_MAX_CHUNKS][8];
+    float xh[C][8], g[C][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+    for (int c = 0; c < C; ++c) {
       const int d = c * 256 + lane * 8;
       if (c < chunks && d < D) {
         float xv[8], dv[8], gm[8];
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
     s1 = warp_sum(s1) / (float)D;
     s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+    for (int c = 0; c < C; ++c) {
       const int d = c * 256 + lane * 8;
       if (c < chunks && d < D) {
         float o[8];
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   }
   // block reduction of the per-warp column partials, then one atomic per column per block
 #pragma unroll
-  for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+  for (int c = 0; c < C; ++c) {
     const int d = c * 256 + lane * 8;
     if (c < chunks && d < D) {
 #pragma unroll
@@ -165,15 +165,29 @@ int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   cudaStream_t st = (cudaStream_t)stream;
   EGB_CHECK(D % 8 == 0 && D <= 256 * LN_MAX_CHUNKS, "layernorm_bwd: unsupported D=%d", D);
   int blocks = (M + 7) / 8;
-  const int cap = egb_num_sms() * 2;
+  const int cap = egb_num_sms() * 4;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)2 * D * sizeof(float);
-  if (dtype == EGB_BF16)
-    layernorm_bwd_kernel<bf16><<<blocks, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (bf16*)dx,
-                                                         dgamma, dbeta, M, D);
-  else
-    layernorm_bwd_kernel<float><<<blocks, 256, smem, st>>>((const float*)dy, (const float*)x, gamma, mean, rstd,
-                                                          (float*)dx, dgamma, dbeta, M, D);
+  const int chunks = (D + 255) / 256;
+#define EGB_LN_BWD(TT, CC)                                                                                         \
+  layernorm_bwd_kernel<TT, CC><<<blocks, 256, smem, st>>>((const TT*)dy, (const TT*)x, gamma, mean, rstd, (TT*)dx, \
+                                                         dgamma, dbeta, M, D)
+  if (dtype == EGB_BF16) {
+    switch (chunks) {
+      case 1: EGB_LN_BWD(bf16, 1); break;
+      case 2: EGB_LN_BWD(bf16, 2); break;
+      case 3: EGB_LN_BWD(bf16, 3); break;
+      default: EGB_LN_BWD(bf16, 4); break;
+    }
+  } else {
+    switch (chunks) {
+      case 1: EGB_LN_BWD(float, 1); break;
+      case 2: EGB_LN_BWD(float, 2); break;
+      case 3: EGB_LN_BWD(float, 3); break;
+      default: EGB_LN_BWD(float, 4); break;
+    }
+  }
+#undef EGB_LN_BWD
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;
