@@ -76,6 +76,7 @@ _SIGNATURES = {
     "egb_attention_fwd": [C.POINTER(AttentionDesc), vp],
     "egb_attention_bwd": [C.POINTER(AttentionDesc), vp],
     "egb_debug_attention_timing": [vp],
+    "egb_debug_gemm_timing": [vp],
     "egb_stft_logmag": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "egb_spec_conv1_pool_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i64, vp],
     "egb_spec_conv1_pool_bwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp],

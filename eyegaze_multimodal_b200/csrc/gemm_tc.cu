@@ -40,7 +40,20 @@ struct TcParams {
   int a_seg, a_shift, b_seg, b_shift;  // inner segmentation (0 = off)
   int m_tiles, n_tiles, k_blocks, split_k, kb_per_split;
   EpiParams epi;
+  long long* dbg;  // optional [gridDim.x][8] cycle counters (egb_debug_gemm_timing)
 };
+
+// cycles spent inside a barrier wait, accumulated into *acc when profiling is on
+#define TIMED_WAIT(acc, stmt)            \
+  do {                                   \
+    if (p.dbg != nullptr) {              \
+      const long long _t0 = clock64();   \
+      stmt;                              \
+      acc += clock64() - _t0;            \
+    } else {                             \
+      stmt;                              \
+    }                                    \
+  } while (0)
 
 template <int BN>
 struct TcConfig {
@@ -160,6 +173,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long t_wait0 = 0, t_wait1 = 0;
+  const long long t_start = p.dbg != nullptr ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -195,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          TIMED_WAIT(t_wait0, ptx::mbar_wait(&empty_bar[stage], phase ^ 1u));
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
@@ -255,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mn = tile / p.split_k;
       const int nt = mn % p.n_tiles;
       const int mt = mn / p.n_tiles;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       epilogue_tile<EF>(p.epi, taddr, mt * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
@@ -268,6 +283,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (p.dbg != nullptr && lane == 0 && warp < 3) {  // 0: producer (empty wait) 1: MMA (full, tempty) 2: epilogue (tfull)
+    long long* o = p.dbg + (long long)blockIdx.x * 8;
+    if (warp == 0) o[0] = t_wait0;
+    if (warp == 1) { o[1] = t_wait0; o[2] = t_wait1; o[4] = clock64() - t_start; }
+    if (warp == 2) o[3] = t_wait0;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -313,6 +334,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long t_wait0 = 0, t_wait1 = 0;
+  const long long t_start = p.dbg != nullptr ? clock64() : 0;
   const uint32_t rank = ptx::cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
@@ -351,7 +374,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          TIMED_WAIT(t_wait0, ptx::mbar_wait(&empty_bar[stage], phase ^ 1u));
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
@@ -376,11 +399,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int ks = tile % p.split_k;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        TIMED_WAIT(t_wait1, ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u));
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+          TIMED_WAIT(t_wait0, ptx::mbar_wait(&full_bar[stage], phase));
           ptx::tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
@@ -415,7 +438,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int mn = tile / p.split_k;
       const int nt = mn % p.n_tiles;
       const int mt = mn / p.n_tiles;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       epilogue_tile<EF>(p.epi, taddr, (mt * 2 + (int)rank) * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
@@ -428,6 +451,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
+  if (p.dbg != nullptr && lane == 0 && warp < 3) {
+    long long* o = p.dbg + (long long)blockIdx.x * 8;
+    if (warp == 0) o[0] = t_wait0;
+    if (warp == 1) { o[1] = t_wait0; o[2] = t_wait1; o[4] = clock64() - t_start; }
+    if (warp == 2) o[3] = t_wait0;
+  }
   ptx::tc_fence_before();
   ptx::cluster_sync();
   if (warp == 1) {
@@ -470,6 +499,7 @@ struct MapKeyHash {
     return (size_t)h;
   }
 };
+long long* g_gemm_dbg = nullptr;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
@@ -639,11 +669,20 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
   p.kb_per_split = (p.k_blocks + split - 1) / split;
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   if (egb_fill_epilogue(d, &p.epi)) return 1;
+  p.dbg = g_gemm_dbg;
   return BN == 256 ? launch_tc2<256>(ma, mb, p, stream) : launch_tc2<128>(ma, mb, p, stream);
 }
 
 }  // namespace
 
+
+// Debug aid: device buffer of [grid][8] int64 receiving per-CTA barrier-wait cycle totals of the following tensor-core
+// GEMM launches: [0] producer waiting for a free stage, [1] MMA warp waiting for operands, [2] MMA warp waiting for
+// a drained accumulator, [3] epilogue warp waiting for an accumulator, [4] kernel cycles.  NULL disables.
+extern "C" int egb_debug_gemm_timing(long long* device_buf) {
+  g_gemm_dbg = device_buf;
+  return 0;
+}
 
 // Called from egb_gemm for in_dtype == EGB_BF16.
 int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
@@ -689,6 +728,7 @@ int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
   p.kb_per_split = (p.k_blocks + split - 1) / split;
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   if (egb_fill_epilogue(d, &p.epi)) return 1;
+  p.dbg = g_gemm_dbg;
   switch (BN) {
     case 256: return launch_tc<256>(ma, mb, p, stream);
     case 128: return launch_tc<128>(ma, mb, p, stream);

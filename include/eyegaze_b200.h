@@ -99,6 +99,9 @@ typedef struct {
 } egb_gemm_desc;
 
 int egb_gemm(const egb_gemm_desc* d, void* stream);
+/* debug aid: [grid][8] int64 device buffer receiving per-CTA barrier-wait cycle totals of the following tensor-core
+ * GEMM launches (NULL disables) */
+int egb_debug_gemm_timing(long long* device_buf);
 
 /* ---------------------------------------------------------------------------------------------
  * dtype casts / weight re-layout (per-step bf16 copies of the fp32 master parameters)

@@ -1,0 +1,71 @@
+"""world_size-2 gloo test (CPU) of the trial-parallel gradient exchange: sharding trials over ranks and averaging the
+bucketed gradients must reproduce the single-process gradient of the full batch; parameters used twice, unused
+parameters and ragged shards are covered."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+from eyegaze_multimodal_b200.parallel import TrialParallel, shard_trials
+
+
+class Toy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.enc = nn.Linear(16, 32)         # applied to both "players": one parameter, two uses per step
+        self.head = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 3))
+        self.unused = nn.Linear(4, 4)        # never reached by the loss
+
+    def forward(self, a, b):
+        return self.head(torch.cat([torch.tanh(self.enc(a)), torch.tanh(self.enc(b))], -1))
+
+
+def _data(n=10):
+    g = torch.Generator().manual_seed(3)
+    return torch.randn(n, 16, generator=g), torch.randn(n, 16, generator=g), torch.randint(0, 3, (n,), generator=g)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)            # different init per rank: the wrapper must broadcast rank 0's weights
+    model = Toy()
+    tp = TrialParallel(model, bucket_mb=0.004)   # tiny buckets: several all-reduces per step
+    assert len(tp.buckets) > 2
+    a, b, y = _data()
+    idx = list(shard_trials(len(y), rank, world))
+    for _ in range(2):                       # second step: buckets re-armed by zero_grad
+        tp.zero_grad()
+        # sum-reduced per-shard loss / global count == mean over the full batch after averaging across ranks
+        loss = nn.functional.cross_entropy(tp(a[idx], b[idx]), y[idx], reduction="sum") * world / len(y)
+        loss.backward()
+        tp.finish()
+    out[rank] = {n: p.grad.clone() for n, p in model.named_parameters()} | {"w0": model.enc.weight.detach().clone()}
+    dist.destroy_process_group()
+
+
+def test_gradients_match_single_process():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    torch.manual_seed(100)
+    ref = Toy()
+    a, b, y = _data()
+    nn.functional.cross_entropy(ref(a, b), y).backward()
+    assert torch.equal(out[0]["w0"], out[1]["w0"]) and torch.equal(out[0]["w0"], ref.enc.weight.detach())
+    for n, p in ref.named_parameters():
+        want = p.grad if p.grad is not None else torch.zeros_like(p)
+        for r in (0, 1):
+            assert torch.allclose(out[r][n], want, atol=1e-6), (n, r)
+
+
+def test_shard_trials_ragged():
+    assert [list(shard_trials(10, r, 4)) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+    assert list(shard_trials(3, 3, 4)) == []
+    assert sum(len(shard_trials(4096, r, 8)) for r in range(8)) == 4096
