@@ -247,7 +247,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # the JSON line must be the only thing on stdout: NCCL_DEBUG=VERSION prints a banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     set_precision(args.precision)
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
@@ -367,7 +371,8 @@ def run_b200(args):
 
     # ---- (3) roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch ---------------
     roofline = None
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:
+        # every rank runs the profiled steps (they contain the gradient all-reduce); rank 0 reports
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.isfile(pk):
@@ -388,9 +393,9 @@ def run_b200(args):
         L.prof_enable(False)
         pr = L.prof_read(0, reset=True)
         step_ms = pe0.elapsed_time(pe1) / n_prof
-        if pr["launches"] > 0 and pr["ms"] > 0:
+        if rank == 0 and pr["launches"] > 0 and pr["ms"] > 0:
             ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma bf16, TMA operands, TMEM accumulators)",
+            roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05.mma bf16, TMA operands, TMEM accumulators)",
                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                         "peak_source": peak_src, "launches_per_step": pr["launches"] / n_prof,
                         "avg_launch_us": pr["ms"] * 1e3 / pr["launches"],
