@@ -116,11 +116,12 @@ __device__ __forceinline__ void mma_ss_kk(uint32_t tmem_d, const uint8_t* a, con
 }
 // acc[tmem_d] = A[tmem: 128 x kdim, packed bf16] . B_tile[kdim rows][d] : B MN-major in shared memory
 // (K step = 16 rows = 2048 B; the packed A operand advances 8 columns per step)
-__device__ __forceinline__ void mma_ts_mn(uint32_t tmem_d, uint32_t tmem_a, const uint8_t* b, int kdim, int d) {
+__device__ __forceinline__ void mma_ts_mn(uint32_t tmem_d, uint32_t tmem_a, const uint8_t* b, int kdim, int d,
+                                          bool accumulate = false) {
   const uint32_t idesc = ptx::make_idesc_bf16(TILE_ROWS, d, 0, 1);
   const uint64_t bd = ptx::make_smem_desc(ptx::smem_u32(b), (uint32_t)kdim * 128u, 1024u);
   for (int ks = 0; ks < kdim / 16; ++ks)
-    umma_bf16_ts(tmem_d, tmem_a + (uint32_t)(8 * ks), bd + (uint64_t)(128 * ks), idesc, ks > 0 ? 1u : 0u);
+    umma_bf16_ts(tmem_d, tmem_a + (uint32_t)(8 * ks), bd + (uint64_t)(128 * ks), idesc, (accumulate || ks > 0) ? 1u : 0u);
 }
 
 // accumulator columns [c_begin, c_end) (multiples of 32) of this thread's row -> scaled bf16 -> global
@@ -301,7 +302,17 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
   ATT_STAMP(7);
 }
 
-// ======================================================================================= backward: dQ (+ delta)
+// ======================================================================================= backward
+// Both backward kernels walk the "other" sequence axis in chunks of 64 columns so that a CTA needs only 256 TMEM
+// columns (S chunk | dP chunk | accumulators) and two CTAs share an SM: while one runs its softmax math the other's
+// MMAs and tile staging proceed.  Per chunk: [S_c, dP_c MMAs] -> threads build bf16 dS_c (and P~_c) in place ->
+// [accumulating MMAs with that chunk as the TMEM A operand] -> next chunk's score MMAs are issued right behind
+// (tcgen05.mma executes in issue order, so they may overwrite the columns the accumulating MMAs just read).
+constexpr uint32_t BW_DP = 64;    // dP chunk columns
+constexpr uint32_t BW_ACC0 = 128; // first accumulator (dQ, or dV)
+constexpr uint32_t BW_ACC1 = 192; // second accumulator (dK)
+
+// -------------------------------------------------------------------------------------- dQ (+ delta)
 template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -342,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
     if (half == 0) p.delta[row_id] = dl;
     lse2 = p.lse[row_id] * LOG2E;
   }
-  if (warp == 0) ptx::tmem_alloc<512>(slot);
+  if (warp == 0) ptx::tmem_alloc<256>(slot);
   ATT_STAMP(1);
   cp_async_wait_all();
   ptx::fence_proxy_async_smem();
@@ -352,32 +363,33 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
   const uint32_t tmem = *slot;
   ATT_STAMP(2);
 
+  const int nchunk = (p.Lk_pad + 63) / 64;
   if (threadIdx.x == 0) {
-    mma_ss_kk(tmem, sQ, sK, p.Lk_pad, d);             // S  = Q K^T
-    mma_ss_kk(tmem + HALF_COL, sG, sV, p.Lk_pad, d);  // dP = dO V^T
+    const int w0 = min(64, p.Lk_pad);
+    mma_ss_kk(tmem, sQ, sK, w0, d);           // S_0  = Q K_0^T
+    mma_ss_kk(tmem + BW_DP, sG, sV, w0, d);   // dP_0 = dO V_0^T
     ptx::umma_commit(&bars[0]);
   }
   const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const int nchunk = (p.Lk_pad + 31) / 32;
   const float sl2 = p.scale * LOG2E;
-  ptx::mbar_wait(&bars[0], 0);
-  ptx::tc_fence_after();
-  ATT_STAMP(3);
-  const int nround = (nchunk + 1) / 2;
-  for (int t = 0; t < nround; ++t) {     // see the forward kernel for the in-place write-back schedule
-    const int c = 2 * t + half;
+  for (int c = 0; c < nchunk; ++c) {
+    const int w = min(64, p.Lk_pad - 64 * c);          // chunk width (multiple of 16)
+    const bool mine = 32 * half < w;
+    ptx::mbar_wait(&bars[0], (uint32_t)(c & 1));
+    ptx::tc_fence_after();
+    if (c == 0) ATT_STAMP(3);
     uint32_t pk[16];
-    if (c < nchunk) {
+    if (mine) {
       uint32_t rs[32], rp[32];
-      ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
-      ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
+      ptx::tmem_ld32(trow + (uint32_t)(32 * half), rs);
+      ptx::tmem_ld32(trow + BW_DP + (uint32_t)(32 * half), rp);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float ds2[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int col = c * 32 + 2 * j + u;
+          const int col = 64 * c + 32 * half + 2 * j + u;
           const float pr = fast_exp2(__uint_as_float(rs[2 * j + u]) * sl2 - lse2);
           float dp = __uint_as_float(rp[2 * j + u]);
           if (DROP) dp = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? dp * p.drop_scale : 0.f;
@@ -387,33 +399,40 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
       }
     }
     ptx::tc_fence_before();
+    __syncthreads();                                     // both halves have consumed the raw chunk
+    ptx::tc_fence_after();
+    if (mine) tmem_st16(trow + (uint32_t)(16 * half), pk);
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
     __syncthreads();
-    ptx::tc_fence_after();
-    if (c < nchunk) tmem_st16(trow + (uint32_t)(c * 16), pk);
+    if (threadIdx.x == 0) {
+      ptx::tc_fence_after();
+      mma_ts_mn(tmem + BW_ACC0, tmem, sK + (size_t)c * 64 * 128, w, d, c > 0);   // dQ += dS_c K_c
+      if (c + 1 < nchunk) {
+        const int w1 = min(64, p.Lk_pad - 64 * (c + 1));
+        mma_ss_kk(tmem, sQ, sK + (size_t)(c + 1) * 64 * 128, w1, d);
+        mma_ss_kk(tmem + BW_DP, sG, sV + (size_t)(c + 1) * 64 * 128, w1, d);
+        ptx::umma_commit(&bars[0]);
+      } else {
+        ptx::umma_commit(&bars[1]);
+      }
+    }
   }
-  ptx::tmem_st_wait();
   ATT_STAMP(4);
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ptx::tc_fence_after();
-    mma_ts_mn(tmem + ACC_COL, tmem, sK, p.Lk_pad, d);  // dQ = dS K
-    ptx::umma_commit(&bars[1]);
-  }
   ptx::mbar_wait(&bars[1], 0);
   ptx::tc_fence_after();
   ATT_STAMP(5);
   {
     bf16* drow = valid ? p.dq + s * p.dq_bs + (long long)i * p.dq_rs + h * d : nullptr;
-    if (d >= 64) store_acc_row(trow + ACC_COL, half * (d / 2), half * (d / 2) + d / 2, p.scale, drow);
-    else if (half == 0) store_acc_row(trow + ACC_COL, 0, d, p.scale, drow);
+    if (d >= 64) store_acc_row(trow + BW_ACC0, half * (d / 2), half * (d / 2) + d / 2, p.scale, drow);
+    else if (half == 0) store_acc_row(trow + BW_ACC0, 0, d, p.scale, drow);
   }
   ATT_STAMP(6);
-  cta_epilogue<512>(tmem);
+  cta_epilogue<256>(tmem);
   ATT_STAMP(7);
 }
 
-// ======================================================================================= backward: dK, dV
+// -------------------------------------------------------------------------------------- dK, dV
 template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -443,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
     s_lse[t] = t < p.Lq ? p.lse[row_base + t] * LOG2E : 0.f;
     s_del[t] = t < p.Lq ? p.delta[row_base + t] : 0.f;
   }
-  if (warp == 0) ptx::tmem_alloc<512>(slot);
+  if (warp == 0) ptx::tmem_alloc<256>(slot);
   ATT_STAMP(1);
   cp_async_wait_all();
   ptx::fence_proxy_async_smem();
@@ -453,35 +472,36 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
   const uint32_t tmem = *slot;
   ATT_STAMP(2);
 
+  const int nchunk = (p.Lq_pad + 63) / 64;
   if (threadIdx.x == 0) {
-    mma_ss_kk(tmem, sK, sQ, p.Lq_pad, d);             // S^T  = K Q^T
-    mma_ss_kk(tmem + HALF_COL, sV, sG, p.Lq_pad, d);  // dP^T = V dO^T
+    const int w0 = min(64, p.Lq_pad);
+    mma_ss_kk(tmem, sK, sQ, w0, d);           // S^T_0  = K Q_0^T
+    mma_ss_kk(tmem + BW_DP, sV, sG, w0, d);   // dP^T_0 = V dO_0^T
     ptx::umma_commit(&bars[0]);
   }
   const int j = k0 + row;
   const bool valid = j < p.Lk;
   const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const int nchunk = (p.Lq_pad + 31) / 32;
   const float sl2 = p.scale * LOG2E;
-  ptx::mbar_wait(&bars[0], 0);
-  ptx::tc_fence_after();
-  ATT_STAMP(3);
-  const int nround = (nchunk + 1) / 2;
-  for (int t = 0; t < nround; ++t) {     // see the forward kernel for the in-place write-back schedule
-    const int c = 2 * t + half;
+  for (int c = 0; c < nchunk; ++c) {
+    const int w = min(64, p.Lq_pad - 64 * c);
+    const bool mine = 32 * half < w;
+    ptx::mbar_wait(&bars[0], (uint32_t)(c & 1));
+    ptx::tc_fence_after();
+    if (c == 0) ATT_STAMP(3);
     uint32_t pkp[16], pks[16];
-    if (c < nchunk) {
+    if (mine) {
       uint32_t rs[32], rp[32];
-      ptx::tmem_ld32(trow + (uint32_t)(c * 32), rs);
-      ptx::tmem_ld32(trow + HALF_COL + (uint32_t)(c * 32), rp);
+      ptx::tmem_ld32(trow + (uint32_t)(32 * half), rs);
+      ptx::tmem_ld32(trow + BW_DP + (uint32_t)(32 * half), rp);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
         float pt2[2], ds2[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int col = c * 32 + 2 * jj + u;    // query index
-          const int ci = min(col, p.Lq_pad - 1);  // columns past Lq_pad are masked; keep their smem index in range
+          const int col = 64 * c + 32 * half + 2 * jj + u;   // query index
+          const int ci = min(col, p.Lq_pad - 1);              // columns past Lq_pad are masked; keep the index in range
           const bool in = col < p.Lq && valid;
           const float pr = in ? fast_exp2(__uint_as_float(rs[2 * jj + u]) * sl2 - s_lse[ci]) : 0.f;
           float dp = __uint_as_float(rp[2 * jj + u]);
@@ -501,30 +521,37 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    if (c < nchunk) {
-      tmem_st16(trow + (uint32_t)(c * 16), pkp);
-      tmem_st16(trow + HALF_COL + (uint32_t)(c * 16), pks);
+    if (mine) {
+      tmem_st16(trow + (uint32_t)(16 * half), pkp);
+      tmem_st16(trow + BW_DP + (uint32_t)(16 * half), pks);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ptx::tc_fence_after();
+      mma_ts_mn(tmem + BW_ACC0, tmem, sG + (size_t)c * 64 * 128, w, d, c > 0);          // dV += P~^T_c dO_c
+      mma_ts_mn(tmem + BW_ACC1, tmem + BW_DP, sQ + (size_t)c * 64 * 128, w, d, c > 0);  // dK += dS^T_c Q_c
+      if (c + 1 < nchunk) {
+        const int w1 = min(64, p.Lq_pad - 64 * (c + 1));
+        mma_ss_kk(tmem, sK, sQ + (size_t)(c + 1) * 64 * 128, w1, d);
+        mma_ss_kk(tmem + BW_DP, sV, sG + (size_t)(c + 1) * 64 * 128, w1, d);
+        ptx::umma_commit(&bars[0]);
+      } else {
+        ptx::umma_commit(&bars[1]);
+      }
     }
   }
-  ptx::tmem_st_wait();
   ATT_STAMP(4);
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ptx::tc_fence_after();
-    mma_ts_mn(tmem + ACC_COL, tmem, sG, p.Lq_pad, d);                        // dV = P~^T dO
-    mma_ts_mn(tmem + HALF_COL + ACC_COL, tmem + HALF_COL, sQ, p.Lq_pad, d);  // dK = dS^T Q
-    ptx::umma_commit(&bars[1]);
-  }
   ptx::mbar_wait(&bars[1], 0);
   ptx::tc_fence_after();
   ATT_STAMP(5);
   if (half == 0)
-    store_acc_row(trow + ACC_COL, 0, d, 1.f, valid ? p.dv + skv * p.dv_bs + (long long)j * p.dv_rs + h * d : nullptr);
+    store_acc_row(trow + BW_ACC0, 0, d, 1.f, valid ? p.dv + skv * p.dv_bs + (long long)j * p.dv_rs + h * d : nullptr);
   else
-    store_acc_row(trow + HALF_COL + ACC_COL, 0, d, p.scale, valid ? p.dk + skv * p.dk_bs + (long long)j * p.dk_rs + h * d : nullptr);
+    store_acc_row(trow + BW_ACC1, 0, d, p.scale, valid ? p.dk + skv * p.dk_bs + (long long)j * p.dk_rs + h * d : nullptr);
   ATT_STAMP(6);
-  cta_epilogue<512>(tmem);
+  cta_epilogue<256>(tmem);
   ATT_STAMP(7);
 }
 

@@ -263,8 +263,27 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// operands of one 8-column run that can be fetched ahead of the math (bias is shared by all rows of a chunk)
+struct EpiPre8 {
+  uint4 res, aux;
+};
+
 template <int F>
-__device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8]) {
+__device__ __forceinline__ void epi_prefetch8(const EpiParams& p, const EpiRow& row, int n, EpiPre8& pre) {
+  if (!row.ok || n >= p.N) return;
+  if (F & (EF_ABWD_RELU | EF_ABWD_GELU)) pre.aux = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux.ptr) + row.aux + n));
+  if (F & EF_RES) pre.res = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res.ptr) + row.res + n));
+}
+
+__device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+
+template <int F>
+__device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8],
+                                          const float (&bias)[8], const EpiPre8& pre) {
   if (!row.ok || n >= p.N) return;
   if (F & EF_ACC) {
     float* c = reinterpret_cast<float*>(p.c.ptr) + row.c + n;
@@ -273,10 +292,8 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
     return;
   }
   if (F & EF_BIAS) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += bias[i];
   }
   if (F & EF_PRE) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, v);
   if (F & EF_RELU) {
@@ -294,7 +311,7 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
   }
   if (F & (EF_ABWD_RELU | EF_ABWD_GELU)) {
     float a[8];
-    ld8(reinterpret_cast<const bf16*>(p.aux.ptr) + row.aux + n, a);
+    unpack8(pre.aux, a);
     if (F & EF_ABWD_RELU) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (a[i] != 0.f) ? v[i] * p.aux_scale : 0.f;
@@ -305,17 +322,11 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
   }
   if (F & EF_RES) {
     float r[8];
-    ld8(reinterpret_cast<const bf16*>(p.res.ptr) + row.res + n, r);
+    unpack8(pre.res, r);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += r[i];
   }
   st8(reinterpret_cast<bf16*>(p.c.ptr) + row.c + n, v);
-}
-
-template <int F>
-__device__ __forceinline__ void epi_dispatch8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8]) {
-  if (F == EF_GENERIC) epi_apply_store_row<8>(p, row, m, n, v);
-  else epi_fast8<F>(p, row, m, n, v);
 }
 
 // host: the specialisation that implements this call exactly, or EF_GENERIC

@@ -30,7 +30,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int EPI_WARPS = 8;
-constexpr int STG_PITCH = 36;  // floats per staged epilogue row (32 + 4: conflict-free 16-byte access)
+constexpr int STG_PITCH = 32;  // floats per staged epilogue row; 16-byte chunks are XOR-swizzled by (row & 7)
 constexpr int STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;
 
 struct TcParams {
@@ -41,6 +41,7 @@ struct TcParams {
   int m_tiles, n_tiles, k_blocks, split_k, kb_per_split;
   EpiParams epi;
   long long* dbg;  // optional [gridDim.x][8] cycle counters (egb_debug_gemm_timing)
+  int dbg_skip;    // experiment switch (EGB_GEMM_SKIPB=1): see the pair producer
 };
 
 // cycles spent inside a barrier wait, accumulated into *acc when profiling is on
@@ -60,7 +61,7 @@ struct TcConfig {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 5 : 7);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -118,20 +119,36 @@ __device__ __forceinline__ void load_operand_tile_2sm(uint8_t* dst, const CUtens
 template <int EF>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRow (&rows)[4], int m_base, int n,
                                                const uint32_t (&r)[32], float* stage, int lane) {
+  const int sub = lane >> 2, cg = (lane & 3) * 8;
+  // Fetch everything the four 8-column runs of this lane need (bias once, residual / act' operand per row) FIRST:
+  // the global-load latency then overlaps the shared-memory transposition instead of being paid once per run.
+  float bias[8];
+  EpiPre8 pre[4];
+  if (EF != EF_GENERIC) {
+    if ((EF & EF_BIAS) && n + cg < epi.N) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + cg));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + cg + 4));
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) epi_prefetch8<EF>(epi, rows[it], n + cg, pre[it]);
+  }
   __syncwarp();                                                 // previous chunk's readers are done
   float4* mine = reinterpret_cast<float4*>(stage + lane * STG_PITCH);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    mine[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                          __uint_as_float(r[4 * i + 3]));
+    mine[i ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
   __syncwarp();
-  const int sub = lane >> 2, cg = (lane & 3) * 8;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
-    const float4* src = reinterpret_cast<const float4*>(stage + (it * 8 + sub) * STG_PITCH + cg);
-    const float4 x = src[0], y = src[1];
+    const int rr = it * 8 + sub;
+    const float4* src = reinterpret_cast<const float4*>(stage + rr * STG_PITCH);
+    const float4 x = src[((lane & 3) * 2) ^ (rr & 7)], y = src[((lane & 3) * 2 + 1) ^ (rr & 7)];
     float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-    epi_dispatch8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v);
+    if (EF == EF_GENERIC) epi_apply_store_row<8>(epi, rows[it], m_base + it * 8 + sub, n + cg, v);
+    else epi_fast8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v, bias, pre[it]);
   }
 }
 
@@ -211,6 +228,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           TIMED_WAIT(t_wait0, ptx::mbar_wait(&empty_bar[stage], phase ^ 1u));
+          if (p.dbg_skip == 2) {   // EXPERIMENT: no loads at all
+            ptx::mbar_arrive(&full_bar[stage]);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
@@ -312,7 +334,7 @@ struct Tc2Config {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 5 : 7;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -375,12 +397,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           TIMED_WAIT(t_wait0, ptx::mbar_wait(&empty_bar[stage], phase ^ 1u));
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          // EXPERIMENT (p.split_k < 0 encodes "skip B on odd k-blocks"): results are wrong, timing shows traffic sensitivity
+          const bool skip_b = p.dbg_skip == 1 && (kb & 1);
+          if (p.dbg_skip == 2) {   // EXPERIMENT: no loads at all (pure MMA + epilogue rate on stale shared memory)
+            if (rank == 0) ptx::mbar_arrive(&full_bar[stage]);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], skip_b ? 2 * Cfg::A_BYTES : 2 * Cfg::STAGE_BYTES);
           const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           load_operand_tile_2sm<BM>(sa, &tmA, lead_bar, p.a_major, p.a_rpg, p.a_seg, p.a_shift, mt * 2 + (int)rank, kb);
-          load_operand_tile_2sm<BN / 2>(sb, &tmB, lead_bar, p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt * 2 + (int)rank, kb);
+          if (!skip_b)
+            load_operand_tile_2sm<BN / 2>(sb, &tmB, lead_bar, p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt * 2 + (int)rank, kb);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -609,7 +639,7 @@ int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p
 
 template <int BN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
-  EGB_EF_SWITCH(launch_tc_ef, BN, BN == 256)
+  EGB_EF_SWITCH(launch_tc_ef, BN, true)
 }
 
 template <int BN, int EF>
@@ -658,11 +688,23 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
   if (d->accumulate) {
     split = d->split_k;
     if (split <= 0) {
+      // pick the split whose work-item count fills whole waves of CTA pairs best (each item keeps >= 16 k-blocks)
       const int tiles = p.m_tiles * p.n_tiles;
-      split = (egb_num_sms() + tiles - 1) / tiles;  // ~2 waves of pair tiles
-      const int max_split = (p.k_blocks + 7) / 8;
-      if (split > max_split) split = max_split;
-      if (split < 1) split = 1;
+      const int pairs = egb_num_sms() / 2;
+      int max_split = p.k_blocks / 16;
+      if (max_split > 64) max_split = 64;
+      if (max_split < 1) max_split = 1;
+      double best = -1.0;
+      split = 1;
+      for (int sp = 1; sp <= max_split; ++sp) {
+        const int kps = (p.k_blocks + sp - 1) / sp;
+        const int items = tiles * ((p.k_blocks + kps - 1) / kps);
+        const int waves = (items + pairs - 1) / pairs;
+        // time ~ waves * (k-blocks per item + fixed per-item cost of the accumulate epilogue, ~12 k-blocks)
+        const double cost = (double)waves * (kps + 12);
+        const double score = 1.0 / cost;
+        if (score > best * 1.0001) { best = score; split = sp; }
+      }
     }
     if (split > p.k_blocks) split = p.k_blocks;
   }
@@ -670,6 +712,8 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   if (egb_fill_epilogue(d, &p.epi)) return 1;
   p.dbg = g_gemm_dbg;
+  static const int skipb = getenv("EGB_GEMM_SKIPB") ? atoi(getenv("EGB_GEMM_SKIPB")) : 0;
+  p.dbg_skip = skipb;
   return BN == 256 ? launch_tc2<256>(ma, mb, p, stream) : launch_tc2<128>(ma, mb, p, stream);
 }
 
@@ -729,6 +773,10 @@ int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   if (egb_fill_epilogue(d, &p.epi)) return 1;
   p.dbg = g_gemm_dbg;
+  {
+    static const int skipb = getenv("EGB_GEMM_SKIPB") ? atoi(getenv("EGB_GEMM_SKIPB")) : 0;
+    p.dbg_skip = skipb;
+  }
   switch (BN) {
     case 256: return launch_tc<256>(ma, mb, p, stream);
     case 128: return launch_tc<128>(ma, mb, p, stream);

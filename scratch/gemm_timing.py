@@ -23,10 +23,7 @@ def run(M, N, K, tag, bias=True, res=False):
     lead = act[act[:, 1] + act[:, 2] > 0]
     ms = e0.elapsed_time(e1)
     print(f"{tag:10s} M={M} N={N} K={K}: {ms*1e3:7.1f} us {2*M*N*K/ms*1e-9:7.1f} TF/s | kernel cyc {act[:,4].mean():9.0f} | producer wait-empty {act[:,0].mean()/act[:,4].mean():5.1%} | MMA wait-operands {lead[:,1].mean()/lead[:,4].mean():5.1%} wait-acc-drain {lead[:,2].mean()/lead[:,4].mean():5.1%} | epilogue wait-acc {act[:,3].mean()/act[:,4].mean():5.1%}")
-for pair in ("1", "0"):
-    os.environ["EGB_GEMM_PAIR"] = pair
-    print("EGB_GEMM_PAIR =", pair, "(note: read once per process; run twice)")
-    break
+print("EGB_GEMM_PAIR =", os.environ.get("EGB_GEMM_PAIR"), "EGB_GEMM_SKIPB =", os.environ.get("EGB_GEMM_SKIPB"))
 run(50432, 768, 3072, "fc2", res=True)
 run(50432, 2304, 768, "qkv")
 run(50432, 3072, 768, "fc1-nobias", bias=False)
