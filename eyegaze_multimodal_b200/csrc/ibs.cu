@@ -132,105 +132,152 @@ __global__ void __launch_bounds__(256) ibs_analytic_kernel(const float* __restri
   }
 }
 
-constexpr int IBS_TI = 8;    // player-1 channels per CTA
-constexpr int IBS_TC = 64;   // time samples per shared-memory chunk
+constexpr int IBS_BI = 32;   // player-1 channels per CTA (8 warps x 4 channels held in registers per thread)
+constexpr int IBS_BJ = 32;   // player-2 channels per CTA (one per lane)
+constexpr int IBS_TC = 32;   // time samples per shared-memory chunk
 constexpr int IBS_NF = 6;    // per-sample derived quantities: phase, cos, sin, p, zx, zp
+constexpr int IBS_PI = IBS_BI + 4;   // pitch of the [t][i] tile (floats): 16-byte aligned groups of 4 channels,
+                                     // conflict-free for the 4-channel x 8-sample staging pattern
+constexpr int IBS_PJ = IBS_TC + 1;
 
 // feature slots in the output: out[b][band][slot][i][j]; slot_of[f] < 0 drops feature f
 struct IbsSlots { int slot_of[7]; int n_out; };
 
+// One CTA = a 32 x 32 block of channel pairs of one (trial, band); the T axis streams through shared memory in
+// chunks.  A thread owns 4 player-1 channels x 1 player-2 channel: per sample it reads its player-2 values once
+// (6 scalar LDS) and the 4 player-1 values of each quantity with one broadcast LDS.128 -- 3 shared-memory loads per
+// pair-sample instead of 12 -- and every channel's sin/cos is derived once per CTA, not once per 8-channel tile.
 __global__ void __launch_bounds__(256) ibs_pairs_kernel(const float* __restrict__ phase, const float* __restrict__ xb,
                                                         const float* __restrict__ stats, const float* __restrict__ pspec,
                                                         float* __restrict__ out, IbsBands bands, IbsSlots slots, int B,
                                                         int C, int T, int lo_min, int nbins) {
   extern __shared__ float sm[];
-  const int ldj = IBS_TC + 1;
-  float* si = sm;                              // [NF][TI][TC]
-  float* sj = si + IBS_NF * IBS_TI * IBS_TC;   // [NF][C][TC+1]
-  const int i0 = blockIdx.x * IBS_TI, bi = blockIdx.y, b = blockIdx.z;
-  const int ti = threadIdx.x >> 5;             // 0..7  -> player-1 channel i0 + ti
-  const int lane = threadIdx.x & 31;           // player-2 channels lane, lane+32, ...
-  const int i = i0 + ti;
+  float* si = sm;                                  // [NF][TC][PI]   (channel fastest)
+  float* sj = si + IBS_NF * IBS_TC * IBS_PI;       // [NF][BJ][TC+1] (time fastest)
+  const int nJ = (C + IBS_BJ - 1) / IBS_BJ;
+  const int i0 = (blockIdx.x / nJ) * IBS_BI, j0 = (blockIdx.x % nJ) * IBS_BJ;
+  const int bi = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long base1 = ((((long long)b * bands.nb + bi) * 2 + 0) * C) * T;
   const long long base2 = ((((long long)b * bands.nb + bi) * 2 + 1) * C) * T;
   const float* st1 = stats + ((((long long)b * bands.nb + bi) * 2 + 0) * C) * 8;
   const float* st2 = stats + ((((long long)b * bands.nb + bi) * 2 + 1) * C) * 8;
-  constexpr int MAXJ = 4;  // C <= 128
-  float a_re[MAXJ], a_im[MAXJ], a_sg[MAXJ], a_w[MAXJ], a_pd[MAXJ], a_pc[MAXJ], a_tc[MAXJ];
+  float a_re[4], a_im[4], a_sg[4], a_w[4], a_pd[4], a_pc[4], a_tc[4];
 #pragma unroll
-  for (int q = 0; q < MAXJ; ++q) a_re[q] = a_im[q] = a_sg[q] = a_w[q] = a_pd[q] = a_pc[q] = a_tc[q] = 0.f;
+  for (int q = 0; q < 4; ++q) a_re[q] = a_im[q] = a_sg[q] = a_w[q] = a_pd[q] = a_pc[q] = a_tc[q] = 0.f;
+
+  // per-channel statistics of the 64 channels of this block: {mean_x, rstd_x, mean_p, rstd_p}
+  __shared__ float4 s_stat[IBS_BI + IBS_BJ];
+  if (threadIdx.x < IBS_BI + IBS_BJ) {
+    const bool is_i = threadIdx.x < IBS_BI;
+    const int ch = is_i ? i0 + threadIdx.x : j0 + threadIdx.x - IBS_BI;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch < C) {
+      const float* sst = (is_i ? st1 : st2) + ch * 8;
+      v = make_float4(sst[0], sst[1], sst[2], sst[3]);
+    }
+    s_stat[threadIdx.x] = v;
+  }
+  // Staging slots of this thread (fixed for all chunks): 4 player-1 elements (4 channels x 8 samples per warp pass)
+  // and 4 player-2 elements (lanes along time).  The raw (phase, xb) values of the NEXT chunk are fetched into
+  // registers before the current chunk's pair loop, so their global-memory latency hides behind the arithmetic.
+  int ri[4], ti[4], rj[4], tj[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = threadIdx.x + k * 256;
+    const int blk = idx >> 5, l = idx & 31;
+    ri[k] = (blk / (IBS_TC / 8)) * 4 + (l >> 3);
+    ti[k] = (blk % (IBS_TC / 8)) * 8 + (l & 7);
+    rj[k] = idx / IBS_TC;
+    tj[k] = idx % IBS_TC;
+  }
+  float raw_ph[8], raw_x[8];
+  auto fetch = [&](int t0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int chi = i0 + ri[k], chj = j0 + rj[k];
+      const bool vi = chi < C && t0 + ti[k] < T, vj = chj < C && t0 + tj[k] < T;
+      const long long oi = base1 + (long long)chi * T + t0 + ti[k], oj = base2 + (long long)chj * T + t0 + tj[k];
+      raw_ph[k] = vi ? __ldg(phase + oi) : 0.f;
+      raw_x[k] = vi ? __ldg(xb + oi) : 0.f;
+      raw_ph[4 + k] = vj ? __ldg(phase + oj) : 0.f;
+      raw_x[4 + k] = vj ? __ldg(xb + oj) : 0.f;
+    }
+  };
+  fetch(0);
+  __syncthreads();   // s_stat visible
 
   for (int t0 = 0; t0 < T; t0 += IBS_TC) {
-    __syncthreads();
-    // stage player-1 tile and all player-2 channels for this time chunk, deriving cos/sin/p/z-scores
-    for (int idx = threadIdx.x; idx < (IBS_TI + C) * IBS_TC; idx += blockDim.x) {
-      const int r = idx / IBS_TC, t = idx % IBS_TC;
-      const bool is_i = r < IBS_TI;
-      const int ch = is_i ? i0 + r : r - IBS_TI;
-      float ph = 0.f, x = 0.f, mx = 0.f, rx = 0.f, mp = 0.f, rp = 0.f;
-      if (ch < C && t0 + t < T) {
-        const long long off = (is_i ? base1 : base2) + (long long)ch * T + t0 + t;
-        const float* s = (is_i ? st1 : st2) + ch * 8;
-        ph = phase[off]; x = xb[off];
-        mx = s[0]; rx = s[1]; mp = s[2]; rp = s[3];
-      }
+    __syncthreads();   // previous chunk's readers are done
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const bool is_i = k < 4;
+      const int r = is_i ? ri[k] : rj[k - 4], t = is_i ? ti[k] : tj[k - 4];
+      const int ch = (is_i ? i0 : j0) + r;
+      const bool valid = ch < C && t0 + t < T;   // samples past T / channels past C contribute exactly zero
+      const float4 st = s_stat[is_i ? r : IBS_BI + r];
+      const float ph = raw_ph[k], x = raw_x[k];
       float sn, cs;
       sincosf(ph, &sn, &cs);
-      const float p = x * x;
-      const bool valid = ch < C && t0 + t < T;
-      float vals[IBS_NF] = {ph, cs, sn, p, (x - mx) * rx, (p - mp) * rp};
-      if (!valid) { vals[1] = 0.f; vals[2] = 0.f; }   // padded samples contribute nothing
+      const float pw = x * x;
+      const float vals[IBS_NF] = {ph, valid ? cs : 0.f, valid ? sn : 0.f, pw, valid ? (x - st.x) * st.y : 0.f,
+                                  valid ? (pw - st.z) * st.w : 0.f};
 #pragma unroll
       for (int f = 0; f < IBS_NF; ++f) {
-        if (is_i) si[(f * IBS_TI + r) * IBS_TC + t] = vals[f];
-        else sj[(f * C + ch) * ldj + t] = vals[f];
+        if (is_i) si[(f * IBS_TC + t) * IBS_PI + r] = vals[f];
+        else sj[(f * IBS_BJ + r) * IBS_PJ + t] = vals[f];
       }
     }
+    if (t0 + IBS_TC < T) fetch(t0 + IBS_TC);
     __syncthreads();
-    if (i < C) {
-      const int tmax = min(IBS_TC, T - t0);
+    // chunk-local partial sums, folded into the running totals once per chunk (two-level summation)
+    float l_re[4], l_im[4], l_sg[4], l_w[4], l_pd[4], l_pc[4], l_tc[4];
 #pragma unroll
-      for (int q = 0; q < MAXJ; ++q) {
-        const int j = q * 32 + lane;
-        if (j < C) {
-          const float* pi = si + ti * IBS_TC;
-          const float* pj = sj + j * ldj;
-          // chunk-local partial sums, folded into the running totals once per chunk (two-level summation)
-          float l_re = 0.f, l_im = 0.f, l_sg = 0.f, l_w = 0.f, l_pd = 0.f, l_pc = 0.f, l_tc = 0.f;
-          for (int t = 0; t < tmax; ++t) {
-            const float ph1 = pi[t], c1 = pi[(1 * IBS_TI) * IBS_TC + t], s1 = pi[(2 * IBS_TI) * IBS_TC + t];
-            const float p1 = pi[(3 * IBS_TI) * IBS_TC + t], zx1 = pi[(4 * IBS_TI) * IBS_TC + t], zp1 = pi[(5 * IBS_TI) * IBS_TC + t];
-            const float ph2 = pj[t], c2 = pj[(1 * C) * ldj + t], s2 = pj[(2 * C) * ldj + t];
-            const float p2 = pj[(3 * C) * ldj + t], zx2 = pj[(4 * C) * ldj + t], zp2 = pj[(5 * C) * ldj + t];
-            const float d = ph1 - ph2;
-            const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-            l_re += c1 * c2 + s1 * s2;
-            l_im += s1 * c2 - c1 * s2;
-            l_sg += sg;
-            l_w += sg * ((p1 + p2) * 0.5f);
-            l_pd += fabsf(d);
-            l_pc = fmaf(zp1, zp2, l_pc);
-            l_tc = fmaf(zx1, zx2, l_tc);
-          }
-          a_re[q] += l_re; a_im[q] += l_im; a_sg[q] += l_sg; a_w[q] += l_w; a_pd[q] += l_pd; a_pc[q] += l_pc; a_tc[q] += l_tc;
-        }
+    for (int q = 0; q < 4; ++q) l_re[q] = l_im[q] = l_sg[q] = l_w[q] = l_pd[q] = l_pc[q] = l_tc[q] = 0.f;
+    const float* pj = sj + lane * IBS_PJ;
+#pragma unroll 8
+    for (int t = 0; t < IBS_TC; ++t) {
+      const float ph2 = pj[t], c2 = pj[(1 * IBS_BJ) * IBS_PJ + t], s2 = pj[(2 * IBS_BJ) * IBS_PJ + t];
+      const float p2 = pj[(3 * IBS_BJ) * IBS_PJ + t], zx2 = pj[(4 * IBS_BJ) * IBS_PJ + t], zp2 = pj[(5 * IBS_BJ) * IBS_PJ + t];
+      const float4* pi = reinterpret_cast<const float4*>(si + t * IBS_PI + warp * 4);
+      const float4 ph1 = pi[0], c1 = pi[(1 * IBS_TC * IBS_PI) / 4], s1 = pi[(2 * IBS_TC * IBS_PI) / 4];
+      const float4 p1 = pi[(3 * IBS_TC * IBS_PI) / 4], zx1 = pi[(4 * IBS_TC * IBS_PI) / 4], zp1 = pi[(5 * IBS_TC * IBS_PI) / 4];
+      const float ph1a[4] = {ph1.x, ph1.y, ph1.z, ph1.w}, c1a[4] = {c1.x, c1.y, c1.z, c1.w}, s1a[4] = {s1.x, s1.y, s1.z, s1.w};
+      const float p1a[4] = {p1.x, p1.y, p1.z, p1.w}, zx1a[4] = {zx1.x, zx1.y, zx1.z, zx1.w}, zp1a[4] = {zp1.x, zp1.y, zp1.z, zp1.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float d = ph1a[q] - ph2;
+        const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        l_re[q] += c1a[q] * c2 + s1a[q] * s2;
+        l_im[q] += s1a[q] * c2 - c1a[q] * s2;
+        l_sg[q] += sg;
+        l_w[q] += sg * ((p1a[q] + p2) * 0.5f);
+        l_pd[q] += fabsf(d);
+        l_pc[q] = fmaf(zp1a[q], zp2, l_pc[q]);
+        l_tc[q] = fmaf(zx1a[q], zx2, l_tc[q]);
       }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a_re[q] += l_re[q]; a_im[q] += l_im[q]; a_sg[q] += l_sg[q]; a_w[q] += l_w[q];
+      a_pd[q] += l_pd[q]; a_pc[q] += l_pc[q]; a_tc[q] += l_tc[q];
     }
   }
-  if (i >= C) return;
+  const int j = j0 + lane;
+  if (j >= C) return;
   const float invT = 1.f / (float)T;
   const int klo = bands.lo[bi], khi = bands.hi[bi];
-  const float* ps1 = pspec + (((long long)b * 2 + 0) * C + i) * nbins;
-  const float sum_p1 = st1[i * 8 + 4];
+  const float* ps2 = pspec + (((long long)b * 2 + 1) * C + j) * nbins;
+  const float sum_p2 = st2[j * 8 + 4];
 #pragma unroll
-  for (int q = 0; q < MAXJ; ++q) {
-    const int j = q * 32 + lane;
-    if (j >= C) continue;
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + warp * 4 + q;
+    if (i >= C) continue;
     float feat[7];
     feat[0] = sqrtf(a_re[q] * a_re[q] + a_im[q] * a_im[q]) * invT;
     feat[1] = fabsf(a_sg[q] * invT);
-    feat[2] = fabsf(a_w[q] / ((sum_p1 + st2[j * 8 + 4]) * 0.5f + 1e-8f));
-    const float* ps2 = pspec + (((long long)b * 2 + 1) * C + j) * nbins;
+    feat[2] = fabsf(a_w[q] / ((st1[i * 8 + 4] + sum_p2) * 0.5f + 1e-8f));
+    const float* ps1 = pspec + (((long long)b * 2 + 0) * C + i) * nbins;
     float coh = 0.f;
     for (int k = klo; k <= khi; ++k) {
       const float pp = ps1[k - lo_min] * ps2[k - lo_min];
@@ -346,13 +393,14 @@ int egb_ibs_connectivity(const float* eeg1, const float* eeg2, const float* twid
   ibs_analytic_kernel<<<dim3(C, 2, B), 256, smem1, st>>>(eeg1, eeg2, (const float2*)twiddle, phase, xb, stats, pspec,
                                                          bands, B, C, T, logT, lo_min, nbins);
   EGB_LAUNCH_CHECK();
-  const size_t smem2 = sizeof(float) * ((size_t)IBS_NF * IBS_TI * IBS_TC + (size_t)IBS_NF * C * (IBS_TC + 1));
+  const size_t smem2 = sizeof(float) * ((size_t)IBS_NF * IBS_TC * IBS_PI + (size_t)IBS_NF * IBS_BJ * IBS_PJ);
   static size_t smem2_set = 0;
   if (smem2 > 48 * 1024 && smem2 > smem2_set) {
     EGB_CUDA(cudaFuncSetAttribute(ibs_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     smem2_set = smem2;
   }
-  ibs_pairs_kernel<<<dim3((C + IBS_TI - 1) / IBS_TI, n_bands, B), 256, smem2, st>>>(phase, xb, stats, pspec, out, bands,
+  const int n_blk = ((C + IBS_BI - 1) / IBS_BI) * ((C + IBS_BJ - 1) / IBS_BJ);
+  ibs_pairs_kernel<<<dim3(n_blk, n_bands, B), 256, smem2, st>>>(phase, xb, stats, pspec, out, bands,
                                                                                   slots, B, C, T, lo_min, nbins);
   egb_count_launch(2);
   EGB_LAUNCH_CHECK();

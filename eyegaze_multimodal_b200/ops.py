@@ -825,7 +825,7 @@ def band_bins(T, fs, bands):
     return lo_hi
 
 
-def ibs_connectivity(eeg1, eeg2, fs, bands, feature_indices, chunk=64):
+def ibs_connectivity(eeg1, eeg2, fs, bands, feature_indices, chunk=256):
     """(B,C,T) x2 fp32 -> (B, n_bands, len(feature_indices), C, C) fp32.  Batch is processed in chunks so the
     phase / band-passed scratch stays bounded."""
     _require_cuda(eeg1, eeg2)
