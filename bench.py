@@ -433,9 +433,32 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    # stdout carries exactly ONE JSON line: anything a library prints while we run (NCCL's version banner, warnings
+    # from C code) is diverted to stderr at the file-descriptor level and stdout is restored for the final print.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    sys.stdout = real_stdout_proxy = _Tee(real_stdout)
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_b200(args)
+    finally:
+        real_stdout_proxy.flush()
+
+
+class _Tee:
+    """print() goes to the REAL stdout (saved descriptor); C-level writes to fd 1 go to stderr."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def write(self, x):
+        return self.f.write(x)
+
+    def flush(self):
+        self.f.flush()
 
 
 if __name__ == "__main__":

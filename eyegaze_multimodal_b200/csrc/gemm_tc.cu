@@ -72,7 +72,11 @@ struct TcConfig {
 template <int TILE>
 __device__ __forceinline__ void load_operand_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int major,
                                                   int rpg, int seg, int shift, int tile, int kb) {
-  if (major == 0) {
+  if (major == 1 && rpg < 0) {
+    // chunked MN-major map {64 mn, k rows, 64-wide chunks}: ONE box {64, BK, TILE/64} lands as TILE/64 consecutive
+    // [BK rows][128 B] chunks -- exactly the MN-major UMMA layout -- with a single TMA instruction
+    ptx::tma_load_3d(dst, tm, bar, 0, kb * BK, tile * (TILE / 64));
+  } else if (major == 0) {
     int inner0 = kb * BK, row0 = tile * TILE;
     if (seg > 0) { row0 += (inner0 / seg) * shift; inner0 %= seg; }
     ptx::tma_load_3d(dst, tm, bar, inner0, row0 % rpg, row0 / rpg);
@@ -92,7 +96,9 @@ __device__ __forceinline__ void load_operand_tile(uint8_t* dst, const CUtensorMa
 template <int TILE>
 __device__ __forceinline__ void load_operand_tile_2sm(uint8_t* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
                                                       int major, int rpg, int seg, int shift, int tile, int kb) {
-  if (major == 0) {
+  if (major == 1 && rpg < 0) {
+    ptx::tma_load_3d_2sm(dst, tm, bar_cluster_addr, 0, kb * BK, tile * (TILE / 64));
+  } else if (major == 0) {
     int inner0 = kb * BK, row0 = tile * TILE;
     if (seg > 0) { row0 += (inner0 / seg) * shift; inner0 %= seg; }
     ptx::tma_load_3d_2sm(dst, tm, bar_cluster_addr, inner0, row0 % rpg, row0 / rpg);
@@ -570,6 +576,36 @@ int make_map(CUtensorMap* out, const void* ptr, long long inner, long long rows,
 
 // builds the map of one operand. `tile_rows` = BM or BN; `extent_mn` = M or N; K = reduction length
 int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int K, int tile_rows, int* rpg_out) {
+  if (o.major == 1 && o.seg_len == 0 && (o.rows_per_group <= 0 || o.rows_per_group >= K) && (extent_mn % 64) == 0 &&
+      tile_rows >= 64) {
+    // MN-major, single group, MN extent a multiple of 64: 3-D map {64, K rows, extent/64 chunks} (chunk stride 128 B)
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = o.ptr; key.inner = 64; key.rows = K; key.groups = extent_mn / 64; key.rs = o.row_stride; key.gs = -64;
+    key.b0 = 64; key.b1 = BK; key.b2 = tile_rows / 64;
+    *rpg_out = -1;
+    {
+      std::lock_guard<std::mutex> lk(g_maps_mu);
+      auto it = g_maps.find(key);
+      if (it != g_maps.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    EGB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    EGB_CHECK(((uintptr_t)o.ptr % 16) == 0 && (o.row_stride % 8) == 0 && o.row_stride > 0, "TMA operand misaligned");
+    cuuint64_t dims[3] = {64u, (cuuint64_t)K, (cuuint64_t)(extent_mn / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)o.row_stride * 2, 128u};
+    cuuint32_t box[3] = {64u, (cuuint32_t)BK, (cuuint32_t)(tile_rows / 64)};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (chunked MN-major) failed (%d): K=%d extent=%d rs=%lld", (int)r, K,
+              extent_mn, (long long)o.row_stride);
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    if (g_maps.size() > 8192) g_maps.clear();
+    g_maps[key] = *out;
+    return 0;
+  }
   const long long total_rows = o.major == 0 ? extent_mn : K;
   long long rpg = o.rows_per_group > 0 ? o.rows_per_group : total_rows;
   long long groups = (total_rows + rpg - 1) / rpg;

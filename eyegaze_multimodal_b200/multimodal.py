@@ -1,5 +1,6 @@
 """MultimodalFusionModel + its loss -- the glue module the reference defines inside its training script
 (4_Experiments/scripts/train_multimodal_fuzzy_fusion.py:106-179, loss at :436-460)."""
+import os
 from typing import Dict, Optional
 
 import torch
@@ -22,10 +23,29 @@ class MultimodalFusionModel(nn.Module):
             for p in self.eeg_encoder.parameters():
                 p.requires_grad = False
 
+    # The two encoders are independent until the fusion head (train_multimodal_fuzzy_fusion.py:162-166), forward
+    # and backward.  On CUDA the EEG branch is enqueued on a side stream: its latency-bound kernels (FFT / connectivity
+    # / spectrogram prologue, small-K GEMMs) fill the gaps the ViT's big GEMMs leave, and autograd replays each
+    # branch's backward on the stream its forward ran on, so the backward overlaps the same way.
+    concurrent_branches = os.environ.get("EGB_CONCURRENT_BRANCHES", "1") != "0"
+
     def forward(self, img1: torch.Tensor, img2: torch.Tensor, eeg1: torch.Tensor, eeg2: torch.Tensor,
                 labels: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        img_logits = self.gaze_encoder(img1, img2)
-        eeg_logits = self.eeg_encoder(eeg1, eeg2, labels)['logits']
+        if self.concurrent_branches and eeg1.is_cuda:
+            cur = torch.cuda.current_stream(eeg1.device)
+            side = getattr(self, "_side_stream", None)
+            if side is None or side.device != eeg1.device:
+                side = torch.cuda.Stream(device=eeg1.device)
+                object.__setattr__(self, "_side_stream", side)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                eeg_logits = self.eeg_encoder(eeg1, eeg2, labels)['logits']
+            img_logits = self.gaze_encoder(img1, img2)
+            cur.wait_stream(side)
+            eeg_logits.record_stream(cur)
+        else:
+            img_logits = self.gaze_encoder(img1, img2)
+            eeg_logits = self.eeg_encoder(eeg1, eeg2, labels)['logits']
         fused_logits, alpha, aux_info = self.fusion(img_logits, eeg_logits)
         return {'fused_logits': fused_logits, 'img_logits': img_logits, 'eeg_logits': eeg_logits, 'alpha': alpha,
                 'aux_info': aux_info}

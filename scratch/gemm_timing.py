@@ -29,3 +29,25 @@ run(50432, 2304, 768, "qkv")
 run(50432, 3072, 768, "fc1-nobias", bias=False)
 run(71168, 1024, 256, "eeg_ffn1")
 run(8192, 8192, 8192, "cublas-ref", bias=False)
+
+def run_dw(M, N, K, tag):
+    """dW[N_out=M, K_in=N] = dy^T x with K = rows (split-K accumulate)"""
+    dy = torch.randn(K, M, device=dev).bfloat16()
+    x = (torch.randn(K, N, device=dev) * 0.5).bfloat16()
+    with torch.no_grad():
+        for _ in range(3): ops._grad_weight(dy, x, M, N)
+        torch.cuda.synchronize()
+        buf.zero_()
+        L.call("egb_debug_gemm_timing", buf.data_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops._grad_weight(dy, x, M, N); e1.record()
+        torch.cuda.synchronize()
+        L.call("egb_debug_gemm_timing", None)
+    t = buf.float().cpu()
+    act = t[t[:, 4] > 0]
+    lead = act[act[:, 1] + act[:, 2] > 0]
+    ms = e0.elapsed_time(e1)
+    print(f"{tag:10s} dW M={M} N={N} K={K}: {ms*1e3:7.1f} us {2*M*N*K/ms*1e-9:7.1f} TF/s | ctas {len(act)} lead {len(lead)} kernel cyc {lead[:,4].mean():9.0f} (max {lead[:,4].max():9.0f} min {lead[:,4].min():9.0f}) | MMA wait-operands {lead[:,1].mean()/lead[:,4].mean():5.1%} wait-acc-drain {lead[:,2].mean()/lead[:,4].mean():5.1%}")
+run_dw(3072, 768, 50432, "fc1_dw")
+run_dw(2304, 768, 50432, "qkv_dw")
+run_dw(768, 768, 50432, "proj_dw")
