@@ -42,6 +42,7 @@ struct TcParams {
   EpiParams epi;
   long long* dbg;  // optional [gridDim.x][8] cycle counters (egb_debug_gemm_timing)
   int dbg_skip;    // experiment switch (EGB_GEMM_SKIPB=1): see the pair producer
+  int bkt;         // K extent of one pipeline stage of the pair kernel (64 or 128)
 };
 
 // cycles spent inside a barrier wait, accumulated into *acc when profiling is on
@@ -335,20 +336,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // barrier; MMA completion is multicast to both CTAs' "empty" / "accumulator full" barriers; the epilogue warps of
 // both CTAs release the accumulator on the leader's barrier.
 // ================================================================================================
-template <int BN>
+template <int BN, int BKT>
 struct Tc2Config {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int A_BYTES = BM * BKT * 2;
+  static constexpr int B_BYTES = (BN / 2) * BKT * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = (BKT == 128) ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EF>
+// Operand tile of one pipeline stage for the pair kernel.  BKT = 128 ("super-stages") is used when both operands have
+// chunked tensor maps: ONE TMA instruction then brings a whole [TILE x 128] tile (two 64-wide K chunks for a K-major
+// operand, TILE/64 MN chunks of 128 k-rows for an MN-major one).  The per-instruction cost of TMA, not bytes, was what
+// starved the MMA warp (measured: MN-major dW GEMMs 760 -> 1218 TFLOP/s when 4 boxes per stage became 2).
+template <int TILE, int BKT>
+__device__ __forceinline__ void load_stage_operand_2sm(uint8_t* dst, const CUtensorMap* tm, uint32_t bar, int major, int rpg,
+                                                       int seg, int shift, int tile, int kb) {
+  if (BKT == 64) {
+    load_operand_tile_2sm<TILE>(dst, tm, bar, major, rpg, seg, shift, tile, kb);
+  } else if (major == 0) {   // chunked K-major map {64 k, rows, K/64 chunks}: box {64, TILE, 2}
+    ptx::tma_load_3d_2sm(dst, tm, bar, 0, tile * TILE, kb * (BKT / 64));
+  } else {                   // chunked MN-major map {64 mn, k rows, extent/64 chunks}: box {64, BKT, TILE/64}
+    ptx::tma_load_3d_2sm(dst, tm, bar, 0, kb * BKT, tile * (TILE / 64));
+  }
+}
+
+template <int BN, int EF, int BKT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Cfg = Tc2Config<BN>;
+  using Cfg = Tc2Config<BN, BKT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
@@ -414,9 +431,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          load_operand_tile_2sm<BM>(sa, &tmA, lead_bar, p.a_major, p.a_rpg, p.a_seg, p.a_shift, mt * 2 + (int)rank, kb);
+          load_stage_operand_2sm<BM, BKT>(sa, &tmA, lead_bar, p.a_major, p.a_rpg, p.a_seg, p.a_shift, mt * 2 + (int)rank, kb);
           if (!skip_b)
-            load_operand_tile_2sm<BN / 2>(sb, &tmB, lead_bar, p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt * 2 + (int)rank, kb);
+            load_stage_operand_2sm<BN / 2, BKT>(sb, &tmB, lead_bar, p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt * 2 + (int)rank, kb);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -444,12 +461,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) {
             const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
             const uint32_t sb = sa + Cfg::A_BYTES;
-            const uint64_t adesc = ptx::make_smem_desc(sa, p.a_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
-            const uint64_t bdesc = ptx::make_smem_desc(sb, p.b_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
+            const uint64_t adesc = ptx::make_smem_desc(sa, p.a_major == 0 ? 16u : (uint32_t)(BKT * 128), 1024u);
+            const uint64_t bdesc = ptx::make_smem_desc(sb, p.b_major == 0 ? 16u : (uint32_t)(BKT * 128), 1024u);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              ptx::umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                                 (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BKT / 16; ++k) {
+              // K-major: 32 B per UMMA_K inside a 64-wide chunk, chunks of [rows][128 B] back to back;
+              // MN-major: 16 k-rows = 2048 B per UMMA_K
+              const uint32_t ao = p.a_major == 0 ? (uint32_t)((k >> 2) * (BM * 128 / 16) + (k & 3) * 2) : (uint32_t)(k * a_adv);
+              const uint32_t bo = p.b_major == 0 ? (uint32_t)((k >> 2) * ((BN / 2) * 128 / 16) + (k & 3) * 2) : (uint32_t)(k * b_adv);
+              ptx::umma_bf16_2sm(tmem_d, adesc + (uint64_t)ao, bdesc + (uint64_t)bo, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit_2sm(&empty_bar[stage], 3);  // both CTAs' smem slots reusable once these MMAs retire
             if (kb == kb1 - 1) ptx::umma_commit_2sm(&tfull_bar[acc], 3);
@@ -575,14 +595,53 @@ int make_map(CUtensorMap* out, const void* ptr, long long inner, long long rows,
 }
 
 // builds the map of one operand. `tile_rows` = BM or BN; `extent_mn` = M or N; K = reduction length
-int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int K, int tile_rows, int* rpg_out) {
+// true when the operand can use a chunked map (single group, no segmentation, 64-aligned extents)
+bool operand_chunkable(const egb_operand& o, int extent_mn, int K) {
+  if (o.seg_len != 0) return false;
+  const long long total_rows = o.major == 0 ? extent_mn : K;
+  if (o.rows_per_group > 0 && o.rows_per_group < total_rows) return false;
+  if (o.major == 0) return (K % 64) == 0;
+  return (extent_mn % 64) == 0;
+}
+
+// chunked K-major map for BK = 128 stages: {64 k, rows, K/64 chunks}, box {64, tile_rows, 2}
+int make_kmajor_chunked_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int K, int tile_rows) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = o.ptr; key.inner = 64; key.rows = extent_mn; key.groups = K / 64; key.rs = o.row_stride; key.gs = -128;
+  key.b0 = 64; key.b1 = tile_rows; key.b2 = 2;
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  EGB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  EGB_CHECK(((uintptr_t)o.ptr % 16) == 0 && (o.row_stride % 8) == 0 && o.row_stride > 0, "TMA operand misaligned");
+  cuuint64_t dims[3] = {64u, (cuuint64_t)extent_mn, (cuuint64_t)(K / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)o.row_stride * 2, 128u};
+  cuuint32_t box[3] = {64u, (cuuint32_t)tile_rows, 2u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (chunked K-major) failed (%d): K=%d extent=%d rs=%lld", (int)r, K,
+            extent_mn, (long long)o.row_stride);
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps[key] = *out;
+  return 0;
+}
+
+int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int K, int tile_rows, int* rpg_out,
+                     int bk = BK) {
   if (o.major == 1 && o.seg_len == 0 && (o.rows_per_group <= 0 || o.rows_per_group >= K) && (extent_mn % 64) == 0 &&
       tile_rows >= 64) {
     // MN-major, single group, MN extent a multiple of 64: 3-D map {64, K rows, extent/64 chunks} (chunk stride 128 B)
     MapKey key;
     memset(&key, 0, sizeof(key));
     key.ptr = o.ptr; key.inner = 64; key.rows = K; key.groups = extent_mn / 64; key.rs = o.row_stride; key.gs = -64;
-    key.b0 = 64; key.b1 = BK; key.b2 = tile_rows / 64;
+    key.b0 = 64; key.b1 = bk; key.b2 = tile_rows / 64;
     *rpg_out = -1;
     {
       std::lock_guard<std::mutex> lk(g_maps_mu);
@@ -594,7 +653,7 @@ int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int 
     EGB_CHECK(((uintptr_t)o.ptr % 16) == 0 && (o.row_stride % 8) == 0 && o.row_stride > 0, "TMA operand misaligned");
     cuuint64_t dims[3] = {64u, (cuuint64_t)K, (cuuint64_t)(extent_mn / 64)};
     cuuint64_t strides[2] = {(cuuint64_t)o.row_stride * 2, 128u};
-    cuuint32_t box[3] = {64u, (cuuint32_t)BK, (cuuint32_t)(tile_rows / 64)};
+    cuuint32_t box[3] = {64u, (cuuint32_t)bk, (cuuint32_t)(tile_rows / 64)};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -678,12 +737,12 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, c
   EGB_EF_SWITCH(launch_tc_ef, BN, true)
 }
 
-template <int BN, int EF>
-int launch_tc2_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
-  using Cfg = Tc2Config<BN>;
+template <int BN, int EF, int BKT>
+int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  using Cfg = Tc2Config<BN, BKT>;
   static bool attr_set = false;
   if (!attr_set) {
-    EGB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    EGB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EF, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
@@ -694,11 +753,17 @@ int launch_tc2_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& 
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
   }
-  gemm_tc2_kernel<BN, EF><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  gemm_tc2_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
   if (prof) egb_prof_end(stream);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, int EF>
+int launch_tc2_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  if (p.bkt == 128) return launch_tc2_ef_bk<BN, EF, 128>(ma, mb, p, stream);
+  return launch_tc2_ef_bk<BN, EF, 64>(ma, mb, p, stream);
 }
 
 template <int BN>
@@ -715,11 +780,20 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
   p.a_seg = d->a.seg_len; p.a_shift = d->a.seg_row_shift;
   p.b_seg = d->b.seg_len; p.b_shift = d->b.seg_row_shift;
   CUtensorMap ma, mb;
-  if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg)) return 1;
-  if (make_operand_map(&mb, d->b, d->N, d->K, BN / 2, &p.b_rpg)) return 1;
+  static const int bk128 = getenv("EGB_GEMM_BK128") ? atoi(getenv("EGB_GEMM_BK128")) : 1;
+  p.bkt = (bk128 && operand_chunkable(d->a, d->M, d->K) && operand_chunkable(d->b, d->N, d->K)) ? 128 : 64;
+  if (p.bkt == 128) {
+    if (d->a.major == 0) { if (make_kmajor_chunked_map(&ma, d->a, d->M, d->K, BM)) return 1; p.a_rpg = -2; }
+    else if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg, 128)) return 1;
+    if (d->b.major == 0) { if (make_kmajor_chunked_map(&mb, d->b, d->N, d->K, BN / 2)) return 1; p.b_rpg = -2; }
+    else if (make_operand_map(&mb, d->b, d->N, d->K, BN / 2, &p.b_rpg, 128)) return 1;
+  } else {
+    if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg)) return 1;
+    if (make_operand_map(&mb, d->b, d->N, d->K, BN / 2, &p.b_rpg)) return 1;
+  }
   p.m_tiles = (d->M + 2 * BM - 1) / (2 * BM);
   p.n_tiles = (d->N + BN - 1) / BN;
-  p.k_blocks = (d->K + BK - 1) / BK;
+  p.k_blocks = (d->K + p.bkt - 1) / p.bkt;
   int split = 1;
   if (d->accumulate) {
     split = d->split_k;
@@ -727,7 +801,7 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
       // pick the split whose work-item count fills whole waves of CTA pairs best (each item keeps >= 16 k-blocks)
       const int tiles = p.m_tiles * p.n_tiles;
       const int pairs = egb_num_sms() / 2;
-      int max_split = p.k_blocks / 16;
+      int max_split = p.k_blocks / (p.bkt == 128 ? 8 : 16);
       if (max_split > 64) max_split = 64;
       if (max_split < 1) max_split = 1;
       double best = -1.0;
@@ -737,7 +811,7 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
         const int items = tiles * ((p.k_blocks + kps - 1) / kps);
         const int waves = (items + pairs - 1) / pairs;
         // time ~ waves * (k-blocks per item + fixed per-item cost of the accumulate epilogue, ~12 k-blocks)
-        const double cost = (double)waves * (kps + 12);
+        const double cost = (double)waves * (kps + (p.bkt == 128 ? 6 : 12));
         const double score = 1.0 / cost;
         if (score > best * 1.0001) { best = score; split = sp; }
       }
