@@ -57,12 +57,12 @@ struct TcParams {
     }                                    \
   } while (0)
 
-template <int BN>
+template <int BN, int BKT = 64>
 struct TcConfig {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int A_BYTES = BM * BKT * 2;
+  static constexpr int B_BYTES = BN * BKT * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 5 : 7);
+  static constexpr int STAGES = (BKT == 128) ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4)) : ((BN == 256) ? 4 : (BN == 128 ? 5 : 7));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -123,6 +123,24 @@ __device__ __forceinline__ void load_operand_tile_2sm(uint8_t* dst, const CUtens
 // activation-backward operand, split-K atomics) becomes sector-exact and 4x denser per instruction.
 // TMEM loads are double buffered: chunk i+1 is in flight while chunk i goes through the math and stores.
 
+
+// One TMA instruction per operand tile and 128-wide K stage, through a "chunk map" {64 elements, rows, 64-wide chunks}
+// (chunk stride 128 B).  K-major: rows = M/N index, chunks run along K (inside one segment for the conv views, whose
+// segments start `shift` rows further down); MN-major: rows = K index, chunks run along M/N.
+template <int TILE, int BKT>
+__device__ __forceinline__ void load_stage_chunked(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int major, int seg,
+                                                   int shift, int tile, int kb) {
+  if (major == 0) {
+    int inner0 = kb * BKT, row0 = tile * TILE;
+    if (seg > 0) { row0 += (inner0 / seg) * shift; inner0 %= seg; }
+    ptx::tma_load_3d(dst, tm, bar, 0, row0, inner0 >> 6);
+  } else {
+    int mn0 = tile * TILE, row0 = kb * BKT;
+    if (seg > 0) { row0 += (mn0 / seg) * shift; mn0 %= seg; }
+    ptx::tma_load_3d(dst, tm, bar, 0, row0, mn0 >> 6);
+  }
+}
+
 template <int EF>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRow (&rows)[4], int m_base, int n,
                                                const uint32_t (&r)[32], float* stage, int lane) {
@@ -180,10 +198,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& epi, uint32_t tad
   }
 }
 
-template <int BN, int EF>
+template <int BN, int EF, int BKT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Cfg = TcConfig<BN>;
+  using Cfg = TcConfig<BN, BKT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
@@ -243,8 +261,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          load_operand_tile<BM>(sa, &tmA, &full_bar[stage], p.a_major, p.a_rpg, p.a_seg, p.a_shift, mt, kb);
-          load_operand_tile<BN>(sb, &tmB, &full_bar[stage], p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt, kb);
+          if (BKT == 128) {
+            load_stage_chunked<BM, BKT>(sa, &tmA, &full_bar[stage], p.a_major, p.a_seg, p.a_shift, mt, kb);
+            load_stage_chunked<BN, BKT>(sb, &tmB, &full_bar[stage], p.b_major, p.b_seg, p.b_shift, nt, kb);
+          } else {
+            load_operand_tile<BM>(sa, &tmA, &full_bar[stage], p.a_major, p.a_rpg, p.a_seg, p.a_shift, mt, kb);
+            load_operand_tile<BN>(sb, &tmB, &full_bar[stage], p.b_major, p.b_rpg, p.b_seg, p.b_shift, nt, kb);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -272,12 +295,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
-          const uint64_t adesc = ptx::make_smem_desc(sa, p.a_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
-          const uint64_t bdesc = ptx::make_smem_desc(sb, p.b_major == 0 ? 16u : (uint32_t)(BK * 128), 1024u);
+          const uint64_t adesc = ptx::make_smem_desc(sa, p.a_major == 0 ? 16u : (uint32_t)(BKT * 128), 1024u);
+          const uint64_t bdesc = ptx::make_smem_desc(sb, p.b_major == 0 ? 16u : (uint32_t)(BKT * 128), 1024u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                           (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BKT / 16; ++k) {
+            const uint32_t ao = p.a_major == 0 ? (uint32_t)((k >> 2) * (BM * 128 / 16) + (k & 3) * 2) : (uint32_t)(k * a_adv);
+            const uint32_t bo = p.b_major == 0 ? (uint32_t)((k >> 2) * (BN * 128 / 16) + (k & 3) * 2) : (uint32_t)(k * b_adv);
+            ptx::umma_bf16(tmem_d, adesc + (uint64_t)ao, bdesc + (uint64_t)bo, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);
@@ -633,6 +657,60 @@ int make_kmajor_chunked_map(CUtensorMap* out, const egb_operand& o, int extent_m
   return 0;
 }
 
+
+// chunk map {64, rows, chunks} with a {64, box_rows, box_chunks} box (see load_stage_chunked)
+int make_chunk_map(CUtensorMap* out, const void* ptr, long long rows, long long chunks, long long rs, int box_rows,
+                   int box_chunks) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = 64; key.rows = rows; key.groups = chunks; key.rs = rs; key.gs = -777;
+  key.b0 = 64; key.b1 = box_rows; key.b2 = box_chunks;
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  EGB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  EGB_CHECK(((uintptr_t)ptr % 16) == 0 && (rs % 8) == 0 && rs > 0, "TMA operand misaligned");
+  cuuint64_t dims[3] = {64u, (cuuint64_t)rows, (cuuint64_t)chunks};
+  cuuint64_t strides[2] = {(cuuint64_t)rs * 2, 128u};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (chunk map) failed (%d): rows=%lld chunks=%lld rs=%lld box=%d,%d", (int)r,
+            rows, chunks, rs, box_rows, box_chunks);
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps[key] = *out;
+  return 0;
+}
+
+// Can this operand be fetched through a chunk map with 128-wide K stages by the single-CTA kernel?
+bool operand_chunkable128(const egb_operand& o, int extent_mn, int K, int tile) {
+  const long long total_rows = o.major == 0 ? extent_mn : K;
+  if (o.rows_per_group > 0 && o.rows_per_group < total_rows) return false;   // grouped views keep the 64-wide path
+  if (o.major == 0) {
+    if (o.seg_len > 0) return (o.seg_len % 128) == 0 && (K % o.seg_len) == 0;
+    return (K % 64) == 0;
+  }
+  if (o.seg_len > 0) return (o.seg_len % tile) == 0 && (extent_mn % o.seg_len) == 0 && tile >= 64;
+  return (extent_mn % 64) == 0 && tile >= 64;
+}
+
+int make_operand_chunk_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int K, int tile) {
+  if (o.major == 0) {
+    long long rows = extent_mn, chunks = K / 64;
+    if (o.seg_len > 0) { rows = extent_mn + (long long)(K / o.seg_len - 1) * o.seg_row_shift; chunks = o.seg_len / 64; }
+    return make_chunk_map(out, o.ptr, rows, chunks, o.row_stride, tile, 2);
+  }
+  long long rows = K, chunks = extent_mn / 64;
+  if (o.seg_len > 0) { rows = K + (long long)(extent_mn / o.seg_len - 1) * o.seg_row_shift; chunks = o.seg_len / 64; }
+  return make_chunk_map(out, o.ptr, rows, chunks, o.row_stride, 128, tile / 64);
+}
+
 int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int K, int tile_rows, int* rpg_out,
                      int bk = BK) {
   if (o.major == 1 && o.seg_len == 0 && (o.rows_per_group <= 0 || o.rows_per_group >= K) && (extent_mn % 64) == 0 &&
@@ -693,12 +771,12 @@ int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int 
   return make_map(out, o.ptr, inner, phys_rows, groups, o.row_stride, o.group_stride, box_rows, box_groups);
 }
 
-template <int BN, int EF>
-int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
-  using Cfg = TcConfig<BN>;
+template <int BN, int EF, int BKT>
+int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  using Cfg = TcConfig<BN, BKT>;
   static bool attr_set = false;
   if (!attr_set) {
-    EGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    EGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EF, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
@@ -708,7 +786,7 @@ int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
   }
-  gemm_tc_kernel<BN, EF><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  gemm_tc_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
   if (prof) egb_prof_end(stream);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
@@ -731,6 +809,12 @@ int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p
     }                                                                                                           \
   }                                                                                                             \
   return FN<BN_, EF_GENERIC>(ma, mb, p, stream);
+
+template <int BN, int EF>
+int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+  if (p.bkt == 128 && BN <= 128) return launch_tc_ef_bk<BN, EF, 128>(ma, mb, p, stream);
+  return launch_tc_ef_bk<BN, EF, 64>(ma, mb, p, stream);
+}
 
 template <int BN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
@@ -861,11 +945,19 @@ int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
   p.a_seg = d->a.seg_len; p.a_shift = d->a.seg_row_shift;
   p.b_seg = d->b.seg_len; p.b_shift = d->b.seg_row_shift;
   CUtensorMap ma, mb;
-  if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg)) return 1;
-  if (make_operand_map(&mb, d->b, d->N, d->K, BN, &p.b_rpg)) return 1;
+  static const int bk128s = getenv("EGB_GEMM_BK128") ? atoi(getenv("EGB_GEMM_BK128")) : 1;
+  p.bkt = (bk128s && BN <= 128 && operand_chunkable128(d->a, d->M, d->K, BM) && operand_chunkable128(d->b, d->N, d->K, BN))
+              ? 128 : 64;
+  if (p.bkt == 128) {
+    if (make_operand_chunk_map(&ma, d->a, d->M, d->K, BM)) return 1;
+    if (make_operand_chunk_map(&mb, d->b, d->N, d->K, BN)) return 1;
+  } else {
+    if (make_operand_map(&ma, d->a, d->M, d->K, BM, &p.a_rpg)) return 1;
+    if (make_operand_map(&mb, d->b, d->N, d->K, BN, &p.b_rpg)) return 1;
+  }
   p.m_tiles = (d->M + BM - 1) / BM;
   p.n_tiles = (d->N + BN - 1) / BN;
-  p.k_blocks = (d->K + BK - 1) / BK;
+  p.k_blocks = (d->K + p.bkt - 1) / p.bkt;
   int split = 1;
   if (d->accumulate) {
     EGB_CHECK(d->c.dtype == EGB_F32, "gemm: accumulate requires an fp32 output");
@@ -873,7 +965,7 @@ int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
     if (split <= 0) {
       const int tiles = p.m_tiles * p.n_tiles;
       split = (2 * egb_num_sms() + tiles - 1) / tiles;
-      const int max_split = (p.k_blocks + 7) / 8;  // keep >= 8 k-blocks per split
+      const int max_split = (p.k_blocks + 7) / 8;  // keep >= 8 k-stages per split
       if (split > max_split) split = max_split;
       if (split < 1) split = 1;
     }
