@@ -84,6 +84,7 @@ _SIGNATURES = {
     "egb_relu_avgpool_bwd": [vp, vp, vp, i32, i32, i32, i32, vp],
     "egb_ibs_connectivity": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32),
                              C.POINTER(i32), i32, vp],
+    "egb_ibs_scalar_features": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp],
     "egb_instnorm_tokens_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp],
     "egb_instnorm_tokens_bwd": [vp, vp, i32, vp, vp, i32, i32, i32, f32, vp],
     "egb_fuzzy_fwd": [C.POINTER(FuzzyDesc), vp, vp, vp, vp, vp, vp],

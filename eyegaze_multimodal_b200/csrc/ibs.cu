@@ -64,8 +64,9 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void __launch_bounds__(256) ibs_analytic_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
                                                            const float2* __restrict__ twiddle, float* __restrict__ phase,
                                                            float* __restrict__ xb, float* __restrict__ stats,
-                                                           float* __restrict__ pspec, IbsBands bands, int B, int C, int T,
-                                                           int logT, int lo_min, int nbins) {
+                                                           float* __restrict__ pspec, float2* __restrict__ cspec,
+                                                           IbsBands bands, int B, int C, int T, int logT, int lo_min,
+                                                           int nbins) {
   extern __shared__ float2 sm2[];
   float2* a = sm2;              // [T]
   float2* X = a + T;            // [T/2 + 1]
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) ibs_analytic_kernel(const float* __restri
   for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
     const float2 v = X[lo_min + k];
     ps[k] = v.x * v.x + v.y * v.y;
+    if (cspec != nullptr) cspec[(((long long)b * 2 + stream) * C + c) * nbins + k] = v;
   }
   const float invT = 1.f / (float)T;
   for (int bi = 0; bi < bands.nb; ++bi) {
@@ -295,6 +297,95 @@ __global__ void __launch_bounds__(256) ibs_pairs_kernel(const float* __restrict_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ legacy scalar IBS features
+// IBSTokenGenerator (dual_eeg_transformer.py:178-470, ablation `ibs_mode: scalar`): per band 7 GLOBAL scalars over all
+// (channel, sample) positions -- channel c of player 1 is compared with channel c of player 2, no pairing:
+//   PLV |mean e^{i d}|, PLI |mean sign d|, wPLI |sum sign(d) w| with w = (p1+p2)/2 normalised over (c, t),
+//   coherence of the channel-averaged cross spectrum, Pearson correlation of the flattened powers (unbiased std),
+//   |mean d|, Pearson correlation of the channel-mean signals.   One CTA per (band, trial); out[b][band*7 + f].
+__global__ void __launch_bounds__(256) ibs_scalar_kernel(const float* __restrict__ phase, const float* __restrict__ xb,
+                                                         const float* __restrict__ stats, const float2* __restrict__ cspec,
+                                                         float* __restrict__ out, IbsBands bands, int B, int C, int T,
+                                                         int lo_min, int nbins) {
+  extern __shared__ float smx[];
+  float* m1 = smx;       // [T] channel-mean of xb, player 1
+  float* m2 = smx + T;   // [T]
+  __shared__ float red[8];
+  const int bi = blockIdx.x, b = blockIdx.y;
+  const long long base1 = ((((long long)b * bands.nb + bi) * 2 + 0) * C) * T;
+  const long long base2 = ((((long long)b * bands.nb + bi) * 2 + 1) * C) * T;
+  const float* st1 = stats + ((((long long)b * bands.nb + bi) * 2 + 0) * C) * 8;
+  const float* st2 = stats + ((((long long)b * bands.nb + bi) * 2 + 1) * C) * 8;
+  // global means of the powers (every channel has T samples, so the mean of the channel means)
+  float mp1 = 0.f, mp2 = 0.f;
+  for (int c = 0; c < C; ++c) { mp1 += st1[c * 8 + 2]; mp2 += st2[c * 8 + 2]; }
+  mp1 /= (float)C; mp2 /= (float)C;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) { m1[t] = 0.f; m2[t] = 0.f; }
+  float s_cos = 0.f, s_sin = 0.f, s_sg = 0.f, s_wsg = 0.f, s_w = 0.f, s_d = 0.f, c11 = 0.f, c22 = 0.f, c12 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float l_cos = 0.f, l_sin = 0.f, l_sg = 0.f, l_wsg = 0.f, l_w = 0.f, l_d = 0.f, l11 = 0.f, l22 = 0.f, l12 = 0.f;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {     // a thread always owns the same samples t
+      const long long o1 = base1 + (long long)c * T + t, o2 = base2 + (long long)c * T + t;
+      const float x1 = xb[o1], x2 = xb[o2];
+      const float d = phase[o1] - phase[o2];
+      float sn, cs;
+      sincosf(d, &sn, &cs);
+      const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+      const float p1 = x1 * x1, p2 = x2 * x2, w = (p1 + p2) * 0.5f;
+      l_cos += cs; l_sin += sn; l_sg += sg; l_wsg += sg * w; l_w += w; l_d += d;
+      const float q1 = p1 - mp1, q2 = p2 - mp2;
+      l11 = fmaf(q1, q1, l11); l22 = fmaf(q2, q2, l22); l12 = fmaf(q1, q2, l12);
+      m1[t] += x1; m2[t] += x2;
+    }
+    s_cos += l_cos; s_sin += l_sin; s_sg += l_sg; s_wsg += l_wsg; s_w += l_w; s_d += l_d; c11 += l11; c22 += l22; c12 += l12;
+  }
+  const float n_all = (float)C * (float)T;
+  s_cos = block_sum(s_cos, red); s_sin = block_sum(s_sin, red); s_sg = block_sum(s_sg, red);
+  s_wsg = block_sum(s_wsg, red); s_w = block_sum(s_w, red); s_d = block_sum(s_d, red);
+  c11 = block_sum(c11, red); c22 = block_sum(c22, red); c12 = block_sum(c12, red);
+  // Pearson correlation of the channel-mean signals (unbiased std + 1e-8, mean of products)
+  const float invC = 1.f / (float)C;
+  float a1 = 0.f, a2 = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) { a1 += m1[t] * invC; a2 += m2[t] * invC; }
+  const float mu1 = block_sum(a1, red) / (float)T, mu2 = block_sum(a2, red) / (float)T;
+  float v1 = 0.f, v2 = 0.f, v12 = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float e1 = m1[t] * invC - mu1, e2 = m2[t] * invC - mu2;
+    v1 = fmaf(e1, e1, v1); v2 = fmaf(e2, e2, v2); v12 = fmaf(e1, e2, v12);
+  }
+  v1 = block_sum(v1, red); v2 = block_sum(v2, red); v12 = block_sum(v12, red);
+  // coherence of the channel-averaged spectra over the in-band bins (all other bins contribute 0 / (0 + 1e-8))
+  float coh = 0.f;
+  const int klo = bands.lo[bi], khi = bands.hi[bi];
+  for (int k = klo + threadIdx.x; k <= khi; k += blockDim.x) {
+    float xr = 0.f, xi = 0.f, pxx = 0.f, pyy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float2 f1 = cspec[(((long long)b * 2 + 0) * C + c) * nbins + (k - lo_min)];
+      const float2 f2 = cspec[(((long long)b * 2 + 1) * C + c) * nbins + (k - lo_min)];
+      xr += f1.x * f2.x + f1.y * f2.y;      // f1 * conj(f2)
+      xi += f1.y * f2.x - f1.x * f2.y;
+      pxx += f1.x * f1.x + f1.y * f1.y;
+      pyy += f2.x * f2.x + f2.y * f2.y;
+    }
+    xr *= invC; xi *= invC; pxx *= invC; pyy *= invC;
+    coh += (xr * xr + xi * xi) / (pxx * pyy + 1e-8f);
+  }
+  coh = block_sum(coh, red);
+  if (threadIdx.x == 0) {
+    float* o = out + ((long long)b * bands.nb + bi) * 7;
+    o[0] = sqrtf(s_cos * s_cos + s_sin * s_sin) / n_all;
+    o[1] = fabsf(s_sg / n_all);
+    o[2] = fabsf(s_wsg / (s_w + 1e-8f));
+    o[3] = coh / (float)(T / 2 + 1);
+    const float sd1 = sqrtf(c11 / (n_all - 1.f)) + 1e-8f, sd2 = sqrtf(c22 / (n_all - 1.f)) + 1e-8f;
+    o[4] = (c12 / n_all) / (sd1 * sd2);
+    o[5] = fabsf(s_d / n_all);
+    const float t1 = sqrtf(v1 / (float)(T - 1)) + 1e-8f, t2 = sqrtf(v2 / (float)(T - 1)) + 1e-8f;
+    o[6] = (v12 / (float)T) / (t1 * t2);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ instance norm over tokens
 // x: [B, NT, P] (P = C*C); per (b, p) normalise over the NT tokens (biased variance, eps), affine.
 // (RobustIBSTokenizer, det:893-901).  Coalesced over p.
@@ -391,7 +482,7 @@ int egb_ibs_connectivity(const float* eeg1, const float* eeg2, const float* twid
     smem1_set = smem1;
   }
   ibs_analytic_kernel<<<dim3(C, 2, B), 256, smem1, st>>>(eeg1, eeg2, (const float2*)twiddle, phase, xb, stats, pspec,
-                                                         bands, B, C, T, logT, lo_min, nbins);
+                                                         nullptr, bands, B, C, T, logT, lo_min, nbins);
   EGB_LAUNCH_CHECK();
   const size_t smem2 = sizeof(float) * ((size_t)IBS_NF * IBS_TC * IBS_PI + (size_t)IBS_NF * IBS_BJ * IBS_PJ);
   static size_t smem2_set = 0;
@@ -402,6 +493,54 @@ int egb_ibs_connectivity(const float* eeg1, const float* eeg2, const float* twid
   const int n_blk = ((C + IBS_BI - 1) / IBS_BI) * ((C + IBS_BJ - 1) / IBS_BJ);
   ibs_pairs_kernel<<<dim3(n_blk, n_bands, B), 256, smem2, st>>>(phase, xb, stats, pspec, out, bands,
                                                                                   slots, B, C, T, lo_min, nbins);
+  egb_count_launch(2);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+
+/* Legacy scalar IBS features (dual_eeg_transformer.py:418-470): out fp32 [B, n_bands*7].  Scratch as for
+ * egb_ibs_connectivity plus cspec: B*2*C*nbins complex (float2). */
+int egb_ibs_scalar_features(const float* eeg1, const float* eeg2, const float* twiddle, float* phase, float* xb,
+                            float* stats, float* pspec, float* cspec, float* out, int B, int C, int T, int n_bands,
+                            const int32_t* band_lo, const int32_t* band_hi, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGB_CHECK(B > 0 && C > 0 && C <= 128, "ibs: unsupported channel count %d", C);
+  EGB_CHECK(T >= 8 && (T & (T - 1)) == 0 && T <= 8192, "ibs: window length %d must be a power of two in [8, 8192]", T);
+  EGB_CHECK(n_bands >= 1 && n_bands <= 8, "ibs: up to 8 bands");
+  int logT = 0;
+  while ((1 << logT) < T) ++logT;
+  IbsBands bands;
+  bands.nb = n_bands;
+  int lo_min = 1 << 30, hi_max = -1;
+  for (int i = 0; i < n_bands; ++i) {
+    bands.lo[i] = band_lo[i];
+    bands.hi[i] = band_hi[i];
+    EGB_CHECK(band_lo[i] >= 0 && band_hi[i] <= T / 2, "ibs: band %d bins [%d,%d] outside [0,%d]", i, band_lo[i], band_hi[i], T / 2);
+    if (band_lo[i] <= band_hi[i]) {
+      if (band_lo[i] < lo_min) lo_min = band_lo[i];
+      if (band_hi[i] > hi_max) hi_max = band_hi[i];
+    }
+  }
+  if (hi_max < lo_min) { lo_min = 0; hi_max = 0; }
+  const int nbins = hi_max - lo_min + 1;
+  const size_t smem1 = sizeof(float2) * ((size_t)T + T / 2 + 1 + T / 2);
+  static size_t smem1_set = 0;
+  if (smem1 > 48 * 1024 && smem1 > smem1_set) {
+    EGB_CUDA(cudaFuncSetAttribute(ibs_analytic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    smem1_set = smem1;
+  }
+  ibs_analytic_kernel<<<dim3(C, 2, B), 256, smem1, st>>>(eeg1, eeg2, (const float2*)twiddle, phase, xb, stats, pspec,
+                                                         (float2*)cspec, bands, B, C, T, logT, lo_min, nbins);
+  EGB_LAUNCH_CHECK();
+  const size_t smem2 = sizeof(float) * 2 * (size_t)T;
+  static size_t smem2_set = 0;
+  if (smem2 > 48 * 1024 && smem2 > smem2_set) {
+    EGB_CUDA(cudaFuncSetAttribute(ibs_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    smem2_set = smem2;
+  }
+  ibs_scalar_kernel<<<dim3(n_bands, B), 256, smem2, st>>>(phase, xb, stats, (const float2*)cspec, out, bands, B, C, T, lo_min,
+                                                          nbins);
   egb_count_launch(2);
   EGB_LAUNCH_CHECK();
   return 0;

@@ -967,8 +967,34 @@ def add_broadcast_rows(x, e):
     return AddRowsBroadcastFn.apply(x, e)
 
 
-def ibs_scalar_features(eeg1, eeg2, fs, bands):
-    raise NotImplementedError("legacy scalar IBS mode (ibs_mode: scalar) kernel not built yet")
+def ibs_scalar_features(eeg1, eeg2, fs, bands, chunk=256):
+    """Legacy scalar IBS token features (det:418-470): (B,C,T) x2 fp32 -> (B, 7 * n_bands) fp32, no gradient."""
+    _require_cuda(eeg1, eeg2)
+    with torch.no_grad():
+        eeg1 = eeg1.detach().contiguous().float()
+        eeg2 = eeg2.detach().contiguous().float()
+        B, Cc, T = eeg1.shape
+        dev = eeg1.device
+        nb = len(bands)
+        bins = band_bins(T, fs, bands)
+        lo = (L.i32 * nb)(*[b[0] for b in bins])
+        hi = (L.i32 * nb)(*[b[1] for b in bins])
+        valid = [b for b in bins if b[0] <= b[1]]
+        nbins = (max(b[1] for b in valid) - min(b[0] for b in valid) + 1) if valid else 1
+        out = torch.empty(B, nb * 7, dtype=torch.float32, device=dev)
+        tw = _twiddle(T, dev)
+        cb = min(B, chunk)
+        phase = torch.empty(cb * nb * 2 * Cc * T, dtype=torch.float32, device=dev)
+        xb = torch.empty_like(phase)
+        stats = torch.empty(cb * nb * 2 * Cc * 8, dtype=torch.float32, device=dev)
+        pspec = torch.empty(cb * 2 * Cc * nbins, dtype=torch.float32, device=dev)
+        cspec = torch.empty(cb * 2 * Cc * nbins * 2, dtype=torch.float32, device=dev)
+        for b0 in range(0, B, cb):
+            n = min(cb, B - b0)
+            L.call("egb_ibs_scalar_features", eeg1[b0:].data_ptr(), eeg2[b0:].data_ptr(), tw.data_ptr(), phase.data_ptr(),
+                   xb.data_ptr(), stats.data_ptr(), pspec.data_ptr(), cspec.data_ptr(), out[b0:].data_ptr(), n, Cc, T, nb,
+                   lo, hi, _stream())
+        return out
 
 
 class TailPoolFn(torch.autograd.Function):

@@ -204,6 +204,11 @@ int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, 
 int egb_ibs_connectivity(const float* eeg1, const float* eeg2, const float* twiddle, float* phase, float* xb,
                          float* stats, float* pspec, float* out, int B, int C, int T, int n_bands, const int32_t* band_lo,
                          const int32_t* band_hi, const int32_t* slot_of, int n_out, void* stream);
+/* Legacy scalar IBS features of IBSTokenGenerator (dual_eeg_transformer.py:418-470, `ibs_mode: scalar`): n_bands x 7 global
+ * scalars per trial -> out fp32 [B, n_bands*7].  Scratch as above plus cspec: B*2*C*nbins complex values (2 floats each). */
+int egb_ibs_scalar_features(const float* eeg1, const float* eeg2, const float* twiddle, float* phase, float* xb,
+                            float* stats, float* pspec, float* cspec, float* out, int B, int C, int T, int n_bands,
+                            const int32_t* band_lo, const int32_t* band_hi, void* stream);
 /* InstanceNorm1d over the token axis per (trial, matrix cell) (dual_eeg_transformer.py:893-901) */
 int egb_instnorm_tokens_fwd(const float* x, const float* gamma, const float* beta, void* y, int dtype, int B, int NT,
                             int P, float eps, int apply_norm, void* stream);

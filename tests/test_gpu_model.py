@@ -28,7 +28,7 @@ def _build(g):
     return m.to(DEV).eval(), kw
 
 
-@pytest.mark.parametrize("name", ["full", "a1_baseline", "phase_noin_nocross"])
+@pytest.mark.parametrize("name", ["full", "a1_baseline", "phase_noin_nocross", "scalar_ibs"])
 def test_golden_forward_backward_fp32(cuda_device, name):
     g = load_golden(f"eeg_model_{name}.npz")
     m, kw = _build(g)
@@ -160,6 +160,28 @@ def test_default_full_model_32x1024(cuda_device):
     """Full EEG encoder of BASELINE configs 2/4 (32 ch x 1024, L = 139)."""
     cfg = O.EEGConfig(in_channels=32, max_len=256)
     _oracle_vs_cuda(cfg, B=4, T=1024, seed=2)
+
+
+def test_cfg5_large_sweep_shape_64x2048(cuda_device):
+    """BASELINE config 5 geometry: 64 channels x 2048 samples (L = 235, 33 STFT frames, 4096-wide IBS matrices)."""
+    cfg = O.EEGConfig(in_channels=64, max_len=512)
+    _oracle_vs_cuda(cfg, B=2, T=2048, seed=5, grads=False)
+
+
+def test_scalar_ibs_features_match_oracle(cuda_device):
+    """Legacy `ibs_mode: scalar` features (28 per trial) against the oracle restatement pinned to the reference."""
+    from eyegaze_multimodal_b200 import ops
+    from eyegaze_multimodal_b200.dual_eeg_transformer import SCALAR_BANDS
+    e1, e2 = eeg_pair_batch(5, 16, 512, seed=11, coupled=True)
+    want = O.ibs_scalar_features(e1, e2, 256.0)
+    got = ops.ibs_scalar_features(e1.to(DEV), e2.to(DEV), 256.0, SCALAR_BANDS).cpu()
+    assert got.shape == want.shape == (5, 28)
+    err = (got - want).abs()
+    # PLI / wPLI (features 1, 2 of each band) contain sign(): allow a handful of flips out of C*T samples
+    smooth = [i for i in range(28) if i % 7 not in (1, 2)]
+    assert err[:, smooth].max() <= 2e-5, err[:, smooth].max()
+    flips = [i for i in range(28) if i % 7 in (1, 2)]
+    assert err[:, flips].max() <= 8.0 / (16 * 512) + 1e-3, err[:, flips].max()
 
 
 def test_train_mode_runs_and_is_stochastic(cuda_device):
