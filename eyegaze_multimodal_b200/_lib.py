@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeyegaze_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ACTBWD_NONE, ACTBWD_RELU_MASK, ACTBWD_GELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_DGRAD = 0, 1, 2, 3
+ACTBWD_NONE, ACTBWD_RELU_MASK, ACTBWD_GELU, ACTBWD_MUL = 0, 1, 2, 3
 
 vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 

@@ -77,6 +77,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
   gelu_parts(x, cdf, g);
   return x * cdf;
 }
+// both at once (the forward epilogue that also saves the derivative for the backward pass)
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  float cdf, g;
+  gelu_parts(x, cdf, g);
+  y = x * cdf;
+  dy = fmaf(x * 0.3989422804014327f, g, cdf);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float cdf, g;
   gelu_parts(x, cdf, g);

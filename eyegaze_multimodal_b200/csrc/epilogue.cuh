@@ -122,7 +122,14 @@ __device__ __forceinline__ void epi_apply_store(const EpiParams& p, int m, int n
     for (int i = 0; i < W; ++i)
       if (i < ncols) v[i] += __ldg(p.bias + n + i);
   }
-  if (p.c_pre.ptr != nullptr) epi_store<W>(p.c_pre, epi_row_offset(p.c_pre, m), n, ncols, v);
+  if (p.act == EGB_ACT_GELU_DGRAD) {
+    float dv[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) gelu_erf_both(v[i], v[i], dv[i]);
+    if (p.c_pre.ptr != nullptr) epi_store<W>(p.c_pre, epi_row_offset(p.c_pre, m), n, ncols, dv);
+  } else if (p.c_pre.ptr != nullptr) {
+    epi_store<W>(p.c_pre, epi_row_offset(p.c_pre, m), n, ncols, v);
+  }
   if (p.act == EGB_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -141,6 +148,9 @@ __device__ __forceinline__ void epi_apply_store(const EpiParams& p, int m, int n
     if (p.act_bwd == EGB_ACTBWD_RELU_MASK) {
 #pragma unroll
       for (int i = 0; i < W; ++i) v[i] = (a[i] != 0.f) ? v[i] * p.aux_scale : 0.f;
+    } else if (p.act_bwd == EGB_ACTBWD_MUL) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[i] *= a[i];
     } else {
 #pragma unroll
       for (int i = 0; i < W; ++i) v[i] *= gelu_erf_grad(a[i]);
@@ -206,7 +216,14 @@ __device__ __forceinline__ void epi_apply_store_row(const EpiParams& p, const Ep
         if (i < ncols) v[i] += __ldg(p.bias + n + i);
     }
   }
-  if (p.c_pre.ptr != nullptr) epi_store<W>(p.c_pre, row.c_pre, n, ncols, v);
+  if (p.act == EGB_ACT_GELU_DGRAD) {
+    float dv[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) gelu_erf_both(v[i], v[i], dv[i]);
+    if (p.c_pre.ptr != nullptr) epi_store<W>(p.c_pre, row.c_pre, n, ncols, dv);
+  } else if (p.c_pre.ptr != nullptr) {
+    epi_store<W>(p.c_pre, row.c_pre, n, ncols, v);
+  }
   if (p.act == EGB_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -225,6 +242,9 @@ __device__ __forceinline__ void epi_apply_store_row(const EpiParams& p, const Ep
     if (p.act_bwd == EGB_ACTBWD_RELU_MASK) {
 #pragma unroll
       for (int i = 0; i < W; ++i) v[i] = (a[i] != 0.f) ? v[i] * p.aux_scale : 0.f;
+    } else if (p.act_bwd == EGB_ACTBWD_MUL) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[i] *= a[i];
     } else {
 #pragma unroll
       for (int i = 0; i < W; ++i) v[i] *= gelu_erf_grad(a[i]);
@@ -256,6 +276,8 @@ __device__ __forceinline__ void epi_apply_store_row(const EpiParams& p, const Ep
 // ---------------------------------------------------------------------------------------------
 enum : int {
   EF_BIAS = 1, EF_RELU = 2, EF_GELU = 4, EF_RES = 8, EF_PRE = 16, EF_ABWD_RELU = 32, EF_ABWD_GELU = 64, EF_ACC = 128,
+  EF_DGELU = 256,     // with EF_GELU | EF_PRE: the saved tensor is gelu'(pre)
+  EF_ABWD_MUL = 512,  // multiply by the saved derivative
   EF_GENERIC = 1 << 20
 };
 
@@ -271,7 +293,7 @@ struct EpiPre8 {
 template <int F>
 __device__ __forceinline__ void epi_prefetch8(const EpiParams& p, const EpiRow& row, int n, EpiPre8& pre) {
   if (!row.ok || n >= p.N) return;
-  if (F & (EF_ABWD_RELU | EF_ABWD_GELU)) pre.aux = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux.ptr) + row.aux + n));
+  if (F & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) pre.aux = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux.ptr) + row.aux + n));
   if (F & EF_RES) pre.res = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res.ptr) + row.res + n));
 }
 
@@ -295,26 +317,36 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += bias[i];
   }
-  if (F & EF_PRE) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, v);
-  if (F & EF_RELU) {
+  if (F & EF_DGELU) {
+    float dv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (F & EF_GELU) {
+    for (int i = 0; i < 8; ++i) gelu_erf_both(v[i], v[i], dv[i]);
+    st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, dv);
+  } else {
+    if (F & EF_PRE) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, v);
+    if (F & EF_RELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (F & EF_GELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    }
   }
   if (p.drop_thresh != 0u) {
     const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = drop_keep(p.seed, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
   }
-  if (F & (EF_ABWD_RELU | EF_ABWD_GELU)) {
+  if (F & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) {
     float a[8];
     unpack8(pre.aux, a);
     if (F & EF_ABWD_RELU) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (a[i] != 0.f) ? v[i] * p.aux_scale : 0.f;
+    } else if (F & EF_ABWD_MUL) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= a[i];
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(a[i]);
@@ -340,15 +372,16 @@ static inline int egb_epi_fast_mask(const EpiParams& e) {
   if (e.bias != nullptr) f |= EF_BIAS;
   if (e.act == EGB_ACT_RELU) f |= EF_RELU;
   if (e.act == EGB_ACT_GELU) f |= EF_GELU;
+  if (e.act == EGB_ACT_GELU_DGRAD) { if (e.c_pre.ptr == nullptr) return EF_GENERIC; f |= EF_GELU | EF_DGELU; }
   if (e.c_pre.ptr != nullptr) { if (!bf16_vec(e.c_pre)) return EF_GENERIC; f |= EF_PRE; }
   if (e.res.ptr != nullptr) { if (!bf16_vec(e.res)) return EF_GENERIC; f |= EF_RES; }
   if (e.act_bwd != EGB_ACTBWD_NONE) {
     if (!bf16_vec(e.aux)) return EF_GENERIC;
-    f |= (e.act_bwd == EGB_ACTBWD_RELU_MASK) ? EF_ABWD_RELU : EF_ABWD_GELU;
+    f |= (e.act_bwd == EGB_ACTBWD_RELU_MASK) ? EF_ABWD_RELU : (e.act_bwd == EGB_ACTBWD_MUL ? EF_ABWD_MUL : EF_ABWD_GELU);
   }
   switch (f) {   // the instantiated set (everything else runs the generic epilogue)
-    case 0: case EF_BIAS: case EF_BIAS | EF_RES: case EF_BIAS | EF_RELU: case EF_BIAS | EF_GELU | EF_PRE:
-    case EF_ABWD_RELU: case EF_ABWD_GELU:
+    case 0: case EF_BIAS: case EF_BIAS | EF_RES: case EF_BIAS | EF_RELU: case EF_BIAS | EF_GELU | EF_PRE | EF_DGELU:
+    case EF_ABWD_RELU: case EF_ABWD_MUL:
       return f;
     default:
       return EF_GENERIC;

@@ -213,6 +213,7 @@ int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e) {
   e->act = d->act;
   e->act_bwd = d->act_bwd;
   EGB_CHECK(d->act_bwd == EGB_ACTBWD_NONE || d->aux.ptr != nullptr, "gemm: act_bwd needs aux");
+  EGB_CHECK(d->act != EGB_ACT_GELU_DGRAD || d->c_pre.ptr != nullptr, "gemm: EGB_ACT_GELU_DGRAD needs c_pre");
   e->aux_scale = d->aux_scale;
   if (d->dropout_p > 0.f) {
     EGB_CHECK(d->dropout_p < 1.f, "gemm: dropout_p must be < 1");

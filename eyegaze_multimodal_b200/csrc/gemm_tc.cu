@@ -801,9 +801,10 @@ int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams
       case EF_BIAS: return FN<BN_, EF_BIAS>(ma, mb, p, stream);                                                 \
       case EF_BIAS | EF_RES: return FN<BN_, EF_BIAS | EF_RES>(ma, mb, p, stream);                               \
       case EF_BIAS | EF_RELU: return FN<BN_, EF_BIAS | EF_RELU>(ma, mb, p, stream);                             \
-      case EF_BIAS | EF_GELU | EF_PRE: return FN<BN_, EF_BIAS | EF_GELU | EF_PRE>(ma, mb, p, stream);           \
+      case EF_BIAS | EF_GELU | EF_PRE | EF_DGELU:                                                               \
+        return FN<BN_, EF_BIAS | EF_GELU | EF_PRE | EF_DGELU>(ma, mb, p, stream);                               \
       case EF_ABWD_RELU: return FN<BN_, EF_ABWD_RELU>(ma, mb, p, stream);                                       \
-      case EF_ABWD_GELU: return FN<BN_, EF_ABWD_GELU>(ma, mb, p, stream);                                       \
+      case EF_ABWD_MUL: return FN<BN_, EF_ABWD_MUL>(ma, mb, p, stream);                                         \
       case EF_ACC: return FN<BN_, EF_ACC>(ma, mb, p, stream);                                                   \
       default: break;                                                                                           \
     }                                                                                                           \

@@ -160,10 +160,11 @@ static int run_case(const Case& cs, int in_dtype, bool check_full, int timing_it
     if (cs.use_bias) x += bias[n];
     const double pre = x;
     if (cs.act == 1) x = x > 0 ? x : 0;
-    if (cs.act == 2) x = gelu_h(x);
+    if (cs.act == 2 || cs.act == 3) x = gelu_h(x);
     const long long off = c_off(m) + n;
     if (cs.act_bwd == 1) x = aux[off] != 0 ? x * 1.25 : 0;
     if (cs.act_bwd == 2) x *= gelu_grad_h(aux[off]);
+    if (cs.act_bwd == 3) x *= aux[off];
     if (cs.use_res) x += res[off];
     if (cs.accumulate) x += cinit[off];
     const double scale = sqrt((double)K) * 0.1 + fabs(x);
@@ -172,8 +173,9 @@ static int run_case(const Case& cs, int in_dtype, bool check_full, int timing_it
     if (fabs(x) > max_ref) max_ref = fabs(x);
     if (err > tol_rel * scale) ++bad;
     if (cs.use_pre) {
-      const double ep = fabs(hpre[off] - pre);
-      if (ep > tol_rel * (sqrt((double)K) * 0.1 + fabs(pre))) ++bad;
+      const double pre_want = cs.act == 3 ? gelu_grad_h(pre) : pre;   // act 3 saves gelu'(pre)
+      const double ep = fabs(hpre[off] - pre_want);
+      if (ep > tol_rel * (sqrt((double)K) * 0.1 + fabs(pre_want))) ++bad;
     }
     ++checked;
   };
@@ -228,6 +230,8 @@ int main(int argc, char** argv) {
       {"nn_dx (B mn-major)", 256, 192, 128, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 1.f},
       {"nn_dx_relu_mask", 333, 256, 1024, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 1.f},
       {"nn_dx_gelu_grad", 333, 384, 512, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 1.f},
+      {"nn_dx_mul_saved_grad", 333, 384, 512, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 0, 0, 0, 1.f},
+      {"nt_gelu_save_dgrad", 1000, 768, 256, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 0, 1, 0, 1, 0, 0, 1.f},
       {"tn_dw (A,B mn-major)", 256, 128, 512, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 1.f},
       {"tn_dw_splitk_acc", 256, 320, 5000, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1.f},
       {"tn_dw_a_only", 192, 128, 304, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 1.f},

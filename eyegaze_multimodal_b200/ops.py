@@ -355,7 +355,9 @@ class Mlp2Fn(torch.autograd.Function):
         pre = None
         if act == L.ACT_GELU:
             pre = torch.empty(tuple(x.shape[:-1]) + (w1.shape[0],), dtype=x.dtype, device=x.device)
-        h = _linear_forward(x, w1c, b1.detach(), None, act, p_mid, s_mid, code, c_pre=pre)
+        # GELU: the epilogue saves gelu'(pre) (not pre), so the backward epilogue is a plain multiply
+        h = _linear_forward(x, w1c, b1.detach(), None, L.ACT_GELU_DGRAD if act == L.ACT_GELU else act, p_mid, s_mid, code,
+                            c_pre=pre)
         y = _linear_forward(h, w2c, b2.detach(), residual, 0, p_out, s_out, F32 if out_f32 else code)
         ctx.save_for_backward(x, h, pre, w1, w2)
         ctx.meta = (act, p_mid, p_out, s_mid, s_out, residual is not None, code)
@@ -377,7 +379,7 @@ class Mlp2Fn(torch.autograd.Function):
             dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_RELU_MASK, aux=h,
                                 aux_scale=1.0 / (1.0 - p_mid) if p_mid > 0 else 1.0)
         elif act == L.ACT_GELU:
-            dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_GELU, aux=pre, dropout_p=p_mid, seed=s_mid)
+            dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_MUL, aux=pre, dropout_p=p_mid, seed=s_mid)
         else:
             dpre1 = _grad_input(dyd, w2c, h.shape, code, dropout_p=p_mid, seed=s_mid)
         dw1 = _grad_weight(dpre1, x, w1.shape[0], w1.shape[1]) if need[2] else None

@@ -74,10 +74,12 @@ typedef struct {
 #define EGB_ACT_NONE 0
 #define EGB_ACT_RELU 1
 #define EGB_ACT_GELU 2
+#define EGB_ACT_GELU_DGRAD 3   /* GELU; c_pre (required) receives gelu'(pre-activation) instead of the pre-activation */
 /* backward-side epilogues: multiply the accumulator by act'(.) read from `aux` */
 #define EGB_ACTBWD_NONE 0
 #define EGB_ACTBWD_RELU_MASK 1 /* aux = forward OUTPUT y (post relu [+dropout]); x *= (y != 0) * aux_scale */
 #define EGB_ACTBWD_GELU 2      /* aux = forward PRE-activation; x *= gelu'(aux) */
+#define EGB_ACTBWD_MUL 3       /* aux = stored activation derivative (EGB_ACT_GELU_DGRAD); x *= aux */
 
 typedef struct {
   int32_t M, N, K;
