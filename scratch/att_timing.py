@@ -4,7 +4,7 @@ import torch
 from eyegaze_multimodal_b200 import _lib as L, ops
 dev = "cuda:0"
 buf = torch.zeros(8, dtype=torch.int64, device=dev)
-names = ["alloc", "stage tiles", "mma1", "softmax/dS", "mma2", "store", "dealloc"]
+names = ["s0", "s1", "s2", "s3", "s4", "s5", "s6"]
 for (S, Lq, D, H, tag) in [(256, 197, 768, 12, "ViT-B"), (512, 139, 256, 8, "EEG")]:
     qkv = (torch.randn(S, Lq, 3 * D, device=dev) * 0.5).bfloat16().requires_grad_(True)
     go = torch.randn(S, Lq, D, device=dev).bfloat16()
