@@ -1,6 +1,7 @@
 """MultimodalFusionModel + its loss -- the glue module the reference defines inside its training script
 (4_Experiments/scripts/train_multimodal_fuzzy_fusion.py:106-179, loss at :436-460)."""
 import os
+import warnings
 from typing import Dict, Optional
 
 import torch
@@ -28,6 +29,10 @@ class MultimodalFusionModel(nn.Module):
     # / spectrogram prologue, small-K GEMMs) fill the gaps the ViT's big GEMMs leave, and autograd replays each
     # branch's backward on the stream its forward ran on, so the backward overlaps the same way.
     concurrent_branches = os.environ.get("EGB_CONCURRENT_BRANCHES", "1") != "0"
+
+    # autograd notes that parameters first touched on the side stream accumulate their gradient there; that is the
+    # intended schedule (the engine inserts the cross-stream waits itself), so the advisory is silenced
+    warnings.filterwarnings("ignore", message="The AccumulateGrad node's stream does not match")
 
     def forward(self, img1: torch.Tensor, img2: torch.Tensor, eeg1: torch.Tensor, eeg2: torch.Tensor,
                 labels: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
