@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="trials per GPU (default: the workload's)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=2, help="trials per CPU-baseline step")
+    ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient all-reduce bucket size (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -259,7 +260,7 @@ def run_b200(args):
 
     model = build_model(wl, dev)
     model.train()
-    tp = TrialParallel(model, bucket_mb=32.0)
+    tp = TrialParallel(model, bucket_mb=args.bucket_mb)
     n_params = sum(p.numel() for p in model.parameters())
 
     # ---- synthetic inputs (seeded per rank: every rank owns different trials) --------------------------------

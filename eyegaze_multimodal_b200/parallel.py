@@ -5,10 +5,13 @@ The reference is single-process (no torch.distributed anywh
 forward and backward (LayerNorm per token, InstanceNorm per trial, no BatchNorm), so the path shards with no
 data-path collective.  Gradients are reduced in flat fp32 buckets:
 
-  * every trainable parameter's ``.grad`` is a *view* into a flat bucket buffer (no gather / scatter copies);
-  * a post-accumulate-grad hook counts a bucket's parameters down during backward; when the last one lands, the
+  * ``zero_grad()`` drops the gradients (``.grad = None``), so autograd hands every parameter its gradient tensor
+    without an accumulation kernel;
+  * a post-accumulate-grad hook counts a bucket's parameters down during backward; when the last one lands, ONE
+    multi-tensor copy packs the bucket's gradients into its flat buffer, ``.grad`` is re-pointed at the views, and the
     bucket's all-reduce (NCCL over NVLink / NVSwitch, average) is enqueued asynchronously, so it overlaps the rest
     of the backward pass (buckets are filled in reverse registration order ~ backward execution order);
+  * with a single rank nothing is packed or reduced at all;
   * ``finish()`` flushes buckets whose parameters received no gradient this step and makes the compute stream wait
     for the communication.
 
@@ -22,11 +25,12 @@ import torch.nn as nn
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "pending", "work", "launched")
+    __slots__ = ("flat", "params", "views", "pending", "work", "launched")
 
-    def __init__(self, flat, params):
+    def __init__(self, flat, params, views):
         self.flat = flat
         self.params = params
+        self.views = views
         self.pending = len(params)
         self.work = None
         self.launched = False
@@ -66,14 +70,15 @@ class TrialParallel(nn.Module):
             # 16-byte aligned slices keep the kernels' vectorised access to parameter gradients legal
             offs, n = [], 0
             for p in g:
-                offs.append(n)
-                n += (p.numel() + 3) // 4 * 4
-            flat = torch.zeros(n, dtype=torch.float32, device=g[0].device)
-            b = _Bucket(flat, g)
-            for p, o in zip(g, offs):
                 if p.dtype != torch.float32:
                     raise TypeError("TrialParallel expects fp32 master parameters")
-                p.grad = flat[o:o + p.numel()].view(p.shape)
+                offs.append(n)
+                n += (p.numel() + 3) // 4 * 4
+            flat = torch.zeros(n if self.world > 1 else 1, dtype=torch.float32, device=g[0].device)
+            views = [flat[o:o + p.numel()].view(p.shape) for p, o in zip(g, offs)] if self.world > 1 else []
+            b = _Bucket(flat, g, views)
+            for p in g:
+                p.grad = None
                 p.register_post_accumulate_grad_hook(self._make_hook(b))
             self.buckets.append(b)
 
@@ -88,6 +93,19 @@ class TrialParallel(nn.Module):
         b.launched = True
         if self.world == 1:
             return
+        if b.flat.is_cuda:
+            # gradients of a branch the model ran on a side stream (MultimodalFusionModel) are produced there
+            side = getattr(self.module, "_side_stream", None)
+            if side is not None:
+                torch.cuda.current_stream(b.flat.device).wait_stream(side)
+        with torch.no_grad():
+            have = [(v, p.grad) for v, p in zip(b.views, b.params) if p.grad is not None]
+            if len(have) != len(b.params):
+                b.flat.zero_()                 # parameters the loss did not reach contribute zeros
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+            for v, p in zip(b.views, b.params):
+                p.grad = v                     # the reduced values are what the optimiser sees
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
@@ -95,9 +113,10 @@ class TrialParallel(nn.Module):
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
-    def zero_grad(self, set_to_none: bool = False) -> None:   # noqa: D401 (views must survive: never set to None)
+    def zero_grad(self, set_to_none: bool = True) -> None:   # noqa: D401
         for b in self.buckets:
-            b.flat.zero_()
+            for p in b.params:
+                p.grad = None
             b.pending = len(b.params)
             b.work = None
             b.launched = False
@@ -115,7 +134,7 @@ class TrialParallel(nn.Module):
                 b.work = None
 
     def grad_bytes(self) -> int:
-        return sum(b.flat.numel() * 4 for b in self.buckets)
+        return sum(sum(p.numel() for p in b.params) * 4 for b in self.buckets)
 
     def flat_grads(self) -> Iterable[torch.Tensor]:
         return [b.flat for b in self.buckets]
