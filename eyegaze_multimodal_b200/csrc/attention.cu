@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttPar
         float pr = sc[jj] * inv;
         if (p.probs != nullptr) p.probs[row_id * p.Lk + j] = pr;
         if (p.drop_thresh != 0u)
-          pr = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + j), p.drop_thresh) ? pr * p.drop_scale : 0.f;
+          pr = drop_keep_att(p.seed, (unsigned long long)(row_id * p.Lk), j, p.drop_thresh) ? pr * p.drop_scale : 0.f;
         pb[warp * p.Lk + j] = pr;
       }
     }
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_dq_kernel(const Att
         }
         const float pr = __expf(a - lse);
         if (p.drop_thresh != 0u)
-          dp = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + j), p.drop_thresh) ? dp * p.drop_scale : 0.f;
+          dp = drop_keep_att(p.seed, (unsigned long long)(row_id * p.Lk), j, p.drop_thresh) ? dp * p.drop_scale : 0.f;
         pb[warp * p.Lk + j] = pr * (dp - dl);
       }
     }
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_dkv_kernel(const At
         const float pr = __expf(a * p.scale - p.lse[row_base + i]);
         float pt = pr;
         if (p.drop_thresh != 0u) {
-          const bool keep = drop_keep(p.seed, (unsigned long long)((row_base + i) * p.Lk + j), p.drop_thresh);
+          const bool keep = drop_keep_att(p.seed, (unsigned long long)((row_base + i) * p.Lk), j, p.drop_thresh);
           pt = keep ? pr * p.drop_scale : 0.f;
           dp = keep ? dp * p.drop_scale : 0.f;
         }
@@ -273,7 +273,7 @@ static int fill_att(const egb_attention_desc* d, AttParams* p) {
   p->S = d->S; p->H = d->H; p->Lq = d->Lq; p->Lk = d->Lk; p->dk_dim = d->head_dim; p->kv_shift = d->kv_shift;
   p->scale = d->scale;
   if (d->dropout_p > 0.f) {
-    p->drop_thresh = drop_threshold(d->dropout_p);
+    p->drop_thresh = drop_threshold16(d->dropout_p);   // 16-bit threshold of the paired decisions
     p->drop_scale = 1.f / (1.f - d->dropout_p);
     p->seed = d->seed;
   }

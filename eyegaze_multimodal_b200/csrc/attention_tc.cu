@@ -15,9 +15,12 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/eyegaze_b200.h"
+#include <cuda.h>
 #include <stdlib.h>
 
 extern void egb_count_launch(int n);
+int egb_tmap_rows64(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long groups, long long rs,
+                    long long gs, int box_rows);
 int egb_prof_enabled();
 void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind);
 void egb_prof_end(cudaStream_t st);
@@ -44,6 +47,11 @@ struct AttTcParams {
   float drop_scale;
   unsigned long long seed;
   long long* dbg;  // optional: phase timestamps (clock64) of CTA (0, 0, S/2), see egb_debug_attention_timing
+  int use_tma;     // pipelined backward: operand tiles arrive by TMA (head_dim 64) instead of cp.async
+};
+// tensor maps of the pipelined backward's operands ({H d, L, S} views, box {64, L_pad, 1}, 128-byte swizzle)
+struct AttMaps {
+  CUtensorMap q, k, v, g, o;
 };
 
 #define ATT_STAMP(slot)                                                                       \
@@ -52,6 +60,20 @@ struct AttTcParams {
         blockIdx.z == gridDim.z / 2)                                                          \
       p.dbg[slot] = clock64();                                                                \
   } while (0)
+
+// same, for a CTA in the middle of a (heads, sequences) grid: the first wave starts all its loads at once and is not
+// representative
+#define ATT_STAMP_MID(slot)                                                                   \
+  do {                                                                                        \
+    if (p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2) \
+      p.dbg[slot] = clock64();                                                                \
+  } while (0)
+
+#ifdef EGB_ATT_TIMING
+#define ATT_CLK(v) const long long v = clock64()
+#else
+#define ATT_CLK(v) const long long v = 0
+#endif
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
@@ -142,6 +164,66 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, int c_begin, int c
       }
     }
   }
+}
+
+// This warp's 32 accumulator rows x ncols (32 or 64) fp32 TMEM columns -> * mul -> bf16 -> global memory, written as
+// whole 64 / 128-byte row segments: the rows are staged in a warp-private 4 KB shared-memory area (16-byte slots
+// XOR-swizzled by row) and each store instruction then covers 32 / (ncols / 8) complete rows.  One thread owns one
+// TMEM lane = one row, so a direct store scatters 32 separate 16-byte pieces per instruction (measured: ~6 K cycles
+// of LSU time per backward CTA).  g0 = first of the warp's rows (may be past the end when rows_valid <= 0).
+__device__ __forceinline__ void store_acc_rows_coalesced(uint32_t taddr, int ncols, float mul, uint8_t* stage, bf16* g0,
+                                                         long long rs, int rows_valid, int lane) {
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t raw[32];
+    ptx::tmem_ld32(taddr + (uint32_t)c0, raw);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 v;
+      v.x = pack_bf16(__uint_as_float(raw[8 * g + 0]) * mul, __uint_as_float(raw[8 * g + 1]) * mul);
+      v.y = pack_bf16(__uint_as_float(raw[8 * g + 2]) * mul, __uint_as_float(raw[8 * g + 3]) * mul);
+      v.z = pack_bf16(__uint_as_float(raw[8 * g + 4]) * mul, __uint_as_float(raw[8 * g + 5]) * mul);
+      v.w = pack_bf16(__uint_as_float(raw[8 * g + 6]) * mul, __uint_as_float(raw[8 * g + 7]) * mul);
+      const int slot = (c0 >> 3) + g;
+      *reinterpret_cast<uint4*>(stage + lane * 128 + ((slot ^ (lane & 7)) << 4)) = v;
+    }
+  }
+  __syncwarp();
+  const int sh = ncols == 64 ? 3 : 2;             // log2(16-byte pieces per row)
+  const int ch = lane & ((1 << sh) - 1), r0 = lane >> sh, rpi = 32 >> sh;
+  for (int it = 0; it < (1 << sh); ++it) {
+    const int rr = it * rpi + r0;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+    if (rr < rows_valid) *reinterpret_cast<uint4*>(g0 + (long long)rr * rs + ch * 8) = v;
+  }
+  __syncwarp();
+}
+
+// Same for exactly 32 columns with a 2 KB staging area per warp (rows pitched 64 B; the slot swizzle keeps both the
+// row-wise writes and the 8-rows-per-instruction read-out free of bank conflicts).
+__device__ __forceinline__ void store_acc_rows32_coalesced(uint32_t taddr, float mul, uint8_t* stage, bf16* g0, long long rs,
+                                                           int rows_valid, int lane) {
+  uint32_t raw[32];
+  ptx::tmem_ld32(taddr, raw);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 v;
+    v.x = pack_bf16(__uint_as_float(raw[8 * g + 0]) * mul, __uint_as_float(raw[8 * g + 1]) * mul);
+    v.y = pack_bf16(__uint_as_float(raw[8 * g + 2]) * mul, __uint_as_float(raw[8 * g + 3]) * mul);
+    v.z = pack_bf16(__uint_as_float(raw[8 * g + 4]) * mul, __uint_as_float(raw[8 * g + 5]) * mul);
+    v.w = pack_bf16(__uint_as_float(raw[8 * g + 6]) * mul, __uint_as_float(raw[8 * g + 7]) * mul);
+    *reinterpret_cast<uint4*>(stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = v;
+  }
+  __syncwarp();
+  const int ch = lane & 3, r0 = lane >> 2;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + r0;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+    if (rr < rows_valid) *reinterpret_cast<uint4*>(g0 + (long long)rr * rs + ch * 8) = v;
+  }
+  __syncwarp();
 }
 
 // barrier init (thread 0) -- TMEM is allocated AFTER the tile copies have been issued, so a CTA that has to wait
@@ -263,12 +345,14 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float e2[2];
+        uint32_t hb = 0;                            // one hash decides both columns of the pair (drop_keep_att)
+        if (DROP) hb = drop_hash(p.seed, (unsigned long long)(row_id * p.Lk + c * 32 + 2 * j));
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int col = c * 32 + 2 * j + u;
           float e = col < p.Lk ? fast_exp2(__uint_as_float(raw[2 * j + u]) * sl2 - mb) : 0.f;
           sum += e;
-          if (DROP) e = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? e * p.drop_scale : 0.f;
+          if (DROP) e = (u ? (hb >> 16) : (hb & 0xFFFFu)) >= p.drop_thresh ? e * p.drop_scale : 0.f;
           e2[u] = e;
         }
         pk[j] = pack_bf16(e2[0], e2[1]);
@@ -394,7 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
           const int col = 64 * c + 32 * half + 2 * j + u;
           const float pr = fast_exp2(__uint_as_float(rs[2 * j + u]) * sl2 - lse2);
           float dp = __uint_as_float(rp[2 * j + u]);
-          if (DROP) dp = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh) ? dp * p.drop_scale : 0.f;
+          if (DROP) dp = drop_keep_att(p.seed, (unsigned long long)(row_id * p.Lk), col, p.drop_thresh) ? dp * p.drop_scale : 0.f;
           ds2[u] = col < p.Lk ? pr * (dp - dl) : 0.f;
         }
         pk[j] = pack_bf16(ds2[0], ds2[1]);
@@ -509,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
           float dp = __uint_as_float(rp[2 * jj + u]);
           float pt = pr;
           if (DROP) {
-            const bool keep = drop_keep(p.seed, (unsigned long long)((row_base + col) * p.Lk + j), p.drop_thresh);
+            const bool keep = drop_keep_att(p.seed, (unsigned long long)((row_base + col) * p.Lk), j, p.drop_thresh);
             pt = keep ? pr * p.drop_scale : 0.f;
             dp = keep ? dp * p.drop_scale : 0.f;
           }
@@ -705,6 +789,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) att_tc_bwd_fused_kernel(const A
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float pt2[2], ds2[2];
+            uint32_t hb = 0;                        // one hash decides both columns of the pair (drop_keep_att)
+            if (DROP) hb = drop_hash(p.seed, (unsigned long long)(row_id * p.Lk + 128 * c + 64 * half + 32 * g + 2 * j));
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int col = 128 * c + 64 * half + 32 * g + 2 * j + u;   // key index
@@ -713,7 +799,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) att_tc_bwd_fused_kernel(const A
               float dp = __uint_as_float(rp[2 * j + u]);
               float pt = pr;
               if (DROP) {
-                const bool keep = drop_keep(p.seed, (unsigned long long)(row_id * p.Lk + col), p.drop_thresh);
+                const bool keep = (u ? (hb >> 16) : (hb & 0xFFFFu)) >= p.drop_thresh;
                 pt = keep ? pr * p.drop_scale : 0.f;
                 dp = keep ? dp * p.drop_scale : 0.f;
               }
@@ -794,6 +880,338 @@ __global__ void __launch_bounds__(TC_THREADS, 1) att_tc_bwd_fused_kernel(const A
   ATT_STAMP(7);
 }
 
+
+// ======================================================================================= pipelined fused backward
+// Same data flow as att_tc_bwd_fused_kernel, re-scheduled so that the tensor core and the softmax threads never wait
+// for each other's latency (measured: in the kernel above every round pays the tcgen05 issue -> commit round trip
+// plus the issuing thread's serial MMA stream on its critical path):
+//   * a dedicated ninth warp issues every MMA; the 256 softmax threads never issue, they only signal mbarriers;
+//   * rounds are 64 keys wide and the score pair (S, dP) is DOUBLE-BUFFERED in TMEM ([0,128) / [128,256)): the
+//     scores of round r+1 are computed while the threads turn round r into P~ / dS;
+//   * dV / dK accumulate once per PAIR of rounds (M = 128 keys) from the two 64-key halves of sP / sDS;
+//   * dQ_t goes to spare TMEM columns when there are any (head_dim 32, or <= 128 keys), else into the score set the
+//     q-tile's last round has just released.
+// Barriers: bar_sp[set] (MMA -> threads: scores ready), bar_rd[set] (threads -> MMA: set consumed, tiles written),
+// bar_acc (pair's accumulating MMAs retired: sP reusable), bar_dq (dQ_t and everything before it retired),
+// bar_dqrd (threads -> MMA: dQ_t read out).
+constexpr int PIPE_THREADS = TC_THREADS + 64;   // 8 softmax warps + 2 MMA-issuing warps
+
+// 32 key columns of one query row of the backward pass: raw scores rs and dP~ = dO V^T rp (fp32 bit patterns from TMEM)
+//   P = exp2(S sl2 - lse2),  P~ = dropout(P),  dS = P (dropout(dP~) - delta)      -> packed bf16 pairs pkp / pks.
+// The loop is bound by instruction issue (two warps per scheduler), so the common case is stripped down: FAST = all
+// 32 columns are real keys and the dropout counter does not carry into its high word -- no per-column predicates,
+// one hash per column PAIR with the high-word product hoisted, keep-tests on the un-extracted halves
+// (lo16 >= t  <=>  h << 16 >= t << 16;  hi16 >= t  <=>  h >= t << 16).  Rows past the sequence end come in with
+// lse2 = +inf, which makes their P exactly 0 without a predicate.  Both paths produce the mask of drop_keep_att().
+template <bool DROP, bool FAST>
+__device__ __forceinline__ void softmax_bwd_cols32(const uint32_t (&rs)[32], const uint32_t (&rp)[32], float sl2, float lse2,
+                                                   float dl, int col0, int Lk, unsigned long long seed,
+                                                   unsigned long long row_lin, uint32_t t16, float drop_scale,
+                                                   uint32_t (&pkp)[16], uint32_t (&pks)[16]) {
+  const unsigned long long base = row_lin + (unsigned long long)col0;
+  const uint32_t lo0 = (uint32_t)base, seed_lo = (uint32_t)seed;
+  const uint32_t hi_term = ((uint32_t)(base >> 32) ^ (uint32_t)(seed >> 32)) * 0x85EBCA77u;
+  const uint32_t t16s = t16 << 16;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float m0 = 1.f, m1 = 1.f;
+    if (DROP) {
+      uint32_t h;
+      if (FAST) {
+        h = ((lo0 + (uint32_t)(2 * j)) ^ seed_lo) * 0x9E3779B1u + hi_term;
+        h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;
+      } else {
+        h = drop_hash(seed, base + (unsigned long long)(2 * j));
+      }
+      m0 = (h << 16) >= t16s ? drop_scale : 0.f;
+      m1 = h >= t16s ? drop_scale : 0.f;
+    }
+    float p0 = fast_exp2(fmaf(__uint_as_float(rs[2 * j]), sl2, -lse2));
+    float p1 = fast_exp2(fmaf(__uint_as_float(rs[2 * j + 1]), sl2, -lse2));
+    if (!FAST) {
+      if (col0 + 2 * j >= Lk) p0 = 0.f;
+      if (col0 + 2 * j + 1 >= Lk) p1 = 0.f;
+    }
+    const float d0 = __uint_as_float(rp[2 * j]), d1 = __uint_as_float(rp[2 * j + 1]);
+    pkp[j] = pack_bf16(p0 * m0, p1 * m1);
+    pks[j] = pack_bf16(p0 * (DROP ? fmaf(d0, m0, -dl) : d0 - dl), p1 * (DROP ? fmaf(d1, m1, -dl) : d1 - dl));
+  }
+}
+
+
+template <bool DROP>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sQ = align1024(smem_raw);
+  uint8_t* sG = sQ + p.Lq_pad * 128;             // dO
+  uint8_t* sK = sG + p.Lq_pad * 128;
+  uint8_t* sV = sK + p.Lk_pad * 128;
+  uint8_t* sP = sV + p.Lk_pad * 128;             // [2 x 64 keys][128 q rows][128 B]   P~ of the current pair of rounds
+  uint8_t* sDS = sP + 2 * TILE_ROWS * 128;       // [nc x 64 keys][128 q rows][128 B]  dS of the current q-tile
+  const int nk = (p.Lk_pad + 127) / 128, nc = (p.Lk_pad + 63) / 64, nq = (p.Lq + 127) / 128;
+  const int R = nq * nc;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + (size_t)nk * 2 * TILE_ROWS * 128);
+  uint64_t* bar_sp = &bars[0];                   // [2]
+  uint64_t* bar_rd = &bars[2];                   // [2]
+  uint64_t* bar_acc = &bars[4];
+  uint64_t* bar_dq = &bars[5];
+  uint64_t* bar_dqrd = &bars[6];
+  uint64_t* bar_ld = &bars[7];                   // TMA tile loads
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int h = blockIdx.x, s = blockIdx.y;
+  const int skv = (s + p.kv_shift) % p.S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+  const int d = p.d;
+  const long long row_base = ((long long)s * p.H + h) * p.Lq;
+  const bool softmax_thread = warp < 8;
+  // TMEM columns: score sets [0,128) [128,256); dV_kc, dK_kc (d columns each per 128-key chunk), dQ
+  const uint32_t DV0 = 256, DK0 = 256 + (uint32_t)(d * nk), DQ0 = 256 + (uint32_t)(2 * d * nk);
+  const bool dq_alias = DQ0 + (uint32_t)d > 512u;
+
+  ATT_STAMP_MID(0);
+  long long w_sp = 0, w_acc = 0, w_dq = 0, w_el = 0, w_wr = 0;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar_sp[0], 1);
+    ptx::mbar_init(&bar_sp[1], 1);
+    ptx::mbar_init(&bar_rd[0], TC_THREADS);
+    ptx::mbar_init(&bar_rd[1], TC_THREADS);
+    ptx::mbar_init(bar_acc, 1);
+    ptx::mbar_init(bar_dq, 1);
+    ptx::mbar_init(bar_dqrd, TC_THREADS);
+    ptx::mbar_init(bar_ld, 1);
+    ptx::fence_barrier_init();
+    if (p.use_tma) {
+      // one bulk tensor copy per tile; rows past the sequence end are zero-filled by the TMA unit.  (The cp.async
+      // path below is capped by the SM's outstanding-request budget at ~16 B/clk against DRAM latency: measured
+      // 8 K cycles for the 132 KB of a ViT-B head, a quarter of the CTA's life.)
+      ptx::mbar_arrive_expect_tx(bar_ld, (uint32_t)((3 * p.Lq_pad + 2 * p.Lk_pad) * 128));
+      ptx::tma_load_3d(sQ, &maps.q, bar_ld, h * d, 0, s);
+      ptx::tma_load_3d(sG, &maps.g, bar_ld, h * d, 0, s);
+      ptx::tma_load_3d(sK, &maps.k, bar_ld, h * d, 0, skv);
+      ptx::tma_load_3d(sV, &maps.v, bar_ld, h * d, 0, skv);
+      ptx::tma_load_3d(sP, &maps.o, bar_ld, h * d, 0, s);
+    }
+  }
+  float dl_t[2] = {0.f, 0.f}, lse_t[2] = {0.f, 0.f};
+  const int n16 = d >> 3;
+  if (softmax_thread) {
+   if (!p.use_tma) {
+    load_rows_sw128(sQ, p.q + s * p.q_bs + h * d, p.q_rs, p.Lq, p.Lq_pad, d);
+    load_rows_sw128(sG, p.d_o + s * p.do_bs + h * d, p.do_rs, p.Lq, p.Lq_pad, d);
+    load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
+    load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+    // delta_i = dO_i . O_i: O is staged like the other tiles (coalesced; a per-thread read of its own row straight
+    // from global memory costs 32 sectors per instruction) into the still idle sP area
+    load_rows_sw128(sP, p.o + s * p.o_bs + h * d, p.o_rs, p.Lq, p.Lq_pad, d);
+   }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = t * TILE_ROWS + row;
+      if (i < p.Lq) lse_t[t] = p.lse[row_base + i];
+    }
+    ATT_STAMP_MID(1);
+    cp_async_wait_all();
+    ptx::fence_proxy_async_smem();
+  } else if (warp == 8) {
+    ptx::tmem_alloc<512>(slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (p.use_tma) ptx::mbar_wait(bar_ld, 0);
+  ATT_STAMP_MID(2);
+
+  if (!softmax_thread) {
+    // ------------------------------------------------------------------------------------------ MMA issuers
+    // Two issuing threads (each tcgen05.commit tracks its own thread's MMAs): warp 8 feeds the score sets, warp 9
+    // the accumulators and dQ -- a single thread's serial instruction stream (~40 cycles per MMA) put the 16
+    // accumulating MMAs of a pair in front of the next scores.
+    if (lane == 0 && warp == 8) {
+      auto issue_scores = [&](int r2) {
+        const int t2 = r2 / nc, c2 = r2 - t2 * nc;
+        const int w2 = min(64, p.Lk_pad - 64 * c2);
+        const uint32_t sb = tmem + 128u * (uint32_t)(r2 & 1);
+        mma_ss_kk(sb, sQ + (size_t)t2 * TILE_ROWS * 128, sK + (size_t)c2 * 64 * 128, w2, d);
+        mma_ss_kk(sb + 64, sG + (size_t)t2 * TILE_ROWS * 128, sV + (size_t)c2 * 64 * 128, w2, d);
+        ptx::umma_commit(&bar_sp[r2 & 1]);
+      };
+      issue_scores(0);
+      if (R > 1) issue_scores(1);
+      for (int r = 0, t = 0, c = 0; r + 2 < R; ++r) {
+        ptx::mbar_wait(&bar_rd[r & 1], (uint32_t)((r >> 1) & 1));   // set r & 1 consumed
+        if (c == nc - 1 && dq_alias) ptx::mbar_wait(bar_dqrd, (uint32_t)(t & 1));   // ... and dQ_t, parked there, read out
+        ptx::tc_fence_after();
+        issue_scores(r + 2);
+        if (++c == nc) { c = 0; ++t; }
+      }
+    } else if (lane == 0 && warp == 9) {
+      for (int r = 0, t = 0, c = 0; r < R; ++r) {
+        const bool last_c = c == nc - 1;
+        if ((c & 1) || last_c) {
+          ptx::mbar_wait(&bar_rd[r & 1], (uint32_t)((r >> 1) & 1));   // P~ / dS tiles of the pair written
+          ptx::tc_fence_after();
+          const uint8_t* gq = sG + (size_t)t * TILE_ROWS * 128;   // dO rows of this q-tile (MN-major B: k rows = queries)
+          const uint8_t* qq = sQ + (size_t)t * TILE_ROWS * 128;
+          const int kc = c >> 1;
+          mma_ss_mnmn(tmem + DV0 + (uint32_t)(d * kc), sP, gq, TILE_ROWS / 16, d, t > 0);                                     // dV_kc += P~^T dO_t
+          mma_ss_mnmn(tmem + DK0 + (uint32_t)(d * kc), sDS + (size_t)kc * 2 * TILE_ROWS * 128, qq, TILE_ROWS / 16, d, t > 0); // dK_kc += dS^T Q_t
+          ptx::umma_commit(bar_acc);
+          if (last_c) {
+            mma_ss_kmn(tmem + (dq_alias ? 128u * (uint32_t)(r & 1) : DQ0), sDS, sK, p.Lk_pad, d);   // dQ_t = dS_t K
+            ptx::umma_commit(bar_dq);
+          }
+        }
+        if (++c == nc) { c = 0; ++t; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------ softmax threads
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sl2 = p.scale * LOG2E;
+    uint8_t* stage = sP + warp * 4096;            // warp-private staging rows of the coalesced result stores
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = t * TILE_ROWS + row;
+      if (i < p.Lq) {
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (u < n16) {
+            const size_t off = (size_t)i * 128 + ((u ^ (i & 7)) << 4);
+            const uint4 gb = *reinterpret_cast<const uint4*>(sG + off);
+            const uint4 ob = *reinterpret_cast<const uint4*>(sP + off);
+            const __nv_bfloat162* oa = reinterpret_cast<const __nv_bfloat162*>(&ob);
+            const __nv_bfloat162* ga = reinterpret_cast<const __nv_bfloat162*>(&gb);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              acc = fmaf(__low2float(oa[v]), __low2float(ga[v]), acc);
+              acc = fmaf(__high2float(oa[v]), __high2float(ga[v]), acc);
+            }
+          }
+        }
+        dl_t[t] = acc;
+        lse_t[t] *= LOG2E;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // O rows consumed: sP may be written
+    auto read_dq = [&](int tq) {
+      ATT_CLK(c0);
+      ptx::mbar_wait(bar_dq, (uint32_t)(tq & 1));
+      ATT_CLK(c1);
+      w_dq += c1 - c0;
+      ptx::tc_fence_after();
+      const uint32_t col = dq_alias ? 128u * (uint32_t)(((tq + 1) * nc - 1) & 1) : DQ0;
+      // sP is idle here (bar_dq covers the accumulating MMAs that read it; this round's tiles are written later)
+      const int r0 = tq * TILE_ROWS + (warp & 3) * 32;
+      const int cb = d >= 64 ? half * 32 : 0;
+      if (d >= 64 || half == 0)
+        store_acc_rows_coalesced(trow + col + (uint32_t)cb, 32, p.scale, stage,
+                                 p.dq + s * p.dq_bs + (long long)r0 * p.dq_rs + h * d + cb, p.dq_rs, p.Lq - r0, lane);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_dqrd);
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // every warp's staging rows are free again
+    };
+    int pairs = 0;                                // accumulating MMA groups issued so far
+    for (int r = 0, t = 0, c = 0; r < R; ++r) {
+      const int set = r & 1;
+      const int w = min(64, p.Lk_pad - 64 * c);
+      const int i = t * TILE_ROWS + row;          // query row of this thread
+      const bool valid = i < p.Lq;
+      const long long row_id = row_base + (valid ? i : 0);
+      const float dl = t == 0 ? dl_t[0] : dl_t[1];
+      const float lse2 = !valid ? INFINITY : t == 0 ? lse_t[0] : lse_t[1];   // +inf: P = 0 on the padding rows
+      ATT_CLK(c0);
+      ptx::mbar_wait(&bar_sp[set], (uint32_t)((r >> 1) & 1));
+      ATT_CLK(c1);
+      w_sp += c1 - c0;
+      ptx::tc_fence_after();
+
+      // this thread: 32 key columns [32 half, 32 half + 32) of the 64-key round
+      uint32_t pkp[16], pks[16];
+      const bool mine = 32 * half < w;
+      if (mine) {
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld32(trow + 128u * (uint32_t)set + (uint32_t)(32 * half), rs);
+        ptx::tmem_ld32(trow + 128u * (uint32_t)set + 64u + (uint32_t)(32 * half), rp);
+        ptx::tmem_ld_wait();
+        const int col0 = 64 * c + 32 * half;      // first key column of this thread
+        const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
+        const bool fast = col0 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)col0) <= 0xFFFFFFFFu - 32u;
+        if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+      }
+      // previous q-tile's dQ: read it out behind this round's arithmetic; its barrier also covers the MMAs that read
+      // the previous q-tile's sDS, which this q-tile now overwrites
+      ATT_CLK(c2);
+      w_el += c2 - c1;
+      if (c == 0 && t > 0) read_dq(t - 1);
+      // the accumulating MMAs of the previous pair read sP: they must have retired before the first overwrite
+      ATT_CLK(c3);
+      if ((c & 1) == 0 && pairs > 0) ptx::mbar_wait(bar_acc, (uint32_t)((pairs - 1) & 1));
+      ATT_CLK(c4);
+      w_acc += c4 - c3;
+      if (mine) {
+        uint8_t* prow = sP + (c & 1) * (TILE_ROWS * 128) + row * 128;
+        uint8_t* srow = sDS + (size_t)c * (TILE_ROWS * 128) + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int slot16 = ((half * 4 + q4) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + slot16) = make_uint4(pkp[4 * q4], pkp[4 * q4 + 1], pkp[4 * q4 + 2], pkp[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(srow + slot16) = make_uint4(pks[4 * q4], pks[4 * q4 + 1], pks[4 * q4 + 2], pks[4 * q4 + 3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_rd[set]);
+      ATT_CLK(c5);
+      w_wr += c5 - c4;
+      if ((c & 1) || c == nc - 1) ++pairs;
+      if (++c == nc) { c = 0; ++t; }
+    }
+    ATT_STAMP_MID(3);
+    // Two key chunks: dV_0 / dK_0 have been final since the last q-tile's first pair retired (bar_acc, waited for in
+    // round c = 2) -- store them while the last pair's MMAs and dQ drain.  Staging goes to sV, which only the score
+    // MMAs read and those have all been consumed (sP / sDS / sQ / sG / sK are still being read).
+    const bool early0 = nk == 2;
+    if (early0) {
+      const int j0 = (warp & 3) * 32;
+      uint8_t* st2 = sV + warp * 2048;
+      for (int c0 = 0; c0 < d; c0 += 32) {
+        if (half == 0)
+          store_acc_rows32_coalesced(trow + DV0 + (uint32_t)c0, 1.f, st2, p.dv + skv * p.dv_bs + (long long)j0 * p.dv_rs + h * d + c0,
+                                     p.dv_rs, p.Lk - j0, lane);
+        else
+          store_acc_rows32_coalesced(trow + DK0 + (uint32_t)c0, p.scale, st2, p.dk + skv * p.dk_bs + (long long)j0 * p.dk_rs + h * d + c0,
+                                     p.dk_rs, p.Lk - j0, lane);
+      }
+    }
+    read_dq(nq - 1);                              // bar_dq of the last q-tile covers every MMA: dV / dK are final
+    for (int kc = early0 ? 1 : 0; kc < nk; ++kc) {
+      const int j0 = kc * TILE_ROWS + (warp & 3) * 32;   // first key row of this warp
+      if (half == 0)
+        store_acc_rows_coalesced(trow + DV0 + (uint32_t)(d * kc), d, 1.f, stage,
+                                 p.dv + skv * p.dv_bs + (long long)j0 * p.dv_rs + h * d, p.dv_rs, p.Lk - j0, lane);
+      else
+        store_acc_rows_coalesced(trow + DK0 + (uint32_t)(d * kc), d, p.scale, stage,
+                                 p.dk + skv * p.dk_bs + (long long)j0 * p.dk_rs + h * d, p.dk_rs, p.Lk - j0, lane);
+    }
+  }
+  ATT_STAMP_MID(4);
+  if (p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2) {
+    p.dbg[8] = w_sp; p.dbg[9] = w_acc; p.dbg[10] = w_dq; p.dbg[11] = w_el; p.dbg[12] = w_wr;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ATT_STAMP_MID(5);
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem);
+  }
+}
+
 template <typename K>
 int set_smem_tc(K kernel, size_t bytes) {
   EGB_CHECK(bytes <= 227 * 1024, "attention_tc: needs %zu bytes of shared memory (> 227 KB)", bytes);
@@ -817,7 +1235,7 @@ int fill_tc(const egb_attention_desc* d, AttTcParams* p) {
   p->Lk_pad = (d->Lk + 15) / 16 * 16;
   p->scale = d->scale;
   if (d->dropout_p > 0.f) {
-    p->drop_thresh = drop_threshold(d->dropout_p);
+    p->drop_thresh = drop_threshold16(d->dropout_p);   // 16-bit threshold of the paired decisions
     p->drop_scale = 1.f / (1.f - d->dropout_p);
     p->seed = d->seed;
   }
@@ -880,15 +1298,32 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
   EGB_CHECK(d->lse && d->d_o && d->dq && d->dk && d->dv, "attention_bwd: missing buffers");
   const bool drop = p.drop_thresh != 0u;
   const bool prof = egb_prof_enabled() != 0;
-  static const int fused = getenv("EGB_ATT_FUSED_BWD") ? atoi(getenv("EGB_ATT_FUSED_BWD")) : 1;
+  static const int fused = getenv("EGB_ATT_FUSED_BWD") ? atoi(getenv("EGB_ATT_FUSED_BWD")) : 2;   // 2 pipelined, 1 fused, 0 two kernels
   const int nk = (p.Lk_pad + 127) / 128;
-  const size_t smem_f = (size_t)(2 * p.Lq_pad + 2 * p.Lk_pad) * 128 + (size_t)(2 + 2 * nk) * TILE_ROWS * 128 + 1024 + 64;
+  const size_t smem_f = (size_t)(2 * p.Lq_pad + 2 * p.Lk_pad) * 128 + (size_t)(2 + 2 * nk) * TILE_ROWS * 128 + 1024 + 128;
   if (fused && smem_f <= 227 * 1024) {
     if (set_smem_tc(att_tc_bwd_fused_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_fused_kernel<false>, smem_f)) return 1;
+    if (set_smem_tc(att_tc_bwd_pipe_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_pipe_kernel<false>, smem_f)) return 1;
     dim3 grid(d->H, d->S);
     if (prof) egb_prof_begin(st, 10.0 * d->S * d->H * (double)d->Lq * d->Lk * d->head_dim,
                              2.0 * d->S * d->H * (double)d->head_dim * (4.0 * d->Lq + 4.0 * d->Lk), 3);
-    if (drop) att_tc_bwd_fused_kernel<true><<<grid, TC_THREADS, smem_f, st>>>(p);
+    if (fused >= 2) {
+      static const int tma = getenv("EGB_ATT_TMA") ? atoi(getenv("EGB_ATT_TMA")) : 1;
+      AttMaps maps;
+      memset(&maps, 0, sizeof(maps));
+      if (tma && d->head_dim == 64) {
+        const long long inner = (long long)d->H * d->head_dim;
+        if (egb_tmap_rows64(&maps.q, d->q, inner, d->Lq, d->S, d->q_rs, d->q_bs, p.Lq_pad) ||
+            egb_tmap_rows64(&maps.g, d->d_o, inner, d->Lq, d->S, d->do_rs, d->do_bs, p.Lq_pad) ||
+            egb_tmap_rows64(&maps.o, d->o, inner, d->Lq, d->S, d->o_rs, d->o_bs, p.Lq_pad) ||
+            egb_tmap_rows64(&maps.k, d->k, inner, d->Lk, d->S, d->k_rs, d->k_bs, p.Lk_pad) ||
+            egb_tmap_rows64(&maps.v, d->v, inner, d->Lk, d->S, d->v_rs, d->v_bs, p.Lk_pad))
+          return 1;
+        p.use_tma = 1;
+      }
+      if (drop) att_tc_bwd_pipe_kernel<true><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
+      else att_tc_bwd_pipe_kernel<false><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
+    } else if (drop) att_tc_bwd_fused_kernel<true><<<grid, TC_THREADS, smem_f, st>>>(p);
     else att_tc_bwd_fused_kernel<false><<<grid, TC_THREADS, smem_f, st>>>(p);
     if (prof) egb_prof_end(st);
     egb_count_launch(1);

@@ -100,6 +100,20 @@ __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint64_t idx) {
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
   return drop_hash(seed, idx) >= thresh;
 }
+// Attention-probability dropout: ONE hash decides TWO adjacent key columns (16 random bits each, p resolved to 2^-16).
+// The softmax loops of the tensor-core attention kernels are bound by integer throughput once dropout is on
+// (measured on the EEG encoder: ~2.2 K of 3.1 K cycles per 128 x 64 round); halving the hashes halves that.
+__device__ __forceinline__ bool drop_keep_att(uint64_t seed, uint64_t row_lin, int col, uint32_t thresh16) {
+  const uint32_t h = drop_hash(seed, row_lin + (uint64_t)(col & ~1));
+  return ((col & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16;
+}
+static inline uint32_t drop_threshold16(float p) {
+  if (!(p > 0.f)) return 0u;
+  double t = (double)p * 65536.0;
+  if (t < 1.0) t = 1.0;
+  if (t > 65535.0) t = 65535.0;
+  return (uint32_t)t;
+}
 static inline uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;
   if (t < 0) t = 0;

@@ -918,6 +918,13 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
 // Debug aid: device buffer of [grid][8] int64 receiving per-CTA barrier-wait cycle totals of the following tensor-core
 // GEMM launches: [0] producer waiting for a free stage, [1] MMA warp waiting for operands, [2] MMA warp waiting for
 // a drained accumulator, [3] epilogue warp waiting for an accumulator, [4] kernel cycles.  NULL disables.
+// 3-D bf16 tensor map {inner, rows, groups} with a {64 elements, box_rows, 1} box, 128-byte swizzle (cached); used by
+// the attention kernels to stage per-head row tiles with one TMA instruction each
+int egb_tmap_rows64(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long groups, long long rs,
+                    long long gs, int box_rows) {
+  return make_map(out, ptr, inner, rows, groups, rs, gs, box_rows, 1);
+}
+
 extern "C" int egb_debug_gemm_timing(long long* device_buf) {
   g_gemm_dbg = device_buf;
   return 0;
