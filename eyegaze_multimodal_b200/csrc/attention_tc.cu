@@ -245,16 +245,55 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem) {
   }
 }
 
+// 32 key columns of one query row of the forward pass: e = exp2(S sl2 - mb) (row sum returned), P~ = dropout(e) packed
+// to bf16 pairs.  FAST = all 32 columns are real keys and the dropout counter does not carry into its high word (see
+// softmax_bwd_cols32 for the reasoning; both produce the mask of drop_keep_att()).
+template <bool DROP, bool FAST>
+__device__ __forceinline__ float softmax_fwd_cols32(const uint32_t (&raw)[32], float sl2, float mb, int col0, int Lk,
+                                                    unsigned long long seed, unsigned long long row_lin, uint32_t t16,
+                                                    float drop_scale, uint32_t (&pk)[16]) {
+  const unsigned long long base = row_lin + (unsigned long long)col0;
+  const uint32_t lo0 = (uint32_t)base, seed_lo = (uint32_t)seed;
+  const uint32_t hi_term = ((uint32_t)(base >> 32) ^ (uint32_t)(seed >> 32)) * 0x85EBCA77u;
+  const uint32_t t16s = t16 << 16;
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float e0 = fast_exp2(fmaf(__uint_as_float(raw[2 * j]), sl2, -mb));
+    float e1 = fast_exp2(fmaf(__uint_as_float(raw[2 * j + 1]), sl2, -mb));
+    if (!FAST) {
+      if (col0 + 2 * j >= Lk) e0 = 0.f;
+      if (col0 + 2 * j + 1 >= Lk) e1 = 0.f;
+    }
+    sum0 += e0;
+    sum1 += e1;
+    if (DROP) {
+      uint32_t h;
+      if (FAST) {
+        h = ((lo0 + (uint32_t)(2 * j)) ^ seed_lo) * 0x9E3779B1u + hi_term;
+        h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;
+      } else {
+        h = drop_hash(seed, base + (unsigned long long)(2 * j));
+      }
+      e0 *= (h << 16) >= t16s ? drop_scale : 0.f;
+      e1 *= h >= t16s ? drop_scale : 0.f;
+    }
+    pk[j] = pack_bf16(e0, e1);
+  }
+  return sum0 + sum1;
+}
+
 // ======================================================================================= forward
 template <bool DROP>
-__global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 3) att_tc_fwd_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
   uint8_t* sK = sQ + TILE_ROWS * 128;
   uint8_t* sV = sK + p.Lk_pad * 128;
   float* s_red = reinterpret_cast<float*>(sV + p.Lk_pad * 128);  // [2][128] cross-half row statistics
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 2 * TILE_ROWS);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bar_ld = &bars[2];                   // TMA tile loads (head_dim 64)
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 3);
   const int q0 = blockIdx.x * TILE_ROWS, h = blockIdx.y, s = blockIdx.z;
   const int skv = (s + p.kv_shift) % p.S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -262,10 +301,23 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
   const int d = p.d;
 
   ATT_STAMP(0);
-  init_bars(bars);
-  load_rows_sw128(sQ, p.q + s * p.q_bs + (long long)q0 * p.q_rs + h * d, p.q_rs, min(TILE_ROWS, p.Lq - q0), TILE_ROWS, d);
-  load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
-  load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::mbar_init(bar_ld, 1);
+    ptx::fence_barrier_init();
+    if (p.use_tma) {   // one bulk tensor copy per tile; rows past the sequence end are zero-filled by the TMA unit
+      ptx::mbar_arrive_expect_tx(bar_ld, (uint32_t)((TILE_ROWS + 2 * p.Lk_pad) * 128));
+      ptx::tma_load_3d(sQ, &maps.q, bar_ld, h * d, q0, s);
+      ptx::tma_load_3d(sK, &maps.k, bar_ld, h * d, 0, skv);
+      ptx::tma_load_3d(sV, &maps.v, bar_ld, h * d, 0, skv);
+    }
+  }
+  if (!p.use_tma) {
+    load_rows_sw128(sQ, p.q + s * p.q_bs + (long long)q0 * p.q_rs + h * d, p.q_rs, min(TILE_ROWS, p.Lq - q0), TILE_ROWS, d);
+    load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
+    load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+  }
   if (warp == 0) ptx::tmem_alloc<256>(slot);
   ATT_STAMP(1);
   cp_async_wait_all();
@@ -274,6 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *slot;
+  if (p.use_tma) ptx::mbar_wait(bar_ld, 0);
   ATT_STAMP(2);
 
   if (threadIdx.x == 0) {
@@ -289,9 +342,12 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
   ptx::tc_fence_after();
   ATT_STAMP(3);
 
+  // Warps whose 32 query rows all lie past the sequence end (EEG: L = 139 leaves 11 rows in the second tile) skip the
+  // softmax arithmetic; their P rows stay undefined, which only reaches O rows that are never stored.
+  const bool warp_live = q0 + (warp & 3) * 32 < p.Lq;
   // pass 1: row maximum of the raw scores (this half's column chunks), combined across the two halves
   float mx = -INFINITY;
-  for (int c = half; c < nchunk; c += 2) {
+  for (int c = half; c < nchunk && warp_live; c += 2) {
     uint32_t raw[32];
     ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
     ptx::tmem_ld_wait();
@@ -338,30 +394,20 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
   for (int t = 0; t < nround; ++t) {
     const int c = 2 * t + half;
     uint32_t pk[16];
-    if (c < nchunk) {
+    const bool mine = c < nchunk && warp_live;
+    if (mine) {
       uint32_t raw[32];
       ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
       ptx::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float e2[2];
-        uint32_t hb = 0;                            // one hash decides both columns of the pair (drop_keep_att)
-        if (DROP) hb = drop_hash(p.seed, (unsigned long long)(row_id * p.Lk + c * 32 + 2 * j));
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int col = c * 32 + 2 * j + u;
-          float e = col < p.Lk ? fast_exp2(__uint_as_float(raw[2 * j + u]) * sl2 - mb) : 0.f;
-          sum += e;
-          if (DROP) e = (u ? (hb >> 16) : (hb & 0xFFFFu)) >= p.drop_thresh ? e * p.drop_scale : 0.f;
-          e2[u] = e;
-        }
-        pk[j] = pack_bf16(e2[0], e2[1]);
-      }
+      const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
+      const bool fast = c * 32 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)(c * 32)) <= 0xFFFFFFFFu - 32u;
+      if (fast) sum += softmax_fwd_cols32<DROP, true>(raw, sl2, mb, c * 32, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pk);
+      else sum += softmax_fwd_cols32<DROP, false>(raw, sl2, mb, c * 32, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pk);
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    if (c < nchunk) tmem_st16(trow + (uint32_t)(c * 16), pk);
+    if (mine) tmem_st16(trow + (uint32_t)(c * 16), pk);
   }
   s_red[half * TILE_ROWS + row] = sum;
   ptx::tmem_st_wait();
@@ -379,9 +425,12 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_fwd_kernel(const AttTcParam
   ptx::tc_fence_after();
   ATT_STAMP(5);
   {
-    bf16* orow = valid ? p.out + s * p.o_bs + (long long)i * p.o_rs + h * d : nullptr;
-    const int per = d >= 64 ? d / 2 : d;  // d = 64: one 32-column chunk per half; d = 32: half 0 stores
-    if (half == 0 || d >= 64) store_acc_row(trow + ACC_COL, half * (d >= 64 ? per : 0), half * (d >= 64 ? per : 0) + per, 1.f / sum, orow);
+    // coalesced store through the Q tile's shared memory (dead since the score MMA retired)
+    const int r0 = q0 + (warp & 3) * 32;
+    const int cb = d >= 64 ? half * 32 : 0;
+    if (half == 0 || d >= 64)
+      store_acc_rows32_coalesced(trow + ACC_COL + (uint32_t)cb, 1.f / sum, sQ + warp * 2048,
+                                 p.out + s * p.o_bs + (long long)r0 * p.o_rs + h * d + cb, p.o_rs, p.Lq - r0, lane);
   }
   ATT_STAMP(6);
   cta_epilogue<256>(tmem);
@@ -1284,8 +1333,19 @@ int egb_attention_tc_fwd(const egb_attention_desc* d, cudaStream_t st) {
   const bool prof = egb_prof_enabled() != 0;
   if (prof) egb_prof_begin(st, 4.0 * d->S * d->H * (double)d->Lq * d->Lk * d->head_dim,
                            2.0 * d->S * d->H * (double)d->head_dim * (2.0 * d->Lq + 2.0 * d->Lk), 2);
-  if (drop) att_tc_fwd_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
-  else att_tc_fwd_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
+  static const int tma = getenv("EGB_ATT_TMA") ? atoi(getenv("EGB_ATT_TMA")) : 1;
+  AttMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (tma && d->head_dim == 64) {
+    const long long inner = (long long)d->H * d->head_dim;
+    if (egb_tmap_rows64(&maps.q, d->q, inner, d->Lq, d->S, d->q_rs, d->q_bs, TILE_ROWS) ||
+        egb_tmap_rows64(&maps.k, d->k, inner, d->Lk, d->S, d->k_rs, d->k_bs, p.Lk_pad) ||
+        egb_tmap_rows64(&maps.v, d->v, inner, d->Lk, d->S, d->v_rs, d->v_bs, p.Lk_pad))
+      return 1;
+    p.use_tma = 1;
+  }
+  if (drop) att_tc_fwd_kernel<true><<<grid, TC_THREADS, smem, st>>>(p, maps);
+  else att_tc_fwd_kernel<false><<<grid, TC_THREADS, smem, st>>>(p, maps);
   if (prof) egb_prof_end(st);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
