@@ -25,6 +25,7 @@ struct EpiParams {
   unsigned drop_thresh;  // 0 = no dropout
   unsigned long long seed;
   int accumulate;
+  int exp;               // EGB_EPI_EXP experiment switch (0 = normal): 1 no residual / act' loads, 2 loads hit row 0 only, 3 no C store
 };
 
 static inline EpiMat make_epimat(const egb_matrix& m, int total_rows) {
@@ -293,8 +294,10 @@ struct EpiPre8 {
 template <int F>
 __device__ __forceinline__ void epi_prefetch8(const EpiParams& p, const EpiRow& row, int n, EpiPre8& pre) {
   if (!row.ok || n >= p.N) return;
-  if (F & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) pre.aux = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux.ptr) + row.aux + n));
-  if (F & EF_RES) pre.res = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res.ptr) + row.res + n));
+  if (p.exp == 1) { pre.aux = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u); pre.res = pre.aux; return; }
+  const long long ra = p.exp == 2 ? 0 : row.aux, rr = p.exp == 2 ? 0 : row.res;
+  if (F & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) pre.aux = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux.ptr) + ra + n));
+  if (F & EF_RES) pre.res = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res.ptr) + rr + n));
 }
 
 __device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
@@ -358,7 +361,7 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += r[i];
   }
-  st8(reinterpret_cast<bf16*>(p.c.ptr) + row.c + n, v);
+  if (p.exp != 3) st8(reinterpret_cast<bf16*>(p.c.ptr) + row.c + n, v);
 }
 
 // host: the specialisation that implements this call exactly, or EF_GENERIC

@@ -7,6 +7,7 @@
 // bf16 problems the tensor-core kernel cannot tile (N < 16, strides not 16-byte aligned) are
 // also routed here (bf16 in, fp32 math); they are the 3-class heads, a few kFLOP each.
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -200,6 +201,7 @@ bool tc_compatible(const egb_gemm_desc* d) {
 }  // namespace
 
 int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e) {
+  static const int epi_exp = getenv("EGB_EPI_EXP") ? atoi(getenv("EGB_EPI_EXP")) : 0;
   memset(e, 0, sizeof(*e));
   e->M = d->M;
   e->N = d->N;
@@ -212,6 +214,7 @@ int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e) {
   e->alpha = d->alpha;
   e->act = d->act;
   e->act_bwd = d->act_bwd;
+  e->exp = epi_exp;
   EGB_CHECK(d->act_bwd == EGB_ACTBWD_NONE || d->aux.ptr != nullptr, "gemm: act_bwd needs aux");
   EGB_CHECK(d->act != EGB_ACT_GELU_DGRAD || d->c_pre.ptr != nullptr, "gemm: EGB_ACT_GELU_DGRAD needs c_pre");
   e->aux_scale = d->aux_scale;

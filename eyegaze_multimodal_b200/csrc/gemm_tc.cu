@@ -141,59 +141,95 @@ __device__ __forceinline__ void load_stage_chunked(uint8_t* dst, const CUtensorM
   }
 }
 
-template <int EF>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRow (&rows)[4], int m_base, int n,
-                                               const uint32_t (&r)[32], float* stage, int lane) {
-  const int sub = lane >> 2, cg = (lane & 3) * 8;
-  // Fetch everything the four 8-column runs of this lane need (bias once, residual / act' operand per row) FIRST:
-  // the global-load latency then overlaps the shared-memory transposition instead of being paid once per run.
+// Global operands of one 32x32 chunk in the transposed (8-column run) layout: bias once, residual / act' operand per
+// row run.  They are fetched a whole chunk AHEAD of their use -- chunk 0 even before the accumulator is ready --
+// because a DRAM round trip per chunk was what bounded the residual / act' epilogues (K = 768: 12.5 us per tile
+// against 5.5 us of MMA).
+struct EpiChunkOps {
   float bias[8];
-  EpiPre8 pre[4];
+  EpiPre8 run[4];
+};
+template <int EF>
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& epi, const EpiRow (&rows)[4], int n, int lane,
+                                                  EpiChunkOps& ops) {
+  const int cg = (lane & 3) * 8;
   if (EF != EF_GENERIC) {
     if ((EF & EF_BIAS) && n + cg < epi.N) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + cg));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + cg + 4));
-      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
-      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+      ops.bias[0] = b0.x; ops.bias[1] = b0.y; ops.bias[2] = b0.z; ops.bias[3] = b0.w;
+      ops.bias[4] = b1.x; ops.bias[5] = b1.y; ops.bias[6] = b1.z; ops.bias[7] = b1.w;
     }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) epi_prefetch8<EF>(epi, rows[it], n + cg, pre[it]);
-  }
-  __syncwarp();                                                 // previous chunk's readers are done
-  float4* mine = reinterpret_cast<float4*>(stage + lane * STG_PITCH);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    mine[i ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rr = it * 8 + sub;
-    const float4* src = reinterpret_cast<const float4*>(stage + rr * STG_PITCH);
-    const float4 x = src[((lane & 3) * 2) ^ (rr & 7)], y = src[((lane & 3) * 2 + 1) ^ (rr & 7)];
-    float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-    if (EF == EF_GENERIC) epi_apply_store_row<8>(epi, rows[it], m_base + it * 8 + sub, n + cg, v);
-    else epi_fast8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v, bias, pre[it]);
+    for (int it = 0; it < 4; ++it) epi_prefetch8<EF>(epi, rows[it], n + cg, ops.run[it]);
   }
 }
 
 template <int EF>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& epi, uint32_t taddr, int m_base, int n0, int col0, int ncol,
-                                              float* stage, int lane) {
-  EpiRow rows[4];
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRow (&rows)[4], int m_base, int n,
+                                               const uint32_t (&r)[32], float* stage, int lane, const EpiChunkOps& ops) {
+  const int sub = lane >> 2, cg = (lane & 3) * 8;
+  __syncwarp();                                                 // previous chunk's readers are done
+  // Explicit shared-space accesses: through a generic pointer the compiler emits generic LD/ST and has to assume
+  // that the global stores of one 8-column run alias the staged loads of the next, which serialises the runs.
+  // All eight staged loads are issued before the math.
+  const uint32_t sbase = ptx::smem_u32(stage);
+  const uint32_t mine = sbase + (uint32_t)(lane * STG_PITCH * 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + (uint32_t)((i ^ (lane & 7)) << 4)), "r"(r[4 * i]),
+                 "r"(r[4 * i + 1]), "r"(r[4 * i + 2]), "r"(r[4 * i + 3])
+                 : "memory");
+  __syncwarp();
+  float v[4][8];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + sub;
+    const uint32_t src = sbase + (uint32_t)(rr * STG_PITCH * 4);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[it][0]), "=f"(v[it][1]), "=f"(v[it][2]), "=f"(v[it][3])
+                 : "r"(src + (uint32_t)((((lane & 3) * 2) ^ (rr & 7)) << 4))
+                 : "memory");
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[it][4]), "=f"(v[it][5]), "=f"(v[it][6]), "=f"(v[it][7])
+                 : "r"(src + (uint32_t)((((lane & 3) * 2 + 1) ^ (rr & 7)) << 4))
+                 : "memory");
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (EF == EF_GENERIC) epi_apply_store_row<8>(epi, rows[it], m_base + it * 8 + sub, n + cg, v[it]);
+    else epi_fast8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v[it], ops.bias, ops.run[it]);
+  }
+}
+
+// before the accumulator is ready: row bookkeeping and the first chunk's operands
+template <int EF>
+__device__ __forceinline__ void epilogue_tile_begin(const EpiParams& epi, int m_base, int n0, int col0, int lane,
+                                                    EpiRow (&rows)[4], EpiChunkOps& ops0) {
 #pragma unroll
   for (int it = 0; it < 4; ++it) rows[it] = epi_row_setup(epi, m_base + it * 8 + (lane >> 2));
-  uint32_t ra[32], rb[32];
-  ptx::tmem_ld32(taddr + (uint32_t)col0, ra);
+  epilogue_prefetch<EF>(epi, rows, n0 + col0, lane, ops0);
+}
+
+template <int EF>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& epi, uint32_t taddr, int m_base, int n0, int col0, int ncol,
+                                              float* stage, int lane, const EpiRow (&rows)[4], EpiChunkOps& opsA) {
+  // One accumulator chunk in registers at a time (a second one pushed the residual / act' variants over the 168
+  // registers a 10-warp CTA allows and the row offsets into local memory); the operand prefetch of the next chunk
+  // is what sits between the TMEM load and its wait.
+  uint32_t ra[32];
+  EpiChunkOps opsB;
 #pragma unroll 1
   for (int c = 0; c < ncol; c += 64) {
+    ptx::tmem_ld32(taddr + (uint32_t)(col0 + c), ra);
+    if (c + 32 < ncol) epilogue_prefetch<EF>(epi, rows, n0 + col0 + c + 32, lane, opsB);
     ptx::tmem_ld_wait();
-    if (c + 32 < ncol) ptx::tmem_ld32(taddr + (uint32_t)(col0 + c + 32), rb);
-    epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c, ra, stage, lane);
+    epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c, ra, stage, lane, opsA);
     if (c + 32 < ncol) {
+      ptx::tmem_ld32(taddr + (uint32_t)(col0 + c + 32), ra);
+      if (c + 64 < ncol) epilogue_prefetch<EF>(epi, rows, n0 + col0 + c + 64, lane, opsA);
       ptx::tmem_ld_wait();
-      if (c + 64 < ncol) ptx::tmem_ld32(taddr + (uint32_t)(col0 + c + 64), ra);
-      epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c + 32, rb, stage, lane);
+      epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c + 32, ra, stage, lane, opsB);
     }
   }
 }
@@ -323,14 +359,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mn = tile / p.split_k;
       const int nt = mn % p.n_tiles;
       const int mt = mn / p.n_tiles;
+      EpiRow rows[4];
+      EpiChunkOps ops0;
+      epilogue_tile_begin<EF>(p.epi, mt * BM + quad * 32, nt * BN, chalf * NCOL, lane, rows, ops0);
       TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       epilogue_tile<EF>(p.epi, taddr, mt * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
-                    stage_all + (warp - 2) * (32 * STG_PITCH), lane);
+                    stage_all + (warp - 2) * (32 * STG_PITCH), lane, rows, ops0);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) ptx::mbar_arrive_relaxed(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -518,14 +557,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int mn = tile / p.split_k;
       const int nt = mn % p.n_tiles;
       const int mt = mn / p.n_tiles;
+      EpiRow rows[4];
+      EpiChunkOps ops0;
+      epilogue_tile_begin<EF>(p.epi, (mt * 2 + (int)rank) * BM + quad * 32, nt * BN, chalf * NCOL, lane, rows, ops0);
       TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       epilogue_tile<EF>(p.epi, taddr, (mt * 2 + (int)rank) * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
-                    stage_all + (warp - 2) * (32 * STG_PITCH), lane);
+                    stage_all + (warp - 2) * (32 * STG_PITCH), lane, rows, ops0);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(acc == 0 ? lead_tempty0 : lead_tempty1);
+      if (lane == 0) ptx::mbar_arrive_cluster_relaxed(acc == 0 ? lead_tempty0 : lead_tempty1);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }

@@ -252,13 +252,21 @@ int main(int argc, char** argv) {
         {"vit_qkv", 50432, 2304, 768, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1.f},
         {"vit_proj_res", 50432, 768, 768, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 1.f},
         {"vit_fc1_gelu", 50432, 3072, 768, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 1, 0, 1, 0, 0, 1.f},
+        {"vit_proj_nores", 50432, 768, 768, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1.f},
+        {"vit_fc1_gelu_dgrad", 50432, 3072, 768, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 0, 1, 0, 1, 0, 0, 1.f},
+        {"vit_dx_fc2_mul", 50432, 3072, 768, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 0, 0, 0, 1.f},
+        {"eeg_proj_res", 71168, 256, 256, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 1.f},
         {"vit_fc2", 50432, 768, 3072, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 1.f},
         {"vit_dx_fc2", 50432, 3072, 768, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 1.f},
         {"vit_dw_fc1", 3072, 768, 50432, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1.f},
         {"eeg_ffn1", 71168, 1024, 256, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 1.f},
         {"eeg_dw_qproj", 256, 256, 71168, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1.f},
     };
-    for (auto& c : big) fails += run_case(c, EGB_BF16, false, c.accumulate ? 0 : (bigonly ? 2 : 10));
+    const char* only = argc > 2 ? argv[2] : nullptr;   // ./gemm_test big <substring>: just the matching big cases, 10 timed launches
+    for (auto& c : big) {
+      if (only != nullptr && strstr(c.name, only) == nullptr) continue;
+      fails += run_case(c, EGB_BF16, false, c.accumulate ? 0 : (bigonly && only == nullptr ? 2 : 10));
+    }
     // fp32 FFMA kernel throughput on one mid-size problem
     Case f = {"f32_ffn1", 8192, 1024, 256, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 1, 0, 1.f};
     fails += run_case(f, EGB_F32, false, 10);

@@ -24,6 +24,9 @@ def run(M, N, K, tag, bias=True, res=False):
     ms = e0.elapsed_time(e1)
     print(f"{tag:10s} M={M} N={N} K={K}: {ms*1e3:7.1f} us {2*M*N*K/ms*1e-9:7.1f} TF/s | kernel cyc {act[:,4].mean():9.0f} | producer wait-empty {act[:,0].mean()/act[:,4].mean():5.1%} | MMA wait-operands {lead[:,1].mean()/lead[:,4].mean():5.1%} wait-acc-drain {lead[:,2].mean()/lead[:,4].mean():5.1%} | epilogue wait-acc {act[:,3].mean()/act[:,4].mean():5.1%}")
 print("EGB_GEMM_PAIR =", os.environ.get("EGB_GEMM_PAIR"), "EGB_GEMM_SKIPB =", os.environ.get("EGB_GEMM_SKIPB"))
+run(50432, 768, 768, "proj_res", res=True)
+run(50432, 768, 768, "proj_nores", res=False)
+run(71168, 256, 256, "eeg_proj", res=True)
 run(50432, 768, 3072, "fc2", res=True)
 run(50432, 2304, 768, "qkv")
 run(50432, 3072, 768, "fc1-nobias", bias=False)
