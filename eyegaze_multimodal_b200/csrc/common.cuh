@@ -90,6 +90,59 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, g, cdf);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two lanes per issued instruction).  The fma pipe retires one
+// warp instruction per two cycles per scheduler, so an element-wise epilogue that has to keep pace with tcgen05
+// (GELU and its derivative behind a K = 768 GEMM: ~17 fma-pipe operations per element against a budget of ~12) is
+// issue-bound in scalar form; in packed form it fits.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+
+// gelu_erf_both() for two elements at once: same Abramowitz-Stegun 7.1.26 form, 14 packed fma-pipe operations,
+// four MUFU (2 x rcp, 2 x ex2) and four sign/abs bit operations per pair.
+__device__ __forceinline__ void gelu_erf_both2(float2 x, float2& y, float2& dy) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = fma2(ax, splat2(0.3275911f * 0.70710678118654752f), splat2(1.0f));
+  float2 t, g;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  const float2 arg = mul2(mul2(x, x), splat2(-0.5f * 1.4426950408889634f));   // -u^2 log2(e), u = x / sqrt(2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.x) : "f"(arg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.y) : "f"(arg.y));
+  float2 poly = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  poly = fma2(t, poly, splat2(1.421413741f));
+  poly = fma2(t, poly, splat2(-0.284496736f));
+  poly = fma2(t, poly, splat2(0.254829592f));
+  const float2 pg = mul2(mul2(poly, t), g);                                   // 1 - erf(|u|)
+  const float2 e = fma2(pg, splat2(-1.0f), splat2(1.0f));                     // erf(|u|)
+  const float2 sh = make_float2(copysignf(0.5f, x.x), copysignf(0.5f, x.y));
+  const float2 cdf = fma2(sh, e, splat2(0.5f));
+  y = mul2(x, cdf);
+  dy = fma2(mul2(x, g), splat2(0.3989422804014327f), cdf);
+}
+
 // Counter-based dropout mask: keep iff hash(seed, idx) >= p * 2^32. Stateless so the backward
 // pass regenerates the mask from (seed, idx) instead of storing it.
 __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint64_t idx) {

@@ -318,12 +318,19 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
   }
   if (F & EF_BIAS) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += bias[i];
+    for (int i = 0; i < 8; i += 2) {
+      const float2 s2 = add2(make_float2(v[i], v[i + 1]), make_float2(bias[i], bias[i + 1]));
+      v[i] = s2.x; v[i + 1] = s2.y;
+    }
   }
   if (F & EF_DGELU) {
     float dv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gelu_erf_both(v[i], v[i], dv[i]);
+    for (int i = 0; i < 8; i += 2) {   // packed pairs: see gelu_erf_both2
+      float2 y2, d2;
+      gelu_erf_both2(make_float2(v[i], v[i + 1]), y2, d2);
+      v[i] = y2.x; v[i + 1] = y2.y; dv[i] = d2.x; dv[i + 1] = d2.y;
+    }
     st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, dv);
   } else {
     if (F & EF_PRE) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, v);
@@ -349,7 +356,10 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
       for (int i = 0; i < 8; ++i) v[i] = (a[i] != 0.f) ? v[i] * p.aux_scale : 0.f;
     } else if (F & EF_ABWD_MUL) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= a[i];
+      for (int i = 0; i < 8; i += 2) {
+        const float2 m2 = mul2(make_float2(v[i], v[i + 1]), make_float2(a[i], a[i + 1]));
+        v[i] = m2.x; v[i + 1] = m2.y;
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(a[i]);
@@ -359,7 +369,10 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
     float r[8];
     unpack8(pre.res, r);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += r[i];
+    for (int i = 0; i < 8; i += 2) {
+      const float2 s2 = add2(make_float2(v[i], v[i + 1]), make_float2(r[i], r[i + 1]));
+      v[i] = s2.x; v[i + 1] = s2.y;
+    }
   }
   if (p.exp != 3) st8(reinterpret_cast<bf16*>(p.c.ptr) + row.c + n, v);
 }
