@@ -73,6 +73,7 @@ _SIGNATURES = {
     "egb_scale_by_device_scalar": [vp, vp, vp, i64, vp],
     "egb_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp],
     "egb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    "egb_layernorm_bwd_res": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "egb_attention_fwd": [C.POINTER(AttentionDesc), vp],
     "egb_attention_bwd": [C.POINTER(AttentionDesc), vp],
     "egb_debug_attention_timing": [vp],

@@ -61,20 +61,46 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
   }
 }
 
+// eight consecutive elements in their storage format (bf16: one 16-byte register quad; fp32: two)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 q;
+  __device__ __forceinline__ void load(const bf16* p) { q = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum dy*xhat; dbeta += sum dy.
-// Optional second output dx2 = dx * dropout-mask (the branch that went through a residual dropout).
+// One warp per row.  The row's x and dy stay in registers in their STORAGE format between the statistics pass and
+// the dx pass and are converted twice: with fp32 copies of xhat and g the kernel sat at the 128-register limit of
+// two CTAs per SM and ptxas serialised the row's loads chunk by chunk (three DRAM round trips per row: 81 us for the
+// ViT-B LayerNorms against 36 us of traffic).  gamma is read from shared memory.
 template <typename T, int C>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(C == 1 ? 256 : 512, C == 1 ? 3 : 1) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, T* __restrict__ dx,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
-                                                            int D) {
-  extern __shared__ float red[];  // [2][D]
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            const T* __restrict__ dres, int M, int D) {
+  extern __shared__ float red[];  // [2][D] column partials, [D] gamma
+  float* sg = red + 2 * D;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  constexpr int chunks = C;
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sg[i] = gamma[i];
   __syncthreads();
   float ag[C][8], ab[C][8];
 #pragma unroll
@@ -83,24 +109,34 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T* __restri
     for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = 0.f;
 
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    Raw8<T> xr[C], dr[C], rr[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (d < D) {
+        xr[c].load(x + (long long)row * D + d);
+        dr[c].load(dy + (long long)row * D + d);
+        if (dres != nullptr) rr[c].load(dres + (long long)row * D + d);   // residual-path gradient, same round trip
+      }
+    }
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[C][8], g[C][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int d = c * 256 + lane * 8;
-      if (c < chunks && d < D) {
-        float xv[8], dv[8], gm[8];
-        ld8(x + (long long)row * D + d, xv);
-        ld8(dy + (long long)row * D + d, dv);
-        ld8(gamma + d, gm);
+      if (d < D) {
+        float xv[8], dv[8];
+        xr[c].unpack(xv);
+        dr[c].unpack(dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(sg + d), g1 = *reinterpret_cast<const float4*>(sg + d + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[c][j] = (xv[j] - mean) * rstd;
-          g[c][j] = dv[j] * gm[j];
-          s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
-          ag[c][j] += dv[j] * xh[c][j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = dv[j] * gm[j];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          ag[c][j] = fmaf(dv[j], xh, ag[c][j]);
           ab[c][j] += dv[j];
         }
       }
@@ -110,10 +146,23 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T* __restri
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int d = c * 256 + lane * 8;
-      if (c < chunks && d < D) {
-        float o[8];
+      if (d < D) {
+        float xv[8], dv[8], o[8];
+        xr[c].unpack(xv);
+        dr[c].unpack(dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(sg + d), g1 = *reinterpret_cast<const float4*>(sg + d + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - s1 - xh[c][j] * s2);
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          o[j] = rstd * (fmaf(dv[j], gm[j], -s1) - xh * s2);
+        }
+        if (dres != nullptr) {   // gradient that reaches x around the normalisation (the residual connection)
+          float rv[8];
+          rr[c].unpack(rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
         st8(dx + (long long)row * D + d, o);
       }
     }
@@ -122,7 +171,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T* __restri
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const int d = c * 256 + lane * 8;
-    if (c < chunks && d < D) {
+    if (d < D) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&red[d + j], ag[c][j]);
@@ -159,19 +208,25 @@ int egb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
   return 0;
 }
 
-/* dgamma / dbeta are ACCUMULATED into (caller zeroes them, or passes live .grad buffers). */
-int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
-                      float* dgamma, float* dbeta, int dtype, int M, int D, void* stream) {
+/* dgamma / dbeta are ACCUMULATED into (caller zeroes them, or passes live .grad buffers).  dres (optional, same
+   shape and dtype as dx) is added to dx: the gradient arriving at x through the residual connection, so that the
+   sum of the two paths costs no extra pass. */
+int egb_layernorm_bwd_res(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                          void* dx, float* dgamma, float* dbeta, const void* dres, int dtype, int M, int D, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   EGB_CHECK(D % 8 == 0 && D <= 256 * LN_MAX_CHUNKS, "layernorm_bwd: unsupported D=%d", D);
-  int blocks = (M + 7) / 8;
-  const int cap = egb_num_sms() * 4;
-  if (blocks > cap) blocks = cap;
-  const size_t smem = (size_t)2 * D * sizeof(float);
+  // 16 warps per CTA, one CTA per SM (two for narrow rows): every CTA ends with 2 D column atomics, and with several
+  // hundred CTAs those serialise per address in L2 (a measurable tail); fewer, fatter CTAs halve it.
+  const size_t smem = (size_t)3 * D * sizeof(float);
   const int chunks = (D + 255) / 256;
+  // wide rows: 16 warps per CTA, one CTA per SM; narrow rows (one chunk): 8 warps, three CTAs per SM
+  const int threads = chunks == 1 ? 256 : 512;
+  int blocks = (M + threads / 32 - 1) / (threads / 32);
+  const int cap = egb_num_sms() * (chunks == 1 ? 3 : 1);
+  if (blocks > cap) blocks = cap;
 #define EGB_LN_BWD(TT, CC)                                                                                         \
-  layernorm_bwd_kernel<TT, CC><<<blocks, 256, smem, st>>>((const TT*)dy, (const TT*)x, gamma, mean, rstd, (TT*)dx, \
-                                                         dgamma, dbeta, M, D)
+  layernorm_bwd_kernel<TT, CC><<<blocks, threads, smem, st>>>((const TT*)dy, (const TT*)x, gamma, mean, rstd, (TT*)dx, \
+                                                         dgamma, dbeta, (const TT*)dres, M, D)
   if (dtype == EGB_BF16) {
     switch (chunks) {
       case 1: EGB_LN_BWD(bf16, 1); break;
@@ -191,6 +246,11 @@ int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;
+}
+
+int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                      float* dgamma, float* dbeta, int dtype, int M, int D, void* stream) {
+  return egb_layernorm_bwd_res(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, nullptr, dtype, M, D, stream);
 }
 
 }  // extern "C"

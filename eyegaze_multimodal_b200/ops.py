@@ -429,6 +429,54 @@ def layernorm(x, gamma, beta, eps):
     return LayerNormFn.apply(x, gamma, beta, float(eps))
 
 
+class LayerNormResidualFn(torch.autograd.Function):
+    """(LayerNorm(x), x) for a pre-norm residual block: the second output is x itself and is meant to be used as
+    the block's residual input.  Backward receives the gradients of both uses of x at once and adds them inside the
+    LayerNorm backward kernel, instead of autograd summing two [tokens, D] tensors in a separate pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _require_cuda(x, gamma)
+        x = x.contiguous()
+        D = x.shape[-1]
+        M = x.numel() // D
+        y = torch.empty_like(x)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+        L.call("egb_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+               rstd.data_ptr(), _code(x), M, D, float(eps), _stream())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        D = x.shape[-1]
+        M = x.numel() // D
+        code = _code(x)
+        dgb = zeros((2, D), torch.float32, x.device)
+        if dy is None:                      # only the residual path was used
+            return dres, dgb[0], dgb[1], None
+        dy = dy.contiguous()
+        if _code(dy) != code:
+            dy = cast(dy, code)
+        if dres is not None:
+            dres = dres.contiguous()
+            if _code(dres) != code:
+                dres = cast(dres, code)
+        dx = torch.empty_like(x)
+        L.call("egb_layernorm_bwd_res", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+               dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), _p(dres), code, M, D, _stream())
+        return dx, dgb[0], dgb[1], None
+
+
+def layernorm_residual(x, gamma, beta, eps):
+    """-> (LayerNorm(x), x as the residual operand); see LayerNormResidualFn."""
+    if not (torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad)):
+        return LayerNormFn.apply(x, gamma, beta, float(eps)), x
+    return LayerNormResidualFn.apply(x, gamma, beta, float(eps))
+
+
 # ------------------------------------------------------------------------------------------------------
 # fused attention
 # ------------------------------------------------------------------------------------------------------

@@ -93,9 +93,13 @@ class Block(nn.Module):
 
     def forward(self, x):
         x = ops.cast(x, compute_code())
-        ctx = self.attn.context(self.norm1(x))
+        # pre-norm residual blocks: the normalisation hands back x as the residual operand, so the two gradients
+        # that meet at x are summed inside the LayerNorm backward kernel
+        h, x = ops.layernorm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        ctx = self.attn.context(h)
         x = ops.linear(ctx, self.attn.proj.weight, self.attn.proj.bias, residual=x)
-        return self.mlp.fused(self.norm2(x), residual=x)
+        h, x = ops.layernorm_residual(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return self.mlp.fused(h, residual=x)
 
 
 class VisionTransformer(nn.Module):

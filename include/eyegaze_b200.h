@@ -155,6 +155,10 @@ int egb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
                       int M, int D, float eps, void* stream);
 int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
                       float* dgamma, float* dbeta, int dtype, int M, int D, void* stream);
+/* same, with dx += dres: the gradient that reaches x around the normalisation (pre-norm residual block,
+ * timm Block.forward `x = x + attn(norm1(x))`), so autograd's separate accumulation pass disappears */
+int egb_layernorm_bwd_res(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                          void* dx, float* dgamma, float* dbeta, const void* dres, int dtype, int M, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused multi-head attention (art.py:203-213; timm Attention): softmax(QK^T*scale) [dropout] V without
