@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
     _fields_ = [("M", i32), ("N", i32), ("K", i32), ("in_dtype", i32), ("a", Operand), ("b", Operand),
                 ("c", Matrix), ("c_pre", Matrix), ("residual", Matrix), ("aux", Matrix), ("bias", vp),
                 ("alpha", f32), ("act", i32), ("act_bwd", i32), ("aux_scale", f32), ("dropout_p", f32),
-                ("dropout_seed", u64), ("accumulate", i32), ("split_k", i32)]
+                ("dropout_seed", u64), ("accumulate", i32), ("split_k", i32), ("c_colsum", vp)]
 
 
 class AttentionDesc(C.Structure):

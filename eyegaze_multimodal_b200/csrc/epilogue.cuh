@@ -25,6 +25,7 @@ struct EpiParams {
   unsigned drop_thresh;  // 0 = no dropout
   unsigned long long seed;
   int accumulate;
+  float* colsum;         // optional [N]: column sums of the stored output are accumulated here
   int exp;               // EGB_EPI_EXP experiment switch (0 = normal): 1 no residual / act' loads, 2 loads hit row 0 only, 3 no C store
 };
 
@@ -279,6 +280,7 @@ enum : int {
   EF_BIAS = 1, EF_RELU = 2, EF_GELU = 4, EF_RES = 8, EF_PRE = 16, EF_ABWD_RELU = 32, EF_ABWD_GELU = 64, EF_ACC = 128,
   EF_DGELU = 256,     // with EF_GELU | EF_PRE: the saved tensor is gelu'(pre)
   EF_ABWD_MUL = 512,  // multiply by the saved derivative
+  EF_COLSUM = 1024,   // accumulate the column sums of the stored tile (bias gradient) -- done by the chunk epilogue
   EF_GENERIC = 1 << 20
 };
 
@@ -395,9 +397,13 @@ static inline int egb_epi_fast_mask(const EpiParams& e) {
     if (!bf16_vec(e.aux)) return EF_GENERIC;
     f |= (e.act_bwd == EGB_ACTBWD_RELU_MASK) ? EF_ABWD_RELU : (e.act_bwd == EGB_ACTBWD_MUL ? EF_ABWD_MUL : EF_ABWD_GELU);
   }
+  if (e.colsum != nullptr) {
+    if (((uintptr_t)e.colsum % 16) != 0) return EF_GENERIC;
+    f |= EF_COLSUM;
+  }
   switch (f) {   // the instantiated set (everything else runs the generic epilogue)
     case 0: case EF_BIAS: case EF_BIAS | EF_RES: case EF_BIAS | EF_RELU: case EF_BIAS | EF_GELU | EF_PRE | EF_DGELU:
-    case EF_ABWD_RELU: case EF_ABWD_MUL:
+    case EF_ABWD_RELU: case EF_ABWD_MUL: case EF_ABWD_RELU | EF_COLSUM: case EF_ABWD_MUL | EF_COLSUM:
       return f;
     default:
       return EF_GENERIC;

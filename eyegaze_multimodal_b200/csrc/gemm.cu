@@ -215,6 +215,7 @@ int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e) {
   e->act = d->act;
   e->act_bwd = d->act_bwd;
   e->exp = epi_exp;
+  e->colsum = d->c_colsum;
   EGB_CHECK(d->act_bwd == EGB_ACTBWD_NONE || d->aux.ptr != nullptr, "gemm: act_bwd needs aux");
   EGB_CHECK(d->act != EGB_ACT_GELU_DGRAD || d->c_pre.ptr != nullptr, "gemm: EGB_ACT_GELU_DGRAD needs c_pre");
   e->aux_scale = d->aux_scale;
@@ -245,6 +246,23 @@ extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
     } else {
       EGB_CHECK(rpg >= d->M, "gemm: zero-init of grouped outputs is not supported");
       EGB_CUDA(cudaMemset2DAsync(d->c.ptr, (size_t)d->c.row_stride * 4, 0, (size_t)d->N * 4, (size_t)d->M, stream));
+    }
+  }
+  if (d->c_colsum != nullptr) {
+    // fused in the tensor-core kernels' specialised epilogues; every other route takes a second pass over C
+    bool fused = false;
+    if (d->in_dtype == EGB_BF16 && tc_compatible(d)) {
+      EpiParams e;
+      if (egb_fill_epilogue(d, &e)) return 1;
+      const int mask = egb_epi_fast_mask(e);
+      fused = mask != EF_GENERIC && (mask & EF_COLSUM) != 0;
+    }
+    if (!fused) {
+      egb_gemm_desc d2 = *d;
+      d2.c_colsum = nullptr;
+      d2.accumulate = d->accumulate == 2 ? 1 : d->accumulate;   // the zero-init above already happened
+      if (egb_gemm(&d2, stream_)) return 1;
+      return egb_colsum(&d->c, d->M, d->N, d->c_colsum, 0, stream_);
     }
   }
   if (d->in_dtype == EGB_BF16 && tc_compatible(d)) return egb_gemm_tc(d, stream);

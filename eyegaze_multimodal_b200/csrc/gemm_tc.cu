@@ -200,6 +200,35 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRo
     if (EF == EF_GENERIC) epi_apply_store_row<8>(epi, rows[it], m_base + it * 8 + sub, n + cg, v[it]);
     else epi_fast8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v[it], ops.bias, ops.run[it]);
   }
+  if (EF != EF_GENERIC && (EF & EF_COLSUM)) {
+    // column sums of the 32 x 32 chunk as stored: this lane's four rows, then the eight lanes that share its columns
+    float cs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      if (rows[it].ok && n + cg < epi.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs[i] += v[it][i];
+      }
+    }
+    // butterfly over the eight lanes that share these columns, halving the columns a lane keeps in every round
+    // (4 + 2 + 1 shuffles instead of 3 x 8): lane (sub, q) ends up with the sum of column cg + sub
+    float a4[4], b2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, (sub & 4) ? cs[i] : cs[i + 4], 16);
+      a4[i] = ((sub & 4) ? cs[i + 4] : cs[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, (sub & 2) ? a4[i] : a4[i + 2], 8);
+      b2[i] = ((sub & 2) ? a4[i + 2] : a4[i]) + recv;
+    }
+    const float recv = __shfl_xor_sync(0xffffffffu, (sub & 1) ? b2[0] : b2[1], 4);
+    const float tot = ((sub & 1) ? b2[1] : b2[0]) + recv;
+    if (n + cg < epi.N) atomicAdd(epi.colsum + n + cg + sub, tot);   // result unused: compiles to RED
+  }
 }
 
 // before the accumulator is ready: row bookkeeping and the first chunk's operands
@@ -847,6 +876,8 @@ int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams
         return FN<BN_, EF_BIAS | EF_GELU | EF_PRE | EF_DGELU>(ma, mb, p, stream);                               \
       case EF_ABWD_RELU: return FN<BN_, EF_ABWD_RELU>(ma, mb, p, stream);                                       \
       case EF_ABWD_MUL: return FN<BN_, EF_ABWD_MUL>(ma, mb, p, stream);                                         \
+      case EF_ABWD_RELU | EF_COLSUM: return FN<BN_, EF_ABWD_RELU | EF_COLSUM>(ma, mb, p, stream);               \
+      case EF_ABWD_MUL | EF_COLSUM: return FN<BN_, EF_ABWD_MUL | EF_COLSUM>(ma, mb, p, stream);                 \
       case EF_ACC: return FN<BN_, EF_ACC>(ma, mb, p, stream);                                                   \
       default: break;                                                                                           \
     }                                                                                                           \

@@ -84,10 +84,11 @@ def zeros(shape, dtype, device):
 
 
 def gemm(M, N, K, in_code, a: L.Operand, b: L.Operand, c: L.Matrix, *, bias=None, c_pre=None, residual=None, aux=None,
-         alpha=1.0, act=0, act_bwd=0, aux_scale=1.0, dropout_p=0.0, seed=0, accumulate=0, split_k=0):
+         alpha=1.0, act=0, act_bwd=0, aux_scale=1.0, dropout_p=0.0, seed=0, accumulate=0, split_k=0, c_colsum=None):
     empty = L.Matrix(None, 0, 0, 0, 0)
     d = L.GemmDesc(M, N, K, in_code, a, b, c, c_pre or empty, residual or empty, aux or empty, _p(bias), alpha, act,
-                   act_bwd, aux_scale, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, accumulate, split_k)
+                   act_bwd, aux_scale, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, accumulate, split_k,
+                   _p(c_colsum))
     L.call("egb_gemm", C.byref(d), _stream())
 
 
@@ -235,8 +236,10 @@ def _linear_forward(x, w2, bias, residual, act, p, seed, out_code, c_pre=None):
     return y
 
 
-def _grad_input(dpre, w2, x_shape, out_code, act_bwd=0, aux=None, aux_scale=1.0, dropout_p=0.0, seed=0):
-    """dx[.., K] = dpre[.., N] . W[N, K]  (W consumed as an MN-major operand, no transposed copy)."""
+def _grad_input(dpre, w2, x_shape, out_code, act_bwd=0, aux=None, aux_scale=1.0, dropout_p=0.0, seed=0, colsum_out=None):
+    """dx[.., K] = dpre[.., N] . W[N, K]  (W consumed as an MN-major operand, no transposed copy).
+    ``colsum_out`` ([K] fp32, zeroed by the caller) receives the column sums of dx -- the bias gradient of the layer
+    that produced x -- from the GEMM epilogue."""
     a, dt = _operand(dpre, 0)
     rows = _rows(dt)[1]
     N, K = w2.shape
@@ -244,7 +247,7 @@ def _grad_input(dpre, w2, x_shape, out_code, act_bwd=0, aux=None, aux_scale=1.0,
     am = _dense_matrix(aux.data_ptr(), _code(aux), K) if aux is not None else None
     gemm(rows, K, N, _code(dt), a, L.Operand(w2.data_ptr(), 1, 0, w2.stride(0), 0, 0, 0),
          _dense_matrix(dx.data_ptr(), out_code, K), act_bwd=act_bwd, aux=am, aux_scale=aux_scale, dropout_p=dropout_p,
-         seed=seed)
+         seed=seed, c_colsum=colsum_out)
     return dx
 
 
@@ -374,16 +377,18 @@ class Mlp2Fn(torch.autograd.Function):
         need = ctx.needs_input_grad
         dw2 = _grad_weight(dyd, h, w2.shape[0], w2.shape[1]) if need[4] else None
         db2 = colsum(dyd, w2.shape[0]) if need[5] else None
-        # dpre1 = (dyd . W2) * act'(.)   -- activation derivative and mid-dropout mask fused in the GEMM epilogue
+        # dpre1 = (dyd . W2) * act'(.)   -- activation derivative, mid-dropout mask AND the first layer's bias gradient
+        # (column sums of dpre1) fused in the GEMM epilogue
+        db1 = zeros((w1.shape[0],), torch.float32, dy.device) if need[3] else None
         if act == L.ACT_RELU:
             dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_RELU_MASK, aux=h,
-                                aux_scale=1.0 / (1.0 - p_mid) if p_mid > 0 else 1.0)
+                                aux_scale=1.0 / (1.0 - p_mid) if p_mid > 0 else 1.0, colsum_out=db1)
         elif act == L.ACT_GELU:
-            dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_MUL, aux=pre, dropout_p=p_mid, seed=s_mid)
+            dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_MUL, aux=pre, dropout_p=p_mid, seed=s_mid,
+                                colsum_out=db1)
         else:
-            dpre1 = _grad_input(dyd, w2c, h.shape, code, dropout_p=p_mid, seed=s_mid)
+            dpre1 = _grad_input(dyd, w2c, h.shape, code, dropout_p=p_mid, seed=s_mid, colsum_out=db1)
         dw1 = _grad_weight(dpre1, x, w1.shape[0], w1.shape[1]) if need[2] else None
-        db1 = colsum(dpre1, w1.shape[0]) if need[3] else None
         dx = _grad_input(dpre1, w1c, x.shape, code) if need[0] else None
         return dx, (dy if has_res else None), dw1, db1, dw2, db2, None, None, None, None
 

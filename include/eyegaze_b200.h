@@ -98,6 +98,9 @@ typedef struct {
   uint64_t dropout_seed;
   int32_t accumulate;  /* 1: C += result (C must be fp32, split-K with red.global.add); 2: zero C first, then accumulate */
   int32_t split_k;     /* 0 = auto */
+  float* c_colsum;     /* optional [N] fp32, ACCUMULATED (caller zeroes): column sums of the stored C -- the bias gradient
+                          of the layer whose pre-activation gradient this GEMM produces (F.linear backward), taken in the
+                          epilogue instead of a second pass over C */
 } egb_gemm_desc;
 
 int egb_gemm(const egb_gemm_desc* d, void* stream);
