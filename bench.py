@@ -407,12 +407,12 @@ def run_b200(args):
             ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05.mma bf16, TMA operands, TMEM accumulators)",
                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                        "traffic": 648334080 if args.workload == "cfg2" else None,
-                        "traffic_note": "dram read 82.3 MB + write 566.0 MB of ONE launch, the largest GEMM of the step "
-                                        "(ViT fc1+GELU, 50432x768x3072; algorithmic 82.2 MB read + 619.7 MB written, part of "
-                                        "which stays in L2), from the ncu --set full capture "
-                                        "profiles/r01_ncu_full_gemm_tc2_fc1_gelu_raw.csv; achieved/avg_launch_us average over "
-                                        "all GEMM launches of the step",
+                        "traffic": 648139264 if args.workload == "cfg2" else None,
+                        "traffic_note": "dram read 82.5 MB + write 565.7 MB of ONE launch, the largest GEMM of the step "
+                                        "(ViT fc1 + GELU + saved GELU', 50432x768x3072, 260 us under ncu; algorithmic 82.2 MB "
+                                        "read + 619.7 MB written, part of which is still in L2 when the kernel ends), from the "
+                                        "ncu --set full capture profiles/r01_ncu_full_gemm_tc2_fc1_gelu_dgrad_v2_raw.csv; "
+                                        "achieved/avg_launch_us average over all GEMM launches of the step",
                         "peak_source": peak_src, "launches_per_step": pr["launches"] / n_prof,
                         "avg_launch_us": pr["ms"] * 1e3 / pr["launches"],
                         "flops_per_launch": pr["flops"] / pr["launches"],
