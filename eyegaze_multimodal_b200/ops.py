@@ -83,6 +83,32 @@ def zeros(shape, dtype, device):
     return t
 
 
+# Small fp32 accumulators (bias / LayerNorm parameter gradients: a few KB each, ~130 per training step) are carved out
+# of 1 MB blocks that are zeroed with ONE memset each, instead of one memset launch per accumulator.  A block belongs to
+# the stream it was zeroed on (the EEG branch runs on a side stream); views keep their block alive.
+_ARENA_FLOATS = 1 << 18
+_arenas = {}
+
+
+def small_zeros(shape, device):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if n > _ARENA_FLOATS // 8:
+        return zeros(shape, torch.float32, device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    blk = _arenas.get(key)
+    need = (n + 63) // 64 * 64                       # 256-byte granules keep every slice 16-byte aligned
+    if blk is None or blk[1] + need > _ARENA_FLOATS:
+        if len(_arenas) > 64:
+            _arenas.clear()
+        blk = [torch.zeros(_ARENA_FLOATS, dtype=torch.float32, device=device), 0]
+        _arenas[key] = blk
+    out = blk[0][blk[1]:blk[1] + n].view(shape)
+    blk[1] += need
+    return out
+
+
 def gemm(M, N, K, in_code, a: L.Operand, b: L.Operand, c: L.Matrix, *, bias=None, c_pre=None, residual=None, aux=None,
          alpha=1.0, act=0, act_bwd=0, aux_scale=1.0, dropout_p=0.0, seed=0, accumulate=0, split_k=0, c_colsum=None):
     empty = L.Matrix(None, 0, 0, 0, 0)
@@ -135,8 +161,8 @@ def copy_strided4(src, dst, sizes, src_strides, dst_strides, src_offset=0, dst_o
 def colsum(x: torch.Tensor, N: int) -> torch.Tensor:
     m, xt = _matrix(x)
     rows = _rows(xt)[1]
-    out = torch.empty(N, dtype=torch.float32, device=x.device)
-    L.call("egb_colsum", C.byref(m), rows, N, out.data_ptr(), 1, _stream())
+    out = small_zeros((N,), x.device)
+    L.call("egb_colsum", C.byref(m), rows, N, out.data_ptr(), 0, _stream())
     return out
 
 
@@ -379,7 +405,7 @@ class Mlp2Fn(torch.autograd.Function):
         db2 = colsum(dyd, w2.shape[0]) if need[5] else None
         # dpre1 = (dyd . W2) * act'(.)   -- activation derivative, mid-dropout mask AND the first layer's bias gradient
         # (column sums of dpre1) fused in the GEMM epilogue
-        db1 = zeros((w1.shape[0],), torch.float32, dy.device) if need[3] else None
+        db1 = small_zeros((w1.shape[0],), dy.device) if need[3] else None
         if act == L.ACT_RELU:
             dpre1 = _grad_input(dyd, w2c, h.shape, code, act_bwd=L.ACTBWD_RELU_MASK, aux=h,
                                 aux_scale=1.0 / (1.0 - p_mid) if p_mid > 0 else 1.0, colsum_out=db1)
@@ -424,7 +450,7 @@ class LayerNormFn(torch.autograd.Function):
         if _code(dy) != _code(x):
             dy = cast(dy, _code(x))
         dx = torch.empty_like(x)
-        dgb = zeros((2, D), torch.float32, x.device)
+        dgb = small_zeros((2, D), x.device)
         L.call("egb_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), _code(x), M, D, _stream())
         return dx, dgb[0], dgb[1], None
@@ -459,7 +485,7 @@ class LayerNormResidualFn(torch.autograd.Function):
         D = x.shape[-1]
         M = x.numel() // D
         code = _code(x)
-        dgb = zeros((2, D), torch.float32, x.device)
+        dgb = small_zeros((2, D), x.device)
         if dy is None:                      # only the residual path was used
             return dres, dgb[0], dgb[1], None
         dy = dy.contiguous()

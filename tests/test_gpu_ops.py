@@ -125,6 +125,57 @@ def test_layernorm(cuda_device, mode, D):
     _close(bg.grad, br.grad, mode, scale=10, msg="dbeta")
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("D", [256, 768])
+def test_layernorm_residual_block(cuda_device, mode, D):
+    """Pre-norm residual block y = x + W LN(x): the gradient that reaches x through the residual operand handed back
+    by ops.layernorm_residual is added inside the LayerNorm backward kernel (egb_layernorm_bwd_res)."""
+    torch.manual_seed(12)
+    x = torch.randn(7, 29, D) * 1.5
+    g, b = 1 + 0.1 * torch.randn(D), 0.1 * torch.randn(D)
+    w, wb = torch.randn(D, D) / math.sqrt(D), 0.1 * torch.randn(D)
+    gy = torch.randn(7, 29, D)
+    xr, gr, br, wr, wbr = [t.clone().requires_grad_(True) for t in (x, g, b, w, wb)]
+    q = (lambda t: t.bfloat16().float()) if mode == "bf16" else (lambda t: t)
+    xq = q(xr)
+    yr = F.linear(q(F.layer_norm(xq, (D,), gr, br, 1e-6)), q(wr), wbr) + xq
+    yr.backward(gy)
+    xg = x.to(DEV).to(_dt(mode)).requires_grad_(True)
+    gg, bg, wg, wbg = _param(g), _param(b), _param(w), _param(wb)
+    h, xres = ops.layernorm_residual(xg, gg, bg, 1e-6)
+    y = ops.linear(h, wg, wbg, residual=xres)
+    y.backward(gy.to(DEV).to(_dt(mode)))
+    _close(y, yr, mode, msg="y")
+    _close(xg.grad, xr.grad, mode, msg="dx (LayerNorm path + residual path)")
+    _close(gg.grad, gr.grad, mode, scale=10, msg="dgamma")
+    _close(bg.grad, br.grad, mode, scale=10, msg="dbeta")
+    _close(wg.grad, wr.grad, mode, scale=math.sqrt(7 * 29), msg="dw")
+
+
+@pytest.mark.parametrize("act_bwd", ["mul", "relu"])
+def test_gemm_epilogue_column_sums(cuda_device, act_bwd):
+    """egb_gemm_desc.c_colsum: the tensor-core epilogue accumulates the column sums of the tile it stores (bias gradient
+    of the layer whose pre-activation gradient the GEMM produces); compared with a separate pass over the output."""
+    torch.manual_seed(13)
+    M, N, K = 1000, 512, 256                     # dpre[M, N] . W[N, K] -> dx[M, K]
+    dpre = (torch.randn(M, N, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(N)).bfloat16()
+    aux = torch.randn(M, K, device=DEV).bfloat16()
+    if act_bwd == "relu":
+        aux = torch.relu(aux)
+    code = L.ACTBWD_MUL if act_bwd == "mul" else L.ACTBWD_RELU_MASK
+    fused = ops.small_zeros((K,), torch.device(DEV))
+    dx1 = ops._grad_input(dpre, w, (M, K), L.BF16, act_bwd=code, aux=aux, colsum_out=fused)
+    dx0 = ops._grad_input(dpre, w, (M, K), L.BF16, act_bwd=code, aux=aux)
+    assert torch.equal(dx0, dx1)
+    want = dx0.float().sum(0)
+    sep = ops.colsum(dx0, K)
+    ref_scale = dx0.float().abs().sum(0).max().item()
+    assert (sep - want).abs().max().item() <= 1e-3 * ref_scale
+    # the fused sums are taken before the bf16 rounding of the stored values: agree to bf16 accuracy of the column mass
+    assert (fused - want).abs().max().item() <= 4e-3 * ref_scale
+
+
 def _ref_attention(q, k, v, H, kv_shift=0):
     S, Lq, D = q.shape
     dk = D // H
