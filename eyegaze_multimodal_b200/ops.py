@@ -199,7 +199,7 @@ class _WeightCache:
             slot = {}
             self._d[p0] = slot
         key = (code, tag, tuple(id(p) for p in params[1:]))
-        ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+        ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params) + (_param_epoch[0],)
         hit = slot.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
@@ -209,6 +209,13 @@ class _WeightCache:
 
 
 wcache = _WeightCache()
+_param_epoch = [0]
+
+
+def bump_param_epoch() -> None:
+    """Invalidate every derived parameter copy (bf16 casts, packed QKV): called by code that updates parameters
+    without going through autograd's version counters (optim.FusedClipAdamW)."""
+    _param_epoch[0] += 1
 
 
 def weight_plain(w: torch.Tensor, code: int) -> torch.Tensor:

@@ -253,6 +253,21 @@ int egb_vit_patchify(const float* img_a, const float* img_b, int64_t a_batch_str
                      float* stats_scratch, int dtype, int B, int H, int W, int ps, int mode, void* stream);
 int egb_fill_row0(const float* cls, const float* pos, void* out, int dtype, int S, int L, int D, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-step tail (the step right after the path): global-norm gradient clipping and AdamW
+ * over all parameters in two launches -- torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step()
+ * (train_art.py:221-229, train_multimodal_fuzzy_fusion.py:464-472).  fp32 parameters, gradients and moments.
+ *   tensor_table : device array of { float* p; const float* g; float* exp_avg; float* exp_avg_sq; int64 step; }
+ *                  (g NULL = skipped; step = the tensor's own 1-based update count, used for the bias corrections)
+ *   chunk_table  : device array of { int32 tensor; int32 n; int64 offset; }, one CTA per chunk
+ * egb_multi_tensor_sqnorm ACCUMULATES sum(g^2) into out_sqnorm (caller zeroes); egb_multi_tensor_adamw reads it on the
+ * device (sqnorm NULL or max_norm <= 0: no clipping).
+ * ------------------------------------------------------------------------------------------- */
+int egb_multi_tensor_sqnorm(const void* tensor_table, const void* chunk_table, int n_chunks, float* out_sqnorm,
+                            void* stream);
+int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
