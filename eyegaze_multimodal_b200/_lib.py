@@ -73,6 +73,8 @@ _SIGNATURES = {
     "egb_scale_by_device_scalar": [vp, vp, vp, i64, vp],
     "egb_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp],
     "egb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    "egb_eeg_window_normalize": [vp, vp, i32, i32, i32, i32, vp],
+    "egb_image_u8_normalize": [vp, vp, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp],
     "egb_multi_tensor_sqnorm": [vp, vp, i32, vp, vp],
     "egb_multi_tensor_adamw": [vp, vp, i32, f32, f32, f32, f32, f32, f32, vp, vp],
     "egb_layernorm_bwd_res": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],

@@ -268,6 +268,17 @@ int egb_multi_tensor_sqnorm(const void* tensor_table, const void* chunk_table, i
 int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
                            float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Input side (the step before the path), on a whole device batch instead of per __getitem__:
+ * egb_eeg_window_normalize: x, out [B, C, T] fp32.  mode 0 = common average reference then per-channel z-score
+ *   (population std + 1e-8; 1_Data/processed/dual_eeg_dataset.py:158-166), mode 1 = whole-window z-score (:196-198).
+ * egb_image_u8_normalize: uint8 [B, H, W, 3] -> fp32 [B, 3, H, W]: ToTensor (/255) + Normalize(mean, std)
+ *   (multimodal_dataset.py:73-83); mean3 / std3 are HOST arrays of three floats.
+ * ------------------------------------------------------------------------------------------- */
+int egb_eeg_window_normalize(const float* x, float* out, int B, int C, int T, int mode, void* stream);
+int egb_image_u8_normalize(const uint8_t* hwc, float* chw, int B, int H, int W, const float* mean3, const float* std3,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif
