@@ -1,16 +1,19 @@
 // Fused multi-head attention on the 5th-generation tensor cores (tcgen05 + TMEM), bf16 operands, fp32 softmax.
 //   forward : S = Q K^T (TMEM) -> row softmax in registers -> P (bf16) written back to TMEM ->
 //             O = P V with the A operand read from TMEM (no shared-memory round trip for P)
-//   backward: dQ kernel  (one CTA per 128 query rows): S and dP = dO V^T in TMEM -> dS -> dQ = dS K
-//             dKV kernel (one CTA per 128 key rows)  : S^T = K Q^T and dP^T = V dO^T in TMEM ->
-//                                                      P~^T, dS^T (bf16, TMEM) -> dV = P~^T dO, dK = dS^T Q
+//   backward: att_tc_bwd_pipe_kernel -- ONE kernel per (batch, head): 8 softmax warps + 2 MMA-issuing warps, 64-key
+//             rounds with the score pair (S, dP = dO V^T) double-buffered in TMEM, P~ / dS staged in shared memory as
+//             K-major tiles and re-read as MN-major A operands for dV = P~^T dO, dK = dS^T Q; dQ = dS K from the same
+//             tiles.  (EGB_ATT_FUSED_BWD=1 / 0 select the two earlier designs kept below: the single-issuer fused kernel
+//             and the dQ + dKV kernel pair with TMEM-resident P / dS.)
 // Sequence lengths on this path are <= 256 (L = 33 / 139 / 235 for the EEG encoder, 197 for the ViT), so the
 // whole key axis is ONE tcgen05 N tile (N <= 256) and no online-softmax rescaling across tiles is needed.
 // One thread owns one TMEM lane = one query (or key) row, so row statistics need no shuffles at all.
 //
-// Operand tiles are staged by the CTA's threads (128-bit loads of the strided per-head slices of the packed
-// [S, L, 3D] projection) directly into the 128-byte-swizzled UMMA layout; the same physical tile serves as a
-// K-major operand (Q K^T, dO V^T) and as an MN-major operand (P V, dS K, dS^T Q, P^T dO).
+// Operand tiles land directly in the 128-byte-swizzled UMMA layout -- by TMA (one bulk tensor copy per tile of the
+// strided per-head slice of the packed [S, L, 3D] projection, head_dim 64) or by cp.async (head_dim 32); the same
+// physical tile serves as a K-major operand (Q K^T, dO V^T) and as an MN-major operand (P V, dS K, dS^T Q, P^T dO).
+// Results leave as whole row segments through a warp-private shared-memory transposition.
 // art.py:203-213 / timm Attention; cross-brain attention (dual_eeg_transformer.py:966-974) via kv_shift.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -1338,11 +1341,9 @@ int egb_attention_tc_fwd(const egb_attention_desc* d, cudaStream_t st) {
   memset(&maps, 0, sizeof(maps));
   if (tma && d->head_dim == 64) {
     const long long inner = (long long)d->H * d->head_dim;
-    if (egb_tmap_rows64(&maps.q, d->q, inner, d->Lq, d->S, d->q_rs, d->q_bs, TILE_ROWS) ||
-        egb_tmap_rows64(&maps.k, d->k, inner, d->Lk, d->S, d->k_rs, d->k_bs, p.Lk_pad) ||
-        egb_tmap_rows64(&maps.v, d->v, inner, d->Lk, d->S, d->v_rs, d->v_bs, p.Lk_pad))
-      return 1;
-    p.use_tma = 1;
+    p.use_tma = !(egb_tmap_rows64(&maps.q, d->q, inner, d->Lq, d->S, d->q_rs, d->q_bs, TILE_ROWS) ||
+                  egb_tmap_rows64(&maps.k, d->k, inner, d->Lk, d->S, d->k_rs, d->k_bs, p.Lk_pad) ||
+                  egb_tmap_rows64(&maps.v, d->v, inner, d->Lk, d->S, d->v_rs, d->v_bs, p.Lk_pad));
   }
   if (drop) att_tc_fwd_kernel<true><<<grid, TC_THREADS, smem, st>>>(p, maps);
   else att_tc_fwd_kernel<false><<<grid, TC_THREADS, smem, st>>>(p, maps);
@@ -1372,14 +1373,13 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
       AttMaps maps;
       memset(&maps, 0, sizeof(maps));
       if (tma && d->head_dim == 64) {
+        // a view the tensor-map encoder rejects (exotic strides) simply keeps the cp.async staging
         const long long inner = (long long)d->H * d->head_dim;
-        if (egb_tmap_rows64(&maps.q, d->q, inner, d->Lq, d->S, d->q_rs, d->q_bs, p.Lq_pad) ||
-            egb_tmap_rows64(&maps.g, d->d_o, inner, d->Lq, d->S, d->do_rs, d->do_bs, p.Lq_pad) ||
-            egb_tmap_rows64(&maps.o, d->o, inner, d->Lq, d->S, d->o_rs, d->o_bs, p.Lq_pad) ||
-            egb_tmap_rows64(&maps.k, d->k, inner, d->Lk, d->S, d->k_rs, d->k_bs, p.Lk_pad) ||
-            egb_tmap_rows64(&maps.v, d->v, inner, d->Lk, d->S, d->v_rs, d->v_bs, p.Lk_pad))
-          return 1;
-        p.use_tma = 1;
+        p.use_tma = !(egb_tmap_rows64(&maps.q, d->q, inner, d->Lq, d->S, d->q_rs, d->q_bs, p.Lq_pad) ||
+                      egb_tmap_rows64(&maps.g, d->d_o, inner, d->Lq, d->S, d->do_rs, d->do_bs, p.Lq_pad) ||
+                      egb_tmap_rows64(&maps.o, d->o, inner, d->Lq, d->S, d->o_rs, d->o_bs, p.Lq_pad) ||
+                      egb_tmap_rows64(&maps.k, d->k, inner, d->Lk, d->S, d->k_rs, d->k_bs, p.Lk_pad) ||
+                      egb_tmap_rows64(&maps.v, d->v, inner, d->Lk, d->S, d->v_rs, d->v_bs, p.Lk_pad));
       }
       if (drop) att_tc_bwd_pipe_kernel<true><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
       else att_tc_bwd_pipe_kernel<false><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
