@@ -166,6 +166,97 @@ __global__ void __launch_bounds__(FTHREADS) gemm_fma_kernel(const FParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 64 x 64 tiles for SMALL problems (the fp32 heads / fusion tail: M = batch, N <= 768, K <= 768).  With 128 x 128
+// tiles those launches occupy 4-12 SMs and every K step costs a thread 1024 FMAs (measured 170 us for 256x256x768);
+// a quarter of the work per thread on four times as many CTAs brings the chain of dependent launches at the end
+// of the forward / start of the backward pass down by ~3x.  Same operand views, same epilogue.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SBM = 64, SBN = 64;
+
+// this thread's 4 elements of a [64 mn x 16 k] operand tile
+template <typename T>
+__device__ __forceinline__ void load_tile64(const FOperand& o, int mn0, int extent_mn, int k0, int k_end, float (&r)[4]) {
+  const int t = threadIdx.x;
+  if (o.major == 0) {
+    const int kq = (t & 3) * 4;
+    const int row = mn0 + (t >> 2);
+    const bool ok = row < extent_mn;
+    load4_guard<T>(o, ok ? op_row_offset(o, row) : 0, k0 + kq, k_end, ok, r);
+  } else {
+    const int mq = (t & 15) * 4;
+    const int k = k0 + (t >> 4);
+    const bool ok = k < k_end;
+    load4_guard<T>(o, ok ? op_row_offset(o, k) : 0, mn0 + mq, extent_mn, ok, r);
+  }
+}
+__device__ __forceinline__ void store_tile64(const FOperand& o, float (*s)[SBM + 4], const float (&r)[4]) {
+  const int t = threadIdx.x;
+  if (o.major == 0) {
+    const int kq = (t & 3) * 4;
+    const int row = t >> 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[kq + j][row] = r[j];
+  } else {
+    *reinterpret_cast<float4*>(&s[t >> 4][(t & 15) * 4]) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FTHREADS) gemm_fma_small_kernel(const FParams p) {
+  __shared__ __align__(16) float As[2][FBK][SBM + 4];
+  __shared__ __align__(16) float Bs[2][FBK][SBN + 4];
+  const int m0 = blockIdx.y * SBM;
+  const int n0 = blockIdx.x * SBN;
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kend = min(p.K, kbeg + p.k_per_split);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  load_tile64<T>(p.a, m0, p.M, kbeg, kend, ra);
+  load_tile64<T>(p.b, n0, p.N, kbeg, kend, rb);
+  store_tile64(p.a, As[0], ra);
+  store_tile64(p.b, Bs[0], rb);
+  __syncthreads();
+
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += FBK) {
+    const bool has_next = k0 + FBK < kend;
+    if (has_next) {
+      load_tile64<T>(p.a, m0, p.M, k0 + FBK, kend, ra);
+      load_tile64<T>(p.b, n0, p.N, k0 + FBK, kend, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < FBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float a[4] = {a0.x, a0.y, a0.z, a0.w};
+      const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (has_next) {
+      store_tile64(p.a, As[buf ^ 1], ra);
+      store_tile64(p.b, Bs[buf ^ 1], rb);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+    epi_apply_store<4>(p.epi, m0 + ty * 4 + i, n0 + tx * 4, v);
+  }
+}
+
 FOperand make_foperand(const egb_operand& o, int extent_mn, int K, int esz) {
   FOperand f;
   f.ptr = (const char*)o.ptr;
@@ -274,7 +365,11 @@ extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
   p.a = make_foperand(d->a, d->M, d->K, esz);
   p.b = make_foperand(d->b, d->N, d->K, esz);
   if (egb_fill_epilogue(d, &p.epi)) return 1;
-  const int mt = (d->M + FBM - 1) / FBM, nt = (d->N + FBN - 1) / FBN;
+  // small problems (fewer 128 x 128 tiles than half the SMs): 64 x 64 tiles, four times the CTAs
+  static const int small_ok = getenv("EGB_GEMM_FMA_SMALL") ? atoi(getenv("EGB_GEMM_FMA_SMALL")) : 1;
+  const bool small = small_ok && ((d->M + FBM - 1) / FBM) * ((d->N + FBN - 1) / FBN) * 2 < egb_num_sms();
+  const int bm = small ? SBM : FBM, bn = small ? SBN : FBN;
+  const int mt = (d->M + bm - 1) / bm, nt = (d->N + bn - 1) / bn;
   int split = 1;
   if (d->accumulate) {
     split = d->split_k;
@@ -291,7 +386,10 @@ extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
   p.split_k = (d->K + kps - 1) / kps;
   dim3 grid(nt, mt, p.split_k);
   EGB_CHECK(mt <= 65535 && p.split_k <= 65535, "gemm: grid too large");
-  if (d->in_dtype == EGB_BF16)
+  if (small) {
+    if (d->in_dtype == EGB_BF16) gemm_fma_small_kernel<bf16><<<grid, FTHREADS, 0, stream>>>(p);
+    else gemm_fma_small_kernel<float><<<grid, FTHREADS, 0, stream>>>(p);
+  } else if (d->in_dtype == EGB_BF16)
     gemm_fma_kernel<bf16><<<grid, FTHREADS, 0, stream>>>(p);
   else
     gemm_fma_kernel<float><<<grid, FTHREADS, 0, stream>>>(p);
