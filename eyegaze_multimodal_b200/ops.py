@@ -88,6 +88,7 @@ def zeros(shape, dtype, device):
 # the stream it was zeroed on (the EEG branch runs on a side stream); views keep their block alive.
 _ARENA_FLOATS = 1 << 18
 _arenas = {}
+_arena_lock = threading.Lock()
 
 
 def small_zeros(shape, device):
@@ -97,16 +98,17 @@ def small_zeros(shape, device):
     if n > _ARENA_FLOATS // 8:
         return zeros(shape, torch.float32, device)
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
-    blk = _arenas.get(key)
     need = (n + 63) // 64 * 64                       # 256-byte granules keep every slice 16-byte aligned
-    if blk is None or blk[1] + need > _ARENA_FLOATS:
-        if len(_arenas) > 64:
-            _arenas.clear()
-        blk = [torch.zeros(_ARENA_FLOATS, dtype=torch.float32, device=device), 0]
-        _arenas[key] = blk
-    out = blk[0][blk[1]:blk[1] + n].view(shape)
-    blk[1] += need
-    return out
+    with _arena_lock:                                # backward runs on autograd's threads
+        blk = _arenas.get(key)
+        if blk is None or blk[1] + need > _ARENA_FLOATS:
+            if len(_arenas) > 64:
+                _arenas.clear()
+            blk = [torch.zeros(_ARENA_FLOATS, dtype=torch.float32, device=device), 0]
+            _arenas[key] = blk
+        off = blk[1]
+        blk[1] += need
+    return blk[0][off:off + n].view(shape)
 
 
 def gemm(M, N, K, in_code, a: L.Operand, b: L.Operand, c: L.Matrix, *, bias=None, c_pre=None, residual=None, aux=None,
