@@ -1,5 +1,6 @@
 """ViT oracle (oracle/vit.py): timm is absent, so the restatement is cross-checked against torchvision's
-VisionTransformer by weight remapping, and against the parameter count the reference documents. CPU only."""
+VisionTransformer and Hugging Face's ViTForImageClassification by weight remapping, and against the parameter count the
+reference documents. CPU only."""
 import numpy as np
 import pytest
 import torch
@@ -62,3 +63,40 @@ def test_wrapper_logic():
     assert torch.equal(w6[:, :3], w3) and torch.equal(w6[:, 3:], w3)
     w6 = V.widen_patch_embed(w3, "average")
     assert torch.allclose(w6[:, 3:], w3.mean(1, keepdim=True).expand_as(w3))
+
+
+def _hf_to_timm(hf_sd, depth, pre):
+    """Hugging Face ViTForImageClassification keys -> timm keys (q / k / v rows stacked into the fused qkv)."""
+    e = "vit.embeddings."
+    sd = {pre + "cls_token": hf_sd[e + "cls_token"], pre + "pos_embed": hf_sd[e + "position_embeddings"],
+          pre + "patch_embed.proj.weight": hf_sd[e + "patch_embeddings.projection.weight"],
+          pre + "patch_embed.proj.bias": hf_sd[e + "patch_embeddings.projection.bias"],
+          pre + "norm.weight": hf_sd["vit.layernorm.weight"], pre + "norm.bias": hf_sd["vit.layernorm.bias"],
+          pre + "head.weight": hf_sd["classifier.weight"], pre + "head.bias": hf_sd["classifier.bias"]}
+    for i in range(depth):
+        s, d = f"vit.encoder.layer.{i}.", f"{pre}blocks.{i}."
+        for a, b in (("layernorm_before", "norm1"), ("layernorm_after", "norm2"), ("attention.output.dense", "attn.proj"),
+                     ("intermediate.dense", "mlp.fc1"), ("output.dense", "mlp.fc2")):
+            sd[d + b + ".weight"], sd[d + b + ".bias"] = hf_sd[s + a + ".weight"], hf_sd[s + a + ".bias"]
+        for part in ("weight", "bias"):
+            sd[d + "attn.qkv." + part] = torch.cat([hf_sd[s + f"attention.attention.{n}.{part}"] for n in ("query", "key", "value")])
+    return sd
+
+
+def test_vit_restatement_matches_huggingface_vit():
+    """A second, independent implementation of the published ViT (transformers' ViTForImageClassification: separate
+    q/k/v projections, its own attention and embedding code) agrees with the restatement after key remapping."""
+    tr = pytest.importorskip("transformers")
+    cfg = tr.ViTConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=256, image_size=32,
+                       patch_size=16, num_channels=6, num_labels=3, hidden_act="gelu", layer_norm_eps=1e-6,
+                       hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, qkv_bias=True)
+    torch.manual_seed(1)
+    m = tr.ViTForImageClassification(cfg).eval()
+    for p in m.parameters():
+        torch.nn.init.normal_(p, std=0.05)
+    sd = _hf_to_timm({k: v.detach() for k, v in m.state_dict().items()}, 2, "backbone.")
+    a, b = torch.randn(3, 3, 32, 32), torch.randn(3, 3, 32, 32)
+    with torch.no_grad():
+        want = m(pixel_values=torch.cat([a, b], 1)).logits
+    got = V.early_fusion_forward(sd, a, b, heads=4, mode="concat")
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-5, rtol=1e-4)
