@@ -671,6 +671,11 @@ class TemporalConvFn(torch.autograd.Function):
         tdt = _TORCH_DT[code]
         ksz = ws[0].shape[2]
         pad = ksz // 2
+        if n > 1 and any(w.requires_grad for w in ws) and (stride < 2 or pad % stride != 0 or pad < stride - 1):
+            # the input-gradient of layers >= 1 runs as `stride` phase GEMMs whose slab geometry needs these
+            raise NotImplementedError("temporal conv frontend: training needs stride >= 2 and (kernel_size // 2) %% stride "
+                                      "== 0 (got kernel_size=%d, stride=%d); the reference configs use 25 / 4"
+                                      % (ksz, stride))
         # channels-last, zero-padded input; group stride kept a multiple of 8 elements for TMA
         Tp = T + 2 * pad
         while (Tp * Cin) % 8:
@@ -745,11 +750,13 @@ class TemporalConvFn(torch.autograd.Function):
                 dbs[i] = db
             if i == 0:
                 break
-            # d(input) via `stride` phase GEMMs (transposed convolution), fused with the previous ReLU(+dropout) mask
-            assert t_in % stride == 0
+            # d(input) via `stride` phase GEMMs (transposed convolution), fused with the previous ReLU(+dropout) mask.
+            # t_in need not be a multiple of the stride: the last row of a phase may land up to stride-1 positions
+            # past the sequence end, i.e. in the zero padding of the saved activation, where the ReLU mask (y != 0)
+            # makes the stored gradient exactly 0 again.
             wp = _conv_weight_phase(ws[i], code, stride, J)
             g_prev = zeros((S, tp_in, c_in), tdt, dev)   # same padded geometry as bufs[i]
-            rows = t_in // stride
+            rows = (t_in + stride - 1) // stride
             slab0 = g_front - (J - 1 - s0)
             for ph in range(stride):
                 a = L.Operand(g.data_ptr() + slab0 * O * g.element_size(), 0, rows, O, g_rp * O, 0, 0)
@@ -1018,10 +1025,12 @@ class SeqAssembleFn(torch.autograd.Function):
         dpos = zeros((max_len, D), torch.float32, dx.device)
         dibs = torch.empty(B, n_ibs, D, dtype=dx.dtype, device=dx.device) if n_ibs else None
         L.call("egb_seq_assemble_bwd", dx.data_ptr(), dpos.data_ptr(), _p(dibs), code, S, B, Lq, D, n_ibs, _stream())
-        dcls = dpos[0].view(1, 1, D)
+        # cls also collects pos row 0's sum: both parameters receive the same batch-summed row, as SEPARATE tensors
+        # (autograd keeps the returned tensors as .grad; aliased gradients would be scaled twice by in-place clipping /
+        # GradScaler.unscale_)
+        dcls = dpos[0].clone().view(1, 1, D)
         dspec = dx[:, 1 + n_ibs:1 + n_ibs + n_spec] if n_spec else None
         dh = dx[:, 1 + n_ibs + n_spec:]
-        # cls also collects pos row 0's sum; both parameters receive the same batch-summed row
         return dcls, dpos, dibs, dspec, dh, None
 
 
@@ -1328,7 +1337,7 @@ class VitEmbedFn(torch.autograd.Function):
             dp = zeros((n + 1, D), torch.float32, dev)
             L.call("egb_seq_assemble_bwd", dx.data_ptr(), dp.data_ptr(), None, code, B, B, n + 1, D, 0, _stream())
             dpos = dp.view(1, n + 1, D)
-            dcls = dp[0].view(1, 1, D)
+            dcls = dp[0].clone().view(1, 1, D)         # never alias two parameters' gradients (see SeqAssembleFn)
         return None, None, dw, db, dcls, dpos, None, None, None
 
 

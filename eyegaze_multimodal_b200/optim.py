@@ -36,9 +36,15 @@ class FusedClipAdamW(torch.optim.Optimizer):
     def _plan(self, group):
         plan = self._plans.get(id(group))
         params = [p for p in group["params"] if p.requires_grad]
-        if plan is not None and plan["ids"] == [id(p) for p in params]:
+        # a plan caches raw addresses: it is valid for the same parameter objects AT the same storage only
+        # (model.to(...) / p.data = ... swap the storage under an unchanged id)
+        key = [(id(p), p.data_ptr()) for p in params]
+        if plan is not None and plan["ids"] == key:
             return plan
+        if plan is not None:
+            self._sync_steps(plan)   # the live step counts move to self.state before the plan is rebuilt
         if not params:
+            self._plans.pop(id(group), None)
             return None
         dev = params[0].device
         for p in params:
@@ -73,7 +79,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
                 chunks.append((i, min(_CHUNK, p.numel() - o), o))
         ch = np.zeros(len(chunks), dtype=[("tensor", "<i4"), ("n", "<i4"), ("offset", "<i8")])
         ch["tensor"], ch["n"], ch["offset"] = zip(*chunks)
-        plan = dict(ids=[id(p) for p in params], params=params, host=host, dev=torch.empty_like(host, device=dev),
+        plan = dict(ids=key, params=params, host=host, dev=torch.empty_like(host, device=dev),
                     chunks=torch.from_numpy(ch.view(np.uint8).copy()).to(dev), n_chunks=len(chunks), m=m_flat, v=v_flat,
                     copied=None, steps=steps, host_np=host.numpy())
         self._plans[id(group)] = plan
@@ -129,8 +135,8 @@ class FusedClipAdamW(torch.optim.Optimizer):
         ops.bump_param_epoch()       # the kernels wrote the parameters behind autograd's version counters
         return loss
 
-    def _sync_steps(self):
-        for plan in self._plans.values():
+    def _sync_steps(self, only=None):
+        for plan in ([only] if only is not None else self._plans.values()):
             for p, k in zip(plan["params"], plan["steps"]):
                 self.state[p]["step"] = torch.tensor(float(k))
 

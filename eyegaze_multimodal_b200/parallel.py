@@ -12,8 +12,14 @@ data-path collective.  Gradients are reduced in flat fp32 buckets:
     bucket's all-reduce (NCCL over NVLink / NVSwitch, average) is enqueued asynchronously, so it overlaps the rest
     of the backward pass (buckets are filled in reverse registration order ~ backward execution order);
   * with a single rank nothing is packed or reduced at all;
-  * ``finish()`` flushes buckets whose parameters received no gradient this step and makes the compute stream wait
-    for the communication.
+  * ``finish()`` flushes buckets whose parameters received no gradient this step, makes the compute stream wait
+    for the communication and RE-ARMS the buckets, so loops that call ``optimizer.zero_grad()`` / ``model.zero_grad()``
+    (as the reference's loops do, train_art.py:216, train_multimodal_fuzzy_fusion.py:434) instead of
+    ``TrialParallel.zero_grad()`` keep reducing every step;
+  * one backward per ``finish()``: gradient accumulation over several backward passes is not supported and raises
+    (a second backward would add local gradients into already reduced buffers);
+  * ragged shards (``B % world != 0``): scale each rank's loss by ``loss_weight(local_B, global_B)`` so the averaged
+    gradients equal the single-process global-batch mean.
 
 ``backend='gloo'`` (CPU tests, world_size 2) takes the same code path with SUM + scale instead of NCCL's AVG.
 """
@@ -85,6 +91,9 @@ class TrialParallel(nn.Module):
     def _make_hook(self, b: _Bucket):
         def hook(_p):
             b.pending -= 1
+            if b.pending < 0:
+                raise RuntimeError("TrialParallel: a parameter received a second gradient before finish() -- one "
+                                   "backward pass per finish(); gradient accumulation is not supported")
             if b.pending == 0:
                 self._launch(b)
         return hook
@@ -113,16 +122,20 @@ class TrialParallel(nn.Module):
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
+    def _rearm(self, b: _Bucket) -> None:
+        b.pending = len(b.params)
+        b.work = None
+        b.launched = False
+
     def zero_grad(self, set_to_none: bool = True) -> None:   # noqa: D401
         for b in self.buckets:
             for p in b.params:
                 p.grad = None
-            b.pending = len(b.params)
-            b.work = None
-            b.launched = False
+            self._rearm(b)
 
     def finish(self) -> None:
-        """Reduce whatever has not been reduced yet and order the compute stream after all communication."""
+        """Reduce whatever has not been reduced yet, order the compute stream after all communication and re-arm the
+        buckets for the next backward pass."""
         for b in self.buckets:
             if not b.launched:
                 self._launch(b)
@@ -131,13 +144,26 @@ class TrialParallel(nn.Module):
                 b.work.wait()
                 if not self._avg:
                     b.flat.div_(self.world)
-                b.work = None
+            if self.world > 1:
+                for v, p in zip(b.views, b.params):
+                    if p.grad is not v:
+                        raise RuntimeError("TrialParallel.finish(): a gradient was replaced after its bucket had been "
+                                           "reduced (second backward pass before finish()?)")
+            self._rearm(b)
 
     def grad_bytes(self) -> int:
         return sum(sum(p.numel() for p in b.params) * 4 for b in self.buckets)
 
     def flat_grads(self) -> Iterable[torch.Tensor]:
         return [b.flat for b in self.buckets]
+
+
+def loss_weight(local_trials: int, global_trials: int, world: Optional[int] = None) -> float:
+    """Factor for a rank's batch-MEAN loss so that the AVG all-reduce of the gradients equals the gradient of the
+    global-batch mean when shards are ragged: (local_B / global_B) * world  (= 1 for even shards)."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    return float(local_trials) * world / float(global_trials)
 
 
 def shard_trials(n_trials: int, rank: Optional[int] = None, world: Optional[int] = None) -> range:

@@ -138,3 +138,47 @@ def test_fuzzy_known_answers_from_reference_selftest():
         FZ.fuzzy_forward(p, uni, uni, "bogus")
     with pytest.raises(ValueError):
         FZ.inverse_softplus(0.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Non-degenerate fixture: a state_dict TRAINED by the unmodified reference on the planted task, whose
+# evaluation predictions cover all three classes with some errors; logits / argmax / ClassificationMetrics were written by
+# the unmodified reference (oracle/make_golden_trained.py).
+# ---------------------------------------------------------------------------------------------------------------------
+def test_trained_fixture_is_not_degenerate():
+    g = load_golden("eeg_model_trained.npz")
+    assert set(g["preds"].tolist()) == {0, 1, 2}
+    acc = float((g["preds"] == g["labels"]).mean())
+    assert 0.5 < acc < 0.97
+    top2 = np.sort(g["out::logits"], axis=-1)
+    assert (top2[:, -1] - top2[:, -2]).min() >= 0.05          # argmax is robust to 1e-4 (fp32) and 2e-2 (bf16) errors
+
+
+def test_oracle_matches_trained_reference_model_and_metrics():
+    from oracle import metrics as M
+    g = load_golden("eeg_model_trained.npz")
+    cfg = _cfg_from(g)
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in golden_state_dict(g).items()}
+    e1, e2 = torch.from_numpy(g["eeg1"]), torch.from_numpy(g["eeg2"])
+    labels = torch.from_numpy(g["labels"])
+    out = O.dual_eeg_forward(sd, e1, e2, cfg, labels)
+    assert np.abs(out["logits"].detach().numpy() - g["out::logits"]).max() <= 1e-4
+    assert np.abs(out["ibs_logits"].detach().numpy() - g["out::ibs_logits"]).max() <= 1e-4
+    preds = out["logits"].argmax(-1).numpy()
+    assert (preds == g["preds"]).all()
+    # oracle/metrics.py == the reference's ClassificationMetrics on the same predictions (exact: both are sklearn calls)
+    want = dict(zip([str(k) for k in g["metric_names"]], g["metric_values"]))
+    got = M.compute_metrics(g["labels"], preds)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert got[k] == pytest.approx(float(v), abs=1e-12), k
+    assert (M.compute_confusion_matrix(g["labels"], preds) == g["confusion"]).all()
+    probs = torch.softmax(out["logits"].detach(), -1).numpy()
+    aucs = M.compute_aucs(g["labels"], probs)
+    for k, v in zip([str(k) for k in g["auc_names"]], g["auc_values"]):
+        assert aucs[k] == pytest.approx(float(v), abs=1e-6), k
+    (out["loss"] + out["loss_ibs_cls"]).backward()
+    for k, v in g.items():
+        if k.startswith("grad::"):
+            e = np.abs(sd[k[6:]].grad.numpy() - v).max()
+            assert e <= 2e-5 + 2e-3 * np.abs(v).max(), (k, e)

@@ -100,3 +100,73 @@ def test_vit_restatement_matches_huggingface_vit():
         want = m(pixel_values=torch.cat([a, b], 1)).logits
     got = V.early_fusion_forward(sd, a, b, heads=4, mode="concat")
     np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-5, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Wrapper logic PINNED to the unmodified reference: tests/golden/vit_wrappers.npz was written by oracle/make_golden_vit.py,
+# which runs /root/reference/3_Models/backbones/{early,late}_fusion_vit.py unchanged with oracle/timm_stub.py (torchvision
+# ViT arithmetic behind timm's attribute surface) in place of the absent timm.  Weights are regenerated from the seeds.
+# ---------------------------------------------------------------------------------------------------------------------
+from conftest import load_golden  # noqa: E402
+from eyegaze_multimodal_b200.synth import gaze_pair_batch  # noqa: E402
+
+
+def _wrapper_golden():
+    g = load_golden("vit_wrappers.npz")
+    s6, s3, sl, simg, scls = (int(x) for x in g["seeds"])
+    return g, str(g["name"]), int(g["B"]), s6, s3, sl, simg, scls
+
+
+def _checksum(sd):
+    return np.array([float(sum(v.double().sum() for v in sd.values())), float(sum(v.double().abs().sum() for v in sd.values()))])
+
+
+@pytest.mark.parametrize("mode", V.EARLY_MODES)
+def test_early_wrapper_matches_reference_golden(mode):
+    g, name, B, s6, s3, _sl, simg, _ = _wrapper_golden()
+    heads = V.VIT_VARIANTS[name][2]
+    cin = 6 if mode == "concat" else 3
+    sd = V.init_vit_state_dict(name, cin, 3, "backbone.", seed=s6 if cin == 6 else s3)
+    np.testing.assert_allclose(_checksum(sd), g[f"early::{mode}::checksum"], rtol=1e-9)     # same regenerated weights
+    a, b = gaze_pair_batch(B, seed=simg)
+    with torch.no_grad():
+        logits = V.early_fusion_forward(sd, a, b, heads, mode)
+        feats = V.early_fusion_features(sd, a, b, heads, mode)
+    np.testing.assert_allclose(logits.numpy(), g[f"early::{mode}::logits"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(feats.numpy(), g[f"early::{mode}::features"], atol=5e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("strategy", ["duplicate", "average"])
+def test_patch_embed_surgery_matches_reference_golden(strategy):
+    g, name, B, _s6, s3, _sl, simg, _ = _wrapper_golden()
+    heads = V.VIT_VARIANTS[name][2]
+    sd = V.init_vit_state_dict(name, 3, 3, "backbone.", seed=s3)
+    w6 = V.widen_patch_embed(sd["backbone.patch_embed.proj.weight"], strategy)
+    np.testing.assert_allclose(w6[:4].numpy(), g[f"surgery::{strategy}::w6_head"], atol=1e-7)
+    np.testing.assert_allclose([float(w6.double().sum()), float(w6.double().abs().sum())], g[f"surgery::{strategy}::w6_sum"], rtol=1e-6)
+    np.testing.assert_allclose(sd["backbone.patch_embed.proj.bias"].numpy(), g[f"surgery::{strategy}::bias"], atol=0)
+    sd["backbone.patch_embed.proj.weight"] = w6
+    a, b = gaze_pair_batch(B, seed=simg)
+    with torch.no_grad():
+        logits = V.early_fusion_forward(sd, a, b, heads, "concat")
+    np.testing.assert_allclose(logits.numpy(), g[f"surgery::{strategy}::logits"], atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", V.LATE_MODES)
+def test_late_wrapper_matches_reference_golden(mode):
+    g, name, B, _s6, _s3, sl, simg, scls = _wrapper_golden()
+    heads = V.VIT_VARIANTS[name][2]
+    sd = V.init_vit_state_dict(name, 3, 0, "encoder.", seed=sl)
+    np.testing.assert_allclose(_checksum(sd), g["late::checksum"], rtol=1e-9)
+    fd = int(g[f"late::{mode}::fused_dim"])
+    gen = torch.Generator().manual_seed(scls)
+    sd["classifier.weight"] = 0.05 * torch.randn(3, fd, generator=gen)
+    sd["classifier.bias"] = 0.05 * torch.randn(3, generator=gen)
+    x1, x2 = gaze_pair_batch(B, seed=simg)
+    with torch.no_grad():
+        logits = V.late_fusion_forward(sd, x1, x2, heads, mode)
+        c1 = V.vit_features(x1, sd, "encoder.", heads)[:, 0]
+        c2 = V.vit_features(x2, sd, "encoder.", heads)[:, 0]
+    np.testing.assert_allclose(logits.numpy(), g[f"late::{mode}::logits"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(V.fuse_features(c1, c2, mode).numpy(), g[f"late::{mode}::fused"], atol=5e-5, rtol=1e-4)
+    np.testing.assert_allclose(c1.numpy(), g["late::cls1"], atol=5e-5, rtol=1e-4)

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 import torch.nn as nn
 
-from eyegaze_multimodal_b200.parallel import TrialParallel, shard_trials
+from eyegaze_multimodal_b200.parallel import TrialParallel, loss_weight, shard_trials
 
 
 class Toy(nn.Module):
@@ -69,3 +69,57 @@ def test_shard_trials_ragged():
     assert [list(shard_trials(10, r, 4)) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
     assert list(shard_trials(3, 3, 4)) == []
     assert sum(len(shard_trials(4096, r, 8)) for r in range(8)) == 4096
+
+
+def _worker_reference_loop(rank, world, port, out):
+    """The reference's loops call optimizer.zero_grad() / model.zero_grad(), never TrialParallel.zero_grad()
+    (train_art.py:216): finish() must re-arm the buckets by itself.  Shards are RAGGED (7 trials over 2 ranks) and each
+    rank uses its batch-MEAN loss scaled by loss_weight(), so the averaged gradients equal the global-batch mean."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100)
+    model = Toy()
+    tp = TrialParallel(model, bucket_mb=0.004)
+    a, b, y = _data(7)
+    idx = list(shard_trials(len(y), rank, world))
+    seen = []
+    for step in range(3):
+        model.zero_grad(set_to_none=True)                # NOT tp.zero_grad()
+        loss = nn.functional.cross_entropy(tp(a[idx], b[idx]), y[idx]) * loss_weight(len(idx), len(y), world)
+        loss.backward()
+        tp.finish()
+        seen.append({n: p.grad.clone() for n, p in model.named_parameters()})
+    # a second backward before finish() must fail loudly instead of silently skipping the reduction
+    model.zero_grad(set_to_none=True)
+    nn.functional.cross_entropy(tp(a[idx], b[idx]), y[idx]).backward()
+    try:
+        nn.functional.cross_entropy(tp(a[idx], b[idx]), y[idx]).backward()
+        raised = False
+    except RuntimeError as e:
+        raised = "gradient accumulation is not supported" in str(e)
+    out[rank] = {"steps": seen, "raised": raised}
+    dist.destroy_process_group()
+
+
+def test_reference_style_loop_rearms_and_ragged_shards():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_reference_loop, args=(2, port, out), nprocs=2, join=True)
+    torch.manual_seed(100)
+    ref = Toy()
+    a, b, y = _data(7)
+    nn.functional.cross_entropy(ref(a, b), y).backward()
+    for r in (0, 1):
+        assert out[r]["raised"]
+        for step in range(3):                            # every step reduced: all three equal the full-batch gradient
+            for n, p in ref.named_parameters():
+                want = p.grad if p.grad is not None else torch.zeros_like(p)
+                assert torch.allclose(out[r]["steps"][step][n], want, atol=1e-6), (n, r, step)
+
+
+def test_loss_weight():
+    assert loss_weight(4, 8, 2) == 1.0
+    assert abs(loss_weight(4, 7, 2) + loss_weight(3, 7, 2) - 2.0) < 1e-12
