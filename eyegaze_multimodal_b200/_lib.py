@@ -51,6 +51,10 @@ class FuzzyDesc(C.Structure):
                 ("mode", i32), ("B", i32), ("num_classes", i32), ("eps_temp", f32), ("eps_log", f32), ("eps_div", f32)]
 
 
+class AdamwState(C.Structure):
+    _fields_ = [("lr", vp), ("step", vp), ("grad_scale", vp), ("found_inf", vp), ("skip_nonfinite", i32)]
+
+
 # name -> argtypes (all return int except where noted); mirrors include/eyegaze_b200.h one to one
 _SIGNATURES = {
     "egb_gemm": [C.POINTER(GemmDesc), vp],
@@ -96,6 +100,17 @@ _SIGNATURES = {
     "egb_fuzzy_bwd": [C.POINTER(FuzzyDesc), vp, vp, vp, vp, vp, vp, vp, vp],
     "egb_vit_patchify": [vp, vp, i64, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "egb_fill_row0": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "egb_seed_epoch_enable": [C.POINTER(vp)],
+    "egb_seed_epoch_advance": [vp],
+    "egb_multi_tensor_adamw_ex": [vp, vp, i32, f32, f32, f32, f32, f32, f32, vp, C.POINTER(AdamwState), vp],
+    "egb_lr_schedule_step": [vp, vp, vp, vp, i32, i32, f32, f32, i32, i32, vp],
+    "egb_accum_scalars": [C.POINTER(vp), i32, vp, vp],
+    "egb_argmax_count": [vp, vp, vp, vp, i32, i32, vp],
+    "egb_l2norm_rows_fwd": [vp, vp, vp, i32, i32, f32, vp],
+    "egb_l2norm_rows_bwd": [vp, vp, vp, vp, i32, i32, vp],
+    "egb_infonce_rows": [vp, vp, i32, i32, vp],
+    "egb_supcon_rows": [vp, vp, vp, vp, vp, i32, vp],
+    "egb_mse_loss": [vp, vp, vp, vp, i64, vp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["egb_last_error", "egb_version", "egb_launch_count"])
 

@@ -38,6 +38,7 @@ struct AttParams {
   unsigned drop_thresh;
   float drop_scale;
   unsigned long long seed;
+  const unsigned long long* epoch;   // device seed epoch (egb_mix_seed), NULL when not enabled
 };
 
 template <typename T>
@@ -54,6 +55,7 @@ __device__ __forceinline__ void load_rows_to_smem(float* dst, int ld, const T* s
 
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttParams p) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ float sm[];
   const int dk = p.dk_dim, ldk = dk + 1;
   float* Ks = sm;                       // [Lk][dk+1]
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttPar
         float pr = sc[jj] * inv;
         if (p.probs != nullptr) p.probs[row_id * p.Lk + j] = pr;
         if (p.drop_thresh != 0u)
-          pr = drop_keep_att(p.seed, (unsigned long long)(row_id * p.Lk), j, p.drop_thresh) ? pr * p.drop_scale : 0.f;
+          pr = drop_keep_att(seed_eff, (unsigned long long)(row_id * p.Lk), j, p.drop_thresh) ? pr * p.drop_scale : 0.f;
         pb[warp * p.Lk + j] = pr;
       }
     }
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttPar
 // Backward A: one warp per query row -> dQ row and delta_i = dO_i . O_i
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_dq_kernel(const AttParams p) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ float sm[];
   const int dk = p.dk_dim, ldk = dk + 1;
   float* Ks = sm;                        // [Lk][dk+1]
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_dq_kernel(const Att
         }
         const float pr = __expf(a - lse);
         if (p.drop_thresh != 0u)
-          dp = drop_keep_att(p.seed, (unsigned long long)(row_id * p.Lk), j, p.drop_thresh) ? dp * p.drop_scale : 0.f;
+          dp = drop_keep_att(seed_eff, (unsigned long long)(row_id * p.Lk), j, p.drop_thresh) ? dp * p.drop_scale : 0.f;
         pb[warp * p.Lk + j] = pr * (dp - dl);
       }
     }
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_dq_kernel(const Att
 // Backward B: one warp per key row -> dK row and dV row (needs delta from kernel A)
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_dkv_kernel(const AttParams p) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ float sm[];
   const int dk = p.dk_dim, ldk = dk + 1;
   float* Qs = sm;                        // [Lq][dk+1]  (unscaled)
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_dkv_kernel(const At
         const float pr = __expf(a * p.scale - p.lse[row_base + i]);
         float pt = pr;
         if (p.drop_thresh != 0u) {
-          const bool keep = drop_keep_att(p.seed, (unsigned long long)((row_base + i) * p.Lk), j, p.drop_thresh);
+          const bool keep = drop_keep_att(seed_eff, (unsigned long long)((row_base + i) * p.Lk), j, p.drop_thresh);
           pt = keep ? pr * p.drop_scale : 0.f;
           dp = keep ? dp * p.drop_scale : 0.f;
         }
@@ -276,6 +280,7 @@ static int fill_att(const egb_attention_desc* d, AttParams* p) {
     p->drop_thresh = drop_threshold16(d->dropout_p);   // 16-bit threshold of the paired decisions
     p->drop_scale = 1.f / (1.f - d->dropout_p);
     p->seed = d->seed;
+    p->epoch = egb_seed_epoch_ptr();
   }
   return 0;
 }

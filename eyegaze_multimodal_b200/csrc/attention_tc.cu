@@ -49,6 +49,7 @@ struct AttTcParams {
   unsigned drop_thresh;
   float drop_scale;
   unsigned long long seed;
+  const unsigned long long* epoch;   // device seed epoch (egb_mix_seed), NULL when not enabled
   long long* dbg;  // optional: phase timestamps (clock64) of CTA (0, 0, S/2), see egb_debug_attention_timing
   int use_tma;     // pipelined backward: operand tiles arrive by TMA (head_dim 64) instead of cp.async
 };
@@ -289,6 +290,7 @@ __device__ __forceinline__ float softmax_fwd_cols32(const uint32_t (&raw)[32], f
 // ======================================================================================= forward
 template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS, 3) att_tc_fwd_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
   uint8_t* sK = sQ + TILE_ROWS * 128;
@@ -404,8 +406,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) att_tc_fwd_kernel(const __grid_
       ptx::tmem_ld_wait();
       const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
       const bool fast = c * 32 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)(c * 32)) <= 0xFFFFFFFFu - 32u;
-      if (fast) sum += softmax_fwd_cols32<DROP, true>(raw, sl2, mb, c * 32, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pk);
-      else sum += softmax_fwd_cols32<DROP, false>(raw, sl2, mb, c * 32, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pk);
+      if (fast) sum += softmax_fwd_cols32<DROP, true>(raw, sl2, mb, c * 32, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pk);
+      else sum += softmax_fwd_cols32<DROP, false>(raw, sl2, mb, c * 32, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pk);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -453,6 +455,7 @@ constexpr uint32_t BW_ACC1 = 192; // second accumulator (dK)
 // -------------------------------------------------------------------------------------- dQ (+ delta)
 template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcParams p) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
   uint8_t* sG = sQ + TILE_ROWS * 128;  // dO tile
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
           const int col = 64 * c + 32 * half + 2 * j + u;
           const float pr = fast_exp2(__uint_as_float(rs[2 * j + u]) * sl2 - lse2);
           float dp = __uint_as_float(rp[2 * j + u]);
-          if (DROP) dp = drop_keep_att(p.seed, (unsigned long long)(row_id * p.Lk), col, p.drop_thresh) ? dp * p.drop_scale : 0.f;
+          if (DROP) dp = drop_keep_att(seed_eff, (unsigned long long)(row_id * p.Lk), col, p.drop_thresh) ? dp * p.drop_scale : 0.f;
           ds2[u] = col < p.Lk ? pr * (dp - dl) : 0.f;
         }
         pk[j] = pack_bf16(ds2[0], ds2[1]);
@@ -573,6 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dq_kernel(const AttTcPa
 // -------------------------------------------------------------------------------------- dK, dV
 template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcParams p) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sK = align1024(smem_raw);   // 128 key rows of this tile
   uint8_t* sV = sK + TILE_ROWS * 128;
@@ -645,7 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS) att_tc_bwd_dkv_kernel(const AttTcP
           float dp = __uint_as_float(rp[2 * jj + u]);
           float pt = pr;
           if (DROP) {
-            const bool keep = drop_keep_att(p.seed, (unsigned long long)((row_base + col) * p.Lk), j, p.drop_thresh);
+            const bool keep = drop_keep_att(seed_eff, (unsigned long long)((row_base + col) * p.Lk), j, p.drop_thresh);
             pt = keep ? pr * p.drop_scale : 0.f;
             dp = keep ? dp * p.drop_scale : 0.f;
           }
@@ -731,6 +735,7 @@ __device__ __forceinline__ void mma_ss_kmn(uint32_t tmem_d, const uint8_t* a, co
 
 template <bool DROP>
 __global__ void __launch_bounds__(TC_THREADS, 1) att_tc_bwd_fused_kernel(const AttTcParams p) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
   uint8_t* sG = sQ + p.Lq_pad * 128;             // dO
@@ -842,7 +847,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) att_tc_bwd_fused_kernel(const A
           for (int j = 0; j < 16; ++j) {
             float pt2[2], ds2[2];
             uint32_t hb = 0;                        // one hash decides both columns of the pair (drop_keep_att)
-            if (DROP) hb = drop_hash(p.seed, (unsigned long long)(row_id * p.Lk + 128 * c + 64 * half + 32 * g + 2 * j));
+            if (DROP) hb = drop_hash(seed_eff, (unsigned long long)(row_id * p.Lk + 128 * c + 64 * half + 32 * g + 2 * j));
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int col = 128 * c + 64 * half + 32 * g + 2 * j + u;   // key index
@@ -993,6 +998,7 @@ __device__ __forceinline__ void softmax_bwd_cols32(const uint32_t (&rs)[32], con
 
 template <bool DROP>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
   uint8_t* sG = sQ + p.Lq_pad * 128;             // dO
@@ -1192,8 +1198,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
         const int col0 = 64 * c + 32 * half;      // first key column of this thread
         const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
         const bool fast = col0 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)col0) <= 0xFFFFFFFFu - 32u;
-        if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
-        else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, p.seed, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
       }
       // previous q-tile's dQ: read it out behind this round's arithmetic; its barrier also covers the MMAs that read
       // the previous q-tile's sDS, which this q-tile now overwrites
@@ -1290,6 +1296,7 @@ int fill_tc(const egb_attention_desc* d, AttTcParams* p) {
     p->drop_thresh = drop_threshold16(d->dropout_p);   // 16-bit threshold of the paired decisions
     p->drop_scale = 1.f / (1.f - d->dropout_p);
     p->seed = d->seed;
+    p->epoch = egb_seed_epoch_ptr();
   }
   p->dbg = g_att_dbg;
   return 0;

@@ -143,6 +143,18 @@ __device__ __forceinline__ void gelu_erf_both2(float2 x, float2& y, float2& dy) 
   dy = fma2(mul2(x, g), splat2(0.3989422804014327f), cdf);
 }
 
+// Device-resident seed epoch (CUDA-graph replays): dropout seeds are launch ARGUMENTS, i.e. frozen into a captured graph.
+// When the host has created the epoch word (egb_seed_epoch_enable), every kernel that draws a mask mixes the CURRENT
+// value of that device word into its seed, and the graph advances the word once per replay (egb_seed_epoch_advance) --
+// forward and backward of one replay see the same value, different replays draw different masks.  NULL = seeds as passed.
+const unsigned long long* egb_seed_epoch_ptr();
+__device__ __forceinline__ unsigned long long egb_mix_seed(unsigned long long seed, const unsigned long long* epoch) {
+  if (epoch == nullptr) return seed;
+  unsigned long long e = __ldg(epoch) * 0x9E3779B97F4A7C15ull;
+  e ^= e >> 29;
+  return seed ^ e;
+}
+
 // Counter-based dropout mask: keep iff hash(seed, idx) >= p * 2^32. Stateless so the backward
 // pass regenerates the mask from (seed, idx) instead of storing it.
 __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint64_t idx) {

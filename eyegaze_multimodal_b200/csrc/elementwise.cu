@@ -312,7 +312,9 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 // out[m,n] = dy[m,n] * keep(seed, m*N+n) / (1-p): regenerates the mask the GEMM epilogue applied.
 template <typename T>
 __global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ out, long long n_elems,
-                                   unsigned thresh, float scale, unsigned long long seed) {
+                                   unsigned thresh, float scale, unsigned long long seed_in,
+                                   const unsigned long long* epoch) {
+  const unsigned long long seed = egb_mix_seed(seed_in, epoch);
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_elems; i += stride) {
     float v[4];
@@ -596,10 +598,10 @@ int egb_dropout_bwd(const void* dy, void* out, int dtype, int64_t n_elems, float
   const int g = grid_for(n_elems / 4, 256);
   if (dtype == EGB_BF16)
     dropout_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)dy, (bf16*)out, n_elems, drop_threshold(p), 1.f / (1.f - p),
-                                               seed);
+                                               seed, egb_seed_epoch_ptr());
   else
     dropout_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)dy, (float*)out, n_elems, drop_threshold(p),
-                                                1.f / (1.f - p), seed);
+                                                1.f / (1.f - p), seed, egb_seed_epoch_ptr());
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;

@@ -24,6 +24,7 @@ struct EpiParams {
   float drop_scale;
   unsigned drop_thresh;  // 0 = no dropout
   unsigned long long seed;
+  const unsigned long long* epoch;   // device seed epoch (egb_mix_seed), NULL when not enabled
   int accumulate;
   float* colsum;         // optional [N]: column sums of the stored output are accumulated here
   int exp;               // EGB_EPI_EXP experiment switch (0 = normal): 1 no residual / act' loads, 2 loads hit row 0 only, 3 no C store
@@ -141,8 +142,9 @@ __device__ __forceinline__ void epi_apply_store(const EpiParams& p, int m, int n
   }
   if (p.drop_thresh != 0u) {
     const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
+    const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);
 #pragma unroll
-    for (int i = 0; i < W; ++i) v[i] = drop_keep(p.seed, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+    for (int i = 0; i < W; ++i) v[i] = drop_keep(seed_eff, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
   }
   if (p.act_bwd != EGB_ACTBWD_NONE) {
     float a[W];
@@ -235,8 +237,9 @@ __device__ __forceinline__ void epi_apply_store_row(const EpiParams& p, const Ep
   }
   if (p.drop_thresh != 0u) {
     const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
+    const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);
 #pragma unroll
-    for (int i = 0; i < W; ++i) v[i] = drop_keep(p.seed, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+    for (int i = 0; i < W; ++i) v[i] = drop_keep(seed_eff, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
   }
   if (p.act_bwd != EGB_ACTBWD_NONE) {
     float a[W];
@@ -347,8 +350,9 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
   }
   if (p.drop_thresh != 0u) {
     const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
+    const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = drop_keep(p.seed, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = drop_keep(seed_eff, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
   }
   if (F & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) {
     float a[8];

@@ -315,6 +315,7 @@ int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e) {
     e->drop_thresh = drop_threshold(d->dropout_p);
     e->drop_scale = 1.f / (1.f - d->dropout_p);
     e->seed = d->dropout_seed;
+    e->epoch = egb_seed_epoch_ptr();
   }
   e->accumulate = d->accumulate;
   EGB_CHECK(!d->accumulate || d->c.dtype == EGB_F32, "gemm: accumulate requires fp32 output");

@@ -17,6 +17,15 @@ void egb_set_error(const char* fmt, ...) {
 }
 void egb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// seed epoch word, one per device (one process drives one GPU; the table covers a multi-device process too)
+static unsigned long long* g_epoch[64] = {nullptr};
+const unsigned long long* egb_seed_epoch_ptr() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return g_epoch[dev];
+}
+static __global__ void seed_epoch_advance_kernel(unsigned long long* e) { *e += 1ull; }
+
 int egb_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -77,6 +86,28 @@ int egb_prof_read(int kind, double* out, int reset) {
     for (auto& r : g_prof) { g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1); }
     g_prof.clear();
   }
+  return 0;
+}
+/* creates (once per device) the device word that all dropout seeds are mixed with; returns its address in *out */
+int egb_seed_epoch_enable(void** out) {
+  int dev = 0;
+  EGB_CUDA(cudaGetDevice(&dev));
+  EGB_CHECK(dev >= 0 && dev < 64, "seed_epoch: device index out of range");
+  if (g_epoch[dev] == nullptr) {
+    unsigned long long* p = nullptr;
+    EGB_CUDA(cudaMalloc(&p, sizeof(unsigned long long)));
+    EGB_CUDA(cudaMemset(p, 0, sizeof(unsigned long long)));
+    g_epoch[dev] = p;
+  }
+  if (out != nullptr) *out = g_epoch[dev];
+  return 0;
+}
+int egb_seed_epoch_advance(void* stream) {
+  const unsigned long long* p = egb_seed_epoch_ptr();
+  EGB_CHECK(p != nullptr, "seed_epoch_advance: call egb_seed_epoch_enable first");
+  seed_epoch_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(const_cast<unsigned long long*>(p));
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
   return 0;
 }
 const char* egb_last_error(void) { return g_err; }

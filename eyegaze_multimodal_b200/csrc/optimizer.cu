@@ -9,6 +9,7 @@
 //   chunk record  c : tensor index, element offset, element count (<= 16384)       -- one CTA per chunk
 #include "common.cuh"
 #include "../../include/eyegaze_b200.h"
+#include <string.h>
 
 extern void egb_count_launch(int n);
 
@@ -59,6 +60,13 @@ __global__ void __launch_bounds__(256) multi_sqnorm_kernel(const TensorRec* __re
 
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, max_norm;
+  // optional device-resident step state (all may be NULL): with these the launch arguments never change from step to
+  // step, so the optimiser tail can live inside a captured CUDA graph and needs no host read or write per step
+  const float* lr_dev;       // learning rate of this group (written by egb_lr_schedule_step)
+  const float* step_dev;     // 1-based update count shared by the group's tensors (bias corrections)
+  const float* grad_scale;   // gradients are divided by this before use (torch.amp.GradScaler's scale)
+  const float* found_inf;    // != 0: skip the whole update (GradScaler's inf / nan verdict)
+  int skip_nonfinite;        // skip the update when the global gradient norm is inf / nan (our own finite check)
 };
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamArgs& a, float clip, float decay,
@@ -76,16 +84,24 @@ __global__ void __launch_bounds__(256) multi_adamw_kernel(const TensorRec* __res
   const ChunkRec c = C[blockIdx.x];
   const TensorRec t = T[c.tensor];
   if (t.g == nullptr) return;
-  float clip = 1.f;
-  if (sqnorm != nullptr && a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / (sqrtf(*sqnorm) + 1e-6f));   // clip_grad_norm_
-  const float decay = 1.f - a.lr * a.weight_decay;
+  if (a.found_inf != nullptr && *a.found_inf != 0.f) return;          // GradScaler: a non-finite gradient skips the step
+  const float inv_scale = a.grad_scale != nullptr ? 1.f / *a.grad_scale : 1.f;
+  float clip = inv_scale;
+  if (sqnorm != nullptr) {
+    const float nrm = sqrtf(*sqnorm) * inv_scale;                     // norm of the UNSCALED gradients
+    if (a.skip_nonfinite && !isfinite(nrm)) return;
+    if (a.max_norm > 0.f) clip *= fminf(1.f, a.max_norm / (nrm + 1e-6f));   // clip_grad_norm_
+  }
+  const float lr = a.lr_dev != nullptr ? *a.lr_dev : a.lr;
+  const float decay = 1.f - lr * a.weight_decay;
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {   // bias corrections of this tensor's step, in double like torch's host code
-    s_bc[0] = (float)(1.0 - pow((double)a.beta1, (double)t.step));
-    s_bc[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)t.step));
+    const double step = a.step_dev != nullptr ? (double)*a.step_dev : (double)t.step;
+    s_bc[0] = (float)(1.0 - pow((double)a.beta1, step));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)a.beta2, step));
   }
   __syncthreads();
-  const float step_size = a.lr / s_bc[0];
+  const float step_size = lr / s_bc[0];
   const float bc2_sqrt = s_bc[1];
   float* p = t.p + c.offset;
   const float* g = t.g + c.offset;
@@ -135,10 +151,21 @@ int egb_multi_tensor_sqnorm(const void* tensor_table, const void* chunk_table, i
 int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
                            float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm,
                            void* stream) {
+  egb_adamw_state none;
+  memset(&none, 0, sizeof(none));
+  return egb_multi_tensor_adamw_ex(tensor_table, chunk_table, n_chunks, lr, beta1, beta2, eps, weight_decay, max_norm,
+                                   sqnorm, &none, stream);
+}
+
+int egb_multi_tensor_adamw_ex(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm,
+                              const egb_adamw_state* state, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  EGB_CHECK(tensor_table && chunk_table && n_chunks > 0, "multi_tensor_adamw: bad arguments");
+  EGB_CHECK(tensor_table && chunk_table && state && n_chunks > 0, "multi_tensor_adamw: bad arguments");
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+  a.lr_dev = state->lr; a.step_dev = state->step; a.grad_scale = state->grad_scale; a.found_inf = state->found_inf;
+  a.skip_nonfinite = state->skip_nonfinite;
   multi_adamw_kernel<<<n_chunks, 256, 0, st>>>((const TensorRec*)tensor_table, (const ChunkRec*)chunk_table, a, sqnorm);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();

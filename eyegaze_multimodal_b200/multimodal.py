@@ -47,7 +47,8 @@ class MultimodalFusionModel(nn.Module):
                 eeg_logits = self.eeg_encoder(eeg1, eeg2, labels)['logits']
             img_logits = self.gaze_encoder(img1, img2)
             cur.wait_stream(side)
-            eeg_logits.record_stream(cur)
+            if not torch.cuda.is_current_stream_capturing():
+                eeg_logits.record_stream(cur)
         else:
             img_logits = self.gaze_encoder(img1, img2)
             eeg_logits = self.eeg_encoder(eeg1, eeg2, labels)['logits']

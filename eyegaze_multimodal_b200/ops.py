@@ -111,6 +111,33 @@ def small_zeros(shape, device):
     return blk[0][off:off + n].view(shape)
 
 
+def reset_arenas() -> None:
+    """Forget the partially used accumulator blocks.  Called when a CUDA-graph capture begins (a block zeroed BEFORE the
+    capture would not be re-zeroed by replays) and when it ends (blocks allocated during capture belong to the graph)."""
+    with _arena_lock:
+        _arenas.clear()
+
+
+_seed_epoch_word = {}
+
+
+def enable_seed_epoch() -> int:
+    """Creates the device word all dropout seeds are mixed with (include/eyegaze_b200.h: egb_seed_epoch_enable) and
+    returns its address.  Needed once before a training step is captured into a CUDA graph."""
+    dev = torch.cuda.current_device()
+    if dev not in _seed_epoch_word:
+        out = L.vp()
+        L.call("egb_seed_epoch_enable", C.byref(out))
+        _seed_epoch_word[dev] = out.value
+    return _seed_epoch_word[dev]
+
+
+def advance_seed_epoch() -> None:
+    """One 1-thread launch on the current stream: the next kernels draw fresh dropout masks (capturable)."""
+    enable_seed_epoch()
+    L.call("egb_seed_epoch_advance", _stream())
+
+
 def gemm(M, N, K, in_code, a: L.Operand, b: L.Operand, c: L.Matrix, *, bias=None, c_pre=None, residual=None, aux=None,
          alpha=1.0, act=0, act_bwd=0, aux_scale=1.0, dropout_p=0.0, seed=0, accumulate=0, split_k=0, c_colsum=None):
     empty = L.Matrix(None, 0, 0, 0, 0)
@@ -803,39 +830,99 @@ def _spec_w2_flip(w, code):
     return wcache.get((w,), code, "spec_w2_flip", build)
 
 
+def _spec_geometry(bins, frames):
+    H1, W1 = bins // 2, frames // 2
+    Wp, Hp = W1 + 2, H1 + 2
+    return H1, W1, Wp, Hp * Wp, 2 * Wp + 8           # H1, W1, padded width, padded rows per image, slack rows
+
+
+def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
+    """STFT-log -> conv1+ReLU+maxpool -> conv2 (+bias).  Returns (img, p1, y2, meta); p1 / y2 are zero-bordered
+    channels-last images, flat [(N*RP + slack) * C]; y2 is the spec_conv[3] output (pre-ReLU)."""
+    eeg1 = eeg1.contiguous().float()
+    eeg2 = eeg2.contiguous().float()
+    B, Cc, T = eeg1.shape
+    N = 2 * B * Cc
+    dev = eeg1.device
+    tdt = _TORCH_DT[code]
+    frames = 1 + T // hop
+    img = torch.empty(N, bins, frames, dtype=torch.float32, device=dev)
+    L.call("egb_stft_logmag", eeg1.data_ptr(), eeg2.data_ptr(), window.data_ptr(), img.data_ptr(), B * Cc, T, n_fft,
+           hop, bins, _stream())
+    H1, W1, Wp, RP, slack = _spec_geometry(bins, frames)
+    p1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
+    L.call("egb_spec_conv1_pool_fwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), p1.data_ptr(), code, N, bins,
+           frames, p1.numel(), _stream())
+    y2 = zeros(((N * RP + slack) * 64,), tdt, dev)
+    w2s = _spec_w2_seg(w2, code)
+    a = L.Operand(p1.data_ptr(), 0, 0, 32, 0, 128, Wp)
+    cm = _dense_matrix(y2.data_ptr() + (Wp + 1) * 64 * y2.element_size(), code, 64)
+    gemm(N * RP, 64, 384, code, a, L.Operand(w2s.data_ptr(), 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
+    return img, p1, y2, (code, N, bins, frames, H1, W1, Wp, RP, slack)
+
+
+def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
+    """Gradients of conv2 / conv1 given dY2 in the padded channels-last layout."""
+    code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+    dev, tdt = dy2.device, _TORCH_DT[code]
+    dw1 = db1 = dw2 = db2 = None
+    if need_b2:
+        db2 = torch.empty(64, dtype=torch.float32, device=dev)
+        m = _dense_matrix(dy2.data_ptr(), code, 64)
+        L.call("egb_colsum", C.byref(m), N * RP, 64, db2.data_ptr(), 1, _stream())
+    esz = dy2.element_size()
+    if need_w2:
+        # dW2[o, (kh, kw4, c)] = sum over flat padded positions of dY[m + Wp + 1, o] * P1[m + kh*Wp, kw4*32 + c]
+        dw = torch.empty(64, 384, dtype=torch.float32, device=dev)
+        gemm(64, 384, N * RP, code, L.Operand(dy2.data_ptr() + (Wp + 1) * 64 * esz, 1, 0, 64, 0, 0, 0),
+             L.Operand(p1.data_ptr(), 1, 0, 32, 0, 128, Wp), _dense_matrix(dw.data_ptr(), F32, 384), accumulate=2)
+        dw2 = dw.view(64, 3, 4, 32)[:, :, :3, :].permute(0, 3, 1, 2)
+    if need_w1:
+        # dP1 (padded layout) = full correlation of dY with the flipped kernel: same implicit GEMM, K = 3 x 256
+        w2f = _spec_w2_flip(w2, code)
+        dp1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
+        a = L.Operand(dy2.data_ptr(), 0, 0, 64, 0, 256, Wp)
+        cm = _dense_matrix(dp1.data_ptr() + (Wp + 1) * 32 * esz, code, 32)
+        gemm(N * RP, 32, 768, code, a, L.Operand(w2f.data_ptr(), 0, 0, 768, 0, 0, 0), cm)
+        dwb = zeros((320,), torch.float32, dev)
+        L.call("egb_spec_conv1_pool_bwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), dp1.data_ptr(), code,
+               dwb.data_ptr(), dwb.data_ptr() + 288 * 4, N, bins, frames, _stream())
+        dw1 = dwb[:288].view(32, 1, 3, 3)
+        db1 = dwb[288:]
+    return dw1, db1, dw2, db2
+
+
+def _spec_padded_to_nchw(buf, meta, ch):
+    """zero-bordered channels-last image buffer -> dense (N, ch, H1, W1) fp32."""
+    code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+    out = torch.empty(N, ch, H1, W1, dtype=torch.float32, device=buf.device)
+    copy_strided4(buf, out, (N, ch, H1, W1), (RP * ch, 1, Wp * ch, ch), (ch * H1 * W1, H1 * W1, W1, 1),
+                  src_offset=(Wp + 1) * ch)
+    return out
+
+
+def _spec_nchw_to_padded(x, meta, ch):
+    """dense (N, ch, H1, W1) -> zero-bordered channels-last buffer in the compute dtype."""
+    code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+    x = x.contiguous()
+    buf = zeros(((N * RP + slack) * ch,), _TORCH_DT[code], x.device)
+    copy_strided4(x, buf, (N, ch, H1, W1), (ch * H1 * W1, H1 * W1, W1, 1), (RP * ch, 1, Wp * ch, ch),
+                  dst_offset=(Wp + 1) * ch)
+    return buf
+
+
 class SpectrogramCNNFn(torch.autograd.Function):
-    """(B,C,T) x2 -> pooled features [2B*C, 1024] (dual_eeg_transformer.py:98-127).  `want_pre` also returns the
-    conv-2 pre-activation in NCHW (what a hook on spec_conv[3] observes)."""
+    """(B,C,T) x2 -> pooled features [2B*C, 1024] (dual_eeg_transformer.py:98-127)."""
 
     @staticmethod
     def forward(ctx, eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
         _require_cuda(eeg1, eeg2, w1, w2)
-        eeg1 = eeg1.contiguous().float()
-        eeg2 = eeg2.contiguous().float()
-        B, Cc, T = eeg1.shape
-        N = 2 * B * Cc
-        dev = eeg1.device
-        tdt = _TORCH_DT[code]
-        frames = 1 + T // hop
-        img = torch.empty(N, bins, frames, dtype=torch.float32, device=dev)
-        L.call("egb_stft_logmag", eeg1.data_ptr(), eeg2.data_ptr(), window.data_ptr(), img.data_ptr(), B * Cc, T, n_fft,
-               hop, bins, _stream())
-        H1, W1 = bins // 2, frames // 2
-        Wp, Hp = W1 + 2, H1 + 2
-        RP = Hp * Wp
-        slack = 2 * Wp + 8
-        p1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
-        L.call("egb_spec_conv1_pool_fwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), p1.data_ptr(), code, N, bins,
-               frames, p1.numel(), _stream())
-        y2 = zeros(((N * RP + slack) * 64,), tdt, dev)
-        w2s = _spec_w2_seg(w2, code)
-        a = L.Operand(p1.data_ptr(), 0, 0, 32, 0, 128, Wp)
-        cm = _dense_matrix(y2.data_ptr() + (Wp + 1) * 64 * y2.element_size(), code, 64)
-        gemm(N * RP, 64, 384, code, a, L.Operand(w2s.data_ptr(), 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
-        pooled = torch.empty(N, 1024, dtype=tdt, device=dev)
+        img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
+        code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+        pooled = torch.empty(N, 1024, dtype=_TORCH_DT[code], device=img.device)
         L.call("egb_relu_avgpool_fwd", y2.data_ptr(), pooled.data_ptr(), code, N, H1, W1, _stream())
         ctx.save_for_backward(img, p1, y2, w1, b1, w2)
-        ctx.meta = (code, N, bins, frames, H1, W1, Wp, RP, slack)
+        ctx.meta = meta
         return pooled
 
     @staticmethod
@@ -849,30 +936,7 @@ class SpectrogramCNNFn(torch.autograd.Function):
         dy2 = zeros(((N * RP + slack) * 64,), tdt, dev)
         L.call("egb_relu_avgpool_bwd", y2.data_ptr(), dpool.data_ptr(), dy2.data_ptr(), code, N, H1, W1, _stream())
         need = ctx.needs_input_grad
-        dw1 = db1 = dw2 = db2 = None
-        if need[6]:
-            db2 = torch.empty(64, dtype=torch.float32, device=dev)
-            m = _dense_matrix(dy2.data_ptr(), code, 64)
-            L.call("egb_colsum", C.byref(m), N * RP, 64, db2.data_ptr(), 1, _stream())
-        esz = dy2.element_size()
-        if need[5]:
-            # dW2[o, (kh, kw4, c)] = sum over flat padded positions of dY[m + Wp + 1, o] * P1[m + kh*Wp, kw4*32 + c]
-            dw = torch.empty(64, 384, dtype=torch.float32, device=dev)
-            gemm(64, 384, N * RP, code, L.Operand(dy2.data_ptr() + (Wp + 1) * 64 * esz, 1, 0, 64, 0, 0, 0),
-                 L.Operand(p1.data_ptr(), 1, 0, 32, 0, 128, Wp), _dense_matrix(dw.data_ptr(), F32, 384), accumulate=2)
-            dw2 = dw.view(64, 3, 4, 32)[:, :, :3, :].permute(0, 3, 1, 2)
-        if need[3] or need[4]:
-            # dP1 (padded layout) = full correlation of dY with the flipped kernel: same implicit GEMM, K = 3 x 256
-            w2f = _spec_w2_flip(w2, code)
-            dp1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
-            a = L.Operand(dy2.data_ptr(), 0, 0, 64, 0, 256, Wp)
-            cm = _dense_matrix(dp1.data_ptr() + (Wp + 1) * 32 * esz, code, 32)
-            gemm(N * RP, 32, 768, code, a, L.Operand(w2f.data_ptr(), 0, 0, 768, 0, 0, 0), cm)
-            dwb = zeros((320,), torch.float32, dev)
-            L.call("egb_spec_conv1_pool_bwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), dp1.data_ptr(), code,
-                   dwb.data_ptr(), dwb.data_ptr() + 288 * 4, N, bins, frames, _stream())
-            dw1 = dwb[:288].view(32, 1, 3, 3)
-            db1 = dwb[288:]
+        dw1, db1, dw2, db2 = _spec_front_bwd(dy2, img, p1, w1, b1, w2, ctx.meta, need[3] or need[4], need[5], need[6])
         return None, None, None, dw1, db1, dw2, db2, None, None, None, None
 
 
@@ -880,20 +944,62 @@ def spectrogram_cnn(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
     return SpectrogramCNNFn.apply(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
 
 
+# -- the same pipeline split at the spec_conv[3] output, for analysis hooks on that module (Grad-CAM,
+#    5_Metrics/eeg_metrics.py:841): the kernels' own conv-2 output and its gradient are handed out as NCHW fp32 tensors
+class SpecConvFrontFn(torch.autograd.Function):
+    """(B,C,T) x2 -> (spec_conv[2] output (N,32,H1,W1), spec_conv[3] output (N,64,H1,W1)), fp32 NCHW, N = 2*B*C."""
+
+    @staticmethod
+    def forward(ctx, eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
+        _require_cuda(eeg1, eeg2, w1, w2)
+        img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
+        ctx.save_for_backward(img, p1, w1, b1, w2)
+        ctx.meta = meta
+        p1n = _spec_padded_to_nchw(p1, meta, 32)
+        ctx.mark_non_differentiable(p1n)
+        return p1n, _spec_padded_to_nchw(y2, meta, 64)
+
+    @staticmethod
+    def backward(ctx, _dp1, dy2n):
+        img, p1, w1, b1, w2 = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dy2 = _spec_nchw_to_padded(dy2n.float(), ctx.meta, 64)
+        dw1, db1, dw2, db2 = _spec_front_bwd(dy2, img, p1, w1, b1, w2, ctx.meta, need[3] or need[4], need[5], need[6])
+        return None, None, None, dw1, db1, dw2, db2, None, None, None, None
+
+
+class SpecPoolFn(torch.autograd.Function):
+    """spec_conv[3] output (N,64,H1,W1) fp32 -> ReLU -> AdaptiveAvgPool(4,4) -> flatten [N, 1024] (compute dtype)."""
+
+    @staticmethod
+    def forward(ctx, y2n, code, bins, frames):
+        N = y2n.shape[0]
+        H1, W1, Wp, RP, slack = _spec_geometry(bins, frames)
+        meta = (code, N, bins, frames, H1, W1, Wp, RP, slack)
+        y2 = _spec_nchw_to_padded(y2n.float(), meta, 64)
+        pooled = torch.empty(N, 1024, dtype=_TORCH_DT[code], device=y2n.device)
+        L.call("egb_relu_avgpool_fwd", y2.data_ptr(), pooled.data_ptr(), code, N, H1, W1, _stream())
+        ctx.save_for_backward(y2)
+        ctx.meta = meta
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpool):
+        code, N, bins, frames, H1, W1, Wp, RP, slack = ctx.meta
+        (y2,) = ctx.saved_tensors
+        dpool = dpool.contiguous()
+        if _code(dpool) != code:
+            dpool = cast(dpool, code)
+        dy2 = zeros(((N * RP + slack) * 64,), _TORCH_DT[code], dpool.device)
+        L.call("egb_relu_avgpool_bwd", y2.data_ptr(), dpool.data_ptr(), dy2.data_ptr(), code, N, H1, W1, _stream())
+        return _spec_padded_to_nchw(dy2, ctx.meta, 64), None, None, None
+
+
 def spectrogram_conv2_nchw(eeg1, eeg2, window, w1, b1, w2, b2, n_fft, hop, bins):
-    """Analysis helper: the spec_conv[3] output (N, 64, H1, W1) in fp32, recomputed with the same kernels."""
-    code = F32
+    """Analysis helper: the spec_conv[3] output (N, 64, H1, W1) in fp32, computed by the same kernels."""
     with torch.no_grad():
-        B, Cc, T = eeg1.shape
-        N = 2 * B * Cc
-        frames = 1 + T // hop
-        H1, W1 = bins // 2, frames // 2
-        Wp, RP = W1 + 2, (H1 + 2) * (W1 + 2)
-        fn_ctx = type("Ctx", (), {"save_for_backward": lambda self, *a: setattr(self, "saved", a),
-                                  "needs_input_grad": (False,) * 11})()
-        SpectrogramCNNFn.forward(fn_ctx, eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
-        y2 = fn_ctx.saved[2][:N * RP * 64].view(N, H1 + 2, Wp, 64)
-        return y2[:, 1:H1 + 1, 1:W1 + 1, :].permute(0, 3, 1, 2).contiguous()
+        img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, F32, n_fft, hop, bins)
+        return _spec_padded_to_nchw(y2, meta, 64)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -1196,6 +1302,144 @@ class CrossEntropyFn(torch.autograd.Function):
 
 def cross_entropy(logits, labels):
     return CrossEntropyFn.apply(logits, labels)
+
+
+# ------------------------------------------------------------------------------------------------------
+# batch-level auxiliary losses (dual_eeg_transformer.py:1255-1371); fp32 (B, d) tokens
+# ------------------------------------------------------------------------------------------------------
+class L2NormalizeRowsFn(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=-1) on a 2-D fp32 tensor."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        x = x.contiguous().float()
+        R, D = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(R, dtype=torch.float32, device=x.device)
+        L.call("egb_l2norm_rows_fwd", x.data_ptr(), y.data_ptr(), inv.data_ptr(), R, D, 1e-12, _stream())
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        L.call("egb_l2norm_rows_bwd", dy.data_ptr(), y.data_ptr(), inv.data_ptr(), dx.data_ptr(), y.shape[0], y.shape[1],
+               _stream())
+        return dx
+
+
+def l2_normalize_rows(x):
+    return L2NormalizeRowsFn.apply(x)
+
+
+class StackRowsFn(torch.autograd.Function):
+    """torch.cat([a, b], dim=0) of 2-D fp32 tensors."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        out = torch.empty(a.shape[0] + b.shape[0], a.shape[1], dtype=torch.float32, device=a.device)
+        D = a.shape[1]
+        copy_strided4(a, out, (1, 1, a.shape[0], D), (0, 0, D, 1), (0, 0, D, 1))
+        copy_strided4(b, out, (1, 1, b.shape[0], D), (0, 0, D, 1), (0, 0, D, 1), dst_offset=a.shape[0] * D)
+        ctx.na = a.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d[:ctx.na], d[ctx.na:]
+
+
+class SimilarityLossFn(torch.autograd.Function):
+    """loss(a . b^T / temperature) for unit-norm rows a [B, d], b [N, d] (fp32):
+    kind 'infonce' = cross_entropy(sim, arange(B)) (det:1290-1302);  kind 'supcon' = supervised contrastive loss over
+    sim = a . a^T with labels (det:1336-1371; b is a).  The row kernel leaves d loss / d sim in place of sim, so the
+    backward pass is the two GEMMs  da = G b / T,  db = G^T a / T."""
+
+    @staticmethod
+    def forward(ctx, a, b, labels, temperature, kind):
+        _require_cuda(a, b)
+        a = a.contiguous().float()
+        same = b is None
+        b = a if same else b.contiguous().float()
+        B, D = a.shape
+        N = b.shape[0]
+        dev = a.device
+        sim = torch.empty(B, N, dtype=torch.float32, device=dev)
+        gemm(B, N, D, F32, L.Operand(a.data_ptr(), 0, 0, D, 0, 0, 0), L.Operand(b.data_ptr(), 0, 0, D, 0, 0, 0),
+             _dense_matrix(sim.data_ptr(), F32, N), alpha=1.0 / temperature)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        if kind == "infonce":
+            L.call("egb_infonce_rows", sim.data_ptr(), loss.data_ptr(), B, N, _stream())
+        else:
+            labels = labels.contiguous().long()
+            scratch = torch.empty(3 * B + 2, dtype=torch.float32, device=dev)
+            L.call("egb_supcon_rows", sim.data_ptr(), labels.data_ptr(), scratch.data_ptr(), scratch.data_ptr() + 12 * B,
+                   loss.data_ptr(), B, _stream())
+        ctx.save_for_backward(a, b, sim)
+        ctx.meta = (temperature, same)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, G = ctx.saved_tensors
+        temperature, same = ctx.meta
+        B, D = a.shape
+        N = b.shape[0]
+        dev = a.device
+        g = g.contiguous().float()
+        # da[B, d] = G[B, N] . b[N, d]   (b consumed as an MN-major operand);   db[N, d] = G^T . a
+        da = torch.empty(B, D, dtype=torch.float32, device=dev)
+        gemm(B, D, N, F32, L.Operand(G.data_ptr(), 0, 0, N, 0, 0, 0), L.Operand(b.data_ptr(), 1, 0, D, 0, 0, 0),
+             _dense_matrix(da.data_ptr(), F32, D), alpha=1.0 / temperature)
+        db = torch.empty(N, D, dtype=torch.float32, device=dev)
+        gemm(N, D, B, F32, L.Operand(G.data_ptr(), 1, 0, N, 0, 0, 0), L.Operand(a.data_ptr(), 1, 0, D, 0, 0, 0),
+             _dense_matrix(db.data_ptr(), F32, D), alpha=1.0 / temperature)
+        if same:
+            da = da + db          # sim = a a^T: both factors are the same tensor
+            db = None
+        out_a = torch.empty_like(da)
+        L.call("egb_scale_by_device_scalar", da.data_ptr(), g.data_ptr(), out_a.data_ptr(), da.numel(), _stream())
+        out_b = None
+        if db is not None:
+            out_b = torch.empty_like(db)
+            L.call("egb_scale_by_device_scalar", db.data_ptr(), g.data_ptr(), out_b.data_ptr(), db.numel(), _stream())
+        return out_a, out_b, None, None, None
+
+
+def infonce_loss(a, b, temperature):
+    return SimilarityLossFn.apply(a, b, None, float(temperature), "infonce")
+
+
+def supcon_loss(a, labels, temperature):
+    return SimilarityLossFn.apply(a, None, labels, float(temperature), "supcon")
+
+
+class MseLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, b)
+        a, b = a.contiguous().float(), b.contiguous().float()
+        da = torch.empty_like(a)
+        loss = torch.empty((), dtype=torch.float32, device=a.device)
+        L.call("egb_mse_loss", a.data_ptr(), b.data_ptr(), da.data_ptr(), loss.data_ptr(), a.numel(), _stream())
+        ctx.save_for_backward(da)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (da,) = ctx.saved_tensors
+        out = torch.empty_like(da)
+        L.call("egb_scale_by_device_scalar", da.data_ptr(), g.contiguous().float().data_ptr(), out.data_ptr(), da.numel(),
+               _stream())
+        return out, -out
+
+
+def mse_loss(a, b):
+    return MseLossFn.apply(a, b)
 
 
 FUZZY_MODES = {"full": 0, "no_temperature": 1, "no_fuzzification": 2, "fixed_weights": 3}

@@ -10,8 +10,26 @@ Drop-in for the two calls the reference's loops make right after ``loss.backward
 ``FusedClipAdamW`` takes ``torch.optim.AdamW``'s constructor arguments (same defaults, same update rule: decoupled weight
 decay, bias-corrected moments) plus ``max_grad_norm``; ``state_dict()`` has AdamW's layout (``step``, ``exp_avg``,
 ``exp_avg_sq`` per parameter), so checkpoints move both ways.  fp32 CUDA parameters only; no CPU path.
+
+The rest of the training-step tail lives here too:
+
+  * ``torch.amp.GradScaler`` (the reference's multimodal loop trains under fp16 autocast,
+    train_multimodal_fuzzy_fusion.py:436-472): the optimizer implements torch's ``_step_supports_amp_scaling`` protocol --
+    ``scaler.step(opt)`` hands over ``grad_scale`` / ``found_inf`` as DEVICE tensors and the kernels un-scale, clip and skip
+    on the device, so the scaler's per-step ``.item()`` on found_inf disappears.  Independently, ``skip_nonfinite=True``
+    skips an update whose global gradient norm (our own norm pass) is inf / nan.
+  * ``capturable=True``: learning rate and step count live in device memory (``DeviceLRSchedule`` advances them), the
+    gradient pointer table is static, so ``step()`` enqueues identical launches every time and can sit inside a captured
+    CUDA graph (graphs.GraphedTrainStep).
+  * ``DeviceLRSchedule``: CosineAnnealingLR (train_art.py:401-409) and linear-warm-up + cosine LambdaLR
+    (train_multimodal_fuzzy_fusion.py:197-214) evaluated by a one-thread kernel; per-group base learning rates
+    (:727-736) are kept.
+  * ``MetricAccumulator``: running sums of loss scalars and the argmax-accuracy count on the device; ONE host read per
+    epoch instead of six ``.item()`` calls per step (train_art.py:224-229).
 """
-from typing import Optional
+import ctypes as C
+import math
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 import torch
@@ -23,14 +41,35 @@ _CHUNK = 16384                       # elements per CTA
 
 
 class FusedClipAdamW(torch.optim.Optimizer):
+    _step_supports_amp_scaling = True    # torch.amp.GradScaler.step() then passes grad_scale / found_inf as device tensors
+
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 max_grad_norm: Optional[float] = None):
+                 max_grad_norm: Optional[float] = None, skip_nonfinite: bool = False, capturable: bool = False):
         if lr < 0 or eps < 0 or weight_decay < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1:
             raise ValueError("invalid AdamW hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.max_grad_norm = max_grad_norm
+        self.skip_nonfinite = skip_nonfinite
+        self.capturable = capturable
         self._plans = {}             # id(group) -> launch plan
         self._sqnorm = None          # device scalar: sum of squared gradients of the last step (all groups)
+        self._dev_state = None       # capturable: [opt_step, lr_0 .. lr_{G-1}] fp32 on the device
+        self._sq_static = None       # capturable: the norm accumulator has a fixed address
+        # (GradScaler.step() sets / deletes the attributes `grad_scale` and `found_inf` around step(); they must not exist
+        # in between: torch multiplies its scale with getattr(optimizer, "grad_scale", 1))
+
+    # -- device-resident step state (capturable mode) --------------------------------------------------
+    def device_state(self) -> torch.Tensor:
+        """[opt_step, lr of group 0, lr of group 1, ...] (fp32, device).  Created on first use from the groups' current
+        ``lr``.  ``step()`` advances opt_step (the bias-correction count) on the device; ``DeviceLRSchedule`` rewrites the
+        learning rates."""
+        if self._dev_state is None:
+            dev = next(p for g in self.param_groups for p in g["params"]).device
+            st = torch.zeros(1 + len(self.param_groups), dtype=torch.float32)
+            for i, g in enumerate(self.param_groups):
+                st[1 + i] = float(g["lr"])
+            self._dev_state = st.to(dev)
+        return self._dev_state
 
     # ------------------------------------------------------------------------------------------------
     def _plan(self, group):
@@ -98,46 +137,92 @@ class FusedClipAdamW(torch.optim.Optimizer):
             if plan is None:
                 continue
             host = plan["host"]
-            if plan["copied"] is not None:
+            if plan["copied"] is not None and not self.capturable:
                 plan["copied"].synchronize()     # the previous step's table upload has left the pinned buffer
             keep = []
             hn, steps = plan["host_np"], plan["steps"]      # numpy views: no tensor objects in the per-parameter loop
+            changed = False
             for i, p in enumerate(plan["params"]):
                 g = p.grad
                 if g is None:
+                    changed |= hn[i, 1] != 0
                     hn[i, 1] = 0
                     continue
                 if g.dtype != torch.float32 or not g.is_contiguous():
+                    if self.capturable:
+                        raise TypeError("capturable FusedClipAdamW needs contiguous fp32 gradients")
                     g = g.float().contiguous()
                     keep.append(g)
+                changed |= hn[i, 1] != g.data_ptr()
                 hn[i, 1] = g.data_ptr()
                 steps[i] += 1                                # per parameter, like torch: one without gradient lags
             hn[:, 4] = steps
-            plan["dev"].copy_(host, non_blocking=True)
-            plan["copied"] = torch.cuda.Event()
-            plan["copied"].record()
+            if self.capturable:
+                # the table is static (gradients live at fixed addresses, the step count is on the device): upload it
+                # only when it changed, never while a graph is being captured
+                # (inside a capture this becomes a memcpy node that re-uploads the same 40-byte records on each replay)
+                if changed or plan["copied"] is None:
+                    plan["dev"].copy_(host, non_blocking=True)
+                    plan["copied"] = True
+            else:
+                plan["dev"].copy_(host, non_blocking=True)
+                plan["copied"] = torch.cuda.Event()
+                plan["copied"].record()
             plans.append((group, plan, keep))
         if not plans:
             return loss
         stream = torch.cuda.current_stream().cuda_stream
+        dev = plans[0][1]["dev"].device
         sq = None
-        if self.max_grad_norm is not None and self.max_grad_norm > 0:
-            sq = ops.small_zeros((1,), plans[0][1]["dev"].device)     # the norm is global: over every group
+        if (self.max_grad_norm is not None and self.max_grad_norm > 0) or self.skip_nonfinite:
+            if self.capturable:
+                if self._sq_static is None:
+                    self._sq_static = torch.zeros(1, dtype=torch.float32, device=dev)
+                sq = self._sq_static
+                L.call("egb_zero", sq.data_ptr(), 4, stream)
+            else:
+                sq = ops.small_zeros((1,), dev)                       # the norm is global: over every group
             for _, plan, _ in plans:
                 L.call("egb_multi_tensor_sqnorm", plan["dev"].data_ptr(), plan["chunks"].data_ptr(), plan["n_chunks"],
                        sq.data_ptr(), stream)
         self._sqnorm = sq
-        for group, plan, _ in plans:
+        st = L.AdamwState()
+        st.skip_nonfinite = 1 if self.skip_nonfinite else 0
+        gs, fi = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
+        keep_amp = []
+        if gs is not None:
+            gs = gs.to(device=dev, dtype=torch.float32).reshape(1)
+            st.grad_scale = gs.data_ptr()
+            keep_amp.append(gs)
+        if fi is not None:
+            fi = fi.to(device=dev, dtype=torch.float32).reshape(1)
+            st.found_inf = fi.data_ptr()
+            keep_amp.append(fi)
+        dstate = self.device_state() if self.capturable else None
+        if dstate is not None:
+            st.step = dstate.data_ptr()
+            # opt_step += 1 on the device, before the update reads it (kind 0 / advance 0 leaves the rates untouched)
+            L.call("egb_lr_schedule_step", dstate.data_ptr() + 4, dstate.data_ptr(), dstate.data_ptr() + 4,
+                   dstate.data_ptr() + 4, 1, 0, 0.0, 0.0, 0, 1, stream)
+        for gi, (group, plan, _) in enumerate(plans):
             b1, b2 = group["betas"]
-            L.call("egb_multi_tensor_adamw", plan["dev"].data_ptr(), plan["chunks"].data_ptr(), plan["n_chunks"],
+            if dstate is not None:
+                st.lr = dstate.data_ptr() + 4 * (1 + self.param_groups.index(group))
+            L.call("egb_multi_tensor_adamw_ex", plan["dev"].data_ptr(), plan["chunks"].data_ptr(), plan["n_chunks"],
                    float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                   float(self.max_grad_norm or 0.0), sq.data_ptr() if sq is not None else None, stream)
+                   float(self.max_grad_norm or 0.0), sq.data_ptr() if sq is not None else None, C.byref(st), stream)
         ops.bump_param_epoch()       # the kernels wrote the parameters behind autograd's version counters
         return loss
 
     def _sync_steps(self, only=None):
+        dev_step = None
+        if self.capturable and self._dev_state is not None:
+            dev_step = float(self._dev_state[0].item())     # graph replays advance the count on the device only
         for plan in ([only] if only is not None else self._plans.values()):
-            for p, k in zip(plan["params"], plan["steps"]):
+            for i, (p, k) in enumerate(zip(plan["params"], plan["steps"])):
+                if dev_step is not None and plan["host_np"][i, 1] != 0:
+                    k = dev_step
+                    plan["steps"][i] = int(dev_step)
                 self.state[p]["step"] = torch.tensor(float(k))
 
     def state_dict(self):
@@ -157,3 +242,115 @@ class FusedClipAdamW(torch.optim.Optimizer):
     def grad_norm(self) -> Optional[torch.Tensor]:
         """Total gradient norm of the last step as a DEVICE scalar (what clip_grad_norm_ returns); no host sync."""
         return None if self._sqnorm is None else self._sqnorm.sqrt().squeeze(0)
+
+
+class DeviceLRSchedule:
+    """Learning-rate schedule evaluated on the device for a ``FusedClipAdamW(capturable=True)``.
+
+    ``kind='cosine'``        : torch.optim.lr_scheduler.CosineAnnealingLR(T_max, eta_min) in closed form, stepped once per
+                               EPOCH by the reference (train_art.py:401-409, 445);
+    ``kind='warmup_cosine'`` : get_linear_warmup_cosine_scheduler (train_multimodal_fuzzy_fusion.py:197-214), a LambdaLR
+                               stepped once per optimizer STEP (:503-504);
+    ``kind='constant'``.
+    Like torch's schedulers, construction sets the learning rates for step 0; ``step()`` advances the counter by one and
+    rewrites every group's rate -- a one-thread kernel, no host value involved, so it can be captured in a CUDA graph.
+    """
+    KINDS = {"constant": 0, "cosine": 1, "warmup_cosine": 2}
+
+    def __init__(self, optimizer: FusedClipAdamW, kind: str = "constant", T_max: float = 1.0, eta_min: float = 0.0,
+                 warmup_steps: float = 0.0, total_steps: float = 1.0):
+        if kind not in self.KINDS:
+            raise ValueError("kind must be one of %s" % sorted(self.KINDS))
+        if not optimizer.capturable:
+            raise ValueError("DeviceLRSchedule drives a FusedClipAdamW(capturable=True)")
+        self.opt, self.kind = optimizer, kind
+        self.p0, self.p1 = (float(T_max), float(eta_min)) if kind == "cosine" else (float(warmup_steps), float(total_steps))
+        st = optimizer.device_state()
+        dev = st.device
+        self.base_lrs = [float(g.setdefault("initial_lr", g["lr"])) for g in optimizer.param_groups]
+        self._base = torch.tensor(self.base_lrs, dtype=torch.float32, device=dev)
+        self._sched = torch.zeros(1, dtype=torch.float32, device=dev)        # the scheduler's own counter
+        self._launch(advance=0)
+
+    def _launch(self, advance: int) -> None:
+        st = self.opt.device_state()
+        L.call("egb_lr_schedule_step", self._sched.data_ptr(), None, self._base.data_ptr(), st.data_ptr() + 4,
+               len(self.base_lrs), self.KINDS[self.kind], self.p0, self.p1, advance, 0,
+               torch.cuda.current_stream().cuda_stream)
+
+    def step(self) -> None:
+        self._launch(advance=1)
+
+    def get_last_lr(self) -> Sequence[float]:
+        """Host read (synchronises): for logging only."""
+        return self.opt.device_state()[1:].tolist()
+
+    def state_dict(self) -> Dict:
+        return {"kind": self.kind, "p0": self.p0, "p1": self.p1, "last_epoch": float(self._sched.item()),
+                "opt_step": float(self.opt.device_state()[0].item()), "base_lrs": list(self.base_lrs)}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.kind, self.p0, self.p1 = sd["kind"], sd["p0"], sd["p1"]
+        self._sched.fill_(sd["last_epoch"])
+        self.opt.device_state()[0] = sd["opt_step"]
+        self._launch(advance=0)
+
+    @staticmethod
+    def reference_factor(kind: str, t: float, p0: float, p1: float) -> float:
+        """The closed forms above on the host (documentation / tests)."""
+        if kind == "cosine":
+            return 0.5 * (1.0 + math.cos(math.pi * t / p0))
+        if kind == "warmup_cosine":
+            if t < p0:
+                return t / max(1.0, p0)
+            return max(0.0, 0.5 * (1.0 + math.cos(math.pi * (t - p0) / max(1.0, p1 - p0))))
+        return 1.0
+
+
+class MetricAccumulator:
+    """Running sums of per-step loss scalars and the argmax accuracy, kept on the device.
+
+    The reference's loops read every loss with ``.item()`` every step (train_art.py:224-229: six synchronisations per
+    step; train_multimodal_fuzzy_fusion.py:507-517: predictions, labels, alphas and five losses) -- each one drains the
+    GPU.  ``add(**scalars)`` / ``add_predictions(logits, labels)`` enqueue one tiny kernel each; ``result()`` does ONE host
+    read (per epoch, or whenever the loop wants to print)."""
+
+    def __init__(self, names: Sequence[str], device):
+        if not 0 < len(names) <= 8:
+            raise ValueError("1..8 named scalars")
+        self.names = list(names)
+        self._acc = torch.zeros(len(names) + 1 + 2, dtype=torch.float32, device=device)   # sums | batches | hits, trials
+        self._zero = torch.zeros((), dtype=torch.float32, device=device)
+
+    def add(self, **scalars: torch.Tensor) -> None:
+        ptrs, keep = (L.vp * len(self.names))(), []
+        for i, n in enumerate(self.names):
+            t = scalars.get(n, self._zero)
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_cuda:
+                t = t.float().to(self._acc.device)
+            t = t.reshape(())
+            keep.append(t)
+            ptrs[i] = t.data_ptr()
+        L.call("egb_accum_scalars", ptrs, len(self.names), self._acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def add_predictions(self, logits: torch.Tensor, labels: torch.Tensor, preds_out: Optional[torch.Tensor] = None) -> None:
+        logits = logits.detach().float().contiguous()
+        labels = labels.contiguous().long()
+        off = 4 * (len(self.names) + 1)
+        L.call("egb_argmax_count", logits.data_ptr(), labels.data_ptr(), self._acc.data_ptr() + off,
+               preds_out.data_ptr() if preds_out is not None else None, logits.shape[0], logits.shape[1],
+               torch.cuda.current_stream().cuda_stream)
+
+    def result(self) -> Dict[str, float]:
+        a = self._acc.tolist()                          # the single host read
+        n = len(self.names)
+        batches = max(a[n], 1.0)
+        out = {k: a[i] / batches for i, k in enumerate(self.names)}
+        out["batches"] = a[n]
+        if a[n + 2] > 0:
+            out["accuracy"] = a[n + 1] / a[n + 2]
+        return out
+
+    def reset(self) -> None:
+        self._acc.zero_()

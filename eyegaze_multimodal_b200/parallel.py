@@ -56,6 +56,9 @@ class TrialParallel(nn.Module):
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t, src=0, group=process_group)
         self.buckets: List[_Bucket] = []
+        # True: the hooks only PACK a bucket when its last gradient lands and finish() issues the all-reduces -- the mode
+        # of a captured training step (graphs.GraphedTrainStep), where NCCL launches stay outside the CUDA graph
+        self.defer_comm = False
         self._build_buckets(int(bucket_mb * (1 << 20)))
 
     # ------------------------------------------------------------------------------------------------
@@ -111,10 +114,15 @@ class TrialParallel(nn.Module):
             have = [(v, p.grad) for v, p in zip(b.views, b.params) if p.grad is not None]
             if len(have) != len(b.params):
                 b.flat.zero_()                 # parameters the loss did not reach contribute zeros
+            have = [(v, g) for v, g in have if g is not v]     # (a replayed graph has already packed into the views)
             if have:
                 torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
             for v, p in zip(b.views, b.params):
                 p.grad = v                     # the reduced values are what the optimiser sees
+        if not self.defer_comm:
+            self._reduce(b)
+
+    def _reduce(self, b: _Bucket) -> None:
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
@@ -136,9 +144,13 @@ class TrialParallel(nn.Module):
     def finish(self) -> None:
         """Reduce whatever has not been reduced yet, order the compute stream after all communication and re-arm the
         buckets for the next backward pass."""
+        if self.defer_comm and self.world > 1 and torch.cuda.is_current_stream_capturing():
+            return                             # capture ends with the packed buckets; the caller reduces after the replay
         for b in self.buckets:
             if not b.launched:
                 self._launch(b)
+            if self.defer_comm and self.world > 1 and b.work is None:
+                self._reduce(b)
         for b in self.buckets:
             if b.work is not None:
                 b.work.wait()
@@ -151,11 +163,61 @@ class TrialParallel(nn.Module):
                                            "reduced (second backward pass before finish()?)")
             self._rearm(b)
 
+    # -- batch-level auxiliary losses (dual_eeg_transformer.py:1255-1371) look ACROSS the batch: gather the shards first
+    def compute_symmetry_loss(self, cls1, cls2):
+        return self._inner().compute_symmetry_loss(cls1, cls2)        # a mean over trials: per shard is exact for even shards
+
+    def compute_ibs_alignment_loss(self, ibs_token, cls1, cls2, temperature: float = 0.07):
+        g = self.group
+        return self._inner().compute_ibs_alignment_loss(gather_trials(ibs_token, g), gather_trials(cls1, g),
+                                                        gather_trials(cls2, g), temperature)
+
+    def compute_ibs_contrastive_loss(self, ibs_tokens, labels, temperature: float = 0.07):
+        g = self.group
+        return self._inner().compute_ibs_contrastive_loss(gather_trials(ibs_tokens, g), gather_trials(labels, g),
+                                                          temperature)
+
+    def _inner(self):
+        m = self.module
+        return getattr(m, "eeg_encoder", m)
+
     def grad_bytes(self) -> int:
         return sum(sum(p.numel() for p in b.params) * 4 for b in self.buckets)
 
     def flat_grads(self) -> Iterable[torch.Tensor]:
         return [b.flat for b in self.buckets]
+
+
+class _GatherTrials(torch.autograd.Function):
+    """All-gather of per-trial rows along dim 0 (equal shards).  Every rank then evaluates the SAME global loss, so the
+    gradient of that loss with respect to this rank's rows is the local slice of the incoming gradient, times `world`
+    because the gradient all-reduce that follows AVERAGES over ranks."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=group)
+        ctx.meta = (rank, world, x.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rank, world, n = ctx.meta
+        return g[rank * n:(rank + 1) * n] * float(world), None
+
+
+def gather_trials(x: torch.Tensor, group=None) -> torch.Tensor:
+    """(B_local, ...) -> (B_global, ...) across the ranks of `group` (identity for a single process)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    if x.is_floating_point() and x.requires_grad:
+        return _GatherTrials.apply(x, group)
+    out = torch.empty((dist.get_world_size(group) * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
 
 
 def loss_weight(local_trials: int, global_trials: int, world: Optional[int] = None) -> float:

@@ -34,6 +34,13 @@ int64_t egb_launch_count(void);
 int egb_prof_enable(int on);
 int egb_prof_read(int kind, double* out, int reset);
 
+/* Device-resident seed epoch for CUDA-graph replays.  Dropout seeds are launch arguments and therefore frozen into a
+ * captured graph; after egb_seed_epoch_enable every mask-drawing kernel of this library mixes the current value of one
+ * device word into its seed, and egb_seed_epoch_advance (one 1-thread launch, capturable) increments that word -- once
+ * per replay, so forward and backward of a replay agree and successive replays draw fresh masks. */
+int egb_seed_epoch_enable(void** device_word_out);
+int egb_seed_epoch_advance(void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Generalised GEMM   C[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )
  *
@@ -267,6 +274,41 @@ int egb_multi_tensor_sqnorm(const void* tensor_table, const void* chunk_table, i
                             void* stream);
 int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
                            float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm, void* stream);
+/* Same update with DEVICE-resident step state, so that no launch argument changes from step to step (CUDA-graph
+ * capturable, no host read / write per step).  Every pointer may be NULL (then the host value / default applies):
+ *   lr         : this group's learning rate (egb_lr_schedule_step writes it; replaces the CosineAnnealingLR / LambdaLR
+ *                host schedulers of train_art.py:401-409, train_multimodal_fuzzy_fusion.py:197-214,743-750)
+ *   step       : 1-based update count used for the bias corrections (replaces the per-tensor table column)
+ *   grad_scale : gradients are divided by it first -- torch.amp.GradScaler's scale (train_multimodal_fuzzy_fusion.py:462)
+ *   found_inf  : != 0 skips the update -- GradScaler's verdict (the `_step_supports_amp_scaling` optimizer protocol)
+ *   skip_nonfinite : skip the update when sqrt(*sqnorm) is inf / nan (the finite check taken from our own norm pass) */
+typedef struct {
+  const float* lr;
+  const float* step;
+  const float* grad_scale;
+  const float* found_inf;
+  int32_t skip_nonfinite;
+} egb_adamw_state;
+int egb_multi_tensor_adamw_ex(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm,
+                              const egb_adamw_state* state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-side training-step state (rest): LR schedules, loss / metric accumulation.
+ * egb_lr_schedule_step: sched[0] (the scheduler's step counter, float) += 1, then for each of the n groups
+ *   lr_out[g] = base_lr[g] * factor(sched[0]);  opt_step (may be NULL) += 1 as well when advance_opt != 0.
+ *   kind 0 constant; kind 1 CosineAnnealingLR(T_max = p0, eta_min = p1) in closed form (train_art.py:401-409; for
+ *   eta_min != 0 lr_out = eta_min + (base - eta_min) * factor); kind 2 linear warm-up for p0 steps then cosine decay to 0
+ *   at p1 total steps (train_multimodal_fuzzy_fusion.py:197-214).  `advance` = 0 recomputes lr_out without stepping.
+ * egb_accum_scalars: acc[i] += *src[i] for i < n (n <= 8 device scalars, e.g. the six losses train_art.py:224-229 reads
+ *   with .item() every step); acc[n] += 1 (batch count).
+ * egb_argmax_count: acc[0] += #(argmax(logits[b]) == labels[b]), acc[1] += B; optional preds[b] (int64) is written
+ *   (train_multimodal_fuzzy_fusion.py:507-509 copies predictions to the host every step).
+ * ------------------------------------------------------------------------------------------- */
+int egb_lr_schedule_step(float* sched, float* opt_step, const float* base_lr, float* lr_out, int n_groups, int kind,
+                         float p0, float p1, int advance, int advance_opt, void* stream);
+int egb_accum_scalars(const float* const* h_src, int n, float* acc, void* stream);
+int egb_argmax_count(const float* logits, const int64_t* labels, float* acc, int64_t* preds, int B, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Input side (the step before the path), on a whole device batch instead of per __getitem__:
@@ -278,6 +320,22 @@ int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, in
 int egb_eeg_window_normalize(const float* x, float* out, int B, int C, int T, int mode, void* stream);
 int egb_image_u8_normalize(const uint8_t* hwc, float* chw, int B, int H, int W, const float* mean3, const float* std3,
                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batch-level auxiliary losses of DualEEGTransformer (dual_eeg_transformer.py:1255-1371); the similarity matrices
+ * themselves are egb_gemm calls.  Every reduction stays on the device (no host read, CUDA-graph capturable).
+ * egb_l2norm_rows_*  : F.normalize(x, dim=-1) (eps 1e-12) and its backward; inv_norm[r] < 0 marks a clamped row.
+ * egb_infonce_rows   : F.cross_entropy(sim[B,N], arange(B)) -> *loss; sim is OVERWRITTEN with d loss / d sim (:1301-1302).
+ * egb_supcon_rows    : supervised contrastive loss over sim[B,B] (exp without max subtraction, self pairs masked,
+ *                      -log(pos/(all+1e-8)+1e-8), mean over the rows that have a positive, 0 if none; :1336-1371);
+ *                      sim is OVERWRITTEN with d loss / d sim; stats: 3*B floats, acc2: 2 floats of scratch.
+ * egb_mse_loss       : F.mse_loss(a, b) -> *loss, da = d loss / d a (= -d loss / d b) (:1255-1260).
+ * ------------------------------------------------------------------------------------------- */
+int egb_l2norm_rows_fwd(const float* x, float* y, float* inv_norm, int rows, int D, float eps, void* stream);
+int egb_l2norm_rows_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int rows, int D, void* stream);
+int egb_infonce_rows(float* sim, float* loss, int B, int N, void* stream);
+int egb_supcon_rows(float* sim, const int64_t* labels, float* stats, float* acc2, float* loss, int B, void* stream);
+int egb_mse_loss(const float* a, const float* b, float* da, float* loss, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

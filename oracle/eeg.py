@@ -64,15 +64,15 @@ class EEGConfig:
 def bandpass_fft(x: Tensor, lo: float, hi: float, fs: float) -> Tensor:
     """det:527-560: rfft -> inclusive frequency mask -> irfft."""
     T = x.shape[-1]
-    freqs = torch.fft.rfftfreq(T, d=1.0 / fs)
-    keep = ((freqs >= lo) & (freqs <= hi)).to(x.dtype)
+    freqs = torch.fft.rfftfreq(T, d=1.0 / fs)                      # evaluated on the host, like the reference (det:548)
+    keep = ((freqs >= lo) & (freqs <= hi)).to(dtype=x.dtype, device=x.device)
     return torch.fft.irfft(torch.fft.rfft(x, dim=-1) * keep, n=T, dim=-1)
 
 
 def hilbert_phase(x: Tensor) -> Tensor:
     """det:562-591: analytic signal through the one-sided spectrum weights, then angle."""
     T = x.shape[-1]
-    h = torch.zeros(T, dtype=x.dtype)
+    h = torch.zeros(T, dtype=x.dtype, device=x.device)
     if T % 2 == 0:
         h[0] = 1
         h[T // 2] = 1
@@ -90,11 +90,15 @@ def _pearson_rows(a: Tensor, b: Tensor) -> Tensor:
     return (an.unsqueeze(2) * bn.unsqueeze(1)).mean(-1)
 
 
+IBS_CHUNK = 4          # trials per vectorised block (bench.py raises it for the eager-on-GPU baseline leg)
+
+
 def ibs_connectivity(eeg1: Tensor, eeg2: Tensor, fs: float = 256.0, feature_type: str = "all",
-                     chunk: int = 4) -> Tensor:
+                     chunk: Optional[int] = None) -> Tensor:
     """IBSConnectivityMatrixGenerator.forward (det:760-819) -> (B, 6, F, C, C), fp32."""
+    chunk = chunk or IBS_CHUNK
     B, C, T = eeg1.shape
-    out = torch.zeros(B, 6, 7, C, C, dtype=torch.float32)
+    out = torch.zeros(B, 6, 7, C, C, dtype=torch.float32, device=eeg1.device)
     for b0 in range(0, B, chunk):
         x1, x2 = eeg1[b0:b0 + chunk], eeg2[b0:b0 + chunk]
         for bi, (lo, hi) in enumerate(IBS_BANDS):
@@ -173,13 +177,20 @@ def spectrogram_logmag(x: Tensor, window: Tensor, cfg: EEGConfig) -> Tensor:
     return torch.log(mag + 1e-8).unsqueeze(1)
 
 
-def spectrogram_tokens(x: Tensor, sd: Dict[str, Tensor], cfg: EEGConfig, pre: str = "spectrogram_generator.") -> Tensor:
-    """SpectrogramTokenGenerator.forward (det:88-135), eval mode."""
+def spectrogram_tokens(x: Tensor, sd: Dict[str, Tensor], cfg: EEGConfig, pre: str = "spectrogram_generator.",
+                       taps: Optional[dict] = None) -> Tensor:
+    """SpectrogramTokenGenerator.forward (det:88-135), eval mode.  ``taps['spec_conv3']`` collects the spec_conv[3] output
+    (what a Grad-CAM hook on that module sees, 5_Metrics/eeg_metrics.py:841), with its gradient retained."""
     B, C, _ = x.shape
     img = spectrogram_logmag(x, sd[pre + "window"], cfg)
     h = F.relu(F.conv2d(img, sd[pre + "spec_conv.0.weight"], sd[pre + "spec_conv.0.bias"], padding=1))
     h = F.max_pool2d(h, 2)
-    h = F.relu(F.conv2d(h, sd[pre + "spec_conv.3.weight"], sd[pre + "spec_conv.3.bias"], padding=1))
+    h = F.conv2d(h, sd[pre + "spec_conv.3.weight"], sd[pre + "spec_conv.3.bias"], padding=1)
+    if taps is not None:
+        if h.requires_grad:
+            h.retain_grad()
+        taps.setdefault("spec_conv3", []).append(h)
+    h = F.relu(h)
     h = F.adaptive_avg_pool2d(h, (4, 4)).flatten(1)
     h = F.relu(F.linear(h, sd[pre + "proj.0.weight"], sd[pre + "proj.0.bias"]))
     h = F.linear(h, sd[pre + "proj.3.weight"], sd[pre + "proj.3.bias"])
@@ -253,11 +264,14 @@ def mlp_head(x: Tensor, sd: Dict[str, Tensor], pre: str) -> Tensor:
 # full forward
 # ------------------------------------------------------------------------------------------------
 def dual_eeg_forward(sd: Dict[str, Tensor], eeg1: Tensor, eeg2: Tensor, cfg: EEGConfig,
-                     labels: Optional[Tensor] = None, ibs_matrices: Optional[Tensor] = None) -> Dict[str, Tensor]:
+                     labels: Optional[Tensor] = None, ibs_matrices: Optional[Tensor] = None,
+                     taps: Optional[dict] = None) -> Dict[str, Tensor]:
     """DualEEGTransformer.forward (det:1110-1253), eval mode (dropout off).
 
     ``ibs_matrices`` lets a caller pass pre-computed connectivity matrices (the generator has no
-    parameters), which keeps repeated oracle calls on one fixture cheap.
+    parameters), which keeps repeated oracle calls on one fixture cheap.  ``taps`` (a dict) collects the tensors the
+    reference's analysis hooks observe: 'spec_conv3' (list: player 1, player 2), 'cross_probs' (list: softmax of
+    z1->z2, z2->z1, what the hook on cross_attn.cross_attn.dropout receives).
     """
     B = eeg1.shape[0]
     h1, h2 = temporal_conv(eeg1, sd, cfg), temporal_conv(eeg2, sd, cfg)
@@ -276,8 +290,8 @@ def dual_eeg_forward(sd: Dict[str, Tensor], eeg1: Tensor, eeg2: Tensor, cfg: EEG
         parts1.append(ibs_tokens)
         parts2.append(ibs_tokens)
     if cfg.use_spectrogram:
-        parts1.append(spectrogram_tokens(eeg1, sd, cfg))
-        parts2.append(spectrogram_tokens(eeg2, sd, cfg))
+        parts1.append(spectrogram_tokens(eeg1, sd, cfg, taps=taps))
+        parts2.append(spectrogram_tokens(eeg2, sd, cfg, taps=taps))
     parts1.append(h1)
     parts2.append(h2)
     s1, s2 = torch.cat(parts1, 1), torch.cat(parts2, 1)
@@ -287,6 +301,10 @@ def dual_eeg_forward(sd: Dict[str, Tensor], eeg1: Tensor, eeg2: Tensor, cfg: EEG
     pos = sd["pos_embed.pos_embed.weight"][:L]
     z1, z2 = encoder(s1 + pos, sd, cfg), encoder(s2 + pos, sd, cfg)
     if cfg.use_cross_attention:
+        if taps is not None:
+            with torch.no_grad():
+                taps["cross_probs"] = [attention_probs(z1, z2, sd, "cross_attn.cross_attn.", cfg.num_heads),
+                                       attention_probs(z2, z1, sd, "cross_attn.cross_attn.", cfg.num_heads)]
         z1, z2 = cross_brain(z1, z2, sd, cfg)
     cls1, cls2 = z1[:, 0], z2[:, 0]
     offset = 1 + cfg.num_ibs_tokens + (cfg.in_channels if cfg.use_spectrogram else 0)   # det:1198-1202
@@ -314,18 +332,18 @@ def symmetry_loss(cls1: Tensor, cls2: Tensor) -> Tensor:
 def ibs_alignment_loss(ibs_token: Tensor, cls1: Tensor, cls2: Tensor, temperature: float = 0.07) -> Tensor:
     n = F.normalize(ibs_token, dim=-1)
     allc = torch.cat([F.normalize(cls1, dim=-1), F.normalize(cls2, dim=-1)], 0)
-    return F.cross_entropy(n @ allc.T / temperature, torch.arange(ibs_token.shape[0]))
+    return F.cross_entropy(n @ allc.T / temperature, torch.arange(ibs_token.shape[0], device=ibs_token.device))
 
 
 def ibs_contrastive_loss(tokens: Tensor, labels: Tensor, temperature: float = 0.07) -> Tensor:
     B = tokens.shape[0]
     t = F.normalize(tokens, p=2, dim=1)
     sim = t @ t.t() / temperature
-    eye = torch.eye(B, dtype=torch.bool)
+    eye = torch.eye(B, dtype=torch.bool, device=tokens.device)
     pos = (labels[:, None] == labels[None, :]).float().masked_fill(eye, 0)
     has = pos.sum(1) > 0
     if has.sum() == 0:
-        return torch.tensor(0.0)
+        return torch.tensor(0.0, device=tokens.device)
     e = torch.exp(sim)
     loss = -torch.log((e * pos).sum(1) / (e.masked_fill(eye, 0).sum(1) + 1e-8) + 1e-8)
     return loss[has].mean()

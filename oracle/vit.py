@@ -31,8 +31,9 @@ EARLY_MODES = ["concat", "add", "subtract", "subtract_abs", "multiply"]  # efv:7
 LATE_MODES = ["concat", "add", "subtract", "multiply", "full"]           # lfv:98
 
 
-def vit_features(x: Tensor, sd: Dict[str, Tensor], pre: str, heads: int, patch: int = 16) -> Tensor:
-    """timm VisionTransformer.forward_features -> (B, 1+N, D) after the final LayerNorm."""
+def vit_features(x: Tensor, sd: Dict[str, Tensor], pre: str, heads: int, patch: int = 16, taps: dict = None) -> Tensor:
+    """timm VisionTransformer.forward_features -> (B, 1+N, D) after the final LayerNorm.  ``taps['last_block']`` receives
+    the output of blocks[-1] with its gradient retained (what 6_Utils/attention_utils.py:196-215 hooks)."""
     w = sd[pre + "patch_embed.proj.weight"]
     D = w.shape[0]
     t = F.conv2d(x, w, sd[pre + "patch_embed.proj.bias"], stride=patch).flatten(2).transpose(1, 2)
@@ -54,6 +55,10 @@ def vit_features(x: Tensor, sd: Dict[str, Tensor], pre: str, heads: int, patch: 
         h = F.layer_norm(t, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-6)
         h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
         t = t + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    if taps is not None:
+        if t.requires_grad:
+            t.retain_grad()
+        taps["last_block"] = t
     return F.layer_norm(t, (D,), sd[pre + "norm.weight"], sd[pre + "norm.bias"], 1e-6)
 
 

@@ -1,0 +1,501 @@
+"""Round-2 parity gates on the GPU (run on the B200 box:  pytest -m gpu):
+
+  * non-degenerate fixture: a state_dict TRAINED by the unmodified reference; identical argmax predictions and identical
+    ``ClassificationMetrics`` output (north_star), fp32 and bf16;
+  * the gaze wrappers against goldens written by the UNMODIFIED reference wrappers (oracle/make_golden_vit.py);
+  * ViT-B / ViT-S (the cfg2 / cfg4 gaze backbones) at their real size against the oracle, forward and backward;
+  * the bench's GEMM shapes (M = 50 432, N = 2304 / 3072 / 768, K = 768 / 3072) incl. split-K dW;
+  * GEMM-epilogue dropout: the mask regenerated in backward is the mask applied in forward;
+  * gradients never alias, survive clip_grad_norm_ and accumulate over two backward passes;
+  * temporal-conv frontend for window lengths that are not multiples of stride^2;
+  * the optional batch-level aux losses against the reference goldens.
+"""
+import ast
+import math
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden_state_dict, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from eyegaze_multimodal_b200 import _lib as L
+    from eyegaze_multimodal_b200 import ops
+    from eyegaze_multimodal_b200.dual_eeg_transformer import DualEEGTransformer
+    from eyegaze_multimodal_b200.early_fusion_vit import EarlyFusionViT
+    from eyegaze_multimodal_b200.late_fusion_vit import LateFusionViT
+    from eyegaze_multimodal_b200.precision import precision
+from eyegaze_multimodal_b200.synth import eeg_pair_batch, gaze_pair_batch
+from oracle import eeg as O
+from oracle import metrics as M
+from oracle import vit as V
+
+DEV = "cuda:0"
+
+
+def _replay_seeds(tag=[0]):
+    """Restart the op-seed sequence: the same sequence of dropout ops then draws the same masks again."""
+    tag[0] += 1
+    torch.manual_seed(900000 + tag[0])
+    ops.next_seed()
+    torch.manual_seed(77)
+
+
+def _relmax(got, want):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    return (got - want).abs().max().item() / (want.abs().max().item() + 1e-30)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 1. trained fixture: identical argmax + identical ClassificationMetrics
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_trained_model_identical_argmax_and_classification_metrics(cuda_device, mode):
+    g = load_golden("eeg_model_trained.npz")
+    kw = ast.literal_eval(str(g["kwargs_repr"]))
+    m = DualEEGTransformer(**kw)
+    m.load_state_dict(golden_state_dict(g), strict=True)
+    m = m.to(DEV).eval()
+    e1, e2 = torch.from_numpy(g["eeg1"]).to(DEV), torch.from_numpy(g["eeg2"]).to(DEV)
+    y = g["labels"]
+    with precision(mode), torch.no_grad():
+        out = m(e1, e2, torch.from_numpy(y).to(DEV))
+    logits = out["logits"].float().cpu().numpy()
+    ref = g["out::logits"]
+    err = np.abs(logits - ref).max()
+    if mode == "fp32":
+        assert err <= 1e-4, f"fp32 logits max abs err {err:.3e}"
+        assert abs(float(out["loss"]) - float(g["out::loss"])) <= 1e-4
+    else:
+        assert err / np.abs(ref).max() <= 2e-2, f"bf16 logits relative err {err / np.abs(ref).max():.3e}"
+    preds = logits.argmax(-1)
+    assert set(g["preds"].tolist()) == {0, 1, 2}                                   # the gate is not degenerate
+    assert (preds == g["preds"]).all(), "argmax predictions differ from the reference"
+    want = dict(zip([str(k) for k in g["metric_names"]], g["metric_values"]))
+    got = M.compute_metrics(y, preds)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert got[k] == pytest.approx(float(v), abs=1e-12), k
+    assert (M.compute_confusion_matrix(y, preds) == g["confusion"]).all()
+    probs = torch.softmax(torch.from_numpy(logits), -1).numpy()
+    aucs = M.compute_aucs(y, probs)
+    for k, v in zip([str(k) for k in g["auc_names"]], g["auc_values"]):
+        assert aucs[k] == pytest.approx(float(v), abs=1e-6 if mode == "fp32" else 2e-2), k
+
+
+def test_trained_model_gradients_fp32(cuda_device):
+    g = load_golden("eeg_model_trained.npz")
+    m = DualEEGTransformer(**ast.literal_eval(str(g["kwargs_repr"])))
+    m.load_state_dict(golden_state_dict(g), strict=True)
+    m = m.to(DEV).eval()
+    e1, e2 = torch.from_numpy(g["eeg1"]).to(DEV), torch.from_numpy(g["eeg2"]).to(DEV)
+    with precision("fp32"):
+        out = m(e1, e2, torch.from_numpy(g["labels"]).to(DEV))
+        (out["loss"] + out["loss_ibs_cls"]).backward()
+    params = dict(m.named_parameters())
+    n = 0
+    for k, v in g.items():
+        if k.startswith("grad::"):
+            e = np.abs(params[k[6:]].grad.cpu().numpy() - v).max()
+            assert e <= 2e-5 + 2e-3 * np.abs(v).max(), (k, e, np.abs(v).max())
+            n += 1
+    assert n >= 5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2. gaze wrappers against the unmodified reference wrappers (goldens), CUDA path directly
+# ---------------------------------------------------------------------------------------------------------------------
+def _wg():
+    g = load_golden("vit_wrappers.npz")
+    s6, s3, sl, simg, scls = (int(x) for x in g["seeds"])
+    return g, str(g["name"]), int(g["B"]), s6, s3, sl, simg, scls
+
+
+@pytest.mark.parametrize("mode", V.EARLY_MODES)
+def test_early_fusion_matches_reference_wrapper_golden(cuda_device, mode):
+    warnings.simplefilter("ignore")
+    g, name, B, s6, s3, _sl, simg, _ = _wg()
+    cin = 6 if mode == "concat" else 3
+    sd = V.init_vit_state_dict(name, cin, 3, "backbone.", seed=s6 if cin == 6 else s3)
+    m = EarlyFusionViT(name, num_classes=3, pretrained=False, fusion_mode=mode)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    a, b = gaze_pair_batch(B, seed=simg)
+    with precision("fp32"), torch.no_grad():
+        logits = m(a.to(DEV), b.to(DEV)).cpu().numpy()
+        feats = m.get_features(a.to(DEV), b.to(DEV)).cpu().numpy()
+    assert np.abs(logits - g[f"early::{mode}::logits"]).max() <= 1e-4
+    assert np.abs(feats - g[f"early::{mode}::features"]).max() <= 3e-4
+
+
+@pytest.mark.parametrize("strategy", ["duplicate", "average"])
+def test_patch_embed_surgery_matches_reference_wrapper_golden(cuda_device, strategy):
+    """The 6-channel surgery done by THIS package's constructor on known 3-channel weights == the reference's."""
+    warnings.simplefilter("ignore")
+    g, name, B, _s6, s3, _sl, simg, _ = _wg()
+    from eyegaze_multimodal_b200 import vit as PV
+    sd3 = V.init_vit_state_dict(name, 3, 3, "backbone.", seed=s3)
+    real = PV.create_model
+
+    def create_with_weights(*args, **kw):
+        mm = real(*args, **kw)
+        mm.load_state_dict({k[len("backbone."):]: v for k, v in sd3.items()}, strict=True)
+        return mm
+    PV.create_model = create_with_weights
+    try:
+        m = EarlyFusionViT(name, num_classes=3, pretrained=False, fusion_mode="concat", weight_init_strategy=strategy)
+    finally:
+        PV.create_model = real
+    w6 = m.backbone.patch_embed.proj.weight.detach()
+    assert np.abs(w6[:4].numpy() - g[f"surgery::{strategy}::w6_head"]).max() <= 1e-7
+    assert np.abs(m.backbone.patch_embed.proj.bias.detach().numpy() - g[f"surgery::{strategy}::bias"]).max() == 0
+    m = m.to(DEV).eval()
+    a, b = gaze_pair_batch(B, seed=simg)
+    with precision("fp32"), torch.no_grad():
+        logits = m(a.to(DEV), b.to(DEV)).cpu().numpy()
+    assert np.abs(logits - g[f"surgery::{strategy}::logits"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("mode", V.LATE_MODES)
+def test_late_fusion_matches_reference_wrapper_golden(cuda_device, mode):
+    warnings.simplefilter("ignore")
+    g, name, B, _s6, _s3, sl, simg, scls = _wg()
+    sd = V.init_vit_state_dict(name, 3, 0, "encoder.", seed=sl)
+    fd = int(g[f"late::{mode}::fused_dim"])
+    gen = torch.Generator().manual_seed(scls)
+    sd["classifier.weight"] = 0.05 * torch.randn(3, fd, generator=gen)
+    sd["classifier.bias"] = 0.05 * torch.randn(3, generator=gen)
+    m = LateFusionViT(name, num_classes=3, pretrained=False, fusion_mode=mode)
+    assert m.fused_dim == fd
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    x1, x2 = gaze_pair_batch(B, seed=simg)
+    with precision("fp32"), torch.no_grad():
+        logits = m(x1.to(DEV), x2.to(DEV)).cpu().numpy()
+        f = m.get_features(x1.to(DEV), x2.to(DEV))
+    assert np.abs(logits - g[f"late::{mode}::logits"]).max() <= 1e-4
+    assert np.abs(f["fused"].cpu().numpy() - g[f"late::{mode}::fused"]).max() <= 5e-4
+    assert np.abs(f["cls1"].cpu().numpy() - g["late::cls1"]).max() <= 3e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3. ViT-B / ViT-S at real size (cfg2 / cfg4 gaze backbones)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["vit_base_patch16_224", "vit_small_patch16_224"])
+def test_real_size_vit_forward_and_backward(cuda_device, name):
+    warnings.simplefilter("ignore")
+    heads = V.VIT_VARIANTS[name][2]
+    B = 4
+    sd = V.init_vit_state_dict(name, 6, 3, "backbone.", seed=31)
+    m = EarlyFusionViT(name, num_classes=3, pretrained=False, fusion_mode="concat")
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    a, b = gaze_pair_batch(B, seed=32)
+    labels = torch.tensor([0, 1, 2, 1])
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = V.early_fusion_forward(sdr, a, b, heads, "concat")
+    F.cross_entropy(want, labels).backward()
+    with precision("fp32"):
+        got = m(a.to(DEV), b.to(DEV))
+        F.cross_entropy(got, labels.to(DEV)).backward()
+    err = (got.detach().cpu() - want.detach()).abs().max().item()
+    assert err <= 1e-4, f"{name} fp32 logits max abs err {err:.3e}"
+    assert torch.equal(got.argmax(-1).cpu(), want.argmax(-1))
+    for k, p in m.named_parameters():
+        r = sdr[k].grad
+        e = (p.grad.cpu() - r).abs().max().item()
+        assert e <= 5e-3 * r.abs().max().item() + 2e-6, f"{name} fp32 grad {k}: {e:.3e} vs max {r.abs().max().item():.3e}"
+    m.zero_grad(set_to_none=True)
+    with precision("bf16"):
+        gb = m(a.to(DEV), b.to(DEV))
+        F.cross_entropy(gb.float(), labels.to(DEV)).backward()
+    rel = (gb.detach().float().cpu() - want.detach()).abs().max().item() / want.detach().abs().max().item()
+    assert rel <= 2e-2, f"{name} bf16 logits relative err {rel:.3e}"
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        r = sdr[k].grad
+        e = (p.grad.float().cpu() - r).abs().max().item() / (r.abs().max().item() + 1e-12)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e <= 3e-2, f"{name} bf16 grad {k}: {e:.3e} of max"
+    print(f"{name}: fp32 logits err {err:.2e}, bf16 rel {rel:.2e}, worst bf16 grad {worst[0]} {worst[1]:.2e}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 4. the bench's GEMM shapes (cta_group::2 pair kernel, persistent multi-wave tile loop, split-K dW)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(50432, 2304, 768, "plain"), (50432, 3072, 768, "gelu"), (50432, 768, 3072, "residual"),
+                                   (50432, 768, 768, "residual")])
+def test_bench_shape_gemms_bf16(cuda_device, shape):
+    Mr, N, K, kind = shape
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g = torch.Generator(device=DEV).manual_seed(5)
+        x = (torch.randn(Mr, K, device=DEV, generator=g) * 0.5).bfloat16()
+        w = torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)
+        b = torch.randn(N, device=DEV, generator=g) * 0.1
+        res = (torch.randn(Mr, N, device=DEV, generator=g) * 0.3).bfloat16()
+        gy = (torch.randn(Mr, N, device=DEV, generator=g)).bfloat16()
+        wq = w.bfloat16().float()
+        xr = x.float().requires_grad_(True)
+        wr = wq.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True)
+        pre = xr @ wr.t() + br
+        yr = pre + res.float() if kind == "residual" else (F.gelu(pre) if kind == "gelu" else pre)
+        yr.backward(gy.float())
+        xg = x.clone().requires_grad_(True)
+        wg, bg = torch.nn.Parameter(w.clone()), torch.nn.Parameter(b.clone())
+        with precision("bf16"):
+            if kind == "gelu":
+                # the fc1 + GELU + saved GELU' epilogue of the ViT MLP, followed by an identity-like second layer
+                w2 = torch.nn.Parameter(torch.eye(N, device=DEV)[:64].contiguous())
+                b2 = torch.nn.Parameter(torch.zeros(64, device=DEV))
+                y = ops.mlp2(xg, wg, bg, w2, b2, L.ACT_GELU)          # y = gelu(pre)[:, :64]
+                y.backward(gy[:, :64].contiguous())
+                yr2 = F.gelu(pre.detach())[:, :64]
+                e = (y.float() - yr2).abs().max().item()
+                assert e <= 1e-2 * yr2.abs().max().item() + 4e-3, f"fc1+gelu {shape}: {e:.3e}"
+                # gradient of the first layer through the saved GELU': compare with autograd on the same slice
+                xr2 = x.float().requires_grad_(True)
+                wr2 = wq.clone().requires_grad_(True)
+                br2 = b.clone().requires_grad_(True)
+                (F.gelu(xr2 @ wr2.t() + br2)[:, :64]).backward(gy[:, :64].float())
+                for nm, got, want in (("dx", xg.grad, xr2.grad), ("dW", wg.grad, wr2.grad), ("db", bg.grad, br2.grad)):
+                    e = _relmax(got, want)
+                    assert e <= 2e-2, f"{nm} {shape}: {e:.3e} of max"
+                return
+            y = ops.linear(xg, wg, bg, residual=res if kind == "residual" else None)
+            y.backward(gy)
+        e = (y.float() - yr.detach()).abs()
+        tol = 8e-3 * yr.detach().abs() + 2e-3 * yr.detach().abs().max()
+        assert (e <= tol).all(), f"y {shape}: worst excess {(e - tol).max().item():.3e}"
+        for nm, got, want in (("dx", xg.grad, xr.grad), ("dW", wg.grad, wr.grad), ("db", bg.grad, br.grad)):
+            e = _relmax(got, want)
+            assert e <= 1e-2, f"{nm} {shape}: {e:.3e} of max"
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 5. GEMM-epilogue dropout: forward mask == the mask regenerated in backward
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_linear_epilogue_dropout_mask_consistency(cuda_device, mode):
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    q = (lambda t: t.bfloat16().float()) if mode == "bf16" else (lambda t: t)
+    Mr, N, K, p = 300, 256, 128, 0.3
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(Mr, K, generator=g) * 0.5
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(Mr, N, generator=g) * 0.3
+    gy = torch.randn(Mr, N, generator=g)
+    with precision(mode):
+        _replay_seeds()
+        xg = x.to(DEV).to(dt).requires_grad_(True)
+        wg, bg = torch.nn.Parameter(w.to(DEV)), torch.nn.Parameter(b.to(DEV))
+        y = ops.linear(xg, wg, bg, p=p)
+        y.backward(gy.to(DEV).to(dt))
+        _replay_seeds()                                            # same seed again: same mask, now with a residual
+        xg2 = x.to(DEV).to(dt).requires_grad_(True)
+        rg = res.to(DEV).to(dt).requires_grad_(True)
+        wg2, bg2 = torch.nn.Parameter(w.to(DEV)), torch.nn.Parameter(b.to(DEV))
+        y2 = ops.linear(xg2, wg2, bg2, residual=rg, p=p)
+        y2.backward(gy.to(DEV).to(dt))
+    mask = (y.detach().float().cpu() != 0).float()
+    keep = mask.mean().item()
+    assert abs(keep - (1 - p)) < 4 * math.sqrt(p * (1 - p) / (Mr * N)) + 1e-3, keep
+    xr, wr, br = q(x).requires_grad_(True), q(w).requires_grad_(True), b.clone().requires_grad_(True)
+    yr = (xr @ wr.t() + br) * mask / (1 - p)
+    yr.backward(q(gy))
+    tol = 2e-4 if mode == "fp32" else 2e-2
+    assert _relmax(y, yr) <= tol
+    for nm, got, want in (("dx", xg.grad, xr.grad), ("dW", wg.grad, wr.grad), ("db", bg.grad, br.grad)):
+        assert _relmax(got, want) <= tol, (nm, _relmax(got, want))
+    # residual variant: y2 = res + the same dropped projection, and the same gradients
+    assert _relmax(y2, yr.detach() + q(res)) <= tol
+    assert _relmax(xg2.grad, xr.grad) <= tol and _relmax(wg2.grad, wr.grad) <= tol and _relmax(bg2.grad, br.grad) <= tol
+    assert _relmax(rg.grad, q(gy)) <= 1e-6
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("act", ["relu", "gelu"])
+def test_mlp2_epilogue_dropout_mask_consistency(cuda_device, mode, act):
+    """FeedForward (relu, p_mid and p_out folded masks, art.py:154-160) and the tokenizer bottleneck (gelu, p_mid)."""
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    q = (lambda t: t.bfloat16().float()) if mode == "bf16" else (lambda t: t)
+    Mr, K, Hd, N = 280, 64, 256, 64
+    p_mid, p_out = 0.25, (0.19 if act == "relu" else 0.0)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(Mr, K, generator=g)
+    w1, b1 = torch.randn(Hd, K, generator=g) / 8, torch.randn(Hd, generator=g) * 0.1
+    w2, b2 = torch.randn(N, Hd, generator=g) / 16, torch.randn(N, generator=g) * 0.5
+    gy = torch.randn(Mr, N, generator=g)
+    code = L.ACT_RELU if act == "relu" else L.ACT_GELU
+    with precision(mode):
+        # the first GEMM alone, same first seed: its zero pattern is the mid mask (dropout is applied after the activation)
+        _replay_seeds()
+        hm = ops.linear(x.to(DEV).to(dt), torch.nn.Parameter(w1.to(DEV)), torch.nn.Parameter(b1.to(DEV)), p=p_mid)
+        mask_mid = (hm.detach().float().cpu() != 0).float()
+        _replay_seeds()
+        xg = x.to(DEV).to(dt).requires_grad_(True)
+        prm = [torch.nn.Parameter(t.to(DEV)) for t in (w1, b1, w2, b2)]
+        y = ops.mlp2(xg, *prm, code, p_mid=p_mid, p_out=p_out)
+        y.backward(gy.to(DEV).to(dt))
+    mask_out = (y.detach().float().cpu() != 0).float() if p_out > 0 else torch.ones(Mr, N)
+    assert abs(mask_mid.mean().item() - (1 - p_mid)) < 0.01
+    if p_out > 0:
+        assert abs(mask_out.mean().item() - (1 - p_out)) < 0.02
+    ps = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    fn = F.relu if act == "relu" else F.gelu
+    h = fn(F.linear(q(ps[0]), q(ps[1]), ps[2])) * mask_mid / (1 - p_mid)
+    yr = F.linear(h if mode == "fp32" else h + (q(h.detach()) - h.detach()), q(ps[3]), ps[4]) * mask_out / (1 - p_out)
+    yr.backward(q(gy))
+    tol = 3e-4 if mode == "fp32" else 3e-2
+    assert _relmax(y, yr) <= tol, _relmax(y, yr)
+    assert _relmax(xg.grad, ps[0].grad) <= tol, _relmax(xg.grad, ps[0].grad)
+    for gp, r, nm in zip(prm, ps[1:], ["dw1", "db1", "dw2", "db2"]):
+        assert _relmax(gp.grad, r.grad) <= tol, (nm, _relmax(gp.grad, r.grad))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 6. gradients: no aliasing, clip_grad_norm_, accumulation over two backward passes (advisor finding)
+# ---------------------------------------------------------------------------------------------------------------------
+def _overlaps(tensors):
+    spans = sorted((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), n) for n, t in tensors)
+    return [(a[2], b[2]) for a, b in zip(spans, spans[1:]) if b[0] < a[1]]
+
+
+def test_parameter_gradients_never_alias_and_accumulate(cuda_device):
+    warnings.simplefilter("ignore")
+    cfg = O.EEGConfig(in_channels=8, d_model=64, num_layers=2, num_heads=4, d_ff=128, max_len=96)
+    sd = O.init_state_dict(cfg, 3)
+    m = DualEEGTransformer(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    e1, e2 = eeg_pair_batch(4, 8, 256, seed=5, coupled=True)
+    labels = torch.tensor([0, 1, 2, 0])
+    sdr = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    for _ in range(2):                                             # reference: two accumulated backward passes
+        ref = O.dual_eeg_forward(sdr, e1, e2, cfg, labels)
+        (ref["loss"] + ref["loss_ibs_cls"]).backward()
+    pnames = {n for n, _ in m.named_parameters()}                  # (buffers such as the STFT window are not clipped)
+    rparams = [v for k, v in sdr.items() if k in pnames and v.grad is not None]
+    rnorm = torch.nn.utils.clip_grad_norm_(rparams, 0.05)
+    with precision("fp32"):
+        for _ in range(2):
+            out = m(e1.to(DEV), e2.to(DEV), labels.to(DEV))
+            (out["loss"] + out["loss_ibs_cls"]).backward()
+    grads = [(n, p.grad) for n, p in m.named_parameters() if p.grad is not None]
+    assert not _overlaps(grads), _overlaps(grads)
+    norm = torch.nn.utils.clip_grad_norm_([p for p in m.parameters() if p.grad is not None], 0.05)
+    assert abs(norm.item() - rnorm.item()) <= 2e-3 * rnorm.item()
+    for n, p in m.named_parameters():
+        if sdr[n].grad is None:
+            continue
+        r = sdr[n].grad
+        e = (p.grad.cpu() - r).abs().max().item()
+        assert e <= 5e-3 * r.abs().max().item() + 2e-6, f"{n}: {e:.3e} vs {r.abs().max().item():.3e}"
+    # the ViT embedding has the same cls / pos-row-0 relation
+    name = "vit_tiny_patch16_224"
+    vm = EarlyFusionViT(name, num_classes=3, pretrained=False, fusion_mode="concat").to(DEV).eval()
+    a, b = gaze_pair_batch(2, seed=1)
+    with precision("fp32"):
+        F.cross_entropy(vm(a.to(DEV), b.to(DEV)), torch.tensor([0, 2], device=DEV)).backward()
+    vg = [(n, p.grad) for n, p in vm.named_parameters() if p.grad is not None]
+    assert not _overlaps(vg), _overlaps(vg)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 7. temporal-conv frontend for any window length (advisor finding): T = 1000 / 500 / 1023
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("T", [1000, 500, 1023, 260])
+def test_temporal_conv_any_window_length(cuda_device, mode, T):
+    B, C, D = 2, 8, 64
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    q = (lambda t: t.bfloat16().float()) if mode == "bf16" else (lambda t: t)
+    g = torch.Generator().manual_seed(6)
+    e1, e2 = torch.randn(B, C, T, generator=g), torch.randn(B, C, T, generator=g)
+    w1, b1 = torch.randn(D, C, 25, generator=g) / math.sqrt(25 * C), torch.randn(D, generator=g) * 0.1
+    w2, b2 = torch.randn(D, D, 25, generator=g) / math.sqrt(25 * D), torch.randn(D, generator=g) * 0.1
+    ps = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2)]
+    x = q(torch.cat([e1, e2], 0))
+    h = q(F.relu(F.conv1d(x, q(ps[0]), ps[1], stride=4, padding=12)))
+    h = F.relu(F.conv1d(h, q(ps[2]), ps[3], stride=4, padding=12)).permute(0, 2, 1)
+    gy = torch.randn(h.shape, generator=g)
+    h.backward(gy)
+    prm = [torch.nn.Parameter(t.to(DEV)) for t in (w1, b1, w2, b2)]
+    code = L.F32 if mode == "fp32" else L.BF16
+    out = ops.temporal_conv(e1.to(DEV), e2.to(DEV), [prm[0], prm[2]], [prm[1], prm[3]], code, 4, 0.0)
+    assert out.shape == h.shape and out.dtype == dt
+    out.backward(gy.to(DEV).to(dt))
+    tol = 1e-4 if mode == "fp32" else 3e-2
+    assert _relmax(out, h) <= tol, _relmax(out, h)
+    for gp, r, nm in zip(prm, ps, ["dw1", "db1", "dw2", "db2"]):
+        assert _relmax(gp.grad, r.grad) <= tol, (nm, T, _relmax(gp.grad, r.grad))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 8. optional batch-level aux losses (det:1255-1371) against the reference goldens
+# ---------------------------------------------------------------------------------------------------------------------
+def test_aux_losses_match_reference_golden(cuda_device):
+    g = load_golden("aux_losses.npz")
+    m = DualEEGTransformer(in_channels=4, d_model=16, num_layers=1, num_heads=2, d_ff=32, max_len=64,
+                           use_spectrogram=False, use_ibs=False).to(DEV)
+    labels = torch.from_numpy(g["labels"]).to(DEV)
+
+    def leafs():
+        return [torch.from_numpy(g[k]).to(DEV).requires_grad_(True) for k in ("ibs", "cls1", "cls2")]
+    cases = {"sym": lambda i, a, b: m.compute_symmetry_loss(a, b),
+             "align": lambda i, a, b: m.compute_ibs_alignment_loss(i, a, b),
+             "align_t05": lambda i, a, b: m.compute_ibs_alignment_loss(i, a, b, temperature=0.5),
+             "contrast": lambda i, a, b: m.compute_ibs_contrastive_loss(i, labels),
+             "contrast_t05": lambda i, a, b: m.compute_ibs_contrastive_loss(i, labels, temperature=0.5),
+             "contrast_single": lambda i, a, b: m.compute_ibs_contrastive_loss(
+                 i, torch.from_numpy(g["contrast_single::labels"]).to(DEV))}
+    for name, fn in cases.items():
+        i, a, b = leafs()
+        loss = fn(i, a, b)
+        assert loss.is_cuda and loss.dim() == 0
+        (loss * 1.5).backward()                                   # a non-unit upstream gradient
+        want = float(g[name + "::loss"])
+        assert abs(float(loss) - want) <= 2e-5 * max(1.0, abs(want)), (name, float(loss), want)
+        for tn, t in (("ibs", i), ("cls1", a), ("cls2", b)):
+            key = f"{name}::grad_{tn}"
+            if key in g:
+                assert t.grad is not None, key
+                e = np.abs(t.grad.cpu().numpy() / 1.5 - g[key]).max()
+                assert e <= 2e-5 + 1e-4 * np.abs(g[key]).max(), (key, e)
+    nopos = m.compute_ibs_contrastive_loss(torch.from_numpy(g["ibs"])[:3].to(DEV), torch.tensor([0, 1, 2], device=DEV))
+    assert float(nopos) == 0.0
+
+
+def test_aux_losses_large_batch_against_oracle(cuda_device):
+    """B = 512 (two row blocks per CTA loop, the GEMM's multi-tile path) against oracle/eeg.py."""
+    g = torch.Generator().manual_seed(8)
+    B, D = 512, 256
+    ibs, c1, c2 = (torch.randn(B, D, generator=g) for _ in range(3))
+    labels = torch.randint(0, 3, (B,), generator=g)
+    m = DualEEGTransformer(in_channels=4, d_model=16, num_layers=1, num_heads=2, d_ff=32, max_len=64,
+                           use_spectrogram=False, use_ibs=False).to(DEV)
+    for name in ("align", "contrast"):
+        r = [t.clone().requires_grad_(True) for t in (ibs, c1, c2)]
+        d = [t.clone().to(DEV).requires_grad_(True) for t in (ibs, c1, c2)]
+        if name == "align":
+            lr, ld = O.ibs_alignment_loss(*r), m.compute_ibs_alignment_loss(*d)
+        else:
+            lr, ld = O.ibs_contrastive_loss(r[0], labels), m.compute_ibs_contrastive_loss(d[0], labels.to(DEV))
+        lr.backward()
+        ld.backward()
+        assert abs(float(ld) - float(lr)) <= 1e-4 * abs(float(lr)), (name, float(ld), float(lr))
+        for a, b in zip(d, r):
+            if b.grad is not None:
+                assert _relmax(a.grad, b.grad) <= 2e-3, (name, _relmax(a.grad, b.grad))

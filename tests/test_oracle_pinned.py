@@ -182,3 +182,26 @@ def test_oracle_matches_trained_reference_model_and_metrics():
         if k.startswith("grad::"):
             e = np.abs(sd[k[6:]].grad.numpy() - v).max()
             assert e <= 2e-5 + 2e-3 * np.abs(v).max(), (k, e)
+
+
+def test_aux_losses_match_reference():
+    """oracle/eeg.py aux losses (det:1255-1371) against values + gradients from the unmodified reference."""
+    g = load_golden("aux_losses.npz")
+    labels = torch.from_numpy(g["labels"])
+
+    def leafs():
+        return [torch.from_numpy(g[k]).clone().requires_grad_(True) for k in ("ibs", "cls1", "cls2")]
+    cases = {"sym": lambda i, a, b: O.symmetry_loss(a, b), "align": lambda i, a, b: O.ibs_alignment_loss(i, a, b),
+             "align_t05": lambda i, a, b: O.ibs_alignment_loss(i, a, b, 0.5),
+             "contrast": lambda i, a, b: O.ibs_contrastive_loss(i, labels),
+             "contrast_t05": lambda i, a, b: O.ibs_contrastive_loss(i, labels, 0.5),
+             "contrast_single": lambda i, a, b: O.ibs_contrastive_loss(i, torch.from_numpy(g["contrast_single::labels"]))}
+    for name, fn in cases.items():
+        i, a, b = leafs()
+        loss = fn(i, a, b)
+        loss.backward()
+        assert abs(float(loss) - float(g[name + "::loss"])) <= 1e-6 * max(1.0, abs(float(g[name + "::loss"]))), name
+        for tn, t in (("ibs", i), ("cls1", a), ("cls2", b)):
+            if f"{name}::grad_{tn}" in g:
+                assert np.abs(t.grad.numpy() - g[f"{name}::grad_{tn}"]).max() <= 1e-6, (name, tn)
+    assert float(O.ibs_contrastive_loss(torch.from_numpy(g["ibs"])[:3], torch.tensor([0, 1, 2]))) == float(g["contrast_nopos::loss"]) == 0.0

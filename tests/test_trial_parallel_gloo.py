@@ -123,3 +123,48 @@ def test_reference_style_loop_rearms_and_ragged_shards():
 def test_loss_weight():
     assert loss_weight(4, 8, 2) == 1.0
     assert abs(loss_weight(4, 7, 2) + loss_weight(3, 7, 2) - 2.0) < 1e-12
+
+
+def _batch_loss(tok, y):
+    """A loss that looks ACROSS the batch (stand-in for the contrastive aux losses, dual_eeg_transformer.py:1305-1371)."""
+    t = nn.functional.normalize(tok, dim=1)
+    sim = t @ t.t() / 0.5
+    same = (y[:, None] == y[None, :]).float()
+    return (torch.logsumexp(sim, 1) - (sim * same).sum(1) / same.sum(1)).mean()
+
+
+def _worker_gather(rank, world, port, out):
+    from eyegaze_multimodal_b200.parallel import gather_trials
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100)
+    model = Toy()
+    tp = TrialParallel(model, bucket_mb=0.004)
+    a, b, y = _data(8)
+    idx = list(shard_trials(len(y), rank, world))
+    tp.zero_grad()
+    tok = tp(a[idx], b[idx])                                 # (B_local, 3) "tokens"
+    loss = _batch_loss(gather_trials(tok), gather_trials(y[idx]))
+    loss.backward()
+    tp.finish()
+    out[rank] = {"loss": loss.detach().clone(), "grads": {n: p.grad.clone() for n, p in model.named_parameters()}}
+    dist.destroy_process_group()
+
+
+def test_gather_trials_makes_batch_level_losses_exact_under_sharding():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_gather, args=(2, port, out), nprocs=2, join=True)
+    torch.manual_seed(100)
+    ref = Toy()
+    a, b, y = _data(8)
+    loss = _batch_loss(ref(a, b), y)
+    loss.backward()
+    for r in (0, 1):
+        assert torch.allclose(out[r]["loss"], loss.detach(), atol=1e-6)
+        for n, p in ref.named_parameters():
+            want = p.grad if p.grad is not None else torch.zeros_like(p)
+            assert torch.allclose(out[r]["grads"][n], want, atol=1e-6), (n, r)
