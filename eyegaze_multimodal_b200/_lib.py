@@ -41,7 +41,8 @@ class AttentionDesc(C.Structure):
                 ("dq_bs", i64), ("dq_rs", i64), ("dk_bs", i64), ("dk_rs", i64), ("dv_bs", i64), ("dv_rs", i64),
                 ("lse", vp), ("delta", vp), ("probs", vp),
                 ("dtype", i32), ("S", i32), ("H", i32), ("Lq", i32), ("Lk", i32), ("head_dim", i32), ("kv_shift", i32),
-                ("scale", f32), ("dropout_p", f32), ("seed", u64)]
+                ("scale", f32), ("dropout_p", f32), ("seed", u64),
+                ("dq_colsum", vp), ("dk_colsum", vp), ("dv_colsum", vp)]
 
 
 class FuzzyDesc(C.Structure):
@@ -52,7 +53,7 @@ class FuzzyDesc(C.Structure):
 
 
 class AdamwState(C.Structure):
-    _fields_ = [("lr", vp), ("step", vp), ("grad_scale", vp), ("found_inf", vp), ("skip_nonfinite", i32)]
+    _fields_ = [("lr", vp), ("ctrl", vp), ("grad_scale", vp), ("use_device_step", i32)]
 
 
 # name -> argtypes (all return int except where noted); mirrors include/eyegaze_b200.h one to one
@@ -82,6 +83,8 @@ _SIGNATURES = {
     "egb_multi_tensor_sqnorm": [vp, vp, i32, vp, vp],
     "egb_multi_tensor_adamw": [vp, vp, i32, f32, f32, f32, f32, f32, f32, vp, vp],
     "egb_layernorm_bwd_res": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    "egb_layernorm_bwd_ex": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    "egb_dropout_bwd_colsum": [vp, vp, i32, i32, i32, f32, u64, vp, vp],
     "egb_attention_fwd": [C.POINTER(AttentionDesc), vp],
     "egb_attention_bwd": [C.POINTER(AttentionDesc), vp],
     "egb_debug_attention_timing": [vp],
@@ -103,6 +106,7 @@ _SIGNATURES = {
     "egb_seed_epoch_enable": [C.POINTER(vp)],
     "egb_seed_epoch_advance": [vp],
     "egb_multi_tensor_adamw_ex": [vp, vp, i32, f32, f32, f32, f32, f32, f32, vp, C.POINTER(AdamwState), vp],
+    "egb_adamw_prepare": [vp, vp, vp, vp, i32, i32, vp],
     "egb_lr_schedule_step": [vp, vp, vp, vp, i32, i32, f32, f32, i32, i32, vp],
     "egb_accum_scalars": [C.POINTER(vp), i32, vp, vp],
     "egb_argmax_count": [vp, vp, vp, vp, i32, i32, vp],

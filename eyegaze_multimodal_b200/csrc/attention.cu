@@ -285,6 +285,22 @@ static int fill_att(const egb_attention_desc* d, AttParams* p) {
   return 0;
 }
 
+// dq_colsum / dk_colsum / dv_colsum of the descriptor for the kernels that do not take them in-kernel: one column-sum
+// pass per gradient tensor
+int egb_attention_colsum_pass(const egb_attention_desc* d, cudaStream_t st) {
+  if (d->dq_colsum == nullptr) return 0;
+  EGB_CHECK(d->dk_colsum != nullptr && d->dv_colsum != nullptr, "attention_bwd: pass all three column-sum buffers or none");
+  const int N = d->H * d->head_dim;
+  egb_matrix m;
+  m.dtype = d->dtype;
+  m.ptr = d->dq; m.rows_per_group = d->Lq; m.row_stride = d->dq_rs; m.group_stride = d->dq_bs;
+  if (egb_colsum(&m, d->S * d->Lq, N, d->dq_colsum, 0, st)) return 1;
+  m.ptr = d->dk; m.rows_per_group = d->Lk; m.row_stride = d->dk_rs; m.group_stride = d->dk_bs;
+  if (egb_colsum(&m, d->S * d->Lk, N, d->dk_colsum, 0, st)) return 1;
+  m.ptr = d->dv; m.rows_per_group = d->Lk; m.row_stride = d->dv_rs; m.group_stride = d->dv_bs;
+  return egb_colsum(&m, d->S * d->Lk, N, d->dv_colsum, 0, st);
+}
+
 int egb_attention_fwd(const egb_attention_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (egb_attention_tc_supported(d, false)) return egb_attention_tc_fwd(d, st);
@@ -327,7 +343,7 @@ int egb_attention_bwd(const egb_attention_desc* d, void* stream) {
   }
   egb_count_launch(2);
   EGB_LAUNCH_CHECK();
-  return 0;
+  return egb_attention_colsum_pass(d, st);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@ extern void egb_count_launch(int n);
 int egb_tmap_rows64(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long groups, long long rs,
                     long long gs, int box_rows);
 int egb_prof_enabled();
+extern "C" int egb_attention_colsum_pass(const egb_attention_desc* d, cudaStream_t st);
 void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind);
 void egb_prof_end(cudaStream_t st);
 
@@ -52,6 +53,7 @@ struct AttTcParams {
   const unsigned long long* epoch;   // device seed epoch (egb_mix_seed), NULL when not enabled
   long long* dbg;  // optional: phase timestamps (clock64) of CTA (0, 0, S/2), see egb_debug_attention_timing
   int use_tma;     // pipelined backward: operand tiles arrive by TMA (head_dim 64) instead of cp.async
+  float *dq_cs, *dk_cs, *dv_cs;   // optional [H*d] fp32, accumulated: column sums of the stored dQ / dK / dV (bias gradients)
 };
 // tensor maps of the pipelined backward's operands ({H d, L, S} views, box {64, L_pad, 1}, 128-byte swizzle)
 struct AttMaps {
@@ -175,8 +177,18 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, int c_begin, int c
 // XOR-swizzled by row) and each store instruction then covers 32 / (ncols / 8) complete rows.  One thread owns one
 // TMEM lane = one row, so a direct store scatters 32 separate 16-byte pieces per instruction (measured: ~6 K cycles
 // of LSU time per backward CTA).  g0 = first of the warp's rows (may be past the end when rows_valid <= 0).
+// 8 packed bf16 values += into acc (column sums of the stored rows)
+__device__ __forceinline__ void add_bf16x8(const uint4& v, float (&acc)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[2 * i] += __low2float(h[i]); acc[2 * i + 1] += __high2float(h[i]); }
+}
+
+// `cs` (optional, shared memory, PRIVATE to the calling warp): column sums of the rows this call stores are added to
+// cs[0 .. ncols) with plain read-modify-writes (fp32 shared-memory atomics are compare-and-swap spin loops: with eight
+// warps on the same 64 words they cost more than the column-sum pass they replace).
 __device__ __forceinline__ void store_acc_rows_coalesced(uint32_t taddr, int ncols, float mul, uint8_t* stage, bf16* g0,
-                                                         long long rs, int rows_valid, int lane) {
+                                                         long long rs, int rows_valid, int lane, float* cs = nullptr) {
   for (int c0 = 0; c0 < ncols; c0 += 32) {
     uint32_t raw[32];
     ptx::tmem_ld32(taddr + (uint32_t)c0, raw);
@@ -195,10 +207,22 @@ __device__ __forceinline__ void store_acc_rows_coalesced(uint32_t taddr, int nco
   __syncwarp();
   const int sh = ncols == 64 ? 3 : 2;             // log2(16-byte pieces per row)
   const int ch = lane & ((1 << sh) - 1), r0 = lane >> sh, rpi = 32 >> sh;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int it = 0; it < (1 << sh); ++it) {
     const int rr = it * rpi + r0;
     const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
-    if (rr < rows_valid) *reinterpret_cast<uint4*>(g0 + (long long)rr * rs + ch * 8) = v;
+    if (rr < rows_valid) {
+      *reinterpret_cast<uint4*>(g0 + (long long)rr * rs + ch * 8) = v;
+      if (cs != nullptr) add_bf16x8(v, acc);
+    }
+  }
+  if (cs != nullptr) {                            // lanes that share `ch` hold different rows of the same 8 columns
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      for (int o = 16; o >= (1 << sh); o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    if (r0 == 0)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[ch * 8 + j] += acc[j];
   }
   __syncwarp();
 }
@@ -206,7 +230,7 @@ __device__ __forceinline__ void store_acc_rows_coalesced(uint32_t taddr, int nco
 // Same for exactly 32 columns with a 2 KB staging area per warp (rows pitched 64 B; the slot swizzle keeps both the
 // row-wise writes and the 8-rows-per-instruction read-out free of bank conflicts).
 __device__ __forceinline__ void store_acc_rows32_coalesced(uint32_t taddr, float mul, uint8_t* stage, bf16* g0, long long rs,
-                                                           int rows_valid, int lane) {
+                                                           int rows_valid, int lane, float* cs = nullptr) {
   uint32_t raw[32];
   ptx::tmem_ld32(taddr, raw);
   ptx::tmem_ld_wait();
@@ -221,11 +245,26 @@ __device__ __forceinline__ void store_acc_rows32_coalesced(uint32_t taddr, float
   }
   __syncwarp();
   const int ch = lane & 3, r0 = lane >> 2;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int rr = it * 8 + r0;
     const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-    if (rr < rows_valid) *reinterpret_cast<uint4*>(g0 + (long long)rr * rs + ch * 8) = v;
+    if (rr < rows_valid) {
+      *reinterpret_cast<uint4*>(g0 + (long long)rr * rs + ch * 8) = v;
+      if (cs != nullptr) add_bf16x8(v, acc);
+    }
+  }
+  if (cs != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+    }
+    if (r0 == 0)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[ch * 8 + j] += acc[j];
   }
   __syncwarp();
 }
@@ -1016,6 +1055,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
   uint64_t* bar_dqrd = &bars[6];
   uint64_t* bar_ld = &bars[7];                   // TMA tile loads
   uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // [8 warps][3][64] column sums of this head's dQ | dK | dV rows, one private slot per softmax warp
+  float* s_cs_all = reinterpret_cast<float*>(slot + 4);
+  const bool want_cs = p.dq_cs != nullptr;
+  if (want_cs)
+    for (int i = threadIdx.x; i < 8 * 192; i += PIPE_THREADS) s_cs_all[i] = 0.f;   // published by the __syncthreads below
+  float* s_cs = s_cs_all + (threadIdx.x >> 5 & 7) * 192;
   const int h = blockIdx.x, s = blockIdx.y;
   const int skv = (s + p.kv_shift) % p.S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1167,7 +1212,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
       const int cb = d >= 64 ? half * 32 : 0;
       if (d >= 64 || half == 0)
         store_acc_rows_coalesced(trow + col + (uint32_t)cb, 32, p.scale, stage,
-                                 p.dq + s * p.dq_bs + (long long)r0 * p.dq_rs + h * d + cb, p.dq_rs, p.Lq - r0, lane);
+                                 p.dq + s * p.dq_bs + (long long)r0 * p.dq_rs + h * d + cb, p.dq_rs, p.Lq - r0, lane,
+                                 want_cs ? s_cs + cb : nullptr);
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_dqrd);
       asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // every warp's staging rows are free again
@@ -1240,10 +1286,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
       for (int c0 = 0; c0 < d; c0 += 32) {
         if (half == 0)
           store_acc_rows32_coalesced(trow + DV0 + (uint32_t)c0, 1.f, st2, p.dv + skv * p.dv_bs + (long long)j0 * p.dv_rs + h * d + c0,
-                                     p.dv_rs, p.Lk - j0, lane);
+                                     p.dv_rs, p.Lk - j0, lane, want_cs ? s_cs + 128 + c0 : nullptr);
         else
           store_acc_rows32_coalesced(trow + DK0 + (uint32_t)c0, p.scale, st2, p.dk + skv * p.dk_bs + (long long)j0 * p.dk_rs + h * d + c0,
-                                     p.dk_rs, p.Lk - j0, lane);
+                                     p.dk_rs, p.Lk - j0, lane, want_cs ? s_cs + 64 + c0 : nullptr);
       }
     }
     read_dq(nq - 1);                              // bar_dq of the last q-tile covers every MMA: dV / dK are final
@@ -1251,10 +1297,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
       const int j0 = kc * TILE_ROWS + (warp & 3) * 32;   // first key row of this warp
       if (half == 0)
         store_acc_rows_coalesced(trow + DV0 + (uint32_t)(d * kc), d, 1.f, stage,
-                                 p.dv + skv * p.dv_bs + (long long)j0 * p.dv_rs + h * d, p.dv_rs, p.Lk - j0, lane);
+                                 p.dv + skv * p.dv_bs + (long long)j0 * p.dv_rs + h * d, p.dv_rs, p.Lk - j0, lane,
+                                 want_cs ? s_cs + 128 : nullptr);
       else
         store_acc_rows_coalesced(trow + DK0 + (uint32_t)(d * kc), d, p.scale, stage,
-                                 p.dk + skv * p.dk_bs + (long long)j0 * p.dk_rs + h * d, p.dk_rs, p.Lk - j0, lane);
+                                 p.dk + skv * p.dk_bs + (long long)j0 * p.dk_rs + h * d, p.dk_rs, p.Lk - j0, lane,
+                                 want_cs ? s_cs + 64 : nullptr);
     }
   }
   ATT_STAMP_MID(4);
@@ -1267,6 +1315,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
   if (warp == 8) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem);
+  }
+  if (want_cs && threadIdx.x < 3 * d) {          // one global atomic per column per CTA
+    const int which = threadIdx.x / d, c = threadIdx.x - which * d;
+    float* dst = which == 0 ? p.dq_cs : which == 1 ? p.dk_cs : p.dv_cs;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_cs_all[w * 192 + which * 64 + c];
+    atomicAdd(dst + h * d + c, v);
   }
 }
 
@@ -1368,7 +1424,10 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
   const bool prof = egb_prof_enabled() != 0;
   static const int fused = getenv("EGB_ATT_FUSED_BWD") ? atoi(getenv("EGB_ATT_FUSED_BWD")) : 2;   // 2 pipelined, 1 fused, 0 two kernels
   const int nk = (p.Lk_pad + 127) / 128;
-  const size_t smem_f = (size_t)(2 * p.Lq_pad + 2 * p.Lk_pad) * 128 + (size_t)(2 + 2 * nk) * TILE_ROWS * 128 + 1024 + 128;
+  size_t smem_f = (size_t)(2 * p.Lq_pad + 2 * p.Lk_pad) * 128 + (size_t)(2 + 2 * nk) * TILE_ROWS * 128 + 1024 + 128;
+  // the in-kernel column sums need 8 x 192 floats more; when they do not fit, the column-sum pass runs afterwards
+  const bool cs_in_kernel = d->dq_colsum != nullptr && smem_f + 8 * 192 * 4 + 32 <= 227 * 1024;
+  if (cs_in_kernel) smem_f += 8 * 192 * 4 + 32;
   if (fused && smem_f <= 227 * 1024) {
     if (set_smem_tc(att_tc_bwd_fused_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_fused_kernel<false>, smem_f)) return 1;
     if (set_smem_tc(att_tc_bwd_pipe_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_pipe_kernel<false>, smem_f)) return 1;
@@ -1388,14 +1447,21 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
                       egb_tmap_rows64(&maps.k, d->k, inner, d->Lk, d->S, d->k_rs, d->k_bs, p.Lk_pad) ||
                       egb_tmap_rows64(&maps.v, d->v, inner, d->Lk, d->S, d->v_rs, d->v_bs, p.Lk_pad));
       }
+      EGB_CHECK((d->dq_colsum == nullptr) == (d->dk_colsum == nullptr) && (d->dq_colsum == nullptr) == (d->dv_colsum == nullptr),
+                "attention_bwd: pass all three column-sum buffers or none");
+      if (cs_in_kernel) { p.dq_cs = d->dq_colsum; p.dk_cs = d->dk_colsum; p.dv_cs = d->dv_colsum; }
       if (drop) att_tc_bwd_pipe_kernel<true><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
       else att_tc_bwd_pipe_kernel<false><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
+      if (prof) egb_prof_end(st);
+      egb_count_launch(1);
+      EGB_LAUNCH_CHECK();
+      return cs_in_kernel ? 0 : egb_attention_colsum_pass(d, st);
     } else if (drop) att_tc_bwd_fused_kernel<true><<<grid, TC_THREADS, smem_f, st>>>(p);
     else att_tc_bwd_fused_kernel<false><<<grid, TC_THREADS, smem_f, st>>>(p);
     if (prof) egb_prof_end(st);
     egb_count_launch(1);
     EGB_LAUNCH_CHECK();
-    return 0;
+    return egb_attention_colsum_pass(d, st);
   }
   EGB_CHECK(d->delta != nullptr, "attention_bwd: missing delta scratch");
   const size_t smem_a = (size_t)(2 * TILE_ROWS + 2 * p.Lk_pad) * 128 + 1024 + 64;
@@ -1417,5 +1483,5 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
   if (prof) egb_prof_end(st);
   egb_count_launch(2);
   EGB_LAUNCH_CHECK();
-  return 0;
+  return egb_attention_colsum_pass(d, st);
 }

@@ -326,6 +326,52 @@ __global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ out
 }
 
 
+// Row-structured variant that also accumulates the column sums of its output (bias gradient): one warp per row, a lane
+// owns 8 consecutive columns of every 256-column chunk, so its column sums stay in registers across rows.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) dropout_bwd_colsum_kernel(const T* __restrict__ dy, T* __restrict__ out, int M, int N,
+                                                                 unsigned thresh, float scale, unsigned long long seed_in,
+                                                                 const unsigned long long* epoch, float* __restrict__ colsum) {
+  const unsigned long long seed = egb_mix_seed(seed_in, epoch);
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float acc[C][8];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (d < N) {
+        float v[8];
+        const long long base = (long long)row * N + d;
+        ld8(dy + base, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = drop_keep(seed, (unsigned long long)(base + j), thresh) ? v[j] * scale : 0.f;
+          acc[c][j] += to_f(from_f<T>(v[j]));
+        }
+        st8(out + base, v);
+      }
+    }
+  }
+  if (colsum != nullptr) {
+    __shared__ float red[C * 256];
+    for (int i = threadIdx.x; i < C * 256; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[c * 256 + j * 32 + lane], acc[c][j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const int c = i >> 8, r = i & 255;
+      atomicAdd(colsum + i, red[c * 256 + (r & 7) * 32 + (r >> 3)]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- activation backward
 // out[m,n] = dy[m,n] * act'(aux[m,n]); dy is a strided 3-level row view, aux/out are dense [M,N].
 //   mode 1: aux = forward output after relu (+dropout): factor = (aux != 0) * scale
@@ -602,6 +648,30 @@ int egb_dropout_bwd(const void* dy, void* out, int dtype, int64_t n_elems, float
   else
     dropout_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)dy, (float*)out, n_elems, drop_threshold(p),
                                                 1.f / (1.f - p), seed, egb_seed_epoch_ptr());
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int egb_dropout_bwd_colsum(const void* dy, void* out, int dtype, int M, int N, float p, uint64_t seed, float* colsum,
+                           void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGB_CHECK(M > 0 && N > 0 && N % 8 == 0 && N <= 1024 && p > 0.f && p < 1.f, "dropout_bwd_colsum: bad arguments");
+  const int chunks = (N + 255) / 256;
+  int blocks = (M + 7) / 8;
+  const int cap = egb_num_sms() * 4;       // few, fat CTAs: each ends with N column atomics
+  if (blocks > cap) blocks = cap;
+  const unsigned th = drop_threshold(p);
+  const float sc = 1.f / (1.f - p);
+  const unsigned long long* ep = egb_seed_epoch_ptr();
+#define EGB_DBC(TT, CC) \
+  dropout_bwd_colsum_kernel<TT, CC><<<blocks, 256, 0, st>>>((const TT*)dy, (TT*)out, M, N, th, sc, seed, ep, colsum)
+  if (dtype == EGB_BF16) {
+    switch (chunks) { case 1: EGB_DBC(bf16, 1); break; case 2: EGB_DBC(bf16, 2); break; case 3: EGB_DBC(bf16, 3); break; default: EGB_DBC(bf16, 4); }
+  } else {
+    switch (chunks) { case 1: EGB_DBC(float, 1); break; case 2: EGB_DBC(float, 2); break; case 3: EGB_DBC(float, 3); break; default: EGB_DBC(float, 4); }
+  }
+#undef EGB_DBC
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;

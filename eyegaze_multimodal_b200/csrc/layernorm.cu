@@ -88,25 +88,33 @@ template <> struct Raw8<float> {
 // the dx pass and are converted twice: with fp32 copies of xhat and g the kernel sat at the 128-register limit of
 // two CTAs per SM and ptxas serialised the row's loads chunk by chunk (three DRAM round trips per row: 81 us for the
 // ViT-B LayerNorms against 36 us of traffic).  gamma is read from shared memory.
+// Threads per CTA / CTAs per SM by row width: the column accumulators (dgamma, dbeta, dx column sums: 3 x 8 floats per
+// 256-column chunk) live in registers, which caps the CTA size for the wide rows (D = 768: 12 warps with <= 168 registers).
+template <int C> struct LnBwdShape {
+  static constexpr int kThreads = C == 1 ? 256 : (C == 2 ? 512 : 384);
+  static constexpr int kCtasPerSm = C == 1 ? 2 : 1;
+};
+
 template <typename T, int C>
-__global__ void __launch_bounds__(C == 1 ? 256 : 512, C == 1 ? 3 : 1) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(LnBwdShape<C>::kThreads, LnBwdShape<C>::kCtasPerSm) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, T* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            const T* __restrict__ dres, int M, int D) {
-  extern __shared__ float red[];  // [2][D] column partials, [D] gamma
-  float* sg = red + 2 * D;
+                                                            const T* __restrict__ dres, float* __restrict__ dx_colsum,
+                                                            int M, int D) {
+  extern __shared__ float red[];  // [3][D] column partials (dgamma, dbeta, dx column sums), [D] gamma
+  float* sg = red + 3 * D;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
   for (int i = threadIdx.x; i < D; i += blockDim.x) sg[i] = gamma[i];
   __syncthreads();
-  float ag[C][8], ab[C][8];
+  float ag[C][8], ab[C][8], ac[C][8];
 #pragma unroll
   for (int c = 0; c < C; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = ac[c][j] = 0.f;
 
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
     Raw8<T> xr[C], dr[C], rr[C];
@@ -164,6 +172,10 @@ __global__ void __launch_bounds__(C == 1 ? 256 : 512, C == 1 ? 3 : 1) layernorm_
           for (int j = 0; j < 8; ++j) o[j] += rv[j];
         }
         st8(dx + (long long)row * D + d, o);
+        // column sums of the STORED dx (rounded to the storage type, as a separate pass over dx would see them): the bias
+        // gradient of the Linear whose output fed this residual stream
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ac[c][j] += to_f(from_f<T>(o[j]));
       }
     }
   }
@@ -176,6 +188,7 @@ __global__ void __launch_bounds__(C == 1 ? 256 : 512, C == 1 ? 3 : 1) layernorm_
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&red[d + j], ag[c][j]);
         atomicAdd(&red[D + d + j], ab[c][j]);
+        if (dx_colsum != nullptr) atomicAdd(&red[2 * D + d + j], ac[c][j]);
       }
     }
   }
@@ -183,6 +196,7 @@ __global__ void __launch_bounds__(C == 1 ? 256 : 512, C == 1 ? 3 : 1) layernorm_
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     atomicAdd(dgamma + i, red[i]);
     atomicAdd(dbeta + i, red[D + i]);
+    if (dx_colsum != nullptr) atomicAdd(dx_colsum + i, red[2 * D + i]);
   }
 }
 
@@ -213,20 +227,28 @@ int egb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
    sum of the two paths costs no extra pass. */
 int egb_layernorm_bwd_res(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                           void* dx, float* dgamma, float* dbeta, const void* dres, int dtype, int M, int D, void* stream) {
+  return egb_layernorm_bwd_ex(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres, nullptr, dtype, M, D, stream);
+}
+
+/* dx_colsum (optional, [D] fp32, ACCUMULATED): column sums of the stored dx -- the bias gradient of the Linear layer
+   whose output was added into the stream this LayerNorm reads (timm `x = x + proj(..)` / `x + fc2(..)`, art.py:293-295),
+   taken while dx is in registers instead of a second pass over dx. */
+int egb_layernorm_bwd_ex(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                         void* dx, float* dgamma, float* dbeta, const void* dres, float* dx_colsum, int dtype, int M,
+                         int D, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   EGB_CHECK(D % 8 == 0 && D <= 256 * LN_MAX_CHUNKS, "layernorm_bwd: unsupported D=%d", D);
-  // 16 warps per CTA, one CTA per SM (two for narrow rows): every CTA ends with 2 D column atomics, and with several
-  // hundred CTAs those serialise per address in L2 (a measurable tail); fewer, fatter CTAs halve it.
-  const size_t smem = (size_t)3 * D * sizeof(float);
+  // few, fat CTAs: every CTA ends with 3 D column atomics, and with several hundred CTAs those serialise per address in
+  // L2 (a measurable tail)
   const int chunks = (D + 255) / 256;
-  // wide rows: 16 warps per CTA, one CTA per SM; narrow rows (one chunk): 8 warps, three CTAs per SM
-  const int threads = chunks == 1 ? 256 : 512;
+  const size_t smem = (size_t)4 * D * sizeof(float);
+  const int threads = chunks == 1 ? LnBwdShape<1>::kThreads : (chunks == 2 ? LnBwdShape<2>::kThreads : LnBwdShape<3>::kThreads);
   int blocks = (M + threads / 32 - 1) / (threads / 32);
-  const int cap = egb_num_sms() * (chunks == 1 ? 3 : 1);
+  const int cap = egb_num_sms() * (chunks == 1 ? LnBwdShape<1>::kCtasPerSm : 1);
   if (blocks > cap) blocks = cap;
 #define EGB_LN_BWD(TT, CC)                                                                                         \
   layernorm_bwd_kernel<TT, CC><<<blocks, threads, smem, st>>>((const TT*)dy, (const TT*)x, gamma, mean, rstd, (TT*)dx, \
-                                                         dgamma, dbeta, (const TT*)dres, M, D)
+                                                         dgamma, dbeta, (const TT*)dres, dx_colsum, M, D)
   if (dtype == EGB_BF16) {
     switch (chunks) {
       case 1: EGB_LN_BWD(bf16, 1); break;

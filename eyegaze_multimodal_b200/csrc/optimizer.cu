@@ -63,11 +63,26 @@ struct AdamArgs {
   // optional device-resident step state (all may be NULL): with these the launch arguments never change from step to
   // step, so the optimiser tail can live inside a captured CUDA graph and needs no host read or write per step
   const float* lr_dev;       // learning rate of this group (written by egb_lr_schedule_step)
-  const float* step_dev;     // 1-based update count shared by the group's tensors (bias corrections)
+  const float* ctrl;         // egb_adamw_prepare's verdict: {skip this step, steps skipped so far, device step count}
   const float* grad_scale;   // gradients are divided by this before use (torch.amp.GradScaler's scale)
-  const float* found_inf;    // != 0: skip the whole update (GradScaler's inf / nan verdict)
-  int skip_nonfinite;        // skip the update when the global gradient norm is inf / nan (our own finite check)
+  int use_dev_step;          // bias corrections from ctrl[2] instead of the per-tensor table column
 };
+
+// One thread, launched between the norm pass and the update: decides ONCE whether this step is skipped (GradScaler's
+// found_inf, or a non-finite global gradient norm) and keeps the counts that make skipped steps invisible to the bias
+// corrections, exactly like torch's fused AdamW under a GradScaler (a skipped step does not advance `step`).
+__global__ void adamw_prepare_kernel(float* ctrl, const float* sqnorm, const float* grad_scale, const float* found_inf,
+                                     int skip_nonfinite, int advance_step) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  bool skip = found_inf != nullptr && *found_inf != 0.f;
+  if (!skip && skip_nonfinite && sqnorm != nullptr) {
+    const float inv = grad_scale != nullptr ? 1.f / *grad_scale : 1.f;
+    skip = !isfinite(sqrtf(*sqnorm) * inv);
+  }
+  ctrl[0] = skip ? 1.f : 0.f;
+  if (skip) ctrl[1] += 1.f;
+  else if (advance_step) ctrl[2] += 1.f;
+}
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamArgs& a, float clip, float decay,
                                       float step_size, float bc2_sqrt) {
@@ -84,19 +99,22 @@ __global__ void __launch_bounds__(256) multi_adamw_kernel(const TensorRec* __res
   const ChunkRec c = C[blockIdx.x];
   const TensorRec t = T[c.tensor];
   if (t.g == nullptr) return;
-  if (a.found_inf != nullptr && *a.found_inf != 0.f) return;          // GradScaler: a non-finite gradient skips the step
+  float skipped = 0.f;
+  if (a.ctrl != nullptr) {
+    if (a.ctrl[0] != 0.f) return;                                     // this step is skipped (egb_adamw_prepare)
+    skipped = a.ctrl[1];
+  }
   const float inv_scale = a.grad_scale != nullptr ? 1.f / *a.grad_scale : 1.f;
   float clip = inv_scale;
-  if (sqnorm != nullptr) {
+  if (sqnorm != nullptr && a.max_norm > 0.f) {
     const float nrm = sqrtf(*sqnorm) * inv_scale;                     // norm of the UNSCALED gradients
-    if (a.skip_nonfinite && !isfinite(nrm)) return;
-    if (a.max_norm > 0.f) clip *= fminf(1.f, a.max_norm / (nrm + 1e-6f));   // clip_grad_norm_
+    clip *= fminf(1.f, a.max_norm / (nrm + 1e-6f));                   // clip_grad_norm_
   }
   const float lr = a.lr_dev != nullptr ? *a.lr_dev : a.lr;
   const float decay = 1.f - lr * a.weight_decay;
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {   // bias corrections of this tensor's step, in double like torch's host code
-    const double step = a.step_dev != nullptr ? (double)*a.step_dev : (double)t.step;
+    const double step = a.use_dev_step ? (double)a.ctrl[2] : (double)t.step - (double)skipped;
     s_bc[0] = (float)(1.0 - pow((double)a.beta1, step));
     s_bc[1] = (float)sqrt(1.0 - pow((double)a.beta2, step));
   }
@@ -157,6 +175,15 @@ int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, in
                                    sqnorm, &none, stream);
 }
 
+int egb_adamw_prepare(float* ctrl, const float* sqnorm, const float* grad_scale, const float* found_inf,
+                      int skip_nonfinite, int advance_step, void* stream) {
+  EGB_CHECK(ctrl != nullptr, "adamw_prepare: ctrl is required");
+  adamw_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ctrl, sqnorm, grad_scale, found_inf, skip_nonfinite, advance_step);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
 int egb_multi_tensor_adamw_ex(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
                               float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm,
                               const egb_adamw_state* state, void* stream) {
@@ -164,8 +191,8 @@ int egb_multi_tensor_adamw_ex(const void* tensor_table, const void* chunk_table,
   EGB_CHECK(tensor_table && chunk_table && state && n_chunks > 0, "multi_tensor_adamw: bad arguments");
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
-  a.lr_dev = state->lr; a.step_dev = state->step; a.grad_scale = state->grad_scale; a.found_inf = state->found_inf;
-  a.skip_nonfinite = state->skip_nonfinite;
+  a.lr_dev = state->lr; a.ctrl = state->ctrl; a.grad_scale = state->grad_scale;
+  a.use_dev_step = state->use_device_step && state->ctrl != nullptr;
   multi_adamw_kernel<<<n_chunks, 256, 0, st>>>((const TensorRec*)tensor_table, (const ChunkRec*)chunk_table, a, sqnorm);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();

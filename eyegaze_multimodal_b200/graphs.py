@@ -31,6 +31,10 @@ class GraphedTrainStep:
     ``example_batch``: dict of CUDA tensors with the shapes / dtypes of every later batch; the step owns static copies
     (``self.batch``) that ``load()`` refills.  ``loss_fn(model, batch) -> scalar tensor`` (or a dict with key 'loss';
     every tensor in the dict becomes a static output readable after ``replay()``).
+
+    No autograd graph of an earlier EAGER step on the default stream may still be alive (e.g. a kept ``loss`` tensor): its
+    AccumulateGrad nodes would run on the legacy default stream during capture, which CUDA rejects
+    (cudaErrorStreamCaptureImplicit).  Drop such tensors first.
     """
 
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example_batch: Dict[str, torch.Tensor],

@@ -11,6 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+from . import torch_ops as TO
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -29,8 +30,8 @@ def normalize_eeg_windows(x: torch.Tensor, enable_preprocessing: bool = True) ->
     if xb.dim() != 3:
         raise ValueError("expected (B, C, T) or (C, T)")
     out = torch.empty_like(xb)
-    L.call("egb_eeg_window_normalize", xb.data_ptr(), out.data_ptr(), xb.shape[0], xb.shape[1], xb.shape[2],
-           0 if enable_preprocessing else 1, _stream())
+    TO.call("eeg_window_normalize", xb, out, xb.shape[0], xb.shape[1], xb.shape[2],
+           0 if enable_preprocessing else 1)
     return out.squeeze(0) if squeeze else out
 
 
@@ -43,7 +44,5 @@ def normalize_images_u8(u8_hwc: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_S
     x = u8_hwc.contiguous()
     B, H, W, _ = x.shape
     out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device)
-    m = (C.c_float * 3)(*[float(v) for v in mean])
-    s = (C.c_float * 3)(*[float(v) for v in std])
-    L.call("egb_image_u8_normalize", x.data_ptr(), out.data_ptr(), B, H, W, m, s, _stream())
+    TO.call("image_u8_normalize", x, out, B, H, W, [float(v) for v in mean], [float(v) for v in std])
     return out

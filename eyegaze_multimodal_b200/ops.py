@@ -1,8 +1,8 @@
 """Host side of the hot path: autograd Functions that launch the sm_100a kernels through the C ABI.
 
-Every Function here enqueues kernels of libeyegaze_b200.so on the current CUDA stream via ctypes
-(raw device pointers + sizes, see include/eyegaze_b200.h); PyTorch only provides device memory, streams and
-the autograd graph between the fused ops.  Activations are stored in the *compute dtype* (fp32 for the
+Every Function here enqueues kernels of libeyegaze_b200.so on the current CUDA stream through the ``torch.library`` ops
+``torch.ops.eyegaze_b200.*`` (torch_ops.py: one op per entry point of include/eyegaze_b200.h, tensors in place of device
+pointers); PyTorch only provides device memory, streams and the autograd graph between the fused ops.  Activations are stored in the *compute dtype* (fp32 for the
 parity mode, bf16 for the throughput mode); parameters stay fp32 ``nn.Parameter``s and are re-cast once
 per parameter version.  Nothing in this file has a CPU or eager fallback.
 """
@@ -14,6 +14,7 @@ import torch
 from torch.utils.weak import WeakIdKeyDictionary
 
 from . import _lib as L
+from . import torch_ops as TO
 
 F32, BF16 = L.F32, L.BF16
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
@@ -42,7 +43,7 @@ def _require_cuda(*ts):
 
 
 def _p(t):
-    return None if t is None else t.data_ptr()
+    return t          # (the registered ops take optional tensors where the C ABI takes nullable pointers)
 
 
 def _rows(t: torch.Tensor):
@@ -63,23 +64,31 @@ def _rows(t: torch.Tensor):
 
 def _operand(t, major):
     t, rows, rpg, rs, gs = _rows(t)
-    return L.Operand(t.data_ptr(), major, rpg, rs, gs, 0, 0), t
+    return TO.Operand(t, major, rpg, rs, gs, 0, 0), t
 
 
 def _matrix(t):
     if t is None:
-        return L.Matrix(None, 0, 0, 0, 0), None
+        return TO.Matrix(None, 0, 0, 0, 0), None
     t, rows, rpg, rs, gs = _rows(t)
-    return L.Matrix(t.data_ptr(), _code(t), rpg, rs, gs), t
+    return TO.Matrix(t, _code(t), rpg, rs, gs), t
 
 
-def _dense_matrix(ptr, code, ld):
-    return L.Matrix(ptr, code, 0, ld, 0)
+def _dense_matrix(t, code, ld):
+    """Dense [rows, ld] matrix starting at the first element of tensor (view) ``t``."""
+    return TO.Matrix(t, code, 0, ld, 0)
+
+
+def _view_at(t, elem_offset=0):
+    """The tensor form of ``t.data_ptr() + elem_offset * itemsize`` (strided sources included)."""
+    if t.is_contiguous():
+        return TO.at(t, elem_offset)
+    return torch.as_strided(t, (1,), (1,), t.storage_offset() + elem_offset)
 
 
 def zeros(shape, dtype, device):
     t = torch.empty(shape, dtype=dtype, device=device)
-    L.call("egb_zero", t.data_ptr(), t.numel() * t.element_size(), _stream())
+    TO.call("zero", t, t.numel() * t.element_size())
     return t
 
 
@@ -127,7 +136,7 @@ def enable_seed_epoch() -> int:
     dev = torch.cuda.current_device()
     if dev not in _seed_epoch_word:
         out = L.vp()
-        L.call("egb_seed_epoch_enable", C.byref(out))
+        L.call("egb_seed_epoch_enable", C.byref(out))       # host-side function (allocates the word): not an op
         _seed_epoch_word[dev] = out.value
     return _seed_epoch_word[dev]
 
@@ -135,25 +144,24 @@ def enable_seed_epoch() -> int:
 def advance_seed_epoch() -> None:
     """One 1-thread launch on the current stream: the next kernels draw fresh dropout masks (capturable)."""
     enable_seed_epoch()
-    L.call("egb_seed_epoch_advance", _stream())
+    TO.call("seed_epoch_advance")
 
 
-def gemm(M, N, K, in_code, a: L.Operand, b: L.Operand, c: L.Matrix, *, bias=None, c_pre=None, residual=None, aux=None,
+def gemm(M, N, K, in_code, a: TO.Operand, b: TO.Operand, c: TO.Matrix, *, bias=None, c_pre=None, residual=None, aux=None,
          alpha=1.0, act=0, act_bwd=0, aux_scale=1.0, dropout_p=0.0, seed=0, accumulate=0, split_k=0, c_colsum=None):
-    empty = L.Matrix(None, 0, 0, 0, 0)
-    d = L.GemmDesc(M, N, K, in_code, a, b, c, c_pre or empty, residual or empty, aux or empty, _p(bias), alpha, act,
-                   act_bwd, aux_scale, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, accumulate, split_k,
-                   _p(c_colsum))
-    L.call("egb_gemm", C.byref(d), _stream())
+    empty = TO.Matrix(None, 0, 0, 0, 0)
+    d = TO.GemmDesc(M, N, K, in_code, a, b, c, c_pre or empty, residual or empty, aux or empty, bias, alpha, act,
+                   act_bwd, aux_scale, float(dropout_p), int(seed), accumulate, split_k, c_colsum)
+    TO.call("gemm", d)
 
 
 def _cast_raw(x: torch.Tensor, code: int) -> torch.Tensor:
     x = x.contiguous()
     out = torch.empty(x.shape, dtype=_TORCH_DT[code], device=x.device)
     if code == F32:
-        L.call("egb_cast_to_f32", x.data_ptr(), _code(x), out.data_ptr(), x.numel(), _stream())
+        TO.call("cast_to_f32", x, _code(x), out, x.numel())
     else:
-        L.call("egb_cast_from_f32", x.data_ptr(), out.data_ptr(), code, x.numel(), _stream())
+        TO.call("cast_from_f32", x, out, code, x.numel())
     return out
 
 
@@ -180,18 +188,15 @@ def cast(x: torch.Tensor, code: int) -> torch.Tensor:
 
 
 def copy_strided4(src, dst, sizes, src_strides, dst_strides, src_offset=0, dst_offset=0):
-    sz = (L.i32 * 4)(*sizes)
-    ss = (L.i64 * 4)(*src_strides)
-    ds = (L.i64 * 4)(*dst_strides)
-    L.call("egb_copy_strided4", src.data_ptr() + src_offset * src.element_size(), _code(src),
-           dst.data_ptr() + dst_offset * dst.element_size(), _code(dst), sz, ss, ds, _stream())
+    sz, ss, ds = [int(v) for v in sizes], [int(v) for v in src_strides], [int(v) for v in dst_strides]
+    TO.call("copy_strided4", _view_at(src, src_offset), _code(src), _view_at(dst, dst_offset), _code(dst), sz, ss, ds)
 
 
 def colsum(x: torch.Tensor, N: int) -> torch.Tensor:
     m, xt = _matrix(x)
     rows = _rows(xt)[1]
     out = small_zeros((N,), x.device)
-    L.call("egb_colsum", C.byref(m), rows, N, out.data_ptr(), 0, _stream())
+    TO.call("colsum", m, rows, N, out, 0)
     return out
 
 
@@ -208,7 +213,7 @@ def next_seed() -> int:
         _seed_state["ctr"] += 1
         x = (base * 0x9E3779B97F4A7C15 + _seed_state["ctr"] * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
         x ^= x >> 31
-        return x
+        return x & 0x7FFFFFFFFFFFFFFF       # 63 bits: travels through int64 op arguments
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -290,10 +295,10 @@ def _linear_forward(x, w2, bias, residual, act, p, seed, out_code, c_pre=None):
     rows = _rows(xt)[1]
     N, K = w2.shape
     y = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=_TORCH_DT[out_code], device=x.device)
-    cm = _dense_matrix(y.data_ptr(), out_code, N)
+    cm = _dense_matrix(y, out_code, N)
     rm, rt = _matrix(residual)
-    pm = _dense_matrix(c_pre.data_ptr(), _code(c_pre), N) if c_pre is not None else None
-    gemm(rows, N, K, _code(xt), a, L.Operand(w2.data_ptr(), 0, 0, w2.stride(0), 0, 0, 0), cm, bias=bias, residual=rm if rt is not None else None,
+    pm = _dense_matrix(c_pre, _code(c_pre), N) if c_pre is not None else None
+    gemm(rows, N, K, _code(xt), a, TO.Operand(w2, 0, 0, w2.stride(0), 0, 0, 0), cm, bias=bias, residual=rm if rt is not None else None,
          c_pre=pm, act=act, dropout_p=p, seed=seed)
     return y
 
@@ -306,9 +311,9 @@ def _grad_input(dpre, w2, x_shape, out_code, act_bwd=0, aux=None, aux_scale=1.0,
     rows = _rows(dt)[1]
     N, K = w2.shape
     dx = torch.empty(tuple(x_shape), dtype=_TORCH_DT[out_code], device=dpre.device)
-    am = _dense_matrix(aux.data_ptr(), _code(aux), K) if aux is not None else None
-    gemm(rows, K, N, _code(dt), a, L.Operand(w2.data_ptr(), 1, 0, w2.stride(0), 0, 0, 0),
-         _dense_matrix(dx.data_ptr(), out_code, K), act_bwd=act_bwd, aux=am, aux_scale=aux_scale, dropout_p=dropout_p,
+    am = _dense_matrix(aux, _code(aux), K) if aux is not None else None
+    gemm(rows, K, N, _code(dt), a, TO.Operand(w2, 1, 0, w2.stride(0), 0, 0, 0),
+         _dense_matrix(dx, out_code, K), act_bwd=act_bwd, aux=am, aux_scale=aux_scale, dropout_p=dropout_p,
          seed=seed, c_colsum=colsum_out)
     return dx
 
@@ -319,7 +324,7 @@ def _grad_weight(dpre, x, N, K):
     b, xt = _operand(x, 1)
     rows = _rows(dt)[1]
     dw = torch.empty(N, K, dtype=torch.float32, device=dpre.device)
-    gemm(N, K, rows, _code(dt), a, b, _dense_matrix(dw.data_ptr(), F32, K), accumulate=2)
+    gemm(N, K, rows, _code(dt), a, b, _dense_matrix(dw, F32, K), accumulate=2)
     return dw
 
 
@@ -329,16 +334,52 @@ def _act_bwd(dy, aux, mode, scale):
     rows = _rows(dt)[1]
     N = dt.shape[-1]
     out = torch.empty(tuple(dy.shape), dtype=dt.dtype, device=dy.device)
-    om = _dense_matrix(out.data_ptr(), _code(out), N)
-    L.call("egb_act_bwd", C.byref(dm), aux.data_ptr(), C.byref(om), rows, N, mode, float(scale), _stream())
+    om = _dense_matrix(out, _code(out), N)
+    TO.call("act_bwd", dm, aux, om, rows, N, mode, float(scale))
     return out
 
 
 def _dropout_bwd(dy, p, seed):
     dy = dy.contiguous()
     out = torch.empty_like(dy)
-    L.call("egb_dropout_bwd", dy.data_ptr(), out.data_ptr(), _code(dy), dy.numel(), float(p), int(seed), _stream())
+    TO.call("dropout_bwd", dy, out, _code(dy), dy.numel(), float(p), int(seed))
     return out
+
+
+def _dropout_bwd_colsum(dy, p, seed, N):
+    """-> (dy * mask / (1-p), its column sums [N] fp32) in ONE pass (the bias gradient of the layer whose epilogue applied
+    the mask); falls back to two passes for row widths the fused kernel does not take."""
+    dy = dy.contiguous()
+    if N % 8 != 0 or N > 1024 or dy.shape[-1] != N:
+        out = _dropout_bwd(dy, p, seed)
+        return out, colsum(out, N)
+    out = torch.empty_like(dy)
+    cs = small_zeros((N,), dy.device)
+    TO.call("dropout_bwd_colsum", dy, out, _code(dy), dy.numel() // N, N, float(p), int(seed),
+           cs)
+    stats["colsum_fused"] += 1
+    return out, cs
+
+
+# Bias gradients without a pass of their own: a kernel that PRODUCES a gradient tensor (LayerNorm backward, attention
+# backward) also accumulates its column sums and hands them along as an attribute of that tensor object; the Linear whose
+# output gradient it is picks them up.  The hint dies with the tensor object, so a gradient that autograd re-creates
+# (accumulation of several consumers, a dtype cast) simply has none and the column-sum pass runs as before.
+stats = {"colsum_fused": 0, "colsum_pass": 0}
+
+
+def _attach_colsum(t, cs):
+    t._egb_colsum = (cs, t._version)       # the version pins the hint to the tensor's CONTENT (autograd may add in place)
+    return t
+
+
+def _bias_grad(dpre, N):
+    hint = getattr(dpre, "_egb_colsum", None)
+    if hint is not None and hint[1] == dpre._version and hint[0].numel() == N and dpre.shape[-1] == N:
+        stats["colsum_fused"] += 1
+        return hint[0]
+    stats["colsum_pass"] += 1
+    return colsum(dpre, N)
 
 
 class LinearFn(torch.autograd.Function):
@@ -372,10 +413,15 @@ class LinearFn(torch.autograd.Function):
         N, K = w2.shape
         if _code(dy) != code:
             dy = cast(dy, code)
+        want_b = has_bias and any(ctx.needs_input_grad[6 + n_w:])
+        db = None
         if act == L.ACT_RELU:
             dpre = _act_bwd(dy, y, 1, 1.0 / (1.0 - p) if p > 0 else 1.0)
         elif p > 0:
-            dpre = _dropout_bwd(dy, p, seed)
+            if want_b:
+                dpre, db = _dropout_bwd_colsum(dy, p, seed, N)
+            else:
+                dpre = _dropout_bwd(dy, p, seed)
         else:
             dpre = dy
         dx = _grad_input(dpre, w2, x.shape, code) if ctx.needs_input_grad[0] else None
@@ -389,8 +435,9 @@ class LinearFn(torch.autograd.Function):
             for i, w in enumerate(weights):
                 dws[i] = dw[r:r + w.shape[0]].view(w.shape)
                 r += w.shape[0]
-        if has_bias and any(ctx.needs_input_grad[6 + n_w:]):
-            db = colsum(dpre, N)
+        if want_b:
+            if db is None:
+                db = _bias_grad(dpre, N)
             r = 0
             for i, w in enumerate(weights):
                 dbs[i] = db[r:r + w.shape[0]]
@@ -435,10 +482,15 @@ class Mlp2Fn(torch.autograd.Function):
         w1c, w2c = weight_plain(w1, code), weight_plain(w2, code)
         if _code(dy) != code:
             dy = cast(dy, code)
-        dyd = _dropout_bwd(dy, p_out, s_out) if p_out > 0 else dy
         need = ctx.needs_input_grad
+        db2 = None
+        if p_out > 0 and need[5]:
+            dyd, db2 = _dropout_bwd_colsum(dy, p_out, s_out, w2.shape[0])
+        else:
+            dyd = _dropout_bwd(dy, p_out, s_out) if p_out > 0 else dy
+            if need[5]:
+                db2 = _bias_grad(dyd, w2.shape[0])
         dw2 = _grad_weight(dyd, h, w2.shape[0], w2.shape[1]) if need[4] else None
-        db2 = colsum(dyd, w2.shape[0]) if need[5] else None
         # dpre1 = (dyd . W2) * act'(.)   -- activation derivative, mid-dropout mask AND the first layer's bias gradient
         # (column sums of dpre1) fused in the GEMM epilogue
         db1 = small_zeros((w1.shape[0],), dy.device) if need[3] else None
@@ -472,8 +524,8 @@ class LayerNormFn(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(M, dtype=torch.float32, device=x.device)
         rstd = torch.empty(M, dtype=torch.float32, device=x.device)
-        L.call("egb_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
-               rstd.data_ptr(), _code(x), M, D, float(eps), _stream())
+        TO.call("layernorm_fwd", x, gamma, beta, y, mean,
+               rstd, _code(x), M, D, float(eps))
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y
 
@@ -486,10 +538,10 @@ class LayerNormFn(torch.autograd.Function):
         if _code(dy) != _code(x):
             dy = cast(dy, _code(x))
         dx = torch.empty_like(x)
-        dgb = small_zeros((2, D), x.device)
-        L.call("egb_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-               dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), _code(x), M, D, _stream())
-        return dx, dgb[0], dgb[1], None
+        dgb = small_zeros((3, D), x.device)        # dgamma | dbeta | column sums of dx (bias gradient of the producer)
+        TO.call("layernorm_bwd_ex", dy, x, gamma, mean, rstd,
+               dx, dgb[0], dgb[1], None, dgb[2], _code(x), M, D)
+        return _attach_colsum(dx, dgb[2]), dgb[0], dgb[1], None
 
 
 def layernorm(x, gamma, beta, eps):
@@ -510,8 +562,8 @@ class LayerNormResidualFn(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(M, dtype=torch.float32, device=x.device)
         rstd = torch.empty(M, dtype=torch.float32, device=x.device)
-        L.call("egb_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
-               rstd.data_ptr(), _code(x), M, D, float(eps), _stream())
+        TO.call("layernorm_fwd", x, gamma, beta, y, mean,
+               rstd, _code(x), M, D, float(eps))
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y, x.view_as(x)
 
@@ -521,7 +573,7 @@ class LayerNormResidualFn(torch.autograd.Function):
         D = x.shape[-1]
         M = x.numel() // D
         code = _code(x)
-        dgb = small_zeros((2, D), x.device)
+        dgb = small_zeros((3, D), x.device)
         if dy is None:                      # only the residual path was used
             return dres, dgb[0], dgb[1], None
         dy = dy.contiguous()
@@ -532,9 +584,9 @@ class LayerNormResidualFn(torch.autograd.Function):
             if _code(dres) != code:
                 dres = cast(dres, code)
         dx = torch.empty_like(x)
-        L.call("egb_layernorm_bwd_res", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-               dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), _p(dres), code, M, D, _stream())
-        return dx, dgb[0], dgb[1], None
+        TO.call("layernorm_bwd_ex", dy, x, gamma, mean, rstd,
+               dx, dgb[0], dgb[1], _p(dres), dgb[2], code, M, D)
+        return _attach_colsum(dx, dgb[2]), dgb[0], dgb[1], None
 
 
 def layernorm_residual(x, gamma, beta, eps):
@@ -547,6 +599,10 @@ def layernorm_residual(x, gamma, beta, eps):
 # ------------------------------------------------------------------------------------------------------
 # fused attention
 # ------------------------------------------------------------------------------------------------------
+import os as _os
+_ATT_COLSUM = _os.environ.get("EGB_ATT_COLSUM", "1") != "0"     # 0: bias gradient of qkv by a separate column-sum pass
+
+
 def _att_strides(t):
     """(batch_stride, row_stride) of a [S, L, H*dk] view with contiguous last dim."""
     return t.stride(0), t.stride(1)
@@ -578,16 +634,16 @@ class AttentionFn(torch.autograd.Function):
         lse = torch.empty(S, heads, Lq, dtype=torch.float32, device=q.device)
         probs = torch.empty(S, heads, Lq, Lk, dtype=torch.float32, device=q.device) if want_probs else None
         seed = next_seed() if p > 0 else 0
-        d = L.AttentionDesc()
-        d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+        d = TO.AttentionDesc()
+        d.q, d.k, d.v, d.o = q, k, v, o
         d.q_bs, d.q_rs = _att_strides(q)
         d.k_bs, d.k_rs = _att_strides(k)
         d.v_bs, d.v_rs = _att_strides(v)
         d.o_bs, d.o_rs = _att_strides(o)
-        d.lse, d.probs = lse.data_ptr(), _p(probs)
+        d.lse, d.probs = lse, probs
         d.dtype, d.S, d.H, d.Lq, d.Lk, d.head_dim, d.kv_shift = code, S, heads, Lq, Lk, dk, kv_shift
         d.scale, d.dropout_p, d.seed = float(scale), float(p), seed
-        L.call("egb_attention_fwd", C.byref(d), _stream())
+        TO.call("attention_fwd", d)
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.meta = (heads, kv_shift, p, scale, seed, packed)
         if want_probs:
@@ -613,24 +669,29 @@ class AttentionFn(torch.autograd.Function):
             dk_ = torch.empty(S, Lk, D, dtype=q.dtype, device=q.device)
             dv = torch.empty(S, Lk, D, dtype=q.dtype, device=q.device)
         delta = torch.empty(S, heads, Lq, dtype=torch.float32, device=q.device)
-        d = L.AttentionDesc()
-        d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+        d = TO.AttentionDesc()
+        d.q, d.k, d.v, d.o = q, k, v, o
         d.q_bs, d.q_rs = _att_strides(q)
         d.k_bs, d.k_rs = _att_strides(k)
         d.v_bs, d.v_rs = _att_strides(v)
         d.o_bs, d.o_rs = _att_strides(o)
-        d.d_o = do.data_ptr()
+        d.d_o = do
         d.do_bs, d.do_rs = _att_strides(do)
-        d.dq, d.dk, d.dv = dq.data_ptr(), dk_.data_ptr(), dv.data_ptr()
+        d.dq, d.dk, d.dv = dq, dk_, dv
         d.dq_bs, d.dq_rs = _att_strides(dq)
         d.dk_bs, d.dk_rs = _att_strides(dk_)
         d.dv_bs, d.dv_rs = _att_strides(dv)
-        d.lse, d.delta, d.probs = lse.data_ptr(), delta.data_ptr(), None
+        d.lse, d.delta, d.probs = lse, delta, None
         d.dtype, d.S, d.H, d.Lq, d.Lk, d.head_dim, d.kv_shift = code, S, heads, Lq, Lk, D // heads, kv_shift
         d.scale, d.dropout_p, d.seed = float(scale), float(p), seed
-        L.call("egb_attention_bwd", C.byref(d), _stream())
+        cs = None
+        if packed and _ATT_COLSUM:
+            # column sums of dq | dk | dv = the bias gradient of the packed qkv projection, taken as the tiles leave the kernel
+            cs = small_zeros((3 * D,), q.device)
+            d.dq_colsum, d.dk_colsum, d.dv_colsum = cs[:D], cs[D:2 * D], cs[2 * D:]
+        TO.call("attention_bwd", d)
         if packed:
-            return dqkv, None, None, None, None, None, None, None, None
+            return (_attach_colsum(dqkv, cs) if cs is not None else dqkv), None, None, None, None, None, None, None, None
         return dq, dk_, dv, None, None, None, None, None, None
 
 
@@ -708,7 +769,7 @@ class TemporalConvFn(torch.autograd.Function):
         while (Tp * Cin) % 8:
             Tp += 1
         xp = torch.empty(S, Tp, Cin, dtype=tdt, device=dev)
-        L.call("egb_eeg_pack", eeg1.data_ptr(), eeg2.data_ptr(), xp.data_ptr(), code, B, Cin, T, pad, Tp, _stream())
+        TO.call("eeg_pack", eeg1, eeg2, xp, code, B, Cin, T, pad, Tp)
         bufs, geo, seeds = [xp], [(T, Tp, Cin)], []
         cur, t_in, tp_in, c_in = xp, T, Tp, Cin
         for i in range(n):
@@ -720,10 +781,10 @@ class TemporalConvFn(torch.autograd.Function):
             wr = _conv_weight(ws[i], code)
             seed = next_seed() if p > 0 else 0
             seeds.append(seed)
-            a = L.Operand(cur.data_ptr(), 0, t_out, stride * c_in, tp_in * c_in, 0, 0)
+            a = TO.Operand(cur, 0, t_out, stride * c_in, tp_in * c_in, 0, 0)
             off = 0 if last else pad * O
-            cm = L.Matrix(out.data_ptr() + off * out.element_size(), code, t_out, O, tp_out * O)
-            gemm(S * t_out, O, ksz * c_in, code, a, L.Operand(wr.data_ptr(), 0, 0, wr.stride(0), 0, 0, 0), cm,
+            cm = TO.Matrix(TO.at(out, off), code, t_out, O, tp_out * O)
+            gemm(S * t_out, O, ksz * c_in, code, a, TO.Operand(wr, 0, 0, wr.stride(0), 0, 0, 0), cm,
                  bias=bs[i].detach(), act=L.ACT_RELU, dropout_p=p, seed=seed)
             bufs.append(out)
             geo.append((t_out, tp_out, O))
@@ -753,8 +814,8 @@ class TemporalConvFn(torch.autograd.Function):
         rp = front + t_out + J
         g = zeros((S, rp, O), tdt, dev)
         dm, dht = _matrix(dh)
-        gm = L.Matrix(g.data_ptr() + front * O * g.element_size(), code, t_out, O, rp * O)
-        L.call("egb_act_bwd", C.byref(dm), bufs[n].data_ptr(), C.byref(gm), S * t_out, O, 1, float(scale), _stream())
+        gm = TO.Matrix(TO.at(g, front * O), code, t_out, O, rp * O)
+        TO.call("act_bwd", dm, bufs[n], gm, S * t_out, O, 1, float(scale))
         g_front, g_rp = front, rp
         if _debug is not None:
             _debug["g0"] = (g.clone(), front, rp)
@@ -762,18 +823,18 @@ class TemporalConvFn(torch.autograd.Function):
             t_out, _, O = geo[i + 1]
             t_in, tp_in, c_in = geo[i]
             src = bufs[i]
-            g_ptr = g.data_ptr() + g_front * O * g.element_size()
+            g_ptr = TO.at(g, g_front * O)
             # dW[O, K*C] = dpre^T . (overlapping-row view of the layer input); db = column sums
             if ctx.needs_input_grad[5 + i]:
                 dw = torch.empty(O, ksz * c_in, dtype=torch.float32, device=dev)
-                gemm(O, ksz * c_in, S * t_out, code, L.Operand(g_ptr, 1, t_out, O, g_rp * O, 0, 0),
-                     L.Operand(src.data_ptr(), 1, t_out, stride * c_in, tp_in * c_in, 0, 0),
-                     _dense_matrix(dw.data_ptr(), F32, ksz * c_in), accumulate=2)
+                gemm(O, ksz * c_in, S * t_out, code, TO.Operand(g_ptr, 1, t_out, O, g_rp * O, 0, 0),
+                     TO.Operand(src, 1, t_out, stride * c_in, tp_in * c_in, 0, 0),
+                     _dense_matrix(dw, F32, ksz * c_in), accumulate=2)
                 dws[i] = dw.view(O, ksz, c_in).permute(0, 2, 1)
             if ctx.needs_input_grad[5 + n + i]:
                 db = torch.empty(O, dtype=torch.float32, device=dev)
-                gmat = L.Matrix(g_ptr, code, t_out, O, g_rp * O)
-                L.call("egb_colsum", C.byref(gmat), S * t_out, O, db.data_ptr(), 1, _stream())
+                gmat = TO.Matrix(g_ptr, code, t_out, O, g_rp * O)
+                TO.call("colsum", gmat, S * t_out, O, db, 1)
                 dbs[i] = db
             if i == 0:
                 break
@@ -786,11 +847,11 @@ class TemporalConvFn(torch.autograd.Function):
             rows = (t_in + stride - 1) // stride
             slab0 = g_front - (J - 1 - s0)
             for ph in range(stride):
-                a = L.Operand(g.data_ptr() + slab0 * O * g.element_size(), 0, rows, O, g_rp * O, 0, 0)
-                bop = L.Operand(wp.data_ptr() + ph * c_in * J * O * wp.element_size(), 0, 0, J * O, 0, 0, 0)
+                a = TO.Operand(TO.at(g, slab0 * O), 0, rows, O, g_rp * O, 0, 0)
+                bop = TO.Operand(TO.at(wp, ph * c_in * J * O), 0, 0, J * O, 0, 0, 0)
                 off = (pad + ph) * c_in
-                cm = L.Matrix(g_prev.data_ptr() + off * g_prev.element_size(), code, rows, stride * c_in, tp_in * c_in)
-                am = L.Matrix(src.data_ptr() + off * src.element_size(), code, rows, stride * c_in, tp_in * c_in)
+                cm = TO.Matrix(TO.at(g_prev, off), code, rows, stride * c_in, tp_in * c_in)
+                am = TO.Matrix(TO.at(src, off), code, rows, stride * c_in, tp_in * c_in)
                 gemm(S * rows, c_in, J * O, code, a, bop, cm, act_bwd=L.ACTBWD_RELU_MASK, aux=am, aux_scale=scale)
             g, g_front, g_rp = g_prev, pad, tp_in
             if _debug is not None:
@@ -847,17 +908,17 @@ def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
     tdt = _TORCH_DT[code]
     frames = 1 + T // hop
     img = torch.empty(N, bins, frames, dtype=torch.float32, device=dev)
-    L.call("egb_stft_logmag", eeg1.data_ptr(), eeg2.data_ptr(), window.data_ptr(), img.data_ptr(), B * Cc, T, n_fft,
-           hop, bins, _stream())
+    TO.call("stft_logmag", eeg1, eeg2, window, img, B * Cc, T, n_fft,
+           hop, bins)
     H1, W1, Wp, RP, slack = _spec_geometry(bins, frames)
     p1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
-    L.call("egb_spec_conv1_pool_fwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), p1.data_ptr(), code, N, bins,
-           frames, p1.numel(), _stream())
+    TO.call("spec_conv1_pool_fwd", img, w1, b1, p1, code, N, bins,
+           frames, p1.numel())
     y2 = zeros(((N * RP + slack) * 64,), tdt, dev)
     w2s = _spec_w2_seg(w2, code)
-    a = L.Operand(p1.data_ptr(), 0, 0, 32, 0, 128, Wp)
-    cm = _dense_matrix(y2.data_ptr() + (Wp + 1) * 64 * y2.element_size(), code, 64)
-    gemm(N * RP, 64, 384, code, a, L.Operand(w2s.data_ptr(), 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
+    a = TO.Operand(p1, 0, 0, 32, 0, 128, Wp)
+    cm = _dense_matrix(TO.at(y2, (Wp + 1) * 64), code, 64)
+    gemm(N * RP, 64, 384, code, a, TO.Operand(w2s, 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
     return img, p1, y2, (code, N, bins, frames, H1, W1, Wp, RP, slack)
 
 
@@ -868,25 +929,25 @@ def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
     dw1 = db1 = dw2 = db2 = None
     if need_b2:
         db2 = torch.empty(64, dtype=torch.float32, device=dev)
-        m = _dense_matrix(dy2.data_ptr(), code, 64)
-        L.call("egb_colsum", C.byref(m), N * RP, 64, db2.data_ptr(), 1, _stream())
+        m = _dense_matrix(dy2, code, 64)
+        TO.call("colsum", m, N * RP, 64, db2, 1)
     esz = dy2.element_size()
     if need_w2:
         # dW2[o, (kh, kw4, c)] = sum over flat padded positions of dY[m + Wp + 1, o] * P1[m + kh*Wp, kw4*32 + c]
         dw = torch.empty(64, 384, dtype=torch.float32, device=dev)
-        gemm(64, 384, N * RP, code, L.Operand(dy2.data_ptr() + (Wp + 1) * 64 * esz, 1, 0, 64, 0, 0, 0),
-             L.Operand(p1.data_ptr(), 1, 0, 32, 0, 128, Wp), _dense_matrix(dw.data_ptr(), F32, 384), accumulate=2)
+        gemm(64, 384, N * RP, code, TO.Operand(TO.at(dy2, (Wp + 1) * 64), 1, 0, 64, 0, 0, 0),
+             TO.Operand(p1, 1, 0, 32, 0, 128, Wp), _dense_matrix(dw, F32, 384), accumulate=2)
         dw2 = dw.view(64, 3, 4, 32)[:, :, :3, :].permute(0, 3, 1, 2)
     if need_w1:
         # dP1 (padded layout) = full correlation of dY with the flipped kernel: same implicit GEMM, K = 3 x 256
         w2f = _spec_w2_flip(w2, code)
         dp1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
-        a = L.Operand(dy2.data_ptr(), 0, 0, 64, 0, 256, Wp)
-        cm = _dense_matrix(dp1.data_ptr() + (Wp + 1) * 32 * esz, code, 32)
-        gemm(N * RP, 32, 768, code, a, L.Operand(w2f.data_ptr(), 0, 0, 768, 0, 0, 0), cm)
+        a = TO.Operand(dy2, 0, 0, 64, 0, 256, Wp)
+        cm = _dense_matrix(TO.at(dp1, (Wp + 1) * 32), code, 32)
+        gemm(N * RP, 32, 768, code, a, TO.Operand(w2f, 0, 0, 768, 0, 0, 0), cm)
         dwb = zeros((320,), torch.float32, dev)
-        L.call("egb_spec_conv1_pool_bwd", img.data_ptr(), w1.data_ptr(), b1.data_ptr(), dp1.data_ptr(), code,
-               dwb.data_ptr(), dwb.data_ptr() + 288 * 4, N, bins, frames, _stream())
+        TO.call("spec_conv1_pool_bwd", img, w1, b1, dp1, code,
+               dwb, dwb[288:], N, bins, frames)
         dw1 = dwb[:288].view(32, 1, 3, 3)
         db1 = dwb[288:]
     return dw1, db1, dw2, db2
@@ -920,7 +981,7 @@ class SpectrogramCNNFn(torch.autograd.Function):
         img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
         code, N, bins, frames, H1, W1, Wp, RP, slack = meta
         pooled = torch.empty(N, 1024, dtype=_TORCH_DT[code], device=img.device)
-        L.call("egb_relu_avgpool_fwd", y2.data_ptr(), pooled.data_ptr(), code, N, H1, W1, _stream())
+        TO.call("relu_avgpool_fwd", y2, pooled, code, N, H1, W1)
         ctx.save_for_backward(img, p1, y2, w1, b1, w2)
         ctx.meta = meta
         return pooled
@@ -934,7 +995,7 @@ class SpectrogramCNNFn(torch.autograd.Function):
         if _code(dpool) != code:
             dpool = cast(dpool, code)
         dy2 = zeros(((N * RP + slack) * 64,), tdt, dev)
-        L.call("egb_relu_avgpool_bwd", y2.data_ptr(), dpool.data_ptr(), dy2.data_ptr(), code, N, H1, W1, _stream())
+        TO.call("relu_avgpool_bwd", y2, dpool, dy2, code, N, H1, W1)
         need = ctx.needs_input_grad
         dw1, db1, dw2, db2 = _spec_front_bwd(dy2, img, p1, w1, b1, w2, ctx.meta, need[3] or need[4], need[5], need[6])
         return None, None, None, dw1, db1, dw2, db2, None, None, None, None
@@ -978,7 +1039,7 @@ class SpecPoolFn(torch.autograd.Function):
         meta = (code, N, bins, frames, H1, W1, Wp, RP, slack)
         y2 = _spec_nchw_to_padded(y2n.float(), meta, 64)
         pooled = torch.empty(N, 1024, dtype=_TORCH_DT[code], device=y2n.device)
-        L.call("egb_relu_avgpool_fwd", y2.data_ptr(), pooled.data_ptr(), code, N, H1, W1, _stream())
+        TO.call("relu_avgpool_fwd", y2, pooled, code, N, H1, W1)
         ctx.save_for_backward(y2)
         ctx.meta = meta
         return pooled
@@ -991,7 +1052,7 @@ class SpecPoolFn(torch.autograd.Function):
         if _code(dpool) != code:
             dpool = cast(dpool, code)
         dy2 = zeros(((N * RP + slack) * 64,), _TORCH_DT[code], dpool.device)
-        L.call("egb_relu_avgpool_bwd", y2.data_ptr(), dpool.data_ptr(), dy2.data_ptr(), code, N, H1, W1, _stream())
+        TO.call("relu_avgpool_bwd", y2, dpool, dy2, code, N, H1, W1)
         return _spec_padded_to_nchw(dy2, ctx.meta, 64), None, None, None
 
 
@@ -1039,12 +1100,12 @@ def ibs_connectivity(eeg1, eeg2, fs, bands, feature_indices, chunk=256):
         dev = eeg1.device
         nb, nf = len(bands), len(feature_indices)
         bins = band_bins(T, fs, bands)
-        lo = (L.i32 * nb)(*[b[0] for b in bins])
-        hi = (L.i32 * nb)(*[b[1] for b in bins])
+        lo = [b[0] for b in bins]
+        hi = [b[1] for b in bins]
         slot = [-1] * 7
         for s, f in enumerate(feature_indices):
             slot[f] = s
-        slot_c = (L.i32 * 7)(*slot)
+        slot_c = list(slot)
         valid = [b for b in bins if b[0] <= b[1]]
         nbins = (max(b[1] for b in valid) - min(b[0] for b in valid) + 1) if valid else 1
         out = torch.empty(B, nb, nf, Cc, Cc, dtype=torch.float32, device=dev)
@@ -1056,9 +1117,9 @@ def ibs_connectivity(eeg1, eeg2, fs, bands, feature_indices, chunk=256):
         pspec = torch.empty(cb * 2 * Cc * nbins, dtype=torch.float32, device=dev)
         for b0 in range(0, B, cb):
             n = min(cb, B - b0)
-            L.call("egb_ibs_connectivity", eeg1[b0:].data_ptr(), eeg2[b0:].data_ptr(), tw.data_ptr(), phase.data_ptr(),
-                   xb.data_ptr(), stats.data_ptr(), pspec.data_ptr(), out[b0:].data_ptr(), n, Cc, T, nb, lo, hi, slot_c,
-                   nf, _stream())
+            TO.call("ibs_connectivity", eeg1[b0:], eeg2[b0:], tw, phase,
+                   xb, stats, pspec, out[b0:], n, Cc, T, nb, lo, hi, slot_c,
+                   nf)
         return out
 
 
@@ -1071,8 +1132,8 @@ class InstNormTokensFn(torch.autograd.Function):
         x = x.contiguous().float()
         B, NT, P = x.shape
         y = torch.empty(B, NT, P, dtype=_TORCH_DT[code], device=x.device)
-        L.call("egb_instnorm_tokens_fwd", x.data_ptr(), _p(gamma), _p(beta), y.data_ptr(), code, B, NT, P, 1e-5,
-               1 if apply_norm else 0, _stream())
+        TO.call("instnorm_tokens_fwd", x, _p(gamma), _p(beta), y, code, B, NT, P, 1e-5,
+               1 if apply_norm else 0)
         ctx.save_for_backward(x)
         ctx.meta = (code, apply_norm)
         return y
@@ -1088,8 +1149,8 @@ class InstNormTokensFn(torch.autograd.Function):
         if _code(dy) != code:
             dy = cast(dy, code)
         dgb = zeros((2, P), torch.float32, x.device)
-        L.call("egb_instnorm_tokens_bwd", x.data_ptr(), dy.data_ptr(), code, dgb[0].data_ptr(), dgb[1].data_ptr(), B, NT,
-               P, 1e-5, _stream())
+        TO.call("instnorm_tokens_bwd", x, dy, code, dgb[0], dgb[1], B, NT,
+               P, 1e-5)
         return None, dgb[0], dgb[1], None, None
 
 
@@ -1117,8 +1178,8 @@ class SeqAssembleFn(torch.autograd.Function):
         spec = cast(spec.contiguous(), code) if spec is not None else None
         h = cast(h.contiguous(), code)
         out = torch.empty(S, Lq, D, dtype=_TORCH_DT[code], device=h.device)
-        L.call("egb_seq_assemble_fwd", cls.data_ptr(), pos.data_ptr(), _p(ibs), _p(spec), h.data_ptr(), out.data_ptr(),
-               code, S, B, Lq, D, n_ibs, n_spec, n_h, _stream())
+        TO.call("seq_assemble_fwd", cls, pos, _p(ibs), _p(spec), h, out,
+               code, S, B, Lq, D, n_ibs, n_spec, n_h)
         ctx.meta = (code, S, B, Lq, D, n_ibs, n_spec, n_h, pos.shape[0])
         return out
 
@@ -1130,7 +1191,7 @@ class SeqAssembleFn(torch.autograd.Function):
             dx = cast(dx, code)
         dpos = zeros((max_len, D), torch.float32, dx.device)
         dibs = torch.empty(B, n_ibs, D, dtype=dx.dtype, device=dx.device) if n_ibs else None
-        L.call("egb_seq_assemble_bwd", dx.data_ptr(), dpos.data_ptr(), _p(dibs), code, S, B, Lq, D, n_ibs, _stream())
+        TO.call("seq_assemble_bwd", dx, dpos, _p(dibs), code, S, B, Lq, D, n_ibs)
         # cls also collects pos row 0's sum: both parameters receive the same batch-summed row, as SEPARATE tensors
         # (autograd keeps the returned tensors as .grad; aliased gradients would be scaled twice by in-place clipping /
         # GradScaler.unscale_)
@@ -1152,7 +1213,7 @@ class AddRowsBroadcastFn(torch.autograd.Function):
         x = x.contiguous()
         B, NT, D = x.shape
         out = torch.empty_like(x)
-        L.call("egb_add_rows_broadcast", x.data_ptr(), e.data_ptr(), out.data_ptr(), _code(x), B * NT, NT, D, _stream())
+        TO.call("add_rows_broadcast", x, e, out, _code(x), B * NT, NT, D)
         ctx.meta = (B, NT, D)
         return out
 
@@ -1163,7 +1224,7 @@ class AddRowsBroadcastFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dyc = dy.contiguous()
             de = zeros((NT, D), torch.float32, dy.device)
-            L.call("egb_seq_assemble_bwd", dyc.data_ptr(), de.data_ptr(), None, _code(dyc), B, B, NT, D, 0, _stream())
+            TO.call("seq_assemble_bwd", dyc, de, None, _code(dyc), B, B, NT, D, 0)
             de = de.view(1, NT, D)
         return dy, de
 
@@ -1182,8 +1243,8 @@ def ibs_scalar_features(eeg1, eeg2, fs, bands, chunk=256):
         dev = eeg1.device
         nb = len(bands)
         bins = band_bins(T, fs, bands)
-        lo = (L.i32 * nb)(*[b[0] for b in bins])
-        hi = (L.i32 * nb)(*[b[1] for b in bins])
+        lo = [b[0] for b in bins]
+        hi = [b[1] for b in bins]
         valid = [b for b in bins if b[0] <= b[1]]
         nbins = (max(b[1] for b in valid) - min(b[0] for b in valid) + 1) if valid else 1
         out = torch.empty(B, nb * 7, dtype=torch.float32, device=dev)
@@ -1196,9 +1257,9 @@ def ibs_scalar_features(eeg1, eeg2, fs, bands, chunk=256):
         cspec = torch.empty(cb * 2 * Cc * nbins * 2, dtype=torch.float32, device=dev)
         for b0 in range(0, B, cb):
             n = min(cb, B - b0)
-            L.call("egb_ibs_scalar_features", eeg1[b0:].data_ptr(), eeg2[b0:].data_ptr(), tw.data_ptr(), phase.data_ptr(),
-                   xb.data_ptr(), stats.data_ptr(), pspec.data_ptr(), cspec.data_ptr(), out[b0:].data_ptr(), n, Cc, T, nb,
-                   lo, hi, _stream())
+            TO.call("ibs_scalar_features", eeg1[b0:], eeg2[b0:], tw, phase,
+                   xb, stats, pspec, cspec, out[b0:], n, Cc, T, nb,
+                   lo, hi)
         return out
 
 
@@ -1218,8 +1279,8 @@ class TailPoolFn(torch.autograd.Function):
         sym = torch.empty(B, 3 * D, dtype=f, device=dev)
         zf = torch.empty(B, 3 * D, dtype=f, device=dev)
         ibs_pool = torch.empty(B, D, dtype=f, device=dev) if n_ibs > 0 else None
-        L.call("egb_tail_pool_fwd", z.data_ptr(), _code(z), cls1.data_ptr(), cls2.data_ptr(), sym.data_ptr(), zf.data_ptr(),
-               _p(ibs_pool), B, Lq, D, n_ibs, offset, 1 if ibs_single else 0, _stream())
+        TO.call("tail_pool_fwd", z, _code(z), cls1, cls2, sym, zf,
+               _p(ibs_pool), B, Lq, D, n_ibs, offset, 1 if ibs_single else 0)
         ctx.save_for_backward(z)
         ctx.meta = (n_ibs, offset, ibs_single)
         mp = zf[:, D:]
@@ -1243,8 +1304,8 @@ class TailPoolFn(torch.autograd.Function):
         if dmp is not None:
             copy_strided4(dmp.contiguous().float(), dzf, (1, 1, B, 2 * D), (0, 0, 2 * D, 1), (0, 0, 3 * D, 1), dst_offset=D)
         dz = torch.empty_like(z)
-        L.call("egb_tail_pool_bwd", z.data_ptr(), _code(z), _p(dcls1), _p(dcls2), dsym.data_ptr(), dzf.data_ptr(), _p(dibs),
-               dz.data_ptr(), B, Lq, D, n_ibs, offset, 1 if ibs_single else 0, _stream())
+        TO.call("tail_pool_bwd", z, _code(z), _p(dcls1), _p(dcls2), dsym, dzf, _p(dibs),
+               dz, B, Lq, D, n_ibs, offset, 1 if ibs_single else 0)
         return dz, None, None, None
 
 
@@ -1287,7 +1348,7 @@ class CrossEntropyFn(torch.autograd.Function):
         B, Cn = logits.shape
         loss = torch.empty((), dtype=torch.float32, device=logits.device)
         dl = torch.empty_like(logits)
-        L.call("egb_cross_entropy", logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), dl.data_ptr(), B, Cn, _stream())
+        TO.call("cross_entropy", logits, labels, loss, dl, B, Cn)
         ctx.save_for_backward(dl)
         return loss
 
@@ -1296,7 +1357,7 @@ class CrossEntropyFn(torch.autograd.Function):
         (dl,) = ctx.saved_tensors
         g = g.contiguous().float()
         out = torch.empty_like(dl)
-        L.call("egb_scale_by_device_scalar", dl.data_ptr(), g.data_ptr(), out.data_ptr(), dl.numel(), _stream())
+        TO.call("scale_by_device_scalar", dl, g, out, dl.numel())
         return out, None
 
 
@@ -1317,7 +1378,7 @@ class L2NormalizeRowsFn(torch.autograd.Function):
         R, D = x.shape
         y = torch.empty_like(x)
         inv = torch.empty(R, dtype=torch.float32, device=x.device)
-        L.call("egb_l2norm_rows_fwd", x.data_ptr(), y.data_ptr(), inv.data_ptr(), R, D, 1e-12, _stream())
+        TO.call("l2norm_rows_fwd", x, y, inv, R, D, 1e-12)
         ctx.save_for_backward(y, inv)
         return y
 
@@ -1326,8 +1387,7 @@ class L2NormalizeRowsFn(torch.autograd.Function):
         y, inv = ctx.saved_tensors
         dy = dy.contiguous().float()
         dx = torch.empty_like(y)
-        L.call("egb_l2norm_rows_bwd", dy.data_ptr(), y.data_ptr(), inv.data_ptr(), dx.data_ptr(), y.shape[0], y.shape[1],
-               _stream())
+        TO.call("l2norm_rows_bwd", dy, y, inv, dx, y.shape[0], y.shape[1])
         return dx
 
 
@@ -1369,16 +1429,16 @@ class SimilarityLossFn(torch.autograd.Function):
         N = b.shape[0]
         dev = a.device
         sim = torch.empty(B, N, dtype=torch.float32, device=dev)
-        gemm(B, N, D, F32, L.Operand(a.data_ptr(), 0, 0, D, 0, 0, 0), L.Operand(b.data_ptr(), 0, 0, D, 0, 0, 0),
-             _dense_matrix(sim.data_ptr(), F32, N), alpha=1.0 / temperature)
+        gemm(B, N, D, F32, TO.Operand(a, 0, 0, D, 0, 0, 0), TO.Operand(b, 0, 0, D, 0, 0, 0),
+             _dense_matrix(sim, F32, N), alpha=1.0 / temperature)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         if kind == "infonce":
-            L.call("egb_infonce_rows", sim.data_ptr(), loss.data_ptr(), B, N, _stream())
+            TO.call("infonce_rows", sim, loss, B, N)
         else:
             labels = labels.contiguous().long()
             scratch = torch.empty(3 * B + 2, dtype=torch.float32, device=dev)
-            L.call("egb_supcon_rows", sim.data_ptr(), labels.data_ptr(), scratch.data_ptr(), scratch.data_ptr() + 12 * B,
-                   loss.data_ptr(), B, _stream())
+            TO.call("supcon_rows", sim, labels, scratch, scratch[3 * B:],
+                   loss, B)
         ctx.save_for_backward(a, b, sim)
         ctx.meta = (temperature, same)
         return loss
@@ -1393,20 +1453,20 @@ class SimilarityLossFn(torch.autograd.Function):
         g = g.contiguous().float()
         # da[B, d] = G[B, N] . b[N, d]   (b consumed as an MN-major operand);   db[N, d] = G^T . a
         da = torch.empty(B, D, dtype=torch.float32, device=dev)
-        gemm(B, D, N, F32, L.Operand(G.data_ptr(), 0, 0, N, 0, 0, 0), L.Operand(b.data_ptr(), 1, 0, D, 0, 0, 0),
-             _dense_matrix(da.data_ptr(), F32, D), alpha=1.0 / temperature)
+        gemm(B, D, N, F32, TO.Operand(G, 0, 0, N, 0, 0, 0), TO.Operand(b, 1, 0, D, 0, 0, 0),
+             _dense_matrix(da, F32, D), alpha=1.0 / temperature)
         db = torch.empty(N, D, dtype=torch.float32, device=dev)
-        gemm(N, D, B, F32, L.Operand(G.data_ptr(), 1, 0, N, 0, 0, 0), L.Operand(a.data_ptr(), 1, 0, D, 0, 0, 0),
-             _dense_matrix(db.data_ptr(), F32, D), alpha=1.0 / temperature)
+        gemm(N, D, B, F32, TO.Operand(G, 1, 0, N, 0, 0, 0), TO.Operand(a, 1, 0, D, 0, 0, 0),
+             _dense_matrix(db, F32, D), alpha=1.0 / temperature)
         if same:
             da = da + db          # sim = a a^T: both factors are the same tensor
             db = None
         out_a = torch.empty_like(da)
-        L.call("egb_scale_by_device_scalar", da.data_ptr(), g.data_ptr(), out_a.data_ptr(), da.numel(), _stream())
+        TO.call("scale_by_device_scalar", da, g, out_a, da.numel())
         out_b = None
         if db is not None:
             out_b = torch.empty_like(db)
-            L.call("egb_scale_by_device_scalar", db.data_ptr(), g.data_ptr(), out_b.data_ptr(), db.numel(), _stream())
+            TO.call("scale_by_device_scalar", db, g, out_b, db.numel())
         return out_a, out_b, None, None, None
 
 
@@ -1425,7 +1485,7 @@ class MseLossFn(torch.autograd.Function):
         a, b = a.contiguous().float(), b.contiguous().float()
         da = torch.empty_like(a)
         loss = torch.empty((), dtype=torch.float32, device=a.device)
-        L.call("egb_mse_loss", a.data_ptr(), b.data_ptr(), da.data_ptr(), loss.data_ptr(), a.numel(), _stream())
+        TO.call("mse_loss", a, b, da, loss, a.numel())
         ctx.save_for_backward(da)
         return loss
 
@@ -1433,8 +1493,7 @@ class MseLossFn(torch.autograd.Function):
     def backward(ctx, g):
         (da,) = ctx.saved_tensors
         out = torch.empty_like(da)
-        L.call("egb_scale_by_device_scalar", da.data_ptr(), g.contiguous().float().data_ptr(), out.data_ptr(), da.numel(),
-               _stream())
+        TO.call("scale_by_device_scalar", da, g.contiguous().float(), out, da.numel())
         return out, -out
 
 
@@ -1446,9 +1505,9 @@ FUZZY_MODES = {"full": 0, "no_temperature": 1, "no_fuzzification": 2, "fixed_wei
 
 
 def _fuzzy_desc(params, mode, B, Cn, eps_temp, eps_log, eps_div):
-    d = L.FuzzyDesc()
+    d = TO.FuzzyDesc()
     (d.tau_img, d.tau_eeg, d.c_reliable, d.c_unreliable_img, d.c_unreliable_eeg, d.log_sigma_reliable_img,
-     d.log_sigma_reliable_eeg, d.log_sigma_unreliable_img, d.log_sigma_unreliable_eeg, d.beta) = [t.data_ptr() for t in params]
+     d.log_sigma_reliable_eeg, d.log_sigma_unreliable_img, d.log_sigma_unreliable_eeg, d.beta) = list(params)
     d.mode, d.B, d.num_classes = mode, B, Cn
     d.eps_temp, d.eps_log, d.eps_div = eps_temp, eps_log, eps_div
     return d
@@ -1469,8 +1528,8 @@ class FuzzyGatingFn(torch.autograd.Function):
         alpha = torch.empty(B, dtype=torch.float32, device=dev)
         aux = torch.empty(B + 1, 16, dtype=torch.float32, device=dev)
         d = _fuzzy_desc(params, mode, B, Cn, eps_temp, eps_log, eps_div)
-        L.call("egb_fuzzy_fwd", C.byref(d), img.data_ptr(), eeg.data_ptr(), fused.data_ptr(), alpha.data_ptr(),
-               aux.data_ptr(), _stream())
+        TO.call("fuzzy_fwd", d, img, eeg, fused, alpha,
+               aux)
         ctx.save_for_backward(img, eeg, *params)
         ctx.meta = (mode, eps_temp, eps_log, eps_div)
         ctx.mark_non_differentiable(aux)
@@ -1489,8 +1548,8 @@ class FuzzyGatingFn(torch.autograd.Function):
         d_eeg = torch.empty_like(eeg)
         dp = zeros((12,), torch.float32, dev)
         d = _fuzzy_desc(params, mode, B, Cn, eps_temp, eps_log, eps_div)
-        L.call("egb_fuzzy_bwd", C.byref(d), img.data_ptr(), eeg.data_ptr(), g_fused.data_ptr(), _p(g_alpha), d_img.data_ptr(),
-               d_eeg.data_ptr(), dp.data_ptr(), _stream())
+        TO.call("fuzzy_bwd", d, img, eeg, g_fused, _p(g_alpha), d_img,
+               d_eeg, dp)
         grads = (dp[0], dp[1], None, dp[2], dp[3], dp[4], dp[5], dp[6], dp[7], dp[8:12])
         return (d_img, d_eeg, None, None, None, None) + grads
 
@@ -1541,21 +1600,21 @@ class VitEmbedFn(torch.autograd.Function):
         patches = torch.empty(B * n, K, dtype=tdt, device=dev)
         stats = torch.empty(Bi * 6, dtype=torch.float32, device=dev) if mode == 4 else None
         if mode == 6:
-            L.call("egb_vit_patchify", img_a.data_ptr(), img_a.data_ptr(), a_bs, a_bs, patches.data_ptr(), None, code, Bi,
-                   H, W, ps, 5, _stream())
-            L.call("egb_vit_patchify", img_b.data_ptr(), img_b.data_ptr(), b_bs, b_bs,
-                   patches.data_ptr() + Bi * n * K * patches.element_size(), None, code, Bi, H, W, ps, 5, _stream())
+            TO.call("vit_patchify", img_a, img_a, a_bs, a_bs, patches, None, code, Bi,
+                   H, W, ps, 5)
+            TO.call("vit_patchify", img_b, img_b, b_bs, b_bs,
+                   TO.at(patches, Bi * n * K), None, code, Bi, H, W, ps, 5)
         else:
-            L.call("egb_vit_patchify", img_a.data_ptr(), img_b.data_ptr(), a_bs, b_bs, patches.data_ptr(), _p(stats), code,
-                   Bi, H, W, ps, mode, _stream())
+            TO.call("vit_patchify", img_a, img_b, a_bs, b_bs, patches, _p(stats), code,
+                   Bi, H, W, ps, mode)
         w2 = weight_plain(w, code)
         out = torch.empty(B, n + 1, D, dtype=tdt, device=dev)
         pos2 = pos.detach().reshape(n + 1, D)
-        cm = L.Matrix(out.data_ptr() + D * out.element_size(), code, n, D, (n + 1) * D)
-        rm = L.Matrix(pos2.data_ptr() + D * 4, F32, n, D, 0)
-        gemm(B * n, D, K, code, L.Operand(patches.data_ptr(), 0, 0, K, 0, 0, 0), L.Operand(w2.data_ptr(), 0, 0, K, 0, 0, 0),
+        cm = TO.Matrix(TO.at(out, D), code, n, D, (n + 1) * D)
+        rm = TO.Matrix(TO.at(pos2, D), F32, n, D, 0)
+        gemm(B * n, D, K, code, TO.Operand(patches, 0, 0, K, 0, 0, 0), TO.Operand(w2, 0, 0, K, 0, 0, 0),
              cm, bias=b.detach() if b is not None else None, residual=rm)
-        L.call("egb_fill_row0", cls.data_ptr(), pos2.data_ptr(), out.data_ptr(), code, B, n + 1, D, _stream())
+        TO.call("fill_row0", cls, pos2, out, code, B, n + 1, D)
         ctx.save_for_backward(patches, w)
         ctx.meta = (code, B, n, D, K, b is not None)
         return out
@@ -1579,7 +1638,7 @@ class VitEmbedFn(torch.autograd.Function):
                 db = colsum(dtok, D)
         if need[4] or need[5]:
             dp = zeros((n + 1, D), torch.float32, dev)
-            L.call("egb_seq_assemble_bwd", dx.data_ptr(), dp.data_ptr(), None, code, B, B, n + 1, D, 0, _stream())
+            TO.call("seq_assemble_bwd", dx, dp, None, code, B, B, n + 1, D, 0)
             dpos = dp.view(1, n + 1, D)
             dcls = dp[0].clone().view(1, 1, D)         # never alias two parameters' gradients (see SeqAssembleFn)
         return None, None, dw, db, dcls, dpos, None, None, None

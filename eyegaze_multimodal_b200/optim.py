@@ -36,6 +36,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from . import torch_ops as TO
 
 _CHUNK = 16384                       # elements per CTA
 
@@ -58,18 +59,26 @@ class FusedClipAdamW(torch.optim.Optimizer):
         # (GradScaler.step() sets / deletes the attributes `grad_scale` and `found_inf` around step(); they must not exist
         # in between: torch multiplies its scale with getattr(optimizer, "grad_scale", 1))
 
-    # -- device-resident step state (capturable mode) --------------------------------------------------
+    # -- device-resident step state --------------------------------------------------------------------
     def device_state(self) -> torch.Tensor:
-        """[opt_step, lr of group 0, lr of group 1, ...] (fp32, device).  Created on first use from the groups' current
-        ``lr``.  ``step()`` advances opt_step (the bias-correction count) on the device; ``DeviceLRSchedule`` rewrites the
-        learning rates."""
+        """fp32 device vector [skip flag, steps skipped, step count, -, lr of group 0, lr of group 1, ...].  The first four
+        words are written by egb_adamw_prepare on every step that needs a device-side verdict (GradScaler / non-finite
+        skip / capturable mode); the learning rates are read by the update kernel in capturable mode and rewritten by
+        ``DeviceLRSchedule``.  Created on first use from the groups' current ``lr``."""
         if self._dev_state is None:
             dev = next(p for g in self.param_groups for p in g["params"]).device
-            st = torch.zeros(1 + len(self.param_groups), dtype=torch.float32)
+            st = torch.zeros(4 + len(self.param_groups), dtype=torch.float32)
             for i, g in enumerate(self.param_groups):
-                st[1 + i] = float(g["lr"])
+                st[4 + i] = float(g["lr"])
             self._dev_state = st.to(dev)
         return self._dev_state
+
+    def device_step(self) -> torch.Tensor:
+        """Capturable mode: the 1-based count of updates actually applied (device scalar view)."""
+        return self.device_state()[2]
+
+    def device_lrs(self) -> torch.Tensor:
+        return self.device_state()[4:]
 
     # ------------------------------------------------------------------------------------------------
     def _plan(self, group):
@@ -171,7 +180,6 @@ class FusedClipAdamW(torch.optim.Optimizer):
             plans.append((group, plan, keep))
         if not plans:
             return loss
-        stream = torch.cuda.current_stream().cuda_stream
         dev = plans[0][1]["dev"].device
         sq = None
         if (self.max_grad_norm is not None and self.max_grad_norm > 0) or self.skip_nonfinite:
@@ -179,50 +187,56 @@ class FusedClipAdamW(torch.optim.Optimizer):
                 if self._sq_static is None:
                     self._sq_static = torch.zeros(1, dtype=torch.float32, device=dev)
                 sq = self._sq_static
-                L.call("egb_zero", sq.data_ptr(), 4, stream)
+                TO.call("zero", sq, 4)
             else:
                 sq = ops.small_zeros((1,), dev)                       # the norm is global: over every group
             for _, plan, _ in plans:
-                L.call("egb_multi_tensor_sqnorm", plan["dev"].data_ptr(), plan["chunks"].data_ptr(), plan["n_chunks"],
-                       sq.data_ptr(), stream)
+                TO.call("multi_tensor_sqnorm", plan["dev"], plan["chunks"], plan["n_chunks"],
+                       sq)
         self._sqnorm = sq
-        st = L.AdamwState()
-        st.skip_nonfinite = 1 if self.skip_nonfinite else 0
+        st = TO.AdamwState()
         gs, fi = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
         keep_amp = []
         if gs is not None:
             gs = gs.to(device=dev, dtype=torch.float32).reshape(1)
-            st.grad_scale = gs.data_ptr()
+            st.grad_scale = gs
             keep_amp.append(gs)
         if fi is not None:
             fi = fi.to(device=dev, dtype=torch.float32).reshape(1)
-            st.found_inf = fi.data_ptr()
             keep_amp.append(fi)
-        dstate = self.device_state() if self.capturable else None
+        needs_verdict = self.capturable or self.skip_nonfinite or fi is not None or self._dev_state is not None
+        dstate = self.device_state() if needs_verdict else None
         if dstate is not None:
-            st.step = dstate.data_ptr()
-            # opt_step += 1 on the device, before the update reads it (kind 0 / advance 0 leaves the rates untouched)
-            L.call("egb_lr_schedule_step", dstate.data_ptr() + 4, dstate.data_ptr(), dstate.data_ptr() + 4,
-                   dstate.data_ptr() + 4, 1, 0, 0.0, 0.0, 0, 1, stream)
+            # one thread decides whether this step is skipped and keeps the skipped / applied counts on the device
+            st.ctrl = dstate
+            st.use_device_step = 1 if self.capturable else 0
+            TO.call("adamw_prepare", dstate, sq if sq is not None else None,
+                   gs if gs is not None else None, fi if fi is not None else None,
+                   1 if self.skip_nonfinite else 0, 1)
         for gi, (group, plan, _) in enumerate(plans):
             b1, b2 = group["betas"]
-            if dstate is not None:
-                st.lr = dstate.data_ptr() + 4 * (1 + self.param_groups.index(group))
-            L.call("egb_multi_tensor_adamw_ex", plan["dev"].data_ptr(), plan["chunks"].data_ptr(), plan["n_chunks"],
+            if self.capturable:
+                st.lr = dstate[4 + self.param_groups.index(group):]
+            TO.call("multi_tensor_adamw_ex", plan["dev"], plan["chunks"], plan["n_chunks"],
                    float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                   float(self.max_grad_norm or 0.0), sq.data_ptr() if sq is not None else None, C.byref(st), stream)
+                   float(self.max_grad_norm or 0.0), sq if sq is not None else None, st)
         ops.bump_param_epoch()       # the kernels wrote the parameters behind autograd's version counters
         return loss
 
     def _sync_steps(self, only=None):
-        dev_step = None
-        if self.capturable and self._dev_state is not None:
-            dev_step = float(self._dev_state[0].item())     # graph replays advance the count on the device only
+        dev_step = skipped = None
+        if self._dev_state is not None:
+            ds = self._dev_state[:3].tolist()
+            skipped = int(ds[1])                            # steps the device skipped (GradScaler / non-finite norm)
+            if self.capturable:
+                dev_step = ds[2]                            # graph replays advance the count on the device only
         for plan in ([only] if only is not None else self._plans.values()):
             for i, (p, k) in enumerate(zip(plan["params"], plan["steps"])):
                 if dev_step is not None and plan["host_np"][i, 1] != 0:
                     k = dev_step
                     plan["steps"][i] = int(dev_step)
+                elif skipped:
+                    k = max(int(k) - skipped, 0)
                 self.state[p]["step"] = torch.tensor(float(k))
 
     def state_dict(self):
@@ -274,25 +288,24 @@ class DeviceLRSchedule:
 
     def _launch(self, advance: int) -> None:
         st = self.opt.device_state()
-        L.call("egb_lr_schedule_step", self._sched.data_ptr(), None, self._base.data_ptr(), st.data_ptr() + 4,
-               len(self.base_lrs), self.KINDS[self.kind], self.p0, self.p1, advance, 0,
-               torch.cuda.current_stream().cuda_stream)
+        TO.call("lr_schedule_step", self._sched, None, self._base, st[4:],
+               len(self.base_lrs), self.KINDS[self.kind], self.p0, self.p1, advance, 0)
 
     def step(self) -> None:
         self._launch(advance=1)
 
     def get_last_lr(self) -> Sequence[float]:
         """Host read (synchronises): for logging only."""
-        return self.opt.device_state()[1:].tolist()
+        return self.opt.device_lrs().tolist()
 
     def state_dict(self) -> Dict:
         return {"kind": self.kind, "p0": self.p0, "p1": self.p1, "last_epoch": float(self._sched.item()),
-                "opt_step": float(self.opt.device_state()[0].item()), "base_lrs": list(self.base_lrs)}
+                "opt_step": float(self.opt.device_step().item()), "base_lrs": list(self.base_lrs)}
 
     def load_state_dict(self, sd: Dict) -> None:
         self.kind, self.p0, self.p1 = sd["kind"], sd["p0"], sd["p1"]
         self._sched.fill_(sd["last_epoch"])
-        self.opt.device_state()[0] = sd["opt_step"]
+        self.opt.device_state()[2] = sd["opt_step"]
         self._launch(advance=0)
 
     @staticmethod
@@ -323,7 +336,7 @@ class MetricAccumulator:
         self._zero = torch.zeros((), dtype=torch.float32, device=device)
 
     def add(self, **scalars: torch.Tensor) -> None:
-        ptrs, keep = (L.vp * len(self.names))(), []
+        keep = []
         for i, n in enumerate(self.names):
             t = scalars.get(n, self._zero)
             t = t.detach()
@@ -331,16 +344,13 @@ class MetricAccumulator:
                 t = t.float().to(self._acc.device)
             t = t.reshape(())
             keep.append(t)
-            ptrs[i] = t.data_ptr()
-        L.call("egb_accum_scalars", ptrs, len(self.names), self._acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        TO.call("accum_scalars", keep, len(self.names), self._acc)
 
     def add_predictions(self, logits: torch.Tensor, labels: torch.Tensor, preds_out: Optional[torch.Tensor] = None) -> None:
         logits = logits.detach().float().contiguous()
         labels = labels.contiguous().long()
-        off = 4 * (len(self.names) + 1)
-        L.call("egb_argmax_count", logits.data_ptr(), labels.data_ptr(), self._acc.data_ptr() + off,
-               preds_out.data_ptr() if preds_out is not None else None, logits.shape[0], logits.shape[1],
-               torch.cuda.current_stream().cuda_stream)
+        TO.call("argmax_count", logits, labels, self._acc[len(self.names) + 1:],
+               preds_out if preds_out is not None else None, logits.shape[0], logits.shape[1])
 
     def result(self) -> Dict[str, float]:
         a = self._acc.tolist()                          # the single host read

@@ -156,6 +156,10 @@ int egb_act_bwd(const egb_matrix* dy, const void* aux, const egb_matrix* out, in
                 void* stream);
 /* out = dy * mask(seed) / (1-p): regenerates the mask a GEMM epilogue applied (index m*N+n) */
 int egb_dropout_bwd(const void* dy, void* out, int dtype, int64_t n_elems, float p, uint64_t seed, void* stream);
+/* same over [M, N] rows (N % 8 == 0, N <= 1024) with colsum (optional [N] fp32, ACCUMULATED) = column sums of `out`:
+ * the bias gradient of the layer whose epilogue applied the mask, in the same pass */
+int egb_dropout_bwd_colsum(const void* dy, void* out, int dtype, int M, int N, float p, uint64_t seed, float* colsum,
+                           void* stream);
 /* mean cross entropy (F.cross_entropy) and d(loss)/d(logits) in one pass; labels are int64 */
 int egb_cross_entropy(const float* logits, const int64_t* labels, float* loss, float* dlogits, int B, int C, void* stream);
 int egb_scale_by_device_scalar(const float* x, const float* g, float* out, int64_t n, void* stream);
@@ -169,6 +173,12 @@ int egb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
  * timm Block.forward `x = x + attn(norm1(x))`), so autograd's separate accumulation pass disappears */
 int egb_layernorm_bwd_res(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                           void* dx, float* dgamma, float* dbeta, const void* dres, int dtype, int M, int D, void* stream);
+/* same, plus dx_colsum (optional [D] fp32, ACCUMULATED): column sums of the stored dx = the bias gradient of the Linear
+ * whose output was added into the stream this LayerNorm reads (art.py:293-295 / timm Block), so F.linear's bias-gradient
+ * pass over dY disappears */
+int egb_layernorm_bwd_ex(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                         void* dx, float* dgamma, float* dbeta, const void* dres, float* dx_colsum, int dtype, int M,
+                         int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused multi-head attention (art.py:203-213; timm Attention): softmax(QK^T*scale) [dropout] V without
@@ -190,6 +200,10 @@ typedef struct {
   int32_t dtype, S, H, Lq, Lk, head_dim, kv_shift;
   float scale, dropout_p;
   uint64_t seed;
+  /* backward only, optional (all three or none): [H*head_dim] fp32 each, ACCUMULATED with the column sums of the stored
+   * dq / dk / dv over all (batch, row) -- the bias gradients of the q / k / v projections (art.py:203-205, timm qkv),
+   * taken while the gradient tiles leave the kernel instead of a second pass over them */
+  float *dq_colsum, *dk_colsum, *dv_colsum;
 } egb_attention_desc;
 int egb_attention_fwd(const egb_attention_desc* d, void* stream);
 /* debug aid: 8 x int64 device buffer receiving clock64() phase stamps of one CTA of the following tensor-core
@@ -278,17 +292,21 @@ int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, in
  * capturable, no host read / write per step).  Every pointer may be NULL (then the host value / default applies):
  *   lr         : this group's learning rate (egb_lr_schedule_step writes it; replaces the CosineAnnealingLR / LambdaLR
  *                host schedulers of train_art.py:401-409, train_multimodal_fuzzy_fusion.py:197-214,743-750)
- *   step       : 1-based update count used for the bias corrections (replaces the per-tensor table column)
+ *   ctrl       : 4 floats written by egb_adamw_prepare: {skip this step, steps skipped so far, device step count, -}
  *   grad_scale : gradients are divided by it first -- torch.amp.GradScaler's scale (train_multimodal_fuzzy_fusion.py:462)
- *   found_inf  : != 0 skips the update -- GradScaler's verdict (the `_step_supports_amp_scaling` optimizer protocol)
- *   skip_nonfinite : skip the update when sqrt(*sqnorm) is inf / nan (the finite check taken from our own norm pass) */
+ *   use_device_step : bias corrections use ctrl[2] instead of the per-tensor step column of the table
+ * egb_adamw_prepare (one thread, between the norm pass and the update): skip = (*found_inf != 0) [GradScaler's verdict,
+ * the `_step_supports_amp_scaling` optimizer protocol] or (skip_nonfinite and sqrt(*sqnorm) / scale is inf / nan) [the
+ * finite check taken from our own norm pass].  A skipped step changes nothing and does not count towards the bias
+ * corrections, like torch's fused AdamW; advance_step != 0 also advances ctrl[2] on a step that is not skipped. */
 typedef struct {
   const float* lr;
-  const float* step;
+  const float* ctrl;
   const float* grad_scale;
-  const float* found_inf;
-  int32_t skip_nonfinite;
+  int32_t use_device_step;
 } egb_adamw_state;
+int egb_adamw_prepare(float* ctrl, const float* sqnorm, const float* grad_scale, const float* found_inf,
+                      int skip_nonfinite, int advance_step, void* stream);
 int egb_multi_tensor_adamw_ex(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
                               float beta2, float eps, float weight_decay, float max_norm, const float* sqnorm,
                               const egb_adamw_state* state, void* stream);

@@ -216,14 +216,22 @@ def test_real_size_vit_forward_and_backward(cuda_device, name):
         F.cross_entropy(gb.float(), labels.to(DEV)).backward()
     rel = (gb.detach().float().cpu() - want.detach()).abs().max().item() / want.detach().abs().max().item()
     assert rel <= 2e-2, f"{name} bf16 logits relative err {rel:.3e}"
+    # bf16 gradients, measured on B200 (tools/bf16_grad_errors.py, profiles/r02_bf16_grad_errors.log): ViT-S weight
+    # matrices <= 2.0e-2 of max, ViT-B <= 3.3e-2; bias / LayerNorm / cls vectors (sums of bf16-rounded gradients over a
+    # handful of trials, heavy cancellation) up to 4.2e-2 (ViT-S) / 6.6e-2 (ViT-B) of max; Frobenius-relative <= 1.6e-2 /
+    # 3.6e-2 for every parameter.
+    lim_mat, lim_vec, lim_fro = (3e-2, 6e-2, 3e-2) if "small" in name else (4e-2, 8e-2, 4.5e-2)
     worst = ("", 0.0)
     for k, p in m.named_parameters():
         assert p.grad is not None, k
         r = sdr[k].grad
-        e = (p.grad.float().cpu() - r).abs().max().item() / (r.abs().max().item() + 1e-12)
+        g = p.grad.float().cpu()
+        e = (g - r).abs().max().item() / (r.abs().max().item() + 1e-12)
+        fro = (g - r).norm().item() / (r.norm().item() + 1e-30)
         if e > worst[1]:
             worst = (k, e)
-        assert e <= 3e-2, f"{name} bf16 grad {k}: {e:.3e} of max"
+        assert e <= (lim_mat if r.dim() >= 2 and r.shape[0] > 1 else lim_vec), f"{name} bf16 grad {k}: {e:.3e} of max"
+        assert fro <= lim_fro, f"{name} bf16 grad {k}: Frobenius-relative {fro:.3e}"
     print(f"{name}: fp32 logits err {err:.2e}, bf16 rel {rel:.2e}, worst bf16 grad {worst[0]} {worst[1]:.2e}")
 
 
@@ -499,3 +507,33 @@ def test_aux_losses_large_batch_against_oracle(cuda_device):
         for a, b in zip(d, r):
             if b.grad is not None:
                 assert _relmax(a.grad, b.grad) <= 2e-3, (name, _relmax(a.grad, b.grad))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 9. bias gradients ride along with the kernels that produce dY (LayerNorm backward, attention backward, dropout backward)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("train", [False, True])
+def test_bias_gradients_come_from_the_producing_kernels(cuda_device, train):
+    warnings.simplefilter("ignore")
+    cfg = O.EEGConfig(in_channels=8, d_model=64, num_layers=2, num_heads=4, d_ff=128, max_len=96)
+    m = DualEEGTransformer(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    m.load_state_dict(O.init_state_dict(cfg, 3), strict=True)
+    m = m.to(DEV).train(train)
+    vm = EarlyFusionViT("vit_tiny_patch16_224", num_classes=3, pretrained=False, fusion_mode="concat").to(DEV).train(train)
+    e1, e2 = eeg_pair_batch(4, 8, 256, seed=5, coupled=True)
+    a, b = gaze_pair_batch(2, seed=1)
+    labels = torch.tensor([0, 1, 2, 0], device=DEV)
+    for mode in ("fp32", "bf16"):
+        ops.stats["colsum_fused"] = ops.stats["colsum_pass"] = 0
+        m.zero_grad(set_to_none=True)
+        vm.zero_grad(set_to_none=True)
+        with precision(mode):
+            out = m(e1.to(DEV), e2.to(DEV), labels)
+            (out["loss"] + out["loss_ibs_cls"]).backward()
+            F.cross_entropy(vm(a.to(DEV), b.to(DEV)), labels[:2]).backward()
+        torch.cuda.synchronize()
+        # per encoder block: qkv bias (attention backward), out_proj bias and ffn.linear2 bias (LayerNorm / dropout backward);
+        # per ViT block: qkv, proj, fc2.  2 EEG blocks + cross attention + 12 ViT blocks => at least 3*2 + 2 + 3*12 = 44
+        assert ops.stats["colsum_fused"] >= 44, ops.stats
+        assert ops.stats["colsum_pass"] <= 8, ops.stats          # heads / tokenizer / patch embedding keep their pass
+    # (values: every parity test in this directory compares these bias gradients with the oracle's)

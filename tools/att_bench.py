@@ -1,8 +1,9 @@
-"""Attention kernels alone at the bench's shapes: CUDA-event timing (default) or a single pass for ncu (--once).
+"""Attention kernels alone at the bench's shapes, timed with CUDA events around CUDA-graph replays (the eager call path
+costs ~100 us of host time per call -- more than the forward kernel runs -- so eager event pairs would time the host).
 
-    python tools/att_bench.py [--once] [--iters 20]
+    python tools/att_bench.py [--once] [--iters 20] [--only vit_b,eeg]
 ViT-B layer: S=256, L=197, 12 heads x 64;  ViT-S: 6 heads x 64;  EEG encoder layer: S=512, L=139, 8 heads x 32, dropout
-0.1;  cfg5 EEG layer: S=1024, L=235."""
+0.1;  cfg5 EEG layer: S=1024, L=235.  --once: one eager forward + backward per shape (for ncu)."""
 import argparse
 import os
 import sys
@@ -24,6 +25,7 @@ def main():
     a = ap.parse_args()
     dev = "cuda:0"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ops.enable_seed_epoch()
     for tag, S, Lq, D, H, p in SHAPES:
         if a.only and tag not in a.only.split(","):
             continue
@@ -33,16 +35,30 @@ def main():
             ops.attention_packed(qkv, H, p=p).backward(go)
             torch.cuda.synchronize()
             continue
-        for _ in range(3):
-            ops.attention_packed(qkv, H, p=p).backward(go)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                qkv.grad = None
+                ops.attention_packed(qkv, H, p=p).backward(go)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        qkv.grad = None
+        ops.reset_arenas()
+        gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gf):
+            o = ops.attention_packed(qkv, H, p=p)
+        with torch.cuda.graph(gb, pool=gf.pool()):
+            o.backward(go)
+        ops.reset_arenas()
         tf = tb = 0.0
         for _ in range(a.iters):
             flush.zero_()
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
-            o = ops.attention_packed(qkv, H, p=p)
+            gf.replay()
             e[1].record()
-            o.backward(go)
+            gb.replay()
             e[2].record()
             torch.cuda.synchronize()
             tf += e[0].elapsed_time(e[1])
