@@ -61,6 +61,7 @@ _SIGNATURES = {
     "egb_gemm": [C.POINTER(GemmDesc), vp],
     "egb_prof_enable": [i32],
     "egb_prof_read": [i32, C.POINTER(C.c_double), i32],
+    "egb_prof_dump": [i32, C.POINTER(C.c_double), i32, C.POINTER(i32)],
     "egb_cast_from_f32": [vp, vp, i32, i64, vp],
     "egb_cast_to_f32": [vp, i32, vp, i64, vp],
     "egb_copy_strided4": [vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), vp],
@@ -155,6 +156,15 @@ def launch_count() -> int:
 
 def prof_enable(on: bool) -> None:
     call("egb_prof_enable", 1 if on else 0)
+
+
+def prof_dump(kind: int = 0, max_records: int = 8192) -> list:
+    """Per-launch records (launch order): dicts with ms, flops, bytes and the launcher's tag (GEMM: M, N, K, variant)."""
+    out = (C.c_double * (8 * max_records))()
+    n = i32(0)
+    call("egb_prof_dump", kind, out, max_records, C.byref(n))
+    return [{"ms": out[8 * i], "flops": out[8 * i + 1], "bytes": out[8 * i + 2], "tag": tuple(out[8 * i + 3:8 * i + 7])}
+            for i in range(n.value)]
 
 
 def prof_read(kind: int = 0, reset: bool = True) -> dict:

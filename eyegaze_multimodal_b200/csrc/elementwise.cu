@@ -109,25 +109,41 @@ __global__ void seq_assemble_kernel(const float* __restrict__ cls, const float* 
 }
 
 // dpos[l,:] += sum_s dX[s,l,:]  (cls and type-embedding gradients are rows of this sum);
-// dibs[b,tok,:] = dX[b,1+tok,:] + dX[B+b,1+tok,:].   grid = (L, D/128-ish)
+// dibs[b,tok,:] = dX[b,1+tok,:] + dX[B+b,1+tok,:].
+// grid = (L, S-splits): a CTA sums SEQ_BWD_SPLIT sequences of one position (eight independent 8-byte loads in flight
+// per thread) and adds its partial row to dpos with fp32 atomics -- with one CTA per position walking all S sequences
+// the kernel was a serial load chain on 139-197 CTAs (183 us for 40 MB).
+constexpr int SEQ_BWD_SPLIT = 32;
 template <typename T>
 __global__ void seq_assemble_bwd_kernel(const T* __restrict__ dx, float* __restrict__ dpos, T* __restrict__ dibs, int S,
                                         int B, int L, int D, int n_ibs) {
   const int l = blockIdx.x;
+  const int s0 = blockIdx.y * SEQ_BWD_SPLIT, s1 = min(S, s0 + SEQ_BWD_SPLIT);
   for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < S; ++s) {
+    const T* src = dx + (long long)l * D + d;
+    int s = s0;
+    for (; s + 8 <= s1; s += 8) {
+      float v[8][4];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ld4(src + (long long)(s + u) * L * D, v[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += v[u][j];
+    }
+    for (; s < s1; ++s) {
       float v[4];
-      ld4(dx + ((long long)s * L + l) * D + d, v);
+      ld4(src + (long long)s * L * D, v);
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] += v[j];
     }
     float* o = dpos + (long long)l * D + d;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] += acc[j];
+    for (int j = 0; j < 4; ++j) atomicAdd(o + j, acc[j]);
   }
   if (dibs != nullptr && l >= 1 && l <= n_ibs) {
-    for (long long i = threadIdx.x; i < (long long)B * (D / 4); i += blockDim.x) {
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < (long long)B * (D / 4); i += (long long)gridDim.y * blockDim.x) {
       const int b = (int)(i / (D / 4)), d = (int)(i % (D / 4)) * 4;
       float a[4], c[4];
       ld4(dx + ((long long)b * L + l) * D + d, a);
@@ -518,10 +534,11 @@ int egb_seq_assemble_bwd(const void* dx, float* dpos, void* dibs, int dtype, int
   cudaStream_t st = (cudaStream_t)stream;
   EGB_CHECK(D % 4 == 0, "seq_assemble_bwd: D%%4");
   const int threads = D / 4 < 64 ? 64 : (D / 4 > 256 ? 256 : D / 4);
+  const dim3 grid(L, (S + SEQ_BWD_SPLIT - 1) / SEQ_BWD_SPLIT);
   if (dtype == EGB_BF16)
-    seq_assemble_bwd_kernel<bf16><<<L, threads, 0, st>>>((const bf16*)dx, dpos, (bf16*)dibs, S, B, L, D, n_ibs);
+    seq_assemble_bwd_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)dx, dpos, (bf16*)dibs, S, B, L, D, n_ibs);
   else
-    seq_assemble_bwd_kernel<float><<<L, threads, 0, st>>>((const float*)dx, dpos, (float*)dibs, S, B, L, D, n_ibs);
+    seq_assemble_bwd_kernel<float><<<grid, threads, 0, st>>>((const float*)dx, dpos, (float*)dibs, S, B, L, D, n_ibs);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;

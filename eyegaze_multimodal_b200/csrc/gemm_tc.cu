@@ -22,6 +22,7 @@ extern void egb_count_launch(int n);
 int egb_prof_enabled();
 void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind);
 void egb_prof_end(cudaStream_t st);
+void egb_prof_tag(double a, double b, double c, double d);
 int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e);
 
 namespace {
@@ -856,6 +857,7 @@ int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams
   if (prof) {
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
+    egb_prof_tag(p.M, p.N, p.K, 1e6 + BN * 1e4 + EF);
   }
   gemm_tc_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
   if (prof) egb_prof_end(stream);
@@ -910,6 +912,7 @@ int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
   if (prof) {
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
+    egb_prof_tag(p.M, p.N, p.K, 2e6 + BN * 1e4 + EF);
   }
   gemm_tc2_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
   if (prof) egb_prof_end(stream);

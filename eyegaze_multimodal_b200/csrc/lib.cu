@@ -41,7 +41,7 @@ int egb_num_sms() {
 // (bench.py's roofline block).  Disabled by default: zero overhead on the normal path.
 // ---------------------------------------------------------------------------------------------
 #include <vector>
-struct ProfRec { cudaEvent_t e0, e1; double flops; double bytes; int kind; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; double bytes; int kind; double tag[4]; };
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
 static std::mutex g_prof_mu;
@@ -60,8 +60,14 @@ void egb_prof_begin(cudaStream_t st, double flops, double bytes, int kind) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r;
   r.e0 = prof_event(); r.e1 = prof_event(); r.flops = flops; r.bytes = bytes; r.kind = kind;
+  r.tag[0] = r.tag[1] = r.tag[2] = r.tag[3] = 0.0;
   cudaEventRecord(r.e0, st);
   g_prof.push_back(r);
+}
+// shape / variant of the launch just begun (per-launch table of egb_prof_dump)
+void egb_prof_tag(double a, double b, double c, double d) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) { double* t = g_prof.back().tag; t[0] = a; t[1] = b; t[2] = c; t[3] = d; }
 }
 void egb_prof_end(cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -71,6 +77,22 @@ void egb_prof_end(cudaStream_t st) {
 extern "C" {
 /* kind: 0 = tcgen05 GEMM, 1 = FFMA GEMM.  out[0..3] = launches, total ms, total flops, total algorithmic bytes */
 int egb_prof_enable(int on) { g_prof_on = on; return 0; }
+/* per-launch records of `kind` (in launch order): out[i*8 ..] = {ms, flops, bytes, tag0..tag3, 0}; *n_out = records written */
+int egb_prof_dump(int kind, double* out, int max_records, int* n_out) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (r.kind != kind || n >= max_records) continue;
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      double* o = out + (size_t)n * 8;
+      o[0] = t; o[1] = r.flops; o[2] = r.bytes; o[3] = r.tag[0]; o[4] = r.tag[1]; o[5] = r.tag[2]; o[6] = r.tag[3]; o[7] = 0.0;
+      ++n;
+    }
+  }
+  *n_out = n;
+  return 0;
+}
 int egb_prof_read(int kind, double* out, int reset) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   double n = 0, ms = 0, fl = 0, by = 0;

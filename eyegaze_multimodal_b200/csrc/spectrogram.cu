@@ -105,8 +105,19 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __res
   for (int i = threadIdx.x; i < 32 * 9 + 32; i += blockDim.x) wsm[i] = i < 288 ? w[i] : bias[i - 288];
   __syncthreads();
   T* o = out + (long long)n * out_img_stride;
+  // blockDim is a multiple of 8, so a thread serves the same channel quad for all its positions: its 36 weights and 4
+  // biases are read into registers once (with the weights re-read from shared memory for every FMA the kernel was
+  // bound by the shared-memory pipe: 355 us for 290 MB)
+  const int cq = threadIdx.x & 7;
+  float wr[4][9], br[4];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    br[cc] = wsm[288 + cq * 4 + cc];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wr[cc][i] = wsm[(cq * 4 + cc) * 9 + i];
+  }
   for (int idx = threadIdx.x; idx < H1 * W1 * 8; idx += blockDim.x) {
-    const int cq = idx & 7, pos = idx >> 3;
+    const int pos = idx >> 3;
     const int ph = pos / W1, pw = pos % W1;
     float patch[4][4];
 #pragma unroll
@@ -116,18 +127,16 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __res
     float res[4];
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-      const int c = cq * 4 + cc;
-      const float* wc = wsm + c * 9;
       float best = 0.f;  // relu(max(.)) == max(0, .)
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          float a = wsm[288 + c];
+          float a = br[cc];
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) a = fmaf(wc[kh * 3 + kw], patch[dy + kh][dx + kw], a);
+            for (int kw = 0; kw < 3; ++kw) a = fmaf(wr[cc][kh * 3 + kw], patch[dy + kh][dx + kw], a);
           best = fmaxf(best, a);
         }
       res[cc] = best;
@@ -154,6 +163,16 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_bwd_kernel(const float* _
     wsm[i] = i < 288 ? w[i] : bias[i - 288];
     acc[i] = 0.f;
   }
+  __syncthreads();
+  // partial sums of this thread's channel stay in registers across all images of the CTA
+  float lw[9], lb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) lw[i] = 0.f;
+  const int c = threadIdx.x & 31;
+  float wr[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wr[i] = wsm[c * 9 + i];
+  const float bc = wsm[288 + c];
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
     __syncthreads();
     for (int i = threadIdx.x; i < (Hh + 2) * ldw; i += blockDim.x) {
@@ -162,40 +181,46 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_bwd_kernel(const float* _
     }
     __syncthreads();
     const T* g = dout + (long long)n * out_img_stride;
-    // thread -> channel c = tid & 31 (so the 32 lanes of a warp hit 32 different accumulators)
-    const int c = threadIdx.x & 31;
-    const float* wc = wsm + c * 9;
-    float lw[9], lb = 0.f;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) lw[i] = 0.f;
+    // thread -> channel c = tid & 31 (so the 32 lanes of a warp hit 32 different accumulators).  The lane's nine
+    // weights live in registers and the 4 x 4 input patch of a pooled position is read ONCE (16 broadcast loads per
+    // warp; the first version issued two shared loads per FMA -- weight and sample -- and was bound by them: 991 us).
     for (int pos = threadIdx.x >> 5; pos < H1 * W1; pos += blockDim.x >> 5) {
       const int ph = pos / W1, pw = pos % W1;
       const float go = to_f(g[((long long)(ph + 1) * Wp + (pw + 1)) * 32 + c]);
-      if (go == 0.f) continue;
+      float patch[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) patch[a][b] = im[(2 * ph + a) * ldw + 2 * pw + b];
       float best = 0.f;
-      int by = -1, bx = 0;
+      int sel = -1;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          float a = wsm[288 + c];
+          float a = bc;
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) a = fmaf(wc[kh * 3 + kw], im[(2 * ph + dy + kh) * ldw + 2 * pw + dx + kw], a);
-          if (a > best) { best = a; by = dy; bx = dx; }   // first maximum wins, as in max_pool2d
+            for (int kw = 0; kw < 3; ++kw) a = fmaf(wr[kh * 3 + kw], patch[dy + kh][dx + kw], a);
+          if (a > best) { best = a; sel = dy * 2 + dx; }   // first maximum wins, as in max_pool2d
         }
-      if (by < 0) continue;  // relu inactive
-      lb += go;
+      const float gs = sel < 0 ? 0.f : go;                // relu inactive: no contribution
+      lb += gs;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) lw[kh * 3 + kw] = fmaf(go, im[(2 * ph + by + kh) * ldw + 2 * pw + bx + kw], lw[kh * 3 + kw]);
+        for (int kw = 0; kw < 3; ++kw) {
+          // sample under tap (kh, kw) of the winning conv output: a select over the four candidates (registers only)
+          const float v0 = patch[kh][kw], v1 = patch[kh][kw + 1], v2 = patch[kh + 1][kw], v3 = patch[kh + 1][kw + 1];
+          const float v = sel == 0 ? v0 : sel == 1 ? v1 : sel == 2 ? v2 : v3;
+          lw[kh * 3 + kw] = fmaf(gs, v, lw[kh * 3 + kw]);
+        }
     }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) atomicAdd(&acc[c * 9 + i], lw[i]);
-    atomicAdd(&acc[288 + c], lb);
   }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) atomicAdd(&acc[c * 9 + i], lw[i]);
+  atomicAdd(&acc[288 + c], lb);
   __syncthreads();
   for (int i = threadIdx.x; i < 320; i += blockDim.x) {
     if (i < 288) atomicAdd(dw + i, acc[i]);
@@ -236,35 +261,56 @@ __global__ void __launch_bounds__(256) relu_avgpool_kernel(const T* __restrict__
 }
 
 // dy (padded layout, zero on the border and where relu is inactive) from dpooled [N, 1024].
+// One CTA per image: its 1024 pooled gradients are staged in shared memory as [bin][channel] fp32, already divided by
+// the bin's element count, so the per-position work is one 16-byte load of y, <= 4 x 2 float4 shared loads and one
+// 16-byte store (the first version gathered the 2-byte pooled gradients straight from global memory with a 32-byte
+// stride, eight per bin and thread: 778 us for 1.07 GB).
 template <typename T>
 __global__ void __launch_bounds__(256) relu_avgpool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dpool,
                                                                T* __restrict__ dy, int N, int H1, int W1, int Wp, int Hp,
                                                                long long img_stride) {
+  __shared__ __align__(16) float g_s[16 * 64];   // [ph*4+pw][c], scaled by 1 / bin size
+  __shared__ int hb[4][2], wb[4][2];
+  const int n = blockIdx.x;
+  if (threadIdx.x < 4) {
+    hb[threadIdx.x][0] = (threadIdx.x * H1) / 4;
+    hb[threadIdx.x][1] = ((threadIdx.x + 1) * H1 + 3) / 4;
+    wb[threadIdx.x][0] = (threadIdx.x * W1) / 4;
+    wb[threadIdx.x][1] = ((threadIdx.x + 1) * W1 + 3) / 4;
+  }
+  __syncthreads();
+  {
+    // thread t reads 4 consecutive pooled gradients (channel c = t / 4, bins 4 (t % 4) ..): coalesced
+    float v[4];
+    ld4(dpool + (long long)n * 1024 + threadIdx.x * 4, v);
+    const int c = threadIdx.x >> 2, ph = threadIdx.x & 3;
+#pragma unroll
+    for (int pw = 0; pw < 4; ++pw)
+      g_s[(ph * 4 + pw) * 64 + c] = v[pw] / (float)((hb[ph][1] - hb[ph][0]) * (wb[pw][1] - wb[pw][0]));
+  }
+  __syncthreads();
   const int per_img = Hp * Wp * 8;
-  const long long total = (long long)N * per_img;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long n = idx / per_img;
-    const int rem = (int)(idx - n * per_img);
+  for (int rem = threadIdx.x; rem < per_img; rem += blockDim.x) {
     const int cg = rem & 7, pos = rem >> 3;
     const int h = pos / Wp - 1, w = pos % Wp - 1;
-    const long long off = n * img_stride + (long long)pos * 64 + cg * 8;
+    const long long off = (long long)n * img_stride + (long long)pos * 64 + cg * 8;
     float g[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = 0.f;
     if (h >= 0 && h < H1 && w >= 0 && w < W1) {
       float v[8];
       ld8(y + off, v);
-      const T* dp = dpool + n * 1024 + (cg * 8) * 16;
       // adaptive bins may overlap when H1 % 4 != 0: sum over every bin containing (h, w)
-      for (int ph = 0; ph < 4; ++ph) {
-        const int h0 = (ph * H1) / 4, h1 = ((ph + 1) * H1 + 3) / 4;
-        if (h < h0 || h >= h1) continue;
-        for (int pw = 0; pw < 4; ++pw) {
-          const int w0 = (pw * W1) / 4, w1 = ((pw + 1) * W1 + 3) / 4;
-          if (w < w0 || w >= w1) continue;
-          const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] += to_f(dp[i * 16 + ph * 4 + pw]) * inv;
+      for (int ph = 0; ph < 4; ++ph) {
+        if (h < hb[ph][0] || h >= hb[ph][1]) continue;
+#pragma unroll
+        for (int pw = 0; pw < 4; ++pw) {
+          if (w < wb[pw][0] || w >= wb[pw][1]) continue;
+          const float4 a = *reinterpret_cast<const float4*>(&g_s[(ph * 4 + pw) * 64 + cg * 8]);
+          const float4 b = *reinterpret_cast<const float4*>(&g_s[(ph * 4 + pw) * 64 + cg * 8 + 4]);
+          g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w;
+          g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
         }
       }
 #pragma unroll
@@ -356,8 +402,7 @@ int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, 
   cudaStream_t st = (cudaStream_t)stream;
   const int Wp = W1 + 2, Hp = H1 + 2;
   const long long istr = (long long)Hp * Wp * 64;
-  long long want = ((long long)N * Hp * Wp * 8 + 255) / 256;
-  const int grid_bwd = (int)(want < 1 ? 1 : (want > 16LL * egb_num_sms() ? 16LL * egb_num_sms() : want));
+  const int grid_bwd = N;                          // one CTA per image
   if (dtype == EGB_BF16)
     relu_avgpool_bwd_kernel<bf16><<<grid_bwd, 256, 0, st>>>((const bf16*)y, (const bf16*)dpool, (bf16*)dy, N, H1, W1, Wp, Hp, istr);
   else

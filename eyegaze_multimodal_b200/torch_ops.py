@@ -31,7 +31,7 @@ from . import _lib as L
 
 NAMESPACE = "eyegaze_b200"
 _LIB = torch.library.Library(NAMESPACE, "DEF")
-_HOST_ONLY = {"egb_prof_enable", "egb_prof_read", "egb_debug_attention_timing", "egb_debug_gemm_timing",
+_HOST_ONLY = {"egb_prof_enable", "egb_prof_read", "egb_prof_dump", "egb_debug_attention_timing", "egb_debug_gemm_timing",
               "egb_seed_epoch_enable"}
 _ARRAY_ELEM = {C.POINTER(L.i32): L.i32, C.POINTER(L.i64): L.i64, C.POINTER(L.f32): L.f32}
 _INTS = (L.i32, L.i64, L.u64)

@@ -33,6 +33,8 @@ int64_t egb_launch_count(void);
  * egb_prof_read: kind 0 = tcgen05 GEMM; out[4] = {launches, total ms, total FLOPs, total algorithmic bytes} */
 int egb_prof_enable(int on);
 int egb_prof_read(int kind, double* out, int reset);
+/* per-launch records in launch order: out[i*8..] = {ms, FLOPs, bytes, tag0..tag3 (GEMM: M, N, K, variant), 0} */
+int egb_prof_dump(int kind, double* out, int max_records, int* n_out);
 
 /* Device-resident seed epoch for CUDA-graph replays.  Dropout seeds are launch arguments and therefore frozen into a
  * captured graph; after egb_seed_epoch_enable every mask-drawing kernel of this library mixes the current value of one

@@ -135,7 +135,7 @@ def test_no_cpu_fallback():
 def test_every_c_entry_point_is_a_registered_torch_op():
     import torch
     from eyegaze_multimodal_b200 import torch_ops as T
-    host_only = {"egb_prof_enable", "egb_prof_read", "egb_debug_attention_timing", "egb_debug_gemm_timing",
+    host_only = {"egb_prof_enable", "egb_prof_read", "egb_prof_dump", "egb_debug_attention_timing", "egb_debug_gemm_timing",
                  "egb_seed_epoch_enable"}
     want = {n[4:] for n in _lib._SIGNATURES if n not in host_only}
     assert set(T.OP_NAMES) == want and len(want) >= 50

@@ -66,3 +66,19 @@ for cfg, T, Bs in ((O.EEGConfig(in_channels=32, max_len=128, use_spectrogram=Fal
             out = m(e1.to(DEV), e2.to(DEV), labels.to(DEV))
             (out["loss"] + out.get("loss_ibs_cls", 0.0)).backward()
         report("EEG use_ibs=%s T=%d B=%d" % (cfg.use_ibs, T, B), list(m.named_parameters()), sdr)
+        # the same op chain in plain PyTorch on the GPU under bf16 autocast (ATen / cuBLAS kernels): how much of the error
+        # above is the precision itself rather than this repository's kernels
+        sdg = {k: v.to(DEV).clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o2 = O.dual_eeg_forward(sdg, e1.to(DEV), e2.to(DEV), cfg, labels.to(DEV))
+            (o2["loss"] + o2.get("loss_ibs_cls", 0.0)).backward()
+
+        class _P:
+            def __init__(self, g):
+                self.grad = g
+        report("   torch autocast(bf16) on cuda, same inputs", [(k, _P(v.grad.cpu())) for k, v in sdg.items() if v.grad is not None], sdr)
+        m.zero_grad(set_to_none=True)
+        with precision("fp32"):
+            out = m(e1.to(DEV), e2.to(DEV), labels.to(DEV))
+            (out["loss"] + out.get("loss_ibs_cls", 0.0)).backward()
+        report("   this path in fp32 mode", list(m.named_parameters()), sdr)

@@ -6,6 +6,11 @@ import re
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
+if len(sys.argv) > 3:                                   # n-th kernel of a multi-kernel export
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    k = int(sys.argv[3])
+    print(rows[starts[k]][1][:90])
+    rows = rows[starts[k]:starts[k + 1]]
 hdr = next(r for r in rows if "Source" in r and "Instructions Executed" in r)
 i_src, i_ex, i_samp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 ops, samp = collections.Counter(), collections.Counter()
