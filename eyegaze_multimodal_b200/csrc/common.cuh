@@ -155,15 +155,35 @@ __device__ __forceinline__ unsigned long long egb_mix_seed(unsigned long long se
   return seed ^ e;
 }
 
-// Counter-based dropout mask: keep iff hash(seed, idx) >= p * 2^32. Stateless so the backward
-// pass regenerates the mask from (seed, idx) instead of storing it.
+// Counter-based dropout mask, stateless so that the backward pass regenerates it from (seed, element index) instead of
+// storing it.  Elements are grouped into aligned RUNS of 8 consecutive indices: one multiply-xorshift hash of
+// (seed, idx >> 3) seeds the run and the run's elements step a 32-bit LCG from there; an element is kept iff its state
+// >= p * 2^32 (the comparison is decided by the state's high bits, the strong ones of an LCG).  Every kernel that touches
+// 8 aligned elements at a time pays one hash and eight multiply-adds instead of eight hashes: the GEMM epilogues of the
+// EEG encoder (dropout after every Linear) were bound by exactly that integer work.
 __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint64_t idx) {
   uint32_t h = ((uint32_t)idx ^ (uint32_t)seed) * 0x9E3779B1u + ((uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32)) * 0x85EBCA77u;
   h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;   // 2-round multiply-xorshift finaliser
   return h;
 }
+__device__ __forceinline__ uint32_t drop_step(uint32_t s) { return s * 0x2C9277B5u + 0xAC564B05u; }
+// state of element `idx` (any index): hash of its run, stepped (idx & 7) times
+__device__ __forceinline__ uint32_t drop_state(uint64_t seed, uint64_t idx) {
+  uint32_t s = drop_hash(seed, idx >> 3);
+  for (int k = (int)(idx & 7); k > 0; --k) s = drop_step(s);
+  return s;
+}
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
-  return drop_hash(seed, idx) >= thresh;
+  return drop_state(seed, idx) >= thresh;
+}
+// v[0..8) <- dropout of the aligned run starting at element index `base` (base % 8 == 0)
+__device__ __forceinline__ void drop_apply_run8(uint64_t seed, uint64_t base, uint32_t thresh, float scale, float (&v)[8]) {
+  uint32_t s = drop_hash(seed, base >> 3);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = s >= thresh ? v[i] * scale : 0.f;
+    s = drop_step(s);
+  }
 }
 // Attention-probability dropout: ONE hash decides TWO adjacent key columns (16 random bits each, p resolved to 2^-16).
 // The softmax loops of the tensor-core attention kernels are bound by integer throughput once dropout is on

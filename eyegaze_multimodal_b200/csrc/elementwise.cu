@@ -335,8 +335,12 @@ __global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ out
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_elems; i += stride) {
     float v[4];
     ld4(dy + i, v);
+    unsigned st = drop_state(seed, (unsigned long long)i);     // i % 4 == 0: the four elements lie in one run
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = drop_keep(seed, (unsigned long long)(i + j), thresh) ? v[j] * scale : 0.f;
+    for (int j = 0; j < 4; ++j) {
+      v[j] = st >= thresh ? v[j] * scale : 0.f;
+      st = drop_step(st);
+    }
     st4(out + i, v);
   }
 }
@@ -363,11 +367,9 @@ __global__ void __launch_bounds__(256) dropout_bwd_colsum_kernel(const T* __rest
         float v[8];
         const long long base = (long long)row * N + d;
         ld8(dy + base, v);
+        drop_apply_run8(seed, (unsigned long long)base, thresh, scale, v);   // N % 8 == 0: base is run-aligned
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = drop_keep(seed, (unsigned long long)(base + j), thresh) ? v[j] * scale : 0.f;
-          acc[c][j] += to_f(from_f<T>(v[j]));
-        }
+        for (int j = 0; j < 8; ++j) acc[c][j] += to_f(from_f<T>(v[j]));
         st8(out + base, v);
       }
     }

@@ -311,16 +311,11 @@ __device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
   for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
 }
 
+// The arithmetic of one 8-column run (everything but the stores): v <- epilogue(v); dv <- gelu'(pre) for EF_DGELU.
+// (m, n) locate the run for the dropout counter.
 template <int F>
-__device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8],
-                                          const float (&bias)[8], const EpiPre8& pre) {
-  if (!row.ok || n >= p.N) return;
-  if (F & EF_ACC) {
-    float* c = reinterpret_cast<float*>(p.c.ptr) + row.c + n;
-    red_add_v4(c, v[0], v[1], v[2], v[3]);
-    red_add_v4(c + 4, v[4], v[5], v[6], v[7]);
-    return;
-  }
+__device__ __forceinline__ void epi_math8(const EpiParams& p, int m, int n, float (&v)[8], const float (&bias)[8],
+                                          const EpiPre8& pre, float (&dv)[8]) {
   if (F & EF_BIAS) {
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
@@ -329,16 +324,17 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
     }
   }
   if (F & EF_DGELU) {
-    float dv[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {   // packed pairs: see gelu_erf_both2
       float2 y2, d2;
       gelu_erf_both2(make_float2(v[i], v[i + 1]), y2, d2);
       v[i] = y2.x; v[i + 1] = y2.y; dv[i] = d2.x; dv[i + 1] = d2.y;
     }
-    st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, dv);
   } else {
-    if (F & EF_PRE) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, v);
+    if (F & EF_PRE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dv[i] = v[i];
+    }
     if (F & EF_RELU) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -348,11 +344,9 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
       for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
     }
   }
-  if (p.drop_thresh != 0u) {
+  if (p.drop_thresh != 0u) {   // n and N are multiples of 8 on this path: the run is aligned
     const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
-    const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = drop_keep(seed_eff, base + i, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+    drop_apply_run8(egb_mix_seed(p.seed, p.epoch), base, p.drop_thresh, p.drop_scale, v);
   }
   if (F & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) {
     float a[8];
@@ -380,6 +374,21 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
       v[i] = s2.x; v[i + 1] = s2.y;
     }
   }
+}
+
+template <int F>
+__device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8],
+                                          const float (&bias)[8], const EpiPre8& pre) {
+  if (!row.ok || n >= p.N) return;
+  if (F & EF_ACC) {
+    float* c = reinterpret_cast<float*>(p.c.ptr) + row.c + n;
+    red_add_v4(c, v[0], v[1], v[2], v[3]);
+    red_add_v4(c + 4, v[4], v[5], v[6], v[7]);
+    return;
+  }
+  float dv[8];
+  epi_math8<F>(p, m, n, v, bias, pre, dv);
+  if (F & (EF_DGELU | EF_PRE)) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, dv);
   if (p.exp != 3) st8(reinterpret_cast<bf16*>(p.c.ptr) + row.c + n, v);
 }
 

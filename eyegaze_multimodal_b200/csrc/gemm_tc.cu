@@ -44,6 +44,7 @@ struct TcParams {
   long long* dbg;  // optional [gridDim.x][8] cycle counters (egb_debug_gemm_timing)
   int dbg_skip;    // experiment switch (EGB_GEMM_SKIPB=1): see the pair producer
   int bkt;         // K extent of one pipeline stage of the pair kernel (64 or 128)
+  int row_epi;     // 1: row-layout epilogue with TMA stores (tmC / tmP are valid)
 };
 
 // cycles spent inside a barrier wait, accumulated into *acc when profiling is on
@@ -264,9 +265,192 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& epi, uint32_t tad
   }
 }
 
+// ================================================================================================
+// Row-layout epilogue with TMA stores.
+// A tcgen05.ld hands every lane ONE ROW of the accumulator (32 consecutive columns).  Instead of transposing each
+// 32 x 32 chunk through shared memory so that the lanes can issue coalesced global stores themselves (8 STS + 8 LDS +
+// 4 predicated STG per chunk and a dependent STS -> LDS round trip: with K = 256 the drain of a tile took three times
+// as long as its MMAs), the lane converts its row segment to bf16, writes the 64 bytes into a warp-private
+// [32 rows][64 B] tile in the 64-byte-swizzled layout (conflict-free 16-byte stores) and ONE lane hands the tile to the
+// TMA unit (cp.async.bulk.tensor store, box {32 columns, 32 rows}).  The TMA unit clips rows >= M / columns >= N, so
+// the store path has no predicates; the two 2 KB tiles of a warp alternate, guarded by cp.async.bulk.wait_group.read.
+// Row-layout operands (residual, activation-backward factor) are read by the lane straight from its own row
+// (4 x 16 B, prefetched a chunk ahead); the bias is a warp-uniform broadcast load.  The accumulator is handed back to
+// the MMA warp as soon as the LAST tcgen05.ld of the tile has completed, before that chunk's arithmetic and stores.
+// Column sums (EF_COLSUM) are taken with a halving butterfly over the 32 rows (31 shuffles per chunk).
+// ================================================================================================
+struct RowOps {
+  uint4 x[4];      // residual or activation-backward operand of this lane's row, 32 columns
+};
+
+template <int EF>
+__device__ __forceinline__ void row_prefetch(const bf16* row_ptr, int n, int N, RowOps& o) {
+  if (EF & (EF_RES | EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (n + 8 * g < N) o.x[g] = __ldg(reinterpret_cast<const uint4*>(row_ptr + n + 8 * g));
+  }
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// one 32 x 32 chunk: this lane's 32 accumulator values r of row m, columns [n, n + 32)
+template <int EF>
+__device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP, int m,
+                                          bool row_ok, int m_warp, int n, const uint32_t (&r)[32], const RowOps& o,
+                                          uint8_t* stage, int lane, uint32_t& nstores) {
+  constexpr bool TWO = (EF & (EF_PRE | EF_DGELU)) != 0;      // second output (pre-activation / gelu')
+  // the tile(s) this chunk writes must have been read out by the TMA unit: with one output the two 2 KB tiles
+  // alternate (one store may stay in flight), with two outputs both are rewritten
+  if (lane == 0) {
+    if (TWO) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>();
+  }
+  __syncwarp();
+  uint8_t* bufC = stage + (TWO ? 0 : (nstores & 1u) * 2048u);
+  uint8_t* bufP = stage + 2048;
+  const uint32_t rowC = ptx::smem_u32(bufC) + (uint32_t)(lane * 64);
+  const uint32_t rowP = ptx::smem_u32(bufP) + (uint32_t)(lane * 64);
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+  float cs[(EF & EF_COLSUM) ? 32 : 1];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8], dv[8], bias[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * g + i]);
+    if ((EF & EF_BIAS) && n + 8 * g < epi.N) {   // warp-uniform address: a broadcast load
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 8 * g));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 8 * g + 4));
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+    EpiPre8 pre;
+    pre.res = o.x[g];
+    pre.aux = o.x[g];
+    epi_math8<EF>(epi, m, n + 8 * g, v, bias, pre, dv);
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowC + (((uint32_t)g ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]),
+                 "r"(pk[2]), "r"(pk[3])
+                 : "memory");
+    if (TWO) {
+      uint32_t pd[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pd[i] = pack2_bf16(dv[2 * i], dv[2 * i + 1]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowP + (((uint32_t)g ^ sw) << 4)), "r"(pd[0]), "r"(pd[1]),
+                   "r"(pd[2]), "r"(pd[3])
+                   : "memory");
+    }
+    if (EF & EF_COLSUM) {
+      // column sums of the values AS STORED (rounded to bf16), rows past M and columns past N contribute nothing
+      const bool ok = row_ok && n + 8 * g < epi.N;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&pk[i]);
+        cs[8 * g + 2 * i] = ok ? __low2float(h) : 0.f;
+        cs[8 * g + 2 * i + 1] = ok ? __high2float(h) : 0.f;
+      }
+    }
+  }
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_2d(tmC, bufC, n, m_warp);
+    if (TWO) ptx::tma_store_2d(tmP, bufP, n, m_warp);
+    ptx::bulk_commit();
+  }
+  ++nstores;
+  if (EF & EF_COLSUM) {
+    // halving butterfly over the warp's 32 rows: after the round with lane bit b a lane keeps the half of its columns
+    // selected by that bit, summed with its partner's; lane l ends up with the sum of column l
+    float a16[16], a8[8], a4[4], a2[2];
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, b16 ? cs[i] : cs[i + 16], 16);
+      a16[i] = (b16 ? cs[i + 16] : cs[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, b8 ? a16[i] : a16[i + 8], 8);
+      a8[i] = (b8 ? a16[i + 8] : a16[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, b4 ? a8[i] : a8[i + 4], 4);
+      a4[i] = (b4 ? a8[i + 4] : a8[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, b2 ? a4[i] : a4[i + 2], 2);
+      a2[i] = (b2 ? a4[i + 2] : a4[i]) + recv;
+    }
+    const float recv = __shfl_xor_sync(0xffffffffu, b1 ? a2[0] : a2[1], 1);
+    const float tot = (b1 ? a2[1] : a2[0]) + recv;
+    if (n + lane < epi.N) atomicAdd(epi.colsum + n + lane, tot);   // result unused: compiles to RED
+  }
+}
+
+// One accumulator tile of one warp: TMEM lane quadrant at taddr (column 0 of the warp's share), rows m_warp + lane,
+// global columns [n_base, n_base + ncol).  `release` hands the accumulator back to the MMA warp.
+template <int EF, typename Release>
+__device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP,
+                                                  uint32_t taddr, int m_warp, int n_base, int ncol, uint8_t* stage,
+                                                  int lane, uint32_t& nstores, Release release) {
+  const int m = m_warp + lane;
+  const bool row_ok = m < epi.M;
+  int nvalid = epi.N - n_base;
+  if (nvalid > ncol) nvalid = ncol;
+  const int nch = m_warp < epi.M ? (nvalid + 31) / 32 : 0;      // warp-uniform
+  if (nch <= 0) { release(); return; }
+  const bf16* row_ptr = nullptr;
+  if (EF & EF_RES) row_ptr = reinterpret_cast<const bf16*>(epi.res.ptr) + epi_row_offset(epi.res, row_ok ? m : 0);
+  if (EF & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL))
+    row_ptr = reinterpret_cast<const bf16*>(epi.aux.ptr) + epi_row_offset(epi.aux, row_ok ? m : 0);
+  uint32_t ra[32], rb[32];
+  RowOps oa, ob;
+  ptx::tmem_ld32(taddr, ra);
+  row_prefetch<EF>(row_ptr, n_base, epi.N, oa);
+#pragma unroll 1
+  for (int c = 0; c < nch; c += 2) {
+    ptx::tmem_ld_wait();
+    if (c + 1 < nch) {
+      ptx::tmem_ld32(taddr + (uint32_t)(32 * (c + 1)), rb);
+      row_prefetch<EF>(row_ptr, n_base + 32 * (c + 1), epi.N, ob);
+    } else {
+      release();
+    }
+    row_chunk<EF>(epi, tmC, tmP, m, row_ok, m_warp, n_base + 32 * c, ra, oa, stage, lane, nstores);
+    if (c + 1 < nch) {
+      ptx::tmem_ld_wait();
+      if (c + 2 < nch) {
+        ptx::tmem_ld32(taddr + (uint32_t)(32 * (c + 2)), ra);
+        row_prefetch<EF>(row_ptr, n_base + 32 * (c + 2), epi.N, oa);
+      } else {
+        release();
+      }
+      row_chunk<EF>(epi, tmC, tmP, m, row_ok, m_warp, n_base + 32 * (c + 1), rb, ob, stage, lane, nstores);
+    }
+  }
+}
+
+// Epilogue variants that run the row-layout path: the ones WITHOUT a row-layout operand.  (Measured with the residual /
+// activation-backward operand read by each lane from its own row -- 32 different 128-byte lines per load instruction --
+// those variants lost 25-80 %: proj + residual 68 -> 121 us, dX-through-GELU' 297 -> 409 us; they keep the transposed
+// epilogue, whose 8-column runs make those reads sector-exact.)
+template <int EF>
+struct RowEpi {
+  static constexpr bool ok = EF != EF_GENERIC &&
+                             (EF & (EF_ACC | EF_RES | EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL | EF_COLSUM)) == 0;
+};
+
 template <int BN, int EF, int BKT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const TcParams p) {
   using Cfg = TcConfig<BN, BKT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -385,24 +569,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NCOL = BN >= 64 ? BN / 2 : BN;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t nstores = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mn = tile / p.split_k;
       const int nt = mn % p.n_tiles;
       const int mt = mn / p.n_tiles;
-      EpiRow rows[4];
-      EpiChunkOps ops0;
-      epilogue_tile_begin<EF>(p.epi, mt * BM + quad * 32, nt * BN, chalf * NCOL, lane, rows, ops0);
-      TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
-      ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<EF>(p.epi, taddr, mt * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
-                    stage_all + (warp - 2) * (32 * STG_PITCH), lane, rows, ops0);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_relaxed(&tempty_bar[acc]);
+      if (RowEpi<EF>::ok && p.row_epi) {
+        TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
+        ptx::tc_fence_after();
+        uint64_t* tb = &tempty_bar[acc];
+        epilogue_tile_row<EF>(p.epi, &tmC, &tmP, taddr + (uint32_t)(chalf * NCOL), mt * BM + quad * 32, nt * BN + chalf * NCOL,
+                              NCOL, reinterpret_cast<uint8_t*>(stage_all + (warp - 2) * (32 * STG_PITCH)), lane, nstores,
+                              [&]() {
+                                ptx::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive_relaxed(tb);
+                              });
+      } else {
+        EpiRow rows[4];
+        EpiChunkOps ops0;
+        epilogue_tile_begin<EF>(p.epi, mt * BM + quad * 32, nt * BN, chalf * NCOL, lane, rows, ops0);
+        TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
+        ptx::tc_fence_after();
+        epilogue_tile<EF>(p.epi, taddr, mt * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
+                      stage_all + (warp - 2) * (32 * STG_PITCH), lane, rows, ops0);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_relaxed(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) ptx::bulk_wait<0>();     // this warp's TMA stores have completed before the CTA's smem goes away
   }
 
   if (p.dbg != nullptr && lane == 0 && warp < 3) {  // 0: producer (empty wait) 1: MMA (full, tempty) 2: epilogue (tfull)
@@ -457,7 +656,8 @@ __device__ __forceinline__ void load_stage_operand_2sm(uint8_t* dst, const CUten
 
 template <int BN, int EF, int BKT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const TcParams p) {
   using Cfg = Tc2Config<BN, BKT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -581,26 +781,41 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int NCOL = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t nstores = 0;
     const uint32_t lead_tempty0 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0);
     const uint32_t lead_tempty1 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[1]), 0);
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int mn = tile / p.split_k;
       const int nt = mn % p.n_tiles;
       const int mt = mn / p.n_tiles;
-      EpiRow rows[4];
-      EpiChunkOps ops0;
-      epilogue_tile_begin<EF>(p.epi, (mt * 2 + (int)rank) * BM + quad * 32, nt * BN, chalf * NCOL, lane, rows, ops0);
-      TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
-      ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<EF>(p.epi, taddr, (mt * 2 + (int)rank) * BM + quad * 32, nt * BN, chalf * NCOL, NCOL,
-                    stage_all + (warp - 2) * (32 * STG_PITCH), lane, rows, ops0);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster_relaxed(acc == 0 ? lead_tempty0 : lead_tempty1);
+      const int m_warp = (mt * 2 + (int)rank) * BM + quad * 32;
+      if (RowEpi<EF>::ok && p.row_epi) {
+        TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
+        ptx::tc_fence_after();
+        const uint32_t tb = acc == 0 ? lead_tempty0 : lead_tempty1;
+        epilogue_tile_row<EF>(p.epi, &tmC, &tmP, taddr + (uint32_t)(chalf * NCOL), m_warp, nt * BN + chalf * NCOL, NCOL,
+                              reinterpret_cast<uint8_t*>(stage_all + (warp - 2) * (32 * STG_PITCH)), lane, nstores, [&]() {
+                                ptx::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive_cluster_relaxed(tb);
+                              });
+      } else {
+        EpiRow rows[4];
+        EpiChunkOps ops0;
+        epilogue_tile_begin<EF>(p.epi, m_warp, nt * BN, chalf * NCOL, lane, rows, ops0);
+        TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
+        ptx::tc_fence_after();
+        epilogue_tile<EF>(p.epi, taddr, m_warp, nt * BN, chalf * NCOL, NCOL,
+                      stage_all + (warp - 2) * (32 * STG_PITCH), lane, rows, ops0);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster_relaxed(acc == 0 ? lead_tempty0 : lead_tempty1);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) ptx::bulk_wait<0>();     // this warp's TMA stores have completed before the CTA's smem goes away
   }
 
   if (p.dbg != nullptr && lane == 0 && warp < 3) {
@@ -687,6 +902,54 @@ int make_map(CUtensorMap* out, const void* ptr, long long inner, long long rows,
     if (g_maps.size() > 8192) g_maps.clear();
     g_maps[key] = *out;
   }
+  return 0;
+}
+
+// 2-D bf16 map of a dense output matrix {N columns, M rows} (row stride ld elements) for the TMA stores of the row-layout
+// epilogue: box {32 columns, 32 rows}, 64-byte swizzle (the layout row_chunk() writes)
+int make_store_map(CUtensorMap* out, const void* ptr, long long N, long long M, long long ld) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = N; key.rows = M; key.groups = 1; key.rs = ld; key.gs = -3232;
+  key.b0 = 32; key.b1 = 32; key.b2 = 1;
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  EGB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed (%d): N=%lld M=%lld ld=%lld", (int)r, N, M, ld);
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps[key] = *out;
+  return 0;
+}
+
+// Decides whether this launch runs the row-layout epilogue and builds its store maps (mc: output, mp: second output).
+int setup_row_epilogue(TcParams* p, CUtensorMap* mc, CUtensorMap* mp) {
+  static const int enabled = getenv("EGB_GEMM_ROWEPI") ? atoi(getenv("EGB_GEMM_ROWEPI")) : 1;
+  memset(mc, 0, sizeof(*mc));
+  memset(mp, 0, sizeof(*mp));
+  p->row_epi = 0;
+  if (!enabled) return 0;
+  const int mask = egb_epi_fast_mask(p->epi);
+  if (mask == EF_GENERIC || (mask & (EF_ACC | EF_RES | EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL | EF_COLSUM)) || p->N < 32) return 0;
+  auto dense = [&](const EpiMat& m) {
+    return m.ptr != nullptr && !m.f32 && m.vec_ok && m.rpg >= p->M && m.rs >= p->N;
+  };
+  if (!dense(p->epi.c)) return 0;
+  if ((mask & EF_PRE) && !dense(p->epi.c_pre)) return 0;
+  if (make_store_map(mc, p->epi.c.ptr, p->N, p->M, p->epi.c.rs)) return 1;
+  if ((mask & EF_PRE) && make_store_map(mp, p->epi.c_pre.ptr, p->N, p->M, p->epi.c_pre.rs)) return 1;
+  p->row_epi = 1;
   return 0;
 }
 
@@ -844,7 +1107,7 @@ int make_operand_map(CUtensorMap* out, const egb_operand& o, int extent_mn, int 
 }
 
 template <int BN, int EF, int BKT>
-int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
   using Cfg = TcConfig<BN, BKT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -859,7 +1122,7 @@ int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
     egb_prof_tag(p.M, p.N, p.K, 1e6 + BN * 1e4 + EF);
   }
-  gemm_tc_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  gemm_tc_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, mc, mp, p);
   if (prof) egb_prof_end(stream);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
@@ -870,35 +1133,35 @@ int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams
 #define EGB_EF_SWITCH(FN, BN_, FAST)                                                                            \
   if (FAST) {                                                                                                   \
     switch (egb_epi_fast_mask(p.epi)) {                                                                         \
-      case 0: return FN<BN_, 0>(ma, mb, p, stream);                                                             \
-      case EF_BIAS: return FN<BN_, EF_BIAS>(ma, mb, p, stream);                                                 \
-      case EF_BIAS | EF_RES: return FN<BN_, EF_BIAS | EF_RES>(ma, mb, p, stream);                               \
-      case EF_BIAS | EF_RELU: return FN<BN_, EF_BIAS | EF_RELU>(ma, mb, p, stream);                             \
+      case 0: return FN<BN_, 0>(ma, mb, mc, mp, p, stream);                                                             \
+      case EF_BIAS: return FN<BN_, EF_BIAS>(ma, mb, mc, mp, p, stream);                                                 \
+      case EF_BIAS | EF_RES: return FN<BN_, EF_BIAS | EF_RES>(ma, mb, mc, mp, p, stream);                               \
+      case EF_BIAS | EF_RELU: return FN<BN_, EF_BIAS | EF_RELU>(ma, mb, mc, mp, p, stream);                             \
       case EF_BIAS | EF_GELU | EF_PRE | EF_DGELU:                                                               \
-        return FN<BN_, EF_BIAS | EF_GELU | EF_PRE | EF_DGELU>(ma, mb, p, stream);                               \
-      case EF_ABWD_RELU: return FN<BN_, EF_ABWD_RELU>(ma, mb, p, stream);                                       \
-      case EF_ABWD_MUL: return FN<BN_, EF_ABWD_MUL>(ma, mb, p, stream);                                         \
-      case EF_ABWD_RELU | EF_COLSUM: return FN<BN_, EF_ABWD_RELU | EF_COLSUM>(ma, mb, p, stream);               \
-      case EF_ABWD_MUL | EF_COLSUM: return FN<BN_, EF_ABWD_MUL | EF_COLSUM>(ma, mb, p, stream);                 \
-      case EF_ACC: return FN<BN_, EF_ACC>(ma, mb, p, stream);                                                   \
+        return FN<BN_, EF_BIAS | EF_GELU | EF_PRE | EF_DGELU>(ma, mb, mc, mp, p, stream);                               \
+      case EF_ABWD_RELU: return FN<BN_, EF_ABWD_RELU>(ma, mb, mc, mp, p, stream);                                       \
+      case EF_ABWD_MUL: return FN<BN_, EF_ABWD_MUL>(ma, mb, mc, mp, p, stream);                                         \
+      case EF_ABWD_RELU | EF_COLSUM: return FN<BN_, EF_ABWD_RELU | EF_COLSUM>(ma, mb, mc, mp, p, stream);               \
+      case EF_ABWD_MUL | EF_COLSUM: return FN<BN_, EF_ABWD_MUL | EF_COLSUM>(ma, mb, mc, mp, p, stream);                 \
+      case EF_ACC: return FN<BN_, EF_ACC>(ma, mb, mc, mp, p, stream);                                                   \
       default: break;                                                                                           \
     }                                                                                                           \
   }                                                                                                             \
-  return FN<BN_, EF_GENERIC>(ma, mb, p, stream);
+  return FN<BN_, EF_GENERIC>(ma, mb, mc, mp, p, stream);
 
 template <int BN, int EF>
-int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
-  if (p.bkt == 128 && BN <= 128) return launch_tc_ef_bk<BN, EF, 128>(ma, mb, p, stream);
-  return launch_tc_ef_bk<BN, EF, 64>(ma, mb, p, stream);
+int launch_tc_ef(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
+  if (p.bkt == 128 && BN <= 128) return launch_tc_ef_bk<BN, EF, 128>(ma, mb, mc, mp, p, stream);
+  return launch_tc_ef_bk<BN, EF, 64>(ma, mb, mc, mp, p, stream);
 }
 
 template <int BN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
   EGB_EF_SWITCH(launch_tc_ef, BN, true)
 }
 
 template <int BN, int EF, int BKT>
-int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
   using Cfg = Tc2Config<BN, BKT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -914,7 +1177,7 @@ int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
     egb_prof_tag(p.M, p.N, p.K, 2e6 + BN * 1e4 + EF);
   }
-  gemm_tc2_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+  gemm_tc2_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, mc, mp, p);
   if (prof) egb_prof_end(stream);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
@@ -922,13 +1185,13 @@ int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
 }
 
 template <int BN, int EF>
-int launch_tc2_ef(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
-  if (p.bkt == 128) return launch_tc2_ef_bk<BN, EF, 128>(ma, mb, p, stream);
-  return launch_tc2_ef_bk<BN, EF, 64>(ma, mb, p, stream);
+int launch_tc2_ef(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
+  if (p.bkt == 128) return launch_tc2_ef_bk<BN, EF, 128>(ma, mb, mc, mp, p, stream);
+  return launch_tc2_ef_bk<BN, EF, 64>(ma, mb, mc, mp, p, stream);
 }
 
 template <int BN>
-int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t stream) {
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
   EGB_EF_SWITCH(launch_tc2_ef, BN, true)
 }
 
@@ -985,7 +1248,9 @@ int gemm_tc_pair(const egb_gemm_desc* d, cudaStream_t stream, int BN) {
   p.dbg = g_gemm_dbg;
   static const int skipb = getenv("EGB_GEMM_SKIPB") ? atoi(getenv("EGB_GEMM_SKIPB")) : 0;
   p.dbg_skip = skipb;
-  return BN == 256 ? launch_tc2<256>(ma, mb, p, stream) : launch_tc2<128>(ma, mb, p, stream);
+  CUtensorMap mc, mp;
+  if (setup_row_epilogue(&p, &mc, &mp)) return 1;
+  return BN == 256 ? launch_tc2<256>(ma, mb, mc, mp, p, stream) : launch_tc2<128>(ma, mb, mc, mp, p, stream);
 }
 
 }  // namespace
@@ -1063,9 +1328,11 @@ int egb_gemm_tc(const egb_gemm_desc* d, cudaStream_t stream) {
     static const int skipb = getenv("EGB_GEMM_SKIPB") ? atoi(getenv("EGB_GEMM_SKIPB")) : 0;
     p.dbg_skip = skipb;
   }
+  CUtensorMap mc, mp;
+  if (setup_row_epilogue(&p, &mc, &mp)) return 1;
   switch (BN) {
-    case 256: return launch_tc<256>(ma, mb, p, stream);
-    case 128: return launch_tc<128>(ma, mb, p, stream);
-    default: return launch_tc<64>(ma, mb, p, stream);
+    case 256: return launch_tc<256>(ma, mb, mc, mp, p, stream);
+    case 128: return launch_tc<128>(ma, mb, mc, mp, p, stream);
+    default: return launch_tc<64>(ma, mb, mc, mp, p, stream);
   }
 }

@@ -33,7 +33,7 @@ def report(tag, named, ref):
         print("    %-50s max-rel %.3e fro-rel %.3e" % (k, e, f))
 
 
-for name, Bs in (("vit_small_patch16_224", (4, 16)), ("vit_base_patch16_224", (4, 8))):
+for name, Bs in (("vit_small_patch16_224", (4, 16)), ("vit_base_patch16_224", (4, 8))) if "--eeg-only" not in sys.argv else ():
     heads = V.VIT_VARIANTS[name][2]
     sd = V.init_vit_state_dict(name, 6, 3, "backbone.", seed=31)
     m = EarlyFusionViT(name, num_classes=3, pretrained=False, fusion_mode="concat")
@@ -50,7 +50,7 @@ for name, Bs in (("vit_small_patch16_224", (4, 16)), ("vit_base_patch16_224", (4
         report("%s B=%d" % (name, B), list(m.named_parameters()), sdr)
 
 for cfg, T, Bs in ((O.EEGConfig(in_channels=32, max_len=128, use_spectrogram=False, use_ibs=False), 512, (8, 32)),
-                   (O.EEGConfig(in_channels=32, max_len=256), 1024, (4, 16))):
+                   (O.EEGConfig(in_channels=32, max_len=256), 1024, (8,))):
     sd = O.init_state_dict(cfg, 2)
     m = DualEEGTransformer(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
     m.load_state_dict(sd, strict=True)
@@ -77,6 +77,18 @@ for cfg, T, Bs in ((O.EEGConfig(in_channels=32, max_len=128, use_spectrogram=Fal
             def __init__(self, g):
                 self.grad = g
         report("   torch autocast(bf16) on cuda, same inputs", [(k, _P(v.grad.cpu())) for k, v in sdg.items() if v.grad is not None], sdr)
+        ratio = []
+        for k, p in m.named_parameters():
+            r = sdr[k].grad
+            if r is None or r.abs().max().item() < 1e-7 or sdg[k].grad is None:
+                continue
+            eo = (p.grad.float().cpu() - r).norm().item() / r.norm().item()
+            et = (sdg[k].grad.float().cpu() - r).norm().item() / r.norm().item()
+            ratio.append((eo / max(et, 1e-9), eo, et, k))
+        ratio.sort(reverse=True)
+        print("   fro-rel ours / torch-autocast, per parameter (all):")
+        for q, eo, et, k in ratio:
+            print("      %-52s ours %.3e torch %.3e ratio %5.2f" % (k, eo, et, q))
         m.zero_grad(set_to_none=True)
         with precision("fp32"):
             out = m(e1.to(DEV), e2.to(DEV), labels.to(DEV))
