@@ -80,6 +80,8 @@ def parse_args():
     ap.add_argument("--no-train-step", action="store_true", help="skip the fwd+bwd+clip+AdamW leg")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg")
     ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient all-reduce bucket size (N>1)")
+    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"],
+                    help="wire dtype of the gradient all-reduce (N>1); bf16 halves the bytes, the optimiser still sees fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -93,7 +95,8 @@ def make_config(args, world):
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
     return {"workload": args.workload + ": " + wl["desc"], "trials_per_gpu": B, "global_batch": B * world,
-            "parallelism": "dp%d (trial-wise shards, gradient all-reduce over NCCL)" % world,
+            "parallelism": "dp%d (trial-wise shards, gradient all-reduce over NCCL%s)" % (
+                world, ", %s on the wire" % args.grad_comm if world > 1 else ""),
             "mode": "train (dropout on), fwd+bwd" if args.mode == "train" else "inference (eval), fwd only",
             "l2": "inputs larger than L2: every step reads a fresh batch of synthetic trials"}
 
@@ -389,7 +392,8 @@ def run_b200(args):
 
     model = build_model(wl, dev)
     model.train(train)
-    tp = TrialParallel(model, bucket_mb=args.bucket_mb)
+    tp = TrialParallel(model, bucket_mb=args.bucket_mb,
+                       comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
     n_params = sum(p.numel() for p in model.parameters())
     loss_fn = make_loss_fn(wl, tp, train)
 

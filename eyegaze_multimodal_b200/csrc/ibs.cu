@@ -28,17 +28,34 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// in-place radix-2 DIT on bit-reversed input; tw[k] = exp(-2 pi i k / T); conj -> inverse transform
-template <bool INVERSE>
-__device__ __forceinline__ void fft_inplace(float2* a, const float2* tw, int T, int logT) {
-  for (int s = 1; s <= logT; ++s) {
-    const int half = 1 << (s - 1);
-    const int tstep = T >> s;
+// In-place radix-2 FFTs over shared memory without any bit-reversal pass:
+//   fft_dif   natural-order input  -> spectrum in BIT-REVERSED order (Gentleman-Sande, stages half = T/2 .. 1)
+//   ifft_dit  bit-reversed input   -> natural-order output           (Cooley-Tukey,     stages half = 1 .. T/2)
+// The band mask is applied to the bit-reversed spectrum element by element (k = brev(index)), so the scatter
+// a[brev(n)] = .. of the first version -- 32 lanes hitting one bank, seven times per channel -- is gone.
+// Twiddles come from a STAGE-CONTIGUOUS table tws[half + pos] = exp(-2 pi i pos / (2 half)): with the single
+// exp(-2 pi i k / T) table a stage's twiddles sit T / (2 half) entries apart, i.e. all in ONE bank for the middle
+// stages (measured on the first version: 362 M bank conflicts per launch, l1tex at 95 % of its throughput).
+__device__ __forceinline__ void fft_dif(float2* a, const float2* tws, int T) {
+  for (int half = T >> 1; half >= 1; half >>= 1) {
     for (int i = threadIdx.x; i < T / 2; i += blockDim.x) {
-      const int grp = i >> (s - 1), pos = i & (half - 1);
-      const int i0 = (grp << s) + pos, i1 = i0 + half;
-      float2 w = tw[pos * tstep];
-      if (INVERSE) w.y = -w.y;
+      const int pos = i & (half - 1);
+      const int i0 = ((i - pos) << 1) + pos, i1 = i0 + half;
+      const float2 w = tws[half + pos];
+      const float2 u = a[i0], v = a[i1];
+      a[i0] = make_float2(u.x + v.x, u.y + v.y);
+      a[i1] = cmul(w, make_float2(u.x - v.x, u.y - v.y));
+    }
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ void ifft_dit(float2* a, const float2* tws, int T) {
+  for (int half = 1; half < T; half <<= 1) {
+    for (int i = threadIdx.x; i < T / 2; i += blockDim.x) {
+      const int pos = i & (half - 1);
+      const int i0 = ((i - pos) << 1) + pos, i1 = i0 + half;
+      float2 w = tws[half + pos];
+      w.y = -w.y;
       const float2 t = cmul(w, a[i1]);
       const float2 u = a[i0];
       a[i0] = make_float2(u.x + t.x, u.y + t.y);
@@ -68,21 +85,25 @@ __global__ void __launch_bounds__(256) ibs_analytic_kernel(const float* __restri
                                                            IbsBands bands, int B, int C, int T, int logT, int lo_min,
                                                            int nbins) {
   extern __shared__ float2 sm2[];
-  float2* a = sm2;              // [T]
-  float2* X = a + T;            // [T/2 + 1]
-  float2* tw = X + T / 2 + 1;   // [T/2]
+  float2* a = sm2;              // [T]  work array
+  float2* X = a + T;            // [T]  forward spectrum, bit-reversed order: X[brev(k)] = X_k
+  float2* tws = X + T;          // [T]  stage-contiguous twiddles
   __shared__ float red[8];
   const int c = blockIdx.x, stream = blockIdx.y, b = blockIdx.z;
   const float* src = (stream == 0 ? e1 : e2) + ((long long)b * C + c) * T;
-  for (int i = threadIdx.x; i < T / 2; i += blockDim.x) tw[i] = twiddle[i];
-  for (int n = threadIdx.x; n < T; n += blockDim.x) a[__brev((unsigned)n) >> (32 - logT)] = make_float2(src[n], 0.f);
+  const int rsh = 32 - logT;
+  for (int i = threadIdx.x + 1; i < T; i += blockDim.x) {
+    const int half = 1 << (31 - __clz(i));
+    tws[i] = twiddle[(i - half) * (T / (2 * half))];
+  }
+  for (int n = threadIdx.x; n < T; n += blockDim.x) a[n] = make_float2(src[n], 0.f);
   __syncthreads();
-  fft_inplace<false>(a, tw, T, logT);
-  for (int k = threadIdx.x; k <= T / 2; k += blockDim.x) X[k] = a[k];
+  fft_dif(a, tws, T);
+  for (int k = threadIdx.x; k < T; k += blockDim.x) X[k] = a[k];
   __syncthreads();
   float* ps = pspec + (((long long)b * 2 + stream) * C + c) * nbins;
   for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
-    const float2 v = X[lo_min + k];
+    const float2 v = X[__brev((unsigned)(lo_min + k)) >> rsh];
     ps[k] = v.x * v.x + v.y * v.y;
     if (cspec != nullptr) cspec[(((long long)b * 2 + stream) * C + c) * nbins + k] = v;
   }
@@ -90,16 +111,17 @@ __global__ void __launch_bounds__(256) ibs_analytic_kernel(const float* __restri
   for (int bi = 0; bi < bands.nb; ++bi) {
     const int lo = bands.lo[bi], hi = bands.hi[bi];
     // one-sided spectrum with the Hilbert weights h_k (1 at DC / Nyquist, 2 elsewhere), scaled by 1/T
-    for (int k = threadIdx.x; k < T; k += blockDim.x) {
+    for (int idx = threadIdx.x; idx < T; idx += blockDim.x) {
+      const int k = (int)(__brev((unsigned)idx) >> rsh);      // frequency held at this position
       float2 v = make_float2(0.f, 0.f);
       if (k >= lo && k <= hi && k <= T / 2) {
         const float h = (k == 0 || k == T / 2) ? invT : 2.f * invT;
-        v = make_float2(X[k].x * h, X[k].y * h);
+        v = make_float2(X[idx].x * h, X[idx].y * h);
       }
-      a[__brev((unsigned)k) >> (32 - logT)] = v;
+      a[idx] = v;
     }
     __syncthreads();
-    fft_inplace<true>(a, tw, T, logT);
+    ifft_dit(a, tws, T);
     // statistics of xb and p = xb^2 (two-pass, unbiased std as torch.std)
     float sx = 0.f, sp = 0.f;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -475,9 +497,9 @@ int egb_ibs_connectivity(const float* eeg1, const float* eeg2, const float* twid
   slots.n_out = n_out;
   for (int f = 0; f < 7; ++f) slots.slot_of[f] = slot_of[f];
 
-  const size_t smem1 = sizeof(float2) * ((size_t)T + T / 2 + 1 + T / 2);
+  const size_t smem1 = sizeof(float2) * 3 * (size_t)T;
   static size_t smem1_set = 0;
-  if (smem1 > 48 * 1024 && smem1 > smem1_set) {
+  if (smem1 + 1024 > 48 * 1024 && smem1 > smem1_set) {   // (+ the kernel's static shared memory)
     EGB_CUDA(cudaFuncSetAttribute(ibs_analytic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     smem1_set = smem1;
   }
@@ -524,9 +546,9 @@ int egb_ibs_scalar_features(const float* eeg1, const float* eeg2, const float* t
   }
   if (hi_max < lo_min) { lo_min = 0; hi_max = 0; }
   const int nbins = hi_max - lo_min + 1;
-  const size_t smem1 = sizeof(float2) * ((size_t)T + T / 2 + 1 + T / 2);
+  const size_t smem1 = sizeof(float2) * 3 * (size_t)T;
   static size_t smem1_set = 0;
-  if (smem1 > 48 * 1024 && smem1 > smem1_set) {
+  if (smem1 + 1024 > 48 * 1024 && smem1 > smem1_set) {   // (+ the kernel's static shared memory)
     EGB_CUDA(cudaFuncSetAttribute(ibs_analytic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     smem1_set = smem1;
   }

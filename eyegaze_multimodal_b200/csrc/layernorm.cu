@@ -1,6 +1,8 @@
 // LayerNorm forward / backward over the last dimension (art.py:283-296,306,328 post-LN blocks, eps 1e-5;
 // timm ViT pre-LN, eps 1e-6).  One warp per row, 128-bit loads, row kept in registers (D <= 1024) so the
 // tensor is read exactly once per pass; mean / rstd are saved in fp32 for the backward.
+#include <stdlib.h>
+#include <stdint.h>
 #include "common.cuh"
 #include "../../include/eyegaze_b200.h"
 
@@ -200,6 +202,191 @@ __global__ void __launch_bounds__(LnBwdShape<C>::kThreads, LnBwdShape<C>::kCtasP
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Staged variant (bf16): the rows of x, dy and the residual gradient are contiguous in memory, so a producer thread
+// streams them into a shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier, LN_ROWS rows per tensor and
+// stage) and the compute warps only ever wait on shared memory.  The register version above keeps one row per warp in
+// flight -- 12 warps x 4.6 KB per SM against ~1.2 us of DRAM latency = 3.3 TB/s measured (the column accumulators take
+// 72 registers per thread, which rules out a second row or more warps); the ring holds LN_STAGES x 12 rows per SM
+// independently of the register file.  A warp copies its row from the ring into registers and releases the slot at
+// once, so the ring is purely a latency-hiding FIFO.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LN_ROWS = 11;      // rows per stage = compute warps per CTA (+ the producer warp = 12 warps: 168 registers each)
+constexpr int LN_STAGES = 3;
+
+__device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ln_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ln_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ln_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ln_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ln_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ln_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ln_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LN_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra LN_WAIT_%=;\n\t}" ::"r"(ln_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void ln_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ln_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(ln_smem_u32(bar))
+               : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__((LN_ROWS + 1) * 32, 1)
+layernorm_bwd_staged_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dx,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta, const bf16* __restrict__ dres,
+                            float* __restrict__ dx_colsum, int M, int D) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int ntens = dres != nullptr ? 3 : 2;
+  const size_t tile_bytes = (size_t)LN_ROWS * D * sizeof(bf16);            // one tensor, one stage
+  uint8_t* ring = ln_smem;                                                  // [LN_STAGES][3][LN_ROWS][D] bf16
+  float* red = reinterpret_cast<float*>(ring + (size_t)LN_STAGES * 3 * tile_bytes);   // [3][D] column partials
+  float* sg = red + 3 * D;                                                  // [D] gamma
+  uint64_t* full = reinterpret_cast<uint64_t*>(sg + D);                     // [LN_STAGES]
+  uint64_t* empty = full + LN_STAGES;                                       // [LN_STAGES]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sg[i] = gamma[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) { ln_mbar_init(&full[s], 1); ln_mbar_init(&empty[s], LN_ROWS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ntiles = (M + LN_ROWS - 1) / LN_ROWS;
+
+  if (warp == LN_ROWS) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        ln_mbar_wait(&empty[s], ph ^ 1u);
+        const int r0 = t * LN_ROWS;
+        const int rows = min(LN_ROWS, M - r0);
+        const uint32_t bytes = (uint32_t)((size_t)rows * D * sizeof(bf16));
+        ln_mbar_expect_tx(&full[s], bytes * (uint32_t)ntens);
+        uint8_t* dst = ring + (size_t)s * 3 * tile_bytes;
+        ln_bulk_load(dst, x + (size_t)r0 * D, bytes, &full[s]);
+        ln_bulk_load(dst + tile_bytes, dy + (size_t)r0 * D, bytes, &full[s]);
+        if (dres != nullptr) ln_bulk_load(dst + 2 * tile_bytes, dres + (size_t)r0 * D, bytes, &full[s]);
+        if (++s == LN_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ compute warps: warp w owns row w of every tile
+  float ag[C][8], ab[C][8], ac[C][8];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = ac[c][j] = 0.f;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int row = t * LN_ROWS + warp;
+    const bool live = row < M;
+    float mean = 0.f, rstd = 0.f;
+    if (live) { mean = mean_in[row]; rstd = rstd_in[row]; }
+    ln_mbar_wait(&full[s], ph);
+    Raw8<bf16> xr[C], dr[C], rr[C];
+    const uint8_t* base = ring + (size_t)s * 3 * tile_bytes + (size_t)warp * D * sizeof(bf16);
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int d = c * 256 + lane * 8;
+        if (d < D) {
+          xr[c].q = *reinterpret_cast<const uint4*>(base + (size_t)d * 2);
+          dr[c].q = *reinterpret_cast<const uint4*>(base + tile_bytes + (size_t)d * 2);
+          if (dres != nullptr) rr[c].q = *reinterpret_cast<const uint4*>(base + 2 * tile_bytes + (size_t)d * 2);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ln_mbar_arrive(&empty[s]);        // the row is in registers: the slot may be refilled
+    if (++s == LN_STAGES) { s = 0; ph ^= 1u; }
+    if (!live) continue;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (d < D) {
+        float xv[8], dv[8];
+        xr[c].unpack(xv);
+        dr[c].unpack(dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(sg + d), g1 = *reinterpret_cast<const float4*>(sg + d + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = dv[j] * gm[j];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          ag[c][j] = fmaf(dv[j], xh, ag[c][j]);
+          ab[c][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int d = c * 256 + lane * 8;
+      if (d < D) {
+        float xv[8], dv[8], o[8];
+        xr[c].unpack(xv);
+        dr[c].unpack(dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(sg + d), g1 = *reinterpret_cast<const float4*>(sg + d + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          o[j] = rstd * (fmaf(dv[j], gm[j], -s1) - xh * s2);
+        }
+        if (dres != nullptr) {
+          float rv[8];
+          rr[c].unpack(rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
+        st8(dx + (long long)row * D + d, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ac[c][j] += to_f(from_f<bf16>(o[j]));
+      }
+    }
+  }
+  // block reduction of the per-warp column partials (compute warps only; the producer warp has left), then one atomic
+  // per column per CTA
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int d = c * 256 + lane * 8;
+    if (d < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[d + j], ag[c][j]);
+        atomicAdd(&red[D + d + j], ab[c][j]);
+        if (dx_colsum != nullptr) atomicAdd(&red[2 * D + d + j], ac[c][j]);
+      }
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(LN_ROWS * 32) : "memory");
+  for (int i = threadIdx.x; i < D; i += LN_ROWS * 32) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[D + i]);
+    if (dx_colsum != nullptr) atomicAdd(dx_colsum + i, red[2 * D + i]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -241,6 +428,38 @@ int egb_layernorm_bwd_ex(const void* dy, const void* x, const float* gamma, cons
   // few, fat CTAs: every CTA ends with 3 D column atomics, and with several hundred CTAs those serialise per address in
   // L2 (a measurable tail)
   const int chunks = (D + 255) / 256;
+  {
+    // bf16 rows stream through the shared-memory ring (EGB_LN_STAGED=0 keeps the register version)
+    static const int staged = getenv("EGB_LN_STAGED") ? atoi(getenv("EGB_LN_STAGED")) : 1;
+    const size_t smem_s = (size_t)LN_STAGES * 3 * LN_ROWS * D * 2 + (size_t)4 * D * sizeof(float) + 2 * LN_STAGES * 8;
+    const bool aligned = ((uintptr_t)dy % 16 == 0) && ((uintptr_t)x % 16 == 0) && (dres == nullptr || (uintptr_t)dres % 16 == 0);
+    // (rows of <= 256 columns: 50 us staged vs 45 us from registers -- one 512-byte row per warp and stage is too little per
+    //  barrier round trip; the ring pays off from two 256-column chunks up: ViT-B 85 -> 77 us)
+    if (staged && dtype == EGB_BF16 && aligned && chunks >= 2 && M >= 4 * LN_ROWS && smem_s <= 200 * 1024) {
+      int blocks = (M + LN_ROWS - 1) / LN_ROWS;
+      if (blocks > egb_num_sms()) blocks = egb_num_sms();
+#define EGB_LN_ST(CC)                                                                                                   \
+  do {                                                                                                                  \
+    static bool attr = false;                                                                                           \
+    if (!attr) {                                                                                                        \
+      EGB_CUDA(cudaFuncSetAttribute(layernorm_bwd_staged_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      attr = true;                                                                                                      \
+    }                                                                                                                   \
+    layernorm_bwd_staged_kernel<CC><<<blocks, (LN_ROWS + 1) * 32, smem_s, st>>>(                                        \
+        (const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (bf16*)dx, dgamma, dbeta, (const bf16*)dres, dx_colsum, M, D); \
+  } while (0)
+      switch (chunks) {
+        case 1: EGB_LN_ST(1); break;
+        case 2: EGB_LN_ST(2); break;
+        case 3: EGB_LN_ST(3); break;
+        default: EGB_LN_ST(4); break;
+      }
+#undef EGB_LN_ST
+      egb_count_launch(1);
+      EGB_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const size_t smem = (size_t)4 * D * sizeof(float);
   const int threads = chunks == 1 ? LnBwdShape<1>::kThreads : (chunks == 2 ? LnBwdShape<2>::kThreads : LnBwdShape<3>::kThreads);
   int blocks = (M + threads / 32 - 1) / (threads / 32);

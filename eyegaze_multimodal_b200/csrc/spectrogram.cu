@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) stft_logmag_kernel(const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                               const float* __restrict__ bias, T* __restrict__ out, int Hh,
-                                                              int Ww, int H1, int W1, int Wp, long long out_img_stride) {
+                                                              int Ww, int H1, int W1, int Wp, long long out_img_stride,
+                                                              unsigned short* __restrict__ amax) {
   extern __shared__ float sm[];
   float* im = sm;                    // [(Hh+2)][(Ww+2)] zero padded
   float* wsm = im + (Hh + 2) * (Ww + 2);  // [32][9] + [32]
@@ -125,9 +126,11 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __res
 #pragma unroll
       for (int b = 0; b < 4; ++b) patch[a][b] = im[(2 * ph + a) * ldw + 2 * pw + b];
     float res[4];
+    unsigned code = 0;   // per channel 3 bits: 0..3 = which of the 2 x 2 conv outputs won the pool, 4 = relu inactive
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       float best = 0.f;  // relu(max(.)) == max(0, .)
+      unsigned sel = 4u;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -137,11 +140,13 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __res
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) a = fmaf(wr[cc][kh * 3 + kw], patch[dy + kh][dx + kw], a);
-          best = fmaxf(best, a);
+          if (a > best) { best = a; sel = (unsigned)(dy * 2 + dx); }   // first maximum wins, as in max_pool2d
         }
       res[cc] = best;
+      code |= sel << (3 * cc);
     }
     st4(o + ((long long)(ph + 1) * Wp + (pw + 1)) * 32 + cq * 4, res);
+    if (amax != nullptr) amax[((long long)n * H1 * W1 + pos) * 8 + cq] = (unsigned short)code;
   }
 }
 
@@ -159,6 +164,9 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_bwd_kernel(const float* _
   float* im = sm;
   float* wsm = im + (Hh + 2) * ldw;   // 288 + 32
   float* acc = wsm + 320;             // 288 + 32 block accumulators
+  // this image's dP1 tile, (H1+2) x Wp x 32 in its storage type (16-byte aligned: the floats before it are a multiple of 4)
+  T* gsm = reinterpret_cast<T*>(acc + 320 + ((4 - (((Hh + 2) * ldw) & 3)) & 3));
+  const int g_vec = (int)(out_img_stride * sizeof(T) / 16);
   for (int i = threadIdx.x; i < 320; i += blockDim.x) {
     wsm[i] = i < 288 ? w[i] : bias[i - 288];
     acc[i] = 0.f;
@@ -179,8 +187,15 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_bwd_kernel(const float* _
       const int y = i / ldw - 1, x = i % ldw - 1;
       im[i] = (y >= 0 && y < Hh && x >= 0 && x < Ww) ? img[(long long)n * Hh * Ww + y * Ww + x] : 0.f;
     }
+    // the whole gradient tile in one sweep of 16-byte loads (all in flight at once): read position by position from
+    // global memory, every warp waited a full DRAM round trip per position (1.39 ms for 268 MB)
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(dout + (long long)n * out_img_stride);
+      uint4* dst = reinterpret_cast<uint4*>(gsm);
+      for (int i = threadIdx.x; i < g_vec; i += blockDim.x) dst[i] = src[i];
+    }
     __syncthreads();
-    const T* g = dout + (long long)n * out_img_stride;
+    const T* g = gsm;
     // thread -> channel c = tid & 31 (so the 32 lanes of a warp hit 32 different accumulators).  The lane's nine
     // weights live in registers and the 4 x 4 input patch of a pooled position is read ONCE (16 broadcast loads per
     // warp; the first version issued two shared loads per FMA -- weight and sample -- and was bound by them: 991 us).
@@ -216,6 +231,67 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_bwd_kernel(const float* _
           const float v = sel == 0 ? v0 : sel == 1 ? v1 : sel == 2 ? v2 : v3;
           lw[kh * 3 + kw] = fmaf(gs, v, lw[kh * 3 + kw]);
         }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) atomicAdd(&acc[c * 9 + i], lw[i]);
+  atomicAdd(&acc[288 + c], lb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 320; i += blockDim.x) {
+    if (i < 288) atomicAdd(dw + i, acc[i]);
+    else atomicAdd(db + (i - 288), acc[i]);
+  }
+}
+
+// Same gradients from the arg-max record the forward kernel wrote (3 bits per pooled output): no conv recomputation --
+// the recomputing kernel above executes 935 M warp instructions per cfg2 step (36 FMAs + 27 selects per pooled output
+// to find the winner again) and was bound by instruction issue at 1.5 ms.  Lane = channel; the nine samples under the
+// winning conv output are read from the shared-memory image at a lane-dependent offset (<= 4 distinct addresses per
+// warp instruction).
+template <typename T>
+__global__ void __launch_bounds__(256) spec_conv1_pool_bwd_rec_kernel(const float* __restrict__ img, const T* __restrict__ dout,
+                                                                      const unsigned short* __restrict__ amax,
+                                                                      float* __restrict__ dw, float* __restrict__ db, int N,
+                                                                      int Hh, int Ww, int H1, int W1, int Wp,
+                                                                      long long out_img_stride) {
+  extern __shared__ float sm[];
+  const int ldw = Ww + 2;
+  float* im = sm;
+  float* acc = im + (Hh + 2) * ldw;
+  T* gsm = reinterpret_cast<T*>(acc + 320 + ((4 - (((Hh + 2) * ldw) & 3)) & 3));
+  unsigned short* asm_ = reinterpret_cast<unsigned short*>(gsm + out_img_stride);
+  const int g_vec = (int)(out_img_stride * sizeof(T) / 16);
+  const int a_vec = H1 * W1;                     // 8 x uint16 = one 16-byte vector per position
+  for (int i = threadIdx.x; i < 320; i += blockDim.x) acc[i] = 0.f;
+  float lw[9], lb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) lw[i] = 0.f;
+  const int c = threadIdx.x & 31;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (Hh + 2) * ldw; i += blockDim.x) {
+      const int y = i / ldw - 1, x = i % ldw - 1;
+      im[i] = (y >= 0 && y < Hh && x >= 0 && x < Ww) ? img[(long long)n * Hh * Ww + y * Ww + x] : 0.f;
+    }
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(dout + (long long)n * out_img_stride);
+      uint4* dst = reinterpret_cast<uint4*>(gsm);
+      for (int i = threadIdx.x; i < g_vec; i += blockDim.x) dst[i] = src[i];
+      const uint4* sa = reinterpret_cast<const uint4*>(amax + (long long)n * H1 * W1 * 8);
+      uint4* da = reinterpret_cast<uint4*>(asm_);
+      for (int i = threadIdx.x; i < a_vec; i += blockDim.x) da[i] = sa[i];
+    }
+    __syncthreads();
+    for (int pos = threadIdx.x >> 5; pos < H1 * W1; pos += blockDim.x >> 5) {
+      const int ph = pos / W1, pw = pos - ph * W1;
+      const unsigned sel = ((unsigned)asm_[pos * 8 + (c >> 2)] >> (3 * (c & 3))) & 7u;
+      const float go = sel < 4u ? to_f(gsm[((ph + 1) * Wp + (pw + 1)) * 32 + c]) : 0.f;
+      const float* src = im + (2 * ph + (int)((sel >> 1) & 1u)) * ldw + 2 * pw + (int)(sel & 1u);
+      lb += go;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) lw[kh * 3 + kw] = fmaf(go, src[kh * ldw + kw], lw[kh * 3 + kw]);
     }
   }
 #pragma unroll
@@ -347,7 +423,7 @@ int egb_stft_logmag(const float* eeg1, const float* eeg2, const float* window, f
 
 /* out must hold N * (H1+2) * Wp * 32 elements (+ slack rows for the implicit-GEMM over-read); this call zeroes it. */
 int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias, void* out, int dtype, int N, int Hh,
-                            int Ww, int64_t out_elems, void* stream) {
+                            int Ww, int64_t out_elems, uint16_t* amax, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int H1 = Hh / 2, W1 = Ww / 2, Wp = W1 + 2;
   EGB_CHECK(H1 > 0 && W1 > 0, "spec_conv1: image too small");
@@ -356,9 +432,9 @@ int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias,
   const size_t smem = sizeof(float) * ((size_t)(Hh + 2) * (Ww + 2) + 320);
   const long long istr = (long long)(H1 + 2) * Wp * 32;
   if (dtype == EGB_BF16)
-    spec_conv1_pool_kernel<bf16><<<N, 256, smem, st>>>(img, w, bias, (bf16*)out, Hh, Ww, H1, W1, Wp, istr);
+    spec_conv1_pool_kernel<bf16><<<N, 256, smem, st>>>(img, w, bias, (bf16*)out, Hh, Ww, H1, W1, Wp, istr, amax);
   else
-    spec_conv1_pool_kernel<float><<<N, 256, smem, st>>>(img, w, bias, (float*)out, Hh, Ww, H1, W1, Wp, istr);
+    spec_conv1_pool_kernel<float><<<N, 256, smem, st>>>(img, w, bias, (float*)out, Hh, Ww, H1, W1, Wp, istr, amax);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;
@@ -366,12 +442,40 @@ int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias,
 
 /* dw (288) and db (32) are accumulated into. */
 int egb_spec_conv1_pool_bwd(const float* img, const float* w, const float* bias, const void* dout, int dtype, float* dw,
-                            float* db, int N, int Hh, int Ww, void* stream) {
+                            float* db, int N, int Hh, int Ww, const uint16_t* amax, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int H1 = Hh / 2, W1 = Ww / 2, Wp = W1 + 2;
-  const size_t smem = sizeof(float) * ((size_t)(Hh + 2) * (Ww + 2) + 640);
   const long long istr = (long long)(H1 + 2) * Wp * 32;
-  int blocks = N < 4 * egb_num_sms() ? N : 4 * egb_num_sms();
+  if (amax != nullptr) {
+    const size_t smem_r = sizeof(float) * ((size_t)(Hh + 2) * (Ww + 2) + 320 + 4) + (size_t)istr * (dtype == EGB_BF16 ? 2 : 4) +
+                          (size_t)H1 * W1 * 16;
+    EGB_CHECK(smem_r <= 200 * 1024, "spec_conv1_pool_bwd: image too large for shared memory");
+    static bool attr_r = false;
+    if (!attr_r) {
+      EGB_CUDA(cudaFuncSetAttribute(spec_conv1_pool_bwd_rec_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      EGB_CUDA(cudaFuncSetAttribute(spec_conv1_pool_bwd_rec_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_r = true;
+    }
+    const int blocks_r = N < 6 * egb_num_sms() ? N : 6 * egb_num_sms();
+    if (dtype == EGB_BF16)
+      spec_conv1_pool_bwd_rec_kernel<bf16><<<blocks_r, 256, smem_r, st>>>(img, (const bf16*)dout, amax, dw, db, N, Hh, Ww, H1, W1,
+                                                                       Wp, istr);
+    else
+      spec_conv1_pool_bwd_rec_kernel<float><<<blocks_r, 256, smem_r, st>>>(img, (const float*)dout, amax, dw, db, N, Hh, Ww, H1,
+                                                                        W1, Wp, istr);
+    egb_count_launch(1);
+    EGB_LAUNCH_CHECK();
+    return 0;
+  }
+  const size_t smem = sizeof(float) * ((size_t)(Hh + 2) * (Ww + 2) + 640 + 4) + (size_t)istr * (dtype == EGB_BF16 ? 2 : 4);
+  EGB_CHECK(smem <= 200 * 1024, "spec_conv1_pool_bwd: image too large for shared memory");
+  static bool attr = false;
+  if (!attr) {
+    EGB_CUDA(cudaFuncSetAttribute(spec_conv1_pool_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    EGB_CUDA(cudaFuncSetAttribute(spec_conv1_pool_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  int blocks = N < 6 * egb_num_sms() ? N : 6 * egb_num_sms();
   if (dtype == EGB_BF16)
     spec_conv1_pool_bwd_kernel<bf16><<<blocks, 256, smem, st>>>(img, w, bias, (const bf16*)dout, dw, db, N, Hh, Ww, H1,
                                                                W1, Wp, istr);

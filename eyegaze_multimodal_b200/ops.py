@@ -897,7 +897,7 @@ def _spec_geometry(bins, frames):
     return H1, W1, Wp, Hp * Wp, 2 * Wp + 8           # H1, W1, padded width, padded rows per image, slack rows
 
 
-def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
+def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins, want_amax=False):
     """STFT-log -> conv1+ReLU+maxpool -> conv2 (+bias).  Returns (img, p1, y2, meta); p1 / y2 are zero-bordered
     channels-last images, flat [(N*RP + slack) * C]; y2 is the spec_conv[3] output (pre-ReLU)."""
     eeg1 = eeg1.contiguous().float()
@@ -912,19 +912,21 @@ def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
            hop, bins)
     H1, W1, Wp, RP, slack = _spec_geometry(bins, frames)
     p1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
+    # arg-max record of the fused max-pool (3 bits per pooled output) for the conv-1 weight gradient; int16 storage
+    amax = torch.empty(N * H1 * W1 * 8, dtype=torch.int16, device=dev) if want_amax else None
     TO.call("spec_conv1_pool_fwd", img, w1, b1, p1, code, N, bins,
-           frames, p1.numel())
+           frames, p1.numel(), amax)
     y2 = zeros(((N * RP + slack) * 64,), tdt, dev)
     w2s = _spec_w2_seg(w2, code)
     a = TO.Operand(p1, 0, 0, 32, 0, 128, Wp)
     cm = _dense_matrix(TO.at(y2, (Wp + 1) * 64), code, 64)
     gemm(N * RP, 64, 384, code, a, TO.Operand(w2s, 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
-    return img, p1, y2, (code, N, bins, frames, H1, W1, Wp, RP, slack)
+    return img, p1, y2, (code, N, bins, frames, H1, W1, Wp, RP, slack, amax)
 
 
 def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
     """Gradients of conv2 / conv1 given dY2 in the padded channels-last layout."""
-    code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+    code, N, bins, frames, H1, W1, Wp, RP, slack, amax = meta
     dev, tdt = dy2.device, _TORCH_DT[code]
     dw1 = db1 = dw2 = db2 = None
     if need_b2:
@@ -947,7 +949,7 @@ def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
         gemm(N * RP, 32, 768, code, a, TO.Operand(w2f, 0, 0, 768, 0, 0, 0), cm)
         dwb = zeros((320,), torch.float32, dev)
         TO.call("spec_conv1_pool_bwd", img, w1, b1, dp1, code,
-               dwb, dwb[288:], N, bins, frames)
+               dwb, dwb[288:], N, bins, frames, amax)
         dw1 = dwb[:288].view(32, 1, 3, 3)
         db1 = dwb[288:]
     return dw1, db1, dw2, db2
@@ -955,7 +957,7 @@ def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
 
 def _spec_padded_to_nchw(buf, meta, ch):
     """zero-bordered channels-last image buffer -> dense (N, ch, H1, W1) fp32."""
-    code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+    code, N, bins, frames, H1, W1, Wp, RP, slack = meta[:9]
     out = torch.empty(N, ch, H1, W1, dtype=torch.float32, device=buf.device)
     copy_strided4(buf, out, (N, ch, H1, W1), (RP * ch, 1, Wp * ch, ch), (ch * H1 * W1, H1 * W1, W1, 1),
                   src_offset=(Wp + 1) * ch)
@@ -964,7 +966,7 @@ def _spec_padded_to_nchw(buf, meta, ch):
 
 def _spec_nchw_to_padded(x, meta, ch):
     """dense (N, ch, H1, W1) -> zero-bordered channels-last buffer in the compute dtype."""
-    code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+    code, N, bins, frames, H1, W1, Wp, RP, slack = meta[:9]
     x = x.contiguous()
     buf = zeros(((N * RP + slack) * ch,), _TORCH_DT[code], x.device)
     copy_strided4(x, buf, (N, ch, H1, W1), (ch * H1 * W1, H1 * W1, W1, 1), (RP * ch, 1, Wp * ch, ch),
@@ -978,8 +980,9 @@ class SpectrogramCNNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
         _require_cuda(eeg1, eeg2, w1, w2)
-        img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
-        code, N, bins, frames, H1, W1, Wp, RP, slack = meta
+        img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins,
+                                            want_amax=ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        code, N, bins, frames, H1, W1, Wp, RP, slack = meta[:9]
         pooled = torch.empty(N, 1024, dtype=_TORCH_DT[code], device=img.device)
         TO.call("relu_avgpool_fwd", y2, pooled, code, N, H1, W1)
         ctx.save_for_backward(img, p1, y2, w1, b1, w2)
@@ -988,7 +991,7 @@ class SpectrogramCNNFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpool):
-        code, N, bins, frames, H1, W1, Wp, RP, slack = ctx.meta
+        code, N, bins, frames, H1, W1, Wp, RP, slack = ctx.meta[:9]
         img, p1, y2, w1, b1, w2 = ctx.saved_tensors
         dev, tdt = dpool.device, _TORCH_DT[code]
         dpool = dpool.contiguous()
@@ -1013,7 +1016,8 @@ class SpecConvFrontFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins):
         _require_cuda(eeg1, eeg2, w1, w2)
-        img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins)
+        img, p1, y2, meta = _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins,
+                                            want_amax=ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
         ctx.save_for_backward(img, p1, w1, b1, w2)
         ctx.meta = meta
         p1n = _spec_padded_to_nchw(p1, meta, 32)
@@ -1046,7 +1050,7 @@ class SpecPoolFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpool):
-        code, N, bins, frames, H1, W1, Wp, RP, slack = ctx.meta
+        code, N, bins, frames, H1, W1, Wp, RP, slack = ctx.meta[:9]
         (y2,) = ctx.saved_tensors
         dpool = dpool.contiguous()
         if _code(dpool) != code:

@@ -31,22 +31,31 @@ import torch.nn as nn
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "views", "pending", "work", "launched")
+    __slots__ = ("flat", "params", "views", "pending", "work", "launched", "comm")
 
-    def __init__(self, flat, params, views):
+    def __init__(self, flat, params, views, comm=None):
         self.flat = flat
         self.params = params
         self.views = views
         self.pending = len(params)
         self.work = None
         self.launched = False
+        self.comm = comm            # optional bf16 wire buffer (comm_dtype=torch.bfloat16)
 
 
 class TrialParallel(nn.Module):
     """Wraps a model; ``forward`` is the model's.  Call ``zero_grad()`` before and ``finish()`` after ``backward()``."""
 
-    def __init__(self, module: nn.Module, bucket_mb: float = 32.0, process_group=None, broadcast: bool = True):
+    def __init__(self, module: nn.Module, bucket_mb: float = 32.0, process_group=None, broadcast: bool = True,
+                 comm_dtype: torch.dtype = torch.float32):
+        """``comm_dtype=torch.bfloat16`` sends the gradients over the wire in bf16 (half the bytes and half the time the
+        NCCL channels share the SMs with backward; the sum over ranks is then rounded to bf16, as with PyTorch DDP's
+        ``bf16_compress_hook``); the optimiser still sees fp32 gradients.  Default: fp32, bit-comparable with the
+        single-process gradient."""
         super().__init__()
+        if comm_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("TrialParallel: comm_dtype must be torch.float32 or torch.bfloat16")
+        self.comm_dtype = comm_dtype
         self.module = module
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -85,7 +94,10 @@ class TrialParallel(nn.Module):
                 n += (p.numel() + 3) // 4 * 4
             flat = torch.zeros(n if self.world > 1 else 1, dtype=torch.float32, device=g[0].device)
             views = [flat[o:o + p.numel()].view(p.shape) for p, o in zip(g, offs)] if self.world > 1 else []
-            b = _Bucket(flat, g, views)
+            comm = None
+            if self.world > 1 and self.comm_dtype != torch.float32:
+                comm = torch.zeros(n, dtype=self.comm_dtype, device=g[0].device)
+            b = _Bucket(flat, g, views, comm)
             for p in g:
                 p.grad = None
                 p.register_post_accumulate_grad_hook(self._make_hook(b))
@@ -124,7 +136,11 @@ class TrialParallel(nn.Module):
 
     def _reduce(self, b: _Bucket) -> None:
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
-        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+        buf = b.flat
+        if b.comm is not None:
+            b.comm.copy_(b.flat)               # one cast kernel: the packed fp32 bucket -> its bf16 wire image
+            buf = b.comm
+        b.work = dist.all_reduce(buf, op=op, group=self.group, async_op=True)
 
     # ------------------------------------------------------------------------------------------------
     def forward(self, *args, **kwargs):
@@ -154,6 +170,8 @@ class TrialParallel(nn.Module):
         for b in self.buckets:
             if b.work is not None:
                 b.work.wait()
+                if b.comm is not None:
+                    b.flat.copy_(b.comm)       # back to the fp32 views the optimiser reads
                 if not self._avg:
                     b.flat.div_(self.world)
             if self.world > 1:
@@ -182,7 +200,9 @@ class TrialParallel(nn.Module):
         return getattr(m, "eeg_encoder", m)
 
     def grad_bytes(self) -> int:
-        return sum(sum(p.numel() for p in b.params) * 4 for b in self.buckets)
+        """Bytes one rank hands to the all-reduce per step."""
+        esz = 2 if self.comm_dtype == torch.bfloat16 else 4
+        return sum(sum(p.numel() for p in b.params) * esz for b in self.buckets)
 
     def flat_grads(self) -> Iterable[torch.Tensor]:
         return [b.flat for b in self.buckets]

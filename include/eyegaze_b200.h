@@ -219,11 +219,14 @@ int egb_attention_bwd(const egb_attention_desc* d, void* stream);
 /* STFT(n_fft, hop, hann window, centre/reflect) -> |.| -> first `bins` -> log(+1e-8); out fp32 [2*n_sig, bins, 1+T/hop] */
 int egb_stft_logmag(const float* eeg1, const float* eeg2, const float* window, float* out, int n_sig_per_stream, int T,
                     int n_fft, int hop, int bins, void* stream);
-/* Conv2d(1->32,3x3,p1)+ReLU+MaxPool2 fused; out = zero-bordered channels-last [N, Hh/2+2, Ww/2+2, 32] */
+/* Conv2d(1->32,3x3,p1)+ReLU+MaxPool2 fused; out = zero-bordered channels-last [N, Hh/2+2, Ww/2+2, 32].
+   amax (optional, [N, (Hh/2)*(Ww/2), 8] uint16): per pooled output 3 bits -- which of the 2x2 conv outputs won the pool
+   (0..3, first maximum as in max_pool2d) or 4 = ReLU inactive; four channels per word.  The backward call that gets the
+   record skips the recomputation of the convolution. */
 int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias, void* out, int dtype, int N, int Hh,
-                            int Ww, int64_t out_elems, void* stream);
+                            int Ww, int64_t out_elems, uint16_t* amax, void* stream);
 int egb_spec_conv1_pool_bwd(const float* img, const float* w, const float* bias, const void* dout, int dtype, float* dw,
-                            float* db, int N, int Hh, int Ww, void* stream);
+                            float* db, int N, int Hh, int Ww, const uint16_t* amax, void* stream);
 /* ReLU + AdaptiveAvgPool2d(4,4) + flatten over the padded conv-2 output [N, H1+2, W1+2, 64] */
 int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int W1, void* stream);
 int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream);

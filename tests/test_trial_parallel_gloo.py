@@ -28,12 +28,12 @@ def _data(n=10):
     return torch.randn(n, 16, generator=g), torch.randn(n, 16, generator=g), torch.randint(0, 3, (n,), generator=g)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, comm_dtype=torch.float32):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(100 + rank)            # different init per rank: the wrapper must broadcast rank 0's weights
     model = Toy()
-    tp = TrialParallel(model, bucket_mb=0.004)   # tiny buckets: several all-reduces per step
+    tp = TrialParallel(model, bucket_mb=0.004, comm_dtype=comm_dtype)   # tiny buckets: several all-reduces per step
     assert len(tp.buckets) > 2
     a, b, y = _data()
     idx = list(shard_trials(len(y), rank, world))
@@ -63,6 +63,27 @@ def test_gradients_match_single_process():
         want = p.grad if p.grad is not None else torch.zeros_like(p)
         for r in (0, 1):
             assert torch.allclose(out[r][n], want, atol=1e-6), (n, r)
+
+
+def test_bf16_wire_gradients_close_to_single_process():
+    """comm_dtype=bfloat16: the buckets cross the wire in bf16, the optimiser still sees fp32 tensors; the result is the
+    single-process gradient up to bf16 rounding of each rank's contribution and of the sum."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out, torch.bfloat16), nprocs=2, join=True)
+    torch.manual_seed(100)
+    ref = Toy()
+    a, b, y = _data()
+    nn.functional.cross_entropy(ref(a, b), y).backward()
+    for n, p in ref.named_parameters():
+        want = p.grad if p.grad is not None else torch.zeros_like(p)
+        for r in (0, 1):
+            assert out[r][n].dtype == torch.float32
+            assert torch.allclose(out[r][n], want, atol=2e-2 * float(want.abs().max()) + 1e-6), (n, r)
+        assert torch.equal(out[0][n], out[1][n])        # every rank ends with the same reduced gradient
 
 
 def test_shard_trials_ragged():
