@@ -233,6 +233,31 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRo
   }
 }
 
+// L2 prefetch of the row-layout operand (residual / activation-backward factor) of a tile this CTA will drain LATER:
+// ncu put 27 % of the dX-through-GELU' kernel's stall samples on the first use of those loads -- fetched one 32 x 32 chunk
+// ahead (~500 cycles) they still arrive from DRAM.  Issued a whole tile ahead they are L2 hits by the time the epilogue
+// asks for them.  `t` = index of the calling thread among the CTA's 256 epilogue threads; rows [m0, m0 + 128), columns
+// [n0, n0 + bn).
+template <int EF>
+__device__ __forceinline__ void epilogue_prefetch_l2(const EpiParams& epi, int m0, int n0, int bn, int t) {
+  // (activation-backward operands only: a residual is the layer's own input, still L2-resident from the forward read --
+  //  prefetching it cost the proj + residual GEMMs 8-13 %)
+  if ((EF & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) == 0 || EF == EF_GENERIC) return;
+  const EpiMat& mat = epi.aux;
+  int cols = epi.N - n0;
+  if (cols > bn) cols = bn;
+  if (cols <= 0) return;
+  const int lines_per_row = (cols * 2 + 127) >> 7;
+  for (int idx = t; idx < 128 * lines_per_row; idx += 256) {
+    const int r = idx / lines_per_row, l = idx - r * lines_per_row;
+    const int m = m0 + r;
+    if (m < epi.M) {
+      const char* ptr = mat.ptr + (epi_row_offset(mat, m) + n0) * 2 + (long long)l * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+  }
+}
+
 // before the accumulator is ready: row bookkeeping and the first chunk's operands
 template <int EF>
 __device__ __forceinline__ void epilogue_tile_begin(const EpiParams& epi, int m_base, int n0, int col0, int lane,
@@ -315,6 +340,51 @@ __device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMa
   const uint32_t rowP = ptx::smem_u32(bufP) + (uint32_t)(lane * 64);
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);
   float cs[(EF & EF_COLSUM) ? 32 : 1];
+  if (EF == (EF_BIAS | EF_GELU | EF_PRE | EF_DGELU)) {
+    // fc1 + GELU + saved GELU': 16 columns (8 packed pairs) at a time through the phase-major evaluation
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int nh = n + 16 * hh;
+      float2 xv[8], yv[8], dv2[8];
+      if (nh < epi.N) {                                   // N % 16 == 0 on this path (checked by the host)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + nh + 4 * q));
+          xv[2 * q] = add2(make_float2(__uint_as_float(r[16 * hh + 4 * q]), __uint_as_float(r[16 * hh + 4 * q + 1])), make_float2(b.x, b.y));
+          xv[2 * q + 1] = add2(make_float2(__uint_as_float(r[16 * hh + 4 * q + 2]), __uint_as_float(r[16 * hh + 4 * q + 3])), make_float2(b.z, b.w));
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xv[q] = make_float2(0.f, 0.f);
+      }
+      gelu_erf_both2n<8>(xv, yv, dv2);
+      if (epi.drop_thresh != 0u) {
+        const unsigned long long seed_eff = egb_mix_seed(epi.seed, epi.epoch);
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v[2 * i] = yv[4 * gg + i].x; v[2 * i + 1] = yv[4 * gg + i].y; }
+          drop_apply_run8(seed_eff, (unsigned long long)m * (unsigned long long)epi.N + (unsigned long long)(nh + 8 * gg),
+                          epi.drop_thresh, epi.drop_scale, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) yv[4 * gg + i] = make_float2(v[2 * i], v[2 * i + 1]);
+        }
+      }
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        const uint32_t g = (uint32_t)(2 * hh + gg);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowC + ((g ^ sw) << 4)),
+                     "r"(pack2_bf16(yv[4 * gg].x, yv[4 * gg].y)), "r"(pack2_bf16(yv[4 * gg + 1].x, yv[4 * gg + 1].y)),
+                     "r"(pack2_bf16(yv[4 * gg + 2].x, yv[4 * gg + 2].y)), "r"(pack2_bf16(yv[4 * gg + 3].x, yv[4 * gg + 3].y))
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowP + ((g ^ sw) << 4)),
+                     "r"(pack2_bf16(dv2[4 * gg].x, dv2[4 * gg].y)), "r"(pack2_bf16(dv2[4 * gg + 1].x, dv2[4 * gg + 1].y)),
+                     "r"(pack2_bf16(dv2[4 * gg + 2].x, dv2[4 * gg + 2].y)), "r"(pack2_bf16(dv2[4 * gg + 3].x, dv2[4 * gg + 3].y))
+                     : "memory");
+      }
+    }
+  } else
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float v[8], dv[8], bias[8];
@@ -587,6 +657,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (lane == 0) ptx::mbar_arrive_relaxed(tb);
                               });
       } else {
+        {
+          const int tn = tile + gridDim.x;              // the next tile of this CTA
+          if (tn < total_tiles) {
+            const int mn2 = tn / p.split_k;
+            epilogue_prefetch_l2<EF>(p.epi, (mn2 / p.n_tiles) * BM, (mn2 % p.n_tiles) * BN, BN, (warp - 2) * 32 + lane);
+          }
+        }
         EpiRow rows[4];
         EpiChunkOps ops0;
         epilogue_tile_begin<EF>(p.epi, mt * BM + quad * 32, nt * BN, chalf * NCOL, lane, rows, ops0);
@@ -801,6 +878,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 if (lane == 0) ptx::mbar_arrive_cluster_relaxed(tb);
                               });
       } else {
+        {
+          const int tn = tile + num_clusters;           // the next tile of this CTA pair
+          if (tn < total_tiles) {
+            const int mn2 = tn / p.split_k;
+            epilogue_prefetch_l2<EF>(p.epi, ((mn2 / p.n_tiles) * 2 + (int)rank) * BM, (mn2 % p.n_tiles) * BN, BN,
+                                     (warp - 2) * 32 + lane);
+          }
+        }
         EpiRow rows[4];
         EpiChunkOps ops0;
         epilogue_tile_begin<EF>(p.epi, m_warp, nt * BN, chalf * NCOL, lane, rows, ops0);
@@ -946,7 +1031,7 @@ int setup_row_epilogue(TcParams* p, CUtensorMap* mc, CUtensorMap* mp) {
     return m.ptr != nullptr && !m.f32 && m.vec_ok && m.rpg >= p->M && m.rs >= p->N;
   };
   if (!dense(p->epi.c)) return 0;
-  if ((mask & EF_PRE) && !dense(p->epi.c_pre)) return 0;
+  if ((mask & EF_PRE) && (!dense(p->epi.c_pre) || (p->N % 16) != 0)) return 0;
   if (make_store_map(mc, p->epi.c.ptr, p->N, p->M, p->epi.c.rs)) return 1;
   if ((mask & EF_PRE) && make_store_map(mp, p->epi.c_pre.ptr, p->N, p->M, p->epi.c_pre.rs)) return 1;
   p->row_epi = 1;
