@@ -1337,6 +1337,332 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
   }
 }
 
+// ======================================================================================= persistent pipelined backward
+// att_tc_bwd_pipe_kernel with ONE CTA PER SM walking over the (batch, head) items: tensor memory and barriers are set up
+// once, and the operand tiles of item i+1 are requested as soon as item i's last MMA has retired, i.e. they arrive
+// while item i's dV / dK rows are still being stored.  O is staged in the (then idle) dS area instead of the P~ area,
+// which doubles as the staging space of those stores.
+template <bool DROP>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
+  const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sQ = align1024(smem_raw);
+  uint8_t* sG = sQ + p.Lq_pad * 128;             // dO
+  uint8_t* sK = sG + p.Lq_pad * 128;
+  uint8_t* sV = sK + p.Lk_pad * 128;
+  uint8_t* sP = sV + p.Lk_pad * 128;             // [2 x 64 keys][128 q rows][128 B]   P~ of the current pair of rounds
+  uint8_t* sDS = sP + 2 * TILE_ROWS * 128;       // [nc x 64 keys][128 q rows][128 B]  dS of the current q-tile; O at item start
+  const int nk = (p.Lk_pad + 127) / 128, nc = (p.Lk_pad + 63) / 64, nq = (p.Lq + 127) / 128;
+  const int R = nq * nc;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + (size_t)nk * 2 * TILE_ROWS * 128);
+  uint64_t* bar_sp = &bars[0];                   // [2]
+  uint64_t* bar_rd = &bars[2];                   // [2]
+  uint64_t* bar_acc = &bars[4];
+  uint64_t* bar_dq = &bars[5];
+  uint64_t* bar_dqrd = &bars[6];
+  uint64_t* bar_ld = &bars[7];                   // [2] TMA tile loads of even / odd items of this CTA
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 9);
+  // [8 warps][3][64] column sums of this head's dQ | dK | dV rows, one private slot per softmax warp
+  float* s_cs_all = reinterpret_cast<float*>(slot + 4);
+  const bool want_cs = p.dq_cs != nullptr;
+  float* s_cs = s_cs_all + (threadIdx.x >> 5 & 7) * 192;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+  const int d = p.d;
+  const bool softmax_thread = warp < 8;
+  // TMEM columns: score sets [0,128) [128,256); dV_kc, dK_kc (d columns each per 128-key chunk), dQ
+  const uint32_t DV0 = 256, DK0 = 256 + (uint32_t)(d * nk), DQ0 = 256 + (uint32_t)(2 * d * nk);
+  const bool dq_alias = DQ0 + (uint32_t)d > 512u;
+  const int n_items = p.H * p.S;
+  const int n16 = d >> 3;
+  long long w_sp = 0, w_acc = 0, w_dq = 0, w_el = 0, w_wr = 0;
+
+  auto init_round_bars = [&](bool again) {
+    if (again) {                                 // an mbarrier object must be invalidated before it is initialised anew
+      for (int i = 0; i < 7; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&bars[i])) : "memory");
+    }
+    ptx::mbar_init(&bar_sp[0], 1);
+    ptx::mbar_init(&bar_sp[1], 1);
+    ptx::mbar_init(&bar_rd[0], TC_THREADS);
+    ptx::mbar_init(&bar_rd[1], TC_THREADS);
+    ptx::mbar_init(bar_acc, 1);
+    ptx::mbar_init(bar_dq, 1);
+    ptx::mbar_init(bar_dqrd, TC_THREADS);
+  };
+  // operand tiles of one item: Q, dO, K, V and O (O goes to the sDS area, idle between items).  TMA: thread 0 arms the
+  // item's load barrier and issues five bulk tensor copies; cp.async: every softmax thread issues its share.
+  auto issue_loads = [&](int item, int k) {
+    const int hh = item % p.H, ss = item / p.H;
+    const int skv2 = (ss + p.kv_shift) % p.S;
+    if (p.use_tma) {
+      if (threadIdx.x == 0) {
+        uint64_t* bl = &bar_ld[k & 1];
+        ptx::mbar_arrive_expect_tx(bl, (uint32_t)((3 * p.Lq_pad + 2 * p.Lk_pad) * 128));
+        ptx::tma_load_3d(sQ, &maps.q, bl, hh * d, 0, ss);
+        ptx::tma_load_3d(sG, &maps.g, bl, hh * d, 0, ss);
+        ptx::tma_load_3d(sK, &maps.k, bl, hh * d, 0, skv2);
+        ptx::tma_load_3d(sV, &maps.v, bl, hh * d, 0, skv2);
+        ptx::tma_load_3d(sDS, &maps.o, bl, hh * d, 0, ss);
+      }
+    } else if (softmax_thread) {
+      load_rows_sw128(sQ, p.q + ss * p.q_bs + hh * d, p.q_rs, p.Lq, p.Lq_pad, d);
+      load_rows_sw128(sG, p.d_o + ss * p.do_bs + hh * d, p.do_rs, p.Lq, p.Lq_pad, d);
+      load_rows_sw128(sK, p.k + skv2 * p.k_bs + hh * d, p.k_rs, p.Lk, p.Lk_pad, d);
+      load_rows_sw128(sV, p.v + skv2 * p.v_bs + hh * d, p.v_rs, p.Lk, p.Lk_pad, d);
+      load_rows_sw128(sDS, p.o + ss * p.o_bs + hh * d, p.o_rs, p.Lq, p.Lq_pad, d);
+    }
+  };
+
+  if (threadIdx.x == 0) {
+    init_round_bars(false);
+    ptx::mbar_init(&bar_ld[0], 1);
+    ptx::mbar_init(&bar_ld[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<512>(slot);
+  issue_loads(blockIdx.x, 0);                    // (bar_ld is initialised by the issuing thread itself)
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  int k_item = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k_item) {
+  const int h = item % p.H, s = item / p.H;
+  const int skv = (s + p.kv_shift) % p.S;
+  const long long row_base = ((long long)s * p.H + h) * p.Lq;
+  const int next_item = item + gridDim.x;
+  float dl_t[2] = {0.f, 0.f}, lse_t[2] = {0.f, 0.f};
+  if (want_cs)
+    for (int i = threadIdx.x; i < 8 * 192; i += PIPE_THREADS) s_cs_all[i] = 0.f;   // published by the __syncthreads below
+  if (softmax_thread) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = t * TILE_ROWS + row;
+      if (i < p.Lq) lse_t[t] = p.lse[row_base + i];
+    }
+    if (!p.use_tma) {
+      cp_async_wait_all();
+      ptx::fence_proxy_async_smem();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();                               // this item's tiles (cp.async) and the re-initialised barriers are visible
+  ptx::tc_fence_after();
+  if (p.use_tma) ptx::mbar_wait(&bar_ld[k_item & 1], (uint32_t)((k_item >> 1) & 1));
+
+  if (!softmax_thread) {
+    // ------------------------------------------------------------------------------------------ MMA issuers
+    // Two issuing threads (each tcgen05.commit tracks its own thread's MMAs): warp 8 feeds the score sets, warp 9
+    // the accumulators and dQ -- a single thread's serial instruction stream (~40 cycles per MMA) put the 16
+    // accumulating MMAs of a pair in front of the next scores.
+    if (lane == 0 && warp == 8) {
+      auto issue_scores = [&](int r2) {
+        const int t2 = r2 / nc, c2 = r2 - t2 * nc;
+        const int w2 = min(64, p.Lk_pad - 64 * c2);
+        const uint32_t sb = tmem + 128u * (uint32_t)(r2 & 1);
+        mma_ss_kk(sb, sQ + (size_t)t2 * TILE_ROWS * 128, sK + (size_t)c2 * 64 * 128, w2, d);
+        mma_ss_kk(sb + 64, sG + (size_t)t2 * TILE_ROWS * 128, sV + (size_t)c2 * 64 * 128, w2, d);
+        ptx::umma_commit(&bar_sp[r2 & 1]);
+      };
+      issue_scores(0);
+      if (R > 1) issue_scores(1);
+      for (int r = 0, t = 0, c = 0; r + 2 < R; ++r) {
+        ptx::mbar_wait(&bar_rd[r & 1], (uint32_t)((r >> 1) & 1));   // set r & 1 consumed
+        if (c == nc - 1 && dq_alias) ptx::mbar_wait(bar_dqrd, (uint32_t)(t & 1));   // ... and dQ_t, parked there, read out
+        ptx::tc_fence_after();
+        issue_scores(r + 2);
+        if (++c == nc) { c = 0; ++t; }
+      }
+    } else if (lane == 0 && warp == 9) {
+      for (int r = 0, t = 0, c = 0; r < R; ++r) {
+        const bool last_c = c == nc - 1;
+        if ((c & 1) || last_c) {
+          ptx::mbar_wait(&bar_rd[r & 1], (uint32_t)((r >> 1) & 1));   // P~ / dS tiles of the pair written
+          ptx::tc_fence_after();
+          const uint8_t* gq = sG + (size_t)t * TILE_ROWS * 128;   // dO rows of this q-tile (MN-major B: k rows = queries)
+          const uint8_t* qq = sQ + (size_t)t * TILE_ROWS * 128;
+          const int kc = c >> 1;
+          mma_ss_mnmn(tmem + DV0 + (uint32_t)(d * kc), sP, gq, TILE_ROWS / 16, d, t > 0);                                     // dV_kc += P~^T dO_t
+          mma_ss_mnmn(tmem + DK0 + (uint32_t)(d * kc), sDS + (size_t)kc * 2 * TILE_ROWS * 128, qq, TILE_ROWS / 16, d, t > 0); // dK_kc += dS^T Q_t
+          ptx::umma_commit(bar_acc);
+          if (last_c) {
+            mma_ss_kmn(tmem + (dq_alias ? 128u * (uint32_t)(r & 1) : DQ0), sDS, sK, p.Lk_pad, d);   // dQ_t = dS_t K
+            ptx::umma_commit(bar_dq);
+          }
+        }
+        if (++c == nc) { c = 0; ++t; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------ softmax threads
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sl2 = p.scale * LOG2E;
+    uint8_t* stage = sP + warp * 4096;            // warp-private staging rows of the coalesced result stores
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = t * TILE_ROWS + row;
+      if (i < p.Lq) {
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (u < n16) {
+            const size_t off = (size_t)i * 128 + ((u ^ (i & 7)) << 4);
+            const uint4 gb = *reinterpret_cast<const uint4*>(sG + off);
+            const uint4 ob = *reinterpret_cast<const uint4*>(sDS + off);
+            const __nv_bfloat162* oa = reinterpret_cast<const __nv_bfloat162*>(&ob);
+            const __nv_bfloat162* ga = reinterpret_cast<const __nv_bfloat162*>(&gb);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              acc = fmaf(__low2float(oa[v]), __low2float(ga[v]), acc);
+              acc = fmaf(__high2float(oa[v]), __high2float(ga[v]), acc);
+            }
+          }
+        }
+        dl_t[t] = acc;
+        lse_t[t] *= LOG2E;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // O rows consumed: sDS may be written
+    auto read_dq = [&](int tq) {
+      ATT_CLK(c0);
+      ptx::mbar_wait(bar_dq, (uint32_t)(tq & 1));
+      ATT_CLK(c1);
+      w_dq += c1 - c0;
+      ptx::tc_fence_after();
+      const uint32_t col = dq_alias ? 128u * (uint32_t)(((tq + 1) * nc - 1) & 1) : DQ0;
+      // sP is idle here (bar_dq covers the accumulating MMAs that read it; this round's tiles are written later)
+      const int r0 = tq * TILE_ROWS + (warp & 3) * 32;
+      const int cb = d >= 64 ? half * 32 : 0;
+      if (d >= 64 || half == 0)
+        store_acc_rows_coalesced(trow + col + (uint32_t)cb, 32, p.scale, stage,
+                                 p.dq + s * p.dq_bs + (long long)r0 * p.dq_rs + h * d + cb, p.dq_rs, p.Lq - r0, lane,
+                                 want_cs ? s_cs + cb : nullptr);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_dqrd);
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // every warp's staging rows are free again
+    };
+    int pairs = 0;                                // accumulating MMA groups issued so far
+    for (int r = 0, t = 0, c = 0; r < R; ++r) {
+      const int set = r & 1;
+      const int w = min(64, p.Lk_pad - 64 * c);
+      const int i = t * TILE_ROWS + row;          // query row of this thread
+      const bool valid = i < p.Lq;
+      const long long row_id = row_base + (valid ? i : 0);
+      const float dl = t == 0 ? dl_t[0] : dl_t[1];
+      const float lse2 = !valid ? INFINITY : t == 0 ? lse_t[0] : lse_t[1];   // +inf: P = 0 on the padding rows
+      ATT_CLK(c0);
+      ptx::mbar_wait(&bar_sp[set], (uint32_t)((r >> 1) & 1));
+      ATT_CLK(c1);
+      w_sp += c1 - c0;
+      ptx::tc_fence_after();
+
+      // this thread: 32 key columns [32 half, 32 half + 32) of the 64-key round
+      uint32_t pkp[16], pks[16];
+      const bool mine = 32 * half < w;
+      if (mine) {
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld32(trow + 128u * (uint32_t)set + (uint32_t)(32 * half), rs);
+        ptx::tmem_ld32(trow + 128u * (uint32_t)set + 64u + (uint32_t)(32 * half), rp);
+        ptx::tmem_ld_wait();
+        const int col0 = 64 * c + 32 * half;      // first key column of this thread
+        const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
+        const bool fast = col0 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)col0) <= 0xFFFFFFFFu - 32u;
+        if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+      }
+      // previous q-tile's dQ: read it out behind this round's arithmetic; its barrier also covers the MMAs that read
+      // the previous q-tile's sDS, which this q-tile now overwrites
+      ATT_CLK(c2);
+      w_el += c2 - c1;
+      if (c == 0 && t > 0) read_dq(t - 1);
+      // the accumulating MMAs of the previous pair read sP: they must have retired before the first overwrite
+      ATT_CLK(c3);
+      if ((c & 1) == 0 && pairs > 0) ptx::mbar_wait(bar_acc, (uint32_t)((pairs - 1) & 1));
+      ATT_CLK(c4);
+      w_acc += c4 - c3;
+      if (mine) {
+        uint8_t* prow = sP + (c & 1) * (TILE_ROWS * 128) + row * 128;
+        uint8_t* srow = sDS + (size_t)c * (TILE_ROWS * 128) + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int slot16 = ((half * 4 + q4) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + slot16) = make_uint4(pkp[4 * q4], pkp[4 * q4 + 1], pkp[4 * q4 + 2], pkp[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(srow + slot16) = make_uint4(pks[4 * q4], pks[4 * q4 + 1], pks[4 * q4 + 2], pks[4 * q4 + 3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_rd[set]);
+      ATT_CLK(c5);
+      w_wr += c5 - c4;
+      if ((c & 1) || c == nc - 1) ++pairs;
+      if (++c == nc) { c = 0; ++t; }
+    }
+    // Two key chunks: dV_0 / dK_0 have been final since the last q-tile's first pair retired (bar_acc, waited for in
+    // round c = 2) -- store them while the last pair's MMAs and dQ drain.  Staging goes to sV, which only the score
+    // MMAs read and those have all been consumed (sP / sDS / sQ / sG / sK are still being read).
+    const bool early0 = nk == 2;
+    if (early0) {
+      const int j0 = (warp & 3) * 32;
+      uint8_t* st2 = sV + warp * 2048;
+      for (int c0 = 0; c0 < d; c0 += 32) {
+        if (half == 0)
+          store_acc_rows32_coalesced(trow + DV0 + (uint32_t)c0, 1.f, st2, p.dv + skv * p.dv_bs + (long long)j0 * p.dv_rs + h * d + c0,
+                                     p.dv_rs, p.Lk - j0, lane, want_cs ? s_cs + 128 + c0 : nullptr);
+        else
+          store_acc_rows32_coalesced(trow + DK0 + (uint32_t)c0, p.scale, st2, p.dk + skv * p.dk_bs + (long long)j0 * p.dk_rs + h * d + c0,
+                                     p.dk_rs, p.Lk - j0, lane, want_cs ? s_cs + 64 + c0 : nullptr);
+      }
+    }
+    read_dq(nq - 1);                              // bar_dq of the last q-tile covers every MMA: dV / dK are final
+    // Every MMA of this item has retired (bar_dq) and every warp is past its sV-staged stores (the bar.sync that ends
+    // read_dq): Q / dO / K / V / sDS are dead -- the next item's tiles stream in under the remaining result stores, the
+    // column-sum flush and the next item's prologue (measured on the one-item-per-CTA kernel: tile loads 4.8 K and
+    // result stores 5 K of a 29 K-cycle CTA ran back to back).
+    if (next_item < n_items) issue_loads(next_item, k_item + 1);
+    for (int kc = early0 ? 1 : 0; kc < nk; ++kc) {
+      const int j0 = kc * TILE_ROWS + (warp & 3) * 32;   // first key row of this warp
+      if (half == 0)
+        store_acc_rows_coalesced(trow + DV0 + (uint32_t)(d * kc), d, 1.f, stage,
+                                 p.dv + skv * p.dv_bs + (long long)j0 * p.dv_rs + h * d, p.dv_rs, p.Lk - j0, lane,
+                                 want_cs ? s_cs + 128 : nullptr);
+      else
+        store_acc_rows_coalesced(trow + DK0 + (uint32_t)(d * kc), d, p.scale, stage,
+                                 p.dk + skv * p.dk_bs + (long long)j0 * p.dk_rs + h * d, p.dk_rs, p.Lk - j0, lane,
+                                 want_cs ? s_cs + 64 : nullptr);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();                               // every warp is done with this item's barriers, TMEM columns and s_cs
+  if (want_cs && threadIdx.x < 3 * d) {          // one global atomic per column per item
+    const int which = threadIdx.x / d, c = threadIdx.x - which * d;
+    float* dst = which == 0 ? p.dq_cs : which == 1 ? p.dk_cs : p.dv_cs;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_cs_all[w * 192 + which * 64 + c];
+    atomicAdd(dst + h * d + c, v);
+  }
+  if (next_item < n_items) {
+    if (threadIdx.x == 0) {                      // fresh phases for the next item's rounds (bar_ld keeps running)
+      init_round_bars(true);
+      ptx::fence_barrier_init();
+    }
+    __syncthreads();                             // s_cs flushed before it is zeroed again
+  }
+  }  // items
+  if (p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
+    p.dbg[8] = w_sp; p.dbg[9] = w_acc; p.dbg[10] = w_dq; p.dbg[11] = w_el; p.dbg[12] = w_wr;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem);
+  }
+}
+
 template <typename K>
 int set_smem_tc(K kernel, size_t bytes) {
   EGB_CHECK(bytes <= 227 * 1024, "attention_tc: needs %zu bytes of shared memory (> 227 KB)", bytes);
@@ -1461,7 +1787,18 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
       EGB_CHECK((d->dq_colsum == nullptr) == (d->dk_colsum == nullptr) && (d->dq_colsum == nullptr) == (d->dv_colsum == nullptr),
                 "attention_bwd: pass all three column-sum buffers or none");
       if (cs_in_kernel) { p.dq_cs = d->dq_colsum; p.dk_cs = d->dk_colsum; p.dv_cs = d->dv_colsum; }
-      if (drop) att_tc_bwd_pipe_kernel<true><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
+      // one persistent CTA per SM that prefetches its next (batch, head) item (EGB_ATT_PERSIST=0: one CTA per item)
+      static const int persist = getenv("EGB_ATT_PERSIST") ? atoi(getenv("EGB_ATT_PERSIST")) : 1;
+      // (head_dim 64 / TMA tiles only: 408 -> 389 us per ViT-B layer; with cp.async staging (head_dim 32) the prefetch
+      //  competes with the result stores for the same LSU queue and the static item split costs more than it saves:
+      //  483 -> 499 us per EEG layer)
+      if (persist && p.use_tma) {
+        if (set_smem_tc(att_tc_bwd_pers_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_pers_kernel<false>, smem_f)) return 1;
+        const int items = d->H * d->S;
+        const int ctas = items < egb_num_sms() ? items : egb_num_sms();
+        if (drop) att_tc_bwd_pers_kernel<true><<<ctas, PIPE_THREADS, smem_f, st>>>(p, maps);
+        else att_tc_bwd_pers_kernel<false><<<ctas, PIPE_THREADS, smem_f, st>>>(p, maps);
+      } else if (drop) att_tc_bwd_pipe_kernel<true><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
       else att_tc_bwd_pipe_kernel<false><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
       if (prof) egb_prof_end(st);
       egb_count_launch(1);
