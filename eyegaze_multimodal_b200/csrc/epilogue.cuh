@@ -183,6 +183,7 @@ __device__ __forceinline__ void epi_apply_store(const EpiParams& p, int m, int n
 // ---------------------------------------------------------------------------------------------
 struct EpiRow {
   long long c, c_pre, res, aux;
+  unsigned long long dbase;   // m * N: element index of the row's first column (dropout counter)
   bool ok;
 };
 
@@ -190,6 +191,7 @@ __device__ __forceinline__ EpiRow epi_row_setup(const EpiParams& p, int m) {
   EpiRow r;
   r.ok = m < p.M;
   r.c = r.c_pre = r.res = r.aux = 0;
+  r.dbase = (unsigned long long)m * (unsigned long long)p.N;
   if (r.ok) {
     r.c = epi_row_offset(p.c, m);
     if (p.c_pre.ptr != nullptr) r.c_pre = epi_row_offset(p.c_pre, m);
@@ -314,8 +316,9 @@ __device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
 // The arithmetic of one 8-column run (everything but the stores): v <- epilogue(v); dv <- gelu'(pre) for EF_DGELU.
 // (m, n) locate the run for the dropout counter.
 template <int F>
-__device__ __forceinline__ void epi_math8(const EpiParams& p, int m, int n, float (&v)[8], const float (&bias)[8],
-                                          const EpiPre8& pre, float (&dv)[8]) {
+__device__ __forceinline__ void epi_math8(const EpiParams& p, unsigned long long seed_eff, unsigned long long row_base,
+                                          int n, float (&v)[8], const float (&bias)[8], const EpiPre8& pre,
+                                          float (&dv)[8]) {
   if (F & EF_BIAS) {
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
@@ -344,10 +347,10 @@ __device__ __forceinline__ void epi_math8(const EpiParams& p, int m, int n, floa
       for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
     }
   }
-  if (p.drop_thresh != 0u) {   // n and N are multiples of 8 on this path: the run is aligned
-    const unsigned long long base = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n;
-    drop_apply_run8(egb_mix_seed(p.seed, p.epoch), base, p.drop_thresh, p.drop_scale, v);
-  }
+  // n and N are multiples of 8 on this path: the run is aligned.  The effective seed (launch seed x device epoch) and
+  // the row's first element index are computed once per kernel / per tile row by the caller: recomputed per 8-column run
+  // (a 64-bit multiply each) they were a third of the instructions of the EEG encoder's dropout epilogues.
+  if (p.drop_thresh != 0u) drop_apply_run8(seed_eff, row_base + (unsigned long long)n, p.drop_thresh, p.drop_scale, v);
   if (F & (EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) {
     float a[8];
     unpack8(pre.aux, a);
@@ -378,7 +381,7 @@ __device__ __forceinline__ void epi_math8(const EpiParams& p, int m, int n, floa
 
 template <int F>
 __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row, int m, int n, float (&v)[8],
-                                          const float (&bias)[8], const EpiPre8& pre) {
+                                          const float (&bias)[8], const EpiPre8& pre, unsigned long long seed_eff) {
   if (!row.ok || n >= p.N) return;
   if (F & EF_ACC) {
     float* c = reinterpret_cast<float*>(p.c.ptr) + row.c + n;
@@ -387,7 +390,7 @@ __device__ __forceinline__ void epi_fast8(const EpiParams& p, const EpiRow& row,
     return;
   }
   float dv[8];
-  epi_math8<F>(p, m, n, v, bias, pre, dv);
+  epi_math8<F>(p, seed_eff, row.dbase, n, v, bias, pre, dv);
   if (F & (EF_DGELU | EF_PRE)) st8(reinterpret_cast<bf16*>(p.c_pre.ptr) + row.c_pre + n, dv);
   if (p.exp != 3) st8(reinterpret_cast<bf16*>(p.c.ptr) + row.c + n, v);
 }

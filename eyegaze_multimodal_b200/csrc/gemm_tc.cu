@@ -169,7 +169,8 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams& epi, const Ep
 
 template <int EF>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRow (&rows)[4], int m_base, int n,
-                                               const uint32_t (&r)[32], float* stage, int lane, const EpiChunkOps& ops) {
+                                               const uint32_t (&r)[32], float* stage, int lane, const EpiChunkOps& ops,
+                                               unsigned long long seed_eff) {
   const int sub = lane >> 2, cg = (lane & 3) * 8;
   __syncwarp();                                                 // previous chunk's readers are done
   // Explicit shared-space accesses: through a generic pointer the compiler emits generic LD/ST and has to assume
@@ -200,7 +201,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& epi, const EpiRo
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     if (EF == EF_GENERIC) epi_apply_store_row<8>(epi, rows[it], m_base + it * 8 + sub, n + cg, v[it]);
-    else epi_fast8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v[it], ops.bias, ops.run[it]);
+    else epi_fast8<EF>(epi, rows[it], m_base + it * 8 + sub, n + cg, v[it], ops.bias, ops.run[it], seed_eff);
   }
   if (EF != EF_GENERIC && (EF & EF_COLSUM)) {
     // column sums of the 32 x 32 chunk as stored: this lane's four rows, then the eight lanes that share its columns
@@ -275,17 +276,18 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& epi, uint32_t tad
   // is what sits between the TMEM load and its wait.
   uint32_t ra[32];
   EpiChunkOps opsB;
+  const unsigned long long seed_eff = epi.drop_thresh != 0u ? egb_mix_seed(epi.seed, epi.epoch) : 0ull;
 #pragma unroll 1
   for (int c = 0; c < ncol; c += 64) {
     ptx::tmem_ld32(taddr + (uint32_t)(col0 + c), ra);
     if (c + 32 < ncol) epilogue_prefetch<EF>(epi, rows, n0 + col0 + c + 32, lane, opsB);
     ptx::tmem_ld_wait();
-    epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c, ra, stage, lane, opsA);
+    epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c, ra, stage, lane, opsA, seed_eff);
     if (c + 32 < ncol) {
       ptx::tmem_ld32(taddr + (uint32_t)(col0 + c + 32), ra);
       if (c + 64 < ncol) epilogue_prefetch<EF>(epi, rows, n0 + col0 + c + 64, lane, opsA);
       ptx::tmem_ld_wait();
-      epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c + 32, ra, stage, lane, opsB);
+      epilogue_chunk<EF>(epi, rows, m_base, n0 + col0 + c + 32, ra, stage, lane, opsB, seed_eff);
     }
   }
 }
@@ -324,9 +326,10 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 // one 32 x 32 chunk: this lane's 32 accumulator values r of row m, columns [n, n + 32)
 template <int EF>
-__device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP, int m,
-                                          bool row_ok, int m_warp, int n, const uint32_t (&r)[32], const RowOps& o,
-                                          uint8_t* stage, int lane, uint32_t& nstores) {
+__device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP,
+                                          unsigned long long seed_eff, unsigned long long row_base, bool row_ok, int m_warp,
+                                          int n, const uint32_t (&r)[32], const RowOps& o, uint8_t* stage, int lane,
+                                          uint32_t& nstores) {
   constexpr bool TWO = (EF & (EF_PRE | EF_DGELU)) != 0;      // second output (pre-activation / gelu')
   // the tile(s) this chunk writes must have been read out by the TMA unit: with one output the two 2 KB tiles
   // alternate (one store may stay in flight), with two outputs both are rewritten
@@ -359,14 +362,12 @@ __device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMa
       }
       gelu_erf_both2n<8>(xv, yv, dv2);
       if (epi.drop_thresh != 0u) {
-        const unsigned long long seed_eff = egb_mix_seed(epi.seed, epi.epoch);
 #pragma unroll
         for (int gg = 0; gg < 2; ++gg) {
           float v[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) { v[2 * i] = yv[4 * gg + i].x; v[2 * i + 1] = yv[4 * gg + i].y; }
-          drop_apply_run8(seed_eff, (unsigned long long)m * (unsigned long long)epi.N + (unsigned long long)(nh + 8 * gg),
-                          epi.drop_thresh, epi.drop_scale, v);
+          drop_apply_run8(seed_eff, row_base + (unsigned long long)(nh + 8 * gg), epi.drop_thresh, epi.drop_scale, v);
 #pragma unroll
           for (int i = 0; i < 4; ++i) yv[4 * gg + i] = make_float2(v[2 * i], v[2 * i + 1]);
         }
@@ -399,7 +400,7 @@ __device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMa
     EpiPre8 pre;
     pre.res = o.x[g];
     pre.aux = o.x[g];
-    epi_math8<EF>(epi, m, n + 8 * g, v, bias, pre, dv);
+    epi_math8<EF>(epi, seed_eff, row_base, n + 8 * g, v, bias, pre, dv);
     uint32_t pk[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
@@ -482,6 +483,8 @@ __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CU
     row_ptr = reinterpret_cast<const bf16*>(epi.aux.ptr) + epi_row_offset(epi.aux, row_ok ? m : 0);
   uint32_t ra[32], rb[32];
   RowOps oa, ob;
+  const unsigned long long seed_eff = epi.drop_thresh != 0u ? egb_mix_seed(epi.seed, epi.epoch) : 0ull;
+  const unsigned long long row_base = (unsigned long long)m * (unsigned long long)epi.N;
   ptx::tmem_ld32(taddr, ra);
   row_prefetch<EF>(row_ptr, n_base, epi.N, oa);
 #pragma unroll 1
@@ -493,7 +496,7 @@ __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CU
     } else {
       release();
     }
-    row_chunk<EF>(epi, tmC, tmP, m, row_ok, m_warp, n_base + 32 * c, ra, oa, stage, lane, nstores);
+    row_chunk<EF>(epi, tmC, tmP, seed_eff, row_base, row_ok, m_warp, n_base + 32 * c, ra, oa, stage, lane, nstores);
     if (c + 1 < nch) {
       ptx::tmem_ld_wait();
       if (c + 2 < nch) {
@@ -502,7 +505,7 @@ __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CU
       } else {
         release();
       }
-      row_chunk<EF>(epi, tmC, tmP, m, row_ok, m_warp, n_base + 32 * (c + 1), rb, ob, stage, lane, nstores);
+      row_chunk<EF>(epi, tmC, tmP, seed_eff, row_base, row_ok, m_warp, n_base + 32 * (c + 1), rb, ob, stage, lane, nstores);
     }
   }
 }
