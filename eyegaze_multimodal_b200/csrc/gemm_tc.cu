@@ -329,19 +329,26 @@ template <int EF>
 __device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                           unsigned long long seed_eff, unsigned long long row_base, bool row_ok, int m_warp,
                                           int n, const uint32_t (&r)[32], const RowOps& o, uint8_t* stage, int lane,
-                                          uint32_t& nstores) {
+                                          uint32_t& nstores, int wide = -1) {
   constexpr bool TWO = (EF & (EF_PRE | EF_DGELU)) != 0;      // second output (pre-activation / gelu')
+  // WIDE mode (single-output variants, `wide` = 0 / 1: first / second 32 columns of a 64-column box): the warp's whole
+  // 4 KB staging area is ONE [32 rows][128 B] tile in the 128-byte-swizzled layout and one TMA store covers 64 columns --
+  // the TMA unit's cost is per instruction, not per byte (32 stores of 2 KB per tile held the K = 256 GEMMs at ~8 K
+  // cycles per tile against 2.8 K of MMA).
   // the tile(s) this chunk writes must have been read out by the TMA unit: with one output the two 2 KB tiles
-  // alternate (one store may stay in flight), with two outputs both are rewritten
-  if (lane == 0) {
-    if (TWO) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>();
+  // alternate (one store may stay in flight), with two outputs -- or the single wide tile -- everything is rewritten
+  if (wide != 1) {
+    if (lane == 0) {
+      if (TWO || wide == 0 || wide == -2) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>();   // (-2: a narrow chunk after wide ones)
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  uint8_t* bufC = stage + (TWO ? 0 : (nstores & 1u) * 2048u);
+  uint8_t* bufC = stage + ((TWO || wide >= 0) ? 0 : (nstores & 1u) * 2048u);
   uint8_t* bufP = stage + 2048;
-  const uint32_t rowC = ptx::smem_u32(bufC) + (uint32_t)(lane * 64);
+  const uint32_t rowC = ptx::smem_u32(bufC) + (uint32_t)(lane * (wide >= 0 ? 128 : 64));
   const uint32_t rowP = ptx::smem_u32(bufP) + (uint32_t)(lane * 64);
-  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+  const uint32_t sw = wide >= 0 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+  const uint32_t goff = wide == 1 ? 4u : 0u;
   float cs[(EF & EF_COLSUM) ? 32 : 1];
   if (EF == (EF_BIAS | EF_GELU | EF_PRE | EF_DGELU)) {
     // fc1 + GELU + saved GELU': 16 columns (8 packed pairs) at a time through the phase-major evaluation
@@ -404,7 +411,7 @@ __device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMa
     uint32_t pk[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowC + (((uint32_t)g ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]),
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowC + ((((uint32_t)g + goff) ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]),
                  "r"(pk[2]), "r"(pk[3])
                  : "memory");
     if (TWO) {
@@ -426,14 +433,17 @@ __device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMa
       }
     }
   }
-  ptx::fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) {
-    ptx::tma_store_2d(tmC, bufC, n, m_warp);
-    if (TWO) ptx::tma_store_2d(tmP, bufP, n, m_warp);
-    ptx::bulk_commit();
+  if (wide != 0) {
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (wide == 1) ptx::tma_store_2d(tmP, bufC, n - 32, m_warp);     // tmP = the 64-column store map of C here
+      else ptx::tma_store_2d(tmC, bufC, n, m_warp);
+      if (TWO) ptx::tma_store_2d(tmP, bufP, n, m_warp);
+      ptx::bulk_commit();
+    }
+    ++nstores;
   }
-  ++nstores;
   if (EF & EF_COLSUM) {
     // halving butterfly over the warp's 32 rows: after the round with lane bit b a lane keeps the half of its columns
     // selected by that bit, summed with its partner's; lane l ends up with the sum of column l
@@ -470,7 +480,7 @@ __device__ __forceinline__ void row_chunk(const EpiParams& epi, const CUtensorMa
 template <int EF, typename Release>
 __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                                   uint32_t taddr, int m_warp, int n_base, int ncol, uint8_t* stage,
-                                                  int lane, uint32_t& nstores, Release release) {
+                                                  int lane, uint32_t& nstores, bool wide_ok, Release release) {
   const int m = m_warp + lane;
   const bool row_ok = m < epi.M;
   int nvalid = epi.N - n_base;
@@ -487,6 +497,8 @@ __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CU
   const unsigned long long row_base = (unsigned long long)m * (unsigned long long)epi.N;
   ptx::tmem_ld32(taddr, ra);
   row_prefetch<EF>(row_ptr, n_base, epi.N, oa);
+  // 64-column boxes when this warp's share is a whole number of them (tmP then carries the wide map of C)
+  const bool wide = (EF & (EF_PRE | EF_DGELU)) == 0 && wide_ok && (ncol & 63) == 0;
 #pragma unroll 1
   for (int c = 0; c < nch; c += 2) {
     ptx::tmem_ld_wait();
@@ -496,7 +508,8 @@ __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CU
     } else {
       release();
     }
-    row_chunk<EF>(epi, tmC, tmP, seed_eff, row_base, row_ok, m_warp, n_base + 32 * c, ra, oa, stage, lane, nstores);
+    const bool pair = wide && c + 1 < nch;
+    row_chunk<EF>(epi, tmC, tmP, seed_eff, row_base, row_ok, m_warp, n_base + 32 * c, ra, oa, stage, lane, nstores, pair ? 0 : (wide ? -2 : -1));
     if (c + 1 < nch) {
       ptx::tmem_ld_wait();
       if (c + 2 < nch) {
@@ -505,7 +518,8 @@ __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CU
       } else {
         release();
       }
-      row_chunk<EF>(epi, tmC, tmP, seed_eff, row_base, row_ok, m_warp, n_base + 32 * (c + 1), rb, ob, stage, lane, nstores);
+      row_chunk<EF>(epi, tmC, tmP, seed_eff, row_base, row_ok, m_warp, n_base + 32 * (c + 1), rb, ob, stage, lane, nstores,
+                    pair ? 1 : (wide ? -2 : -1));
     }
   }
 }
@@ -654,7 +668,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint64_t* tb = &tempty_bar[acc];
         epilogue_tile_row<EF>(p.epi, &tmC, &tmP, taddr + (uint32_t)(chalf * NCOL), mt * BM + quad * 32, nt * BN + chalf * NCOL,
                               NCOL, reinterpret_cast<uint8_t*>(stage_all + (warp - 2) * (32 * STG_PITCH)), lane, nstores,
-                              [&]() {
+                              p.row_epi == 2, [&]() {
                                 ptx::tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) ptx::mbar_arrive_relaxed(tb);
@@ -875,7 +889,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t tb = acc == 0 ? lead_tempty0 : lead_tempty1;
         epilogue_tile_row<EF>(p.epi, &tmC, &tmP, taddr + (uint32_t)(chalf * NCOL), m_warp, nt * BN + chalf * NCOL, NCOL,
-                              reinterpret_cast<uint8_t*>(stage_all + (warp - 2) * (32 * STG_PITCH)), lane, nstores, [&]() {
+                              reinterpret_cast<uint8_t*>(stage_all + (warp - 2) * (32 * STG_PITCH)), lane, nstores,
+                              p.row_epi == 2, [&]() {
                                 ptx::tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) ptx::mbar_arrive_cluster_relaxed(tb);
@@ -995,11 +1010,11 @@ int make_map(CUtensorMap* out, const void* ptr, long long inner, long long rows,
 
 // 2-D bf16 map of a dense output matrix {N columns, M rows} (row stride ld elements) for the TMA stores of the row-layout
 // epilogue: box {32 columns, 32 rows}, 64-byte swizzle (the layout row_chunk() writes)
-int make_store_map(CUtensorMap* out, const void* ptr, long long N, long long M, long long ld) {
+int make_store_map(CUtensorMap* out, const void* ptr, long long N, long long M, long long ld, int box_cols = 32) {
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr; key.inner = N; key.rows = M; key.groups = 1; key.rs = ld; key.gs = -3232;
-  key.b0 = 32; key.b1 = 32; key.b2 = 1;
+  key.b0 = box_cols; key.b1 = 32; key.b2 = 1;
   {
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
@@ -1009,10 +1024,11 @@ int make_store_map(CUtensorMap* out, const void* ptr, long long N, long long M, 
   EGB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 32u};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed (%d): N=%lld M=%lld ld=%lld", (int)r, N, M, ld);
   std::lock_guard<std::mutex> lk(g_maps_mu);
@@ -1038,6 +1054,14 @@ int setup_row_epilogue(TcParams* p, CUtensorMap* mc, CUtensorMap* mp) {
   if (make_store_map(mc, p->epi.c.ptr, p->N, p->M, p->epi.c.rs)) return 1;
   if ((mask & EF_PRE) && make_store_map(mp, p->epi.c_pre.ptr, p->N, p->M, p->epi.c_pre.rs)) return 1;
   p->row_epi = 1;
+  // 64-column store boxes (half the TMA store instructions): measured neutral on every shape of the bench (EEG qkv
+  // 53.2 vs 56.6 us, fc1 + GELU unaffected), i.e. the K = 256 tiles are NOT held up by the number of store instructions;
+  // kept as an experiment switch, off by default
+  static const int wide = getenv("EGB_GEMM_ROWEPI_WIDE") ? atoi(getenv("EGB_GEMM_ROWEPI_WIDE")) : 0;
+  if (wide && !(mask & EF_PRE) && p->N >= 64) {      // single output: the second map slot carries C with 64-column boxes
+    if (make_store_map(mp, p->epi.c.ptr, p->N, p->M, p->epi.c.rs, 64)) return 1;
+    p->row_epi = 2;
+  }
   return 0;
 }
 
