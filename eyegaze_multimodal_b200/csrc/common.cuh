@@ -220,13 +220,23 @@ __device__ __forceinline__ uint32_t drop_state(uint64_t seed, uint64_t idx) {
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
   return drop_state(seed, idx) >= thresh;
 }
-// v[0..8) <- dropout of the aligned run starting at element index `base` (base % 8 == 0)
+// i-fold composition of drop_step: s -> s * mul + add  (mod 2^32), as compile-time constants
+struct DropLeap { uint32_t mul, add; };
+__host__ __device__ constexpr DropLeap drop_leap(int i) {
+  uint32_t m = 1u, a = 0u;
+  for (int k = 0; k < i; ++k) { a = a * 0x2C9277B5u + 0xAC564B05u; m = m * 0x2C9277B5u; }
+  return DropLeap{m, a};
+}
+// v[0..8) <- dropout of the aligned run starting at element index `base` (base % 8 == 0).  The eight states are taken
+// by LEAPFROG from the run's hash (state_i = hash * A^i + C_i, the same values as i sequential steps): eight independent
+// multiply-adds instead of a chain of eight -- the epilogue warps are bound by dependent-instruction latency.
 __device__ __forceinline__ void drop_apply_run8(uint64_t seed, uint64_t base, uint32_t thresh, float scale, float (&v)[8]) {
-  uint32_t s = drop_hash(seed, base >> 3);
+  const uint32_t s0 = drop_hash(seed, base >> 3);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    const DropLeap lp = drop_leap(i);
+    const uint32_t s = s0 * lp.mul + lp.add;
     v[i] = s >= thresh ? v[i] * scale : 0.f;
-    s = drop_step(s);
   }
 }
 // Attention-probability dropout: ONE hash decides TWO adjacent key columns (16 random bits each, p resolved to 2^-16).
