@@ -1247,7 +1247,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
       // this thread: 32 key columns [32 half, 32 half + 32) of the 64-key round
       uint32_t pkp[16], pks[16];
       const bool mine = 32 * half < w;
-      if (mine) {
+      // a warp whose 32 query rows all lie past the sequence end (second q-tile: L = 139 leaves 11 live rows, L = 197
+      // leaves 69) has P = dS = 0 on all of them: it writes the zeros without the TMEM reads and the softmax arithmetic
+      const bool warp_live = t * TILE_ROWS + (warp & 3) * 32 < p.Lq;
+      if (mine && !warp_live) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pkp[j] = pks[j] = 0u;
+      }
+      if (mine && warp_live) {
         uint32_t rs[32], rp[32];
         ptx::tmem_ld32(trow + 128u * (uint32_t)set + (uint32_t)(32 * half), rs);
         ptx::tmem_ld32(trow + 128u * (uint32_t)set + 64u + (uint32_t)(32 * half), rp);
@@ -1561,7 +1568,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
       // this thread: 32 key columns [32 half, 32 half + 32) of the 64-key round
       uint32_t pkp[16], pks[16];
       const bool mine = 32 * half < w;
-      if (mine) {
+      // a warp whose 32 query rows all lie past the sequence end (second q-tile: L = 139 leaves 11 live rows, L = 197
+      // leaves 69) has P = dS = 0 on all of them: it writes the zeros without the TMEM reads and the softmax arithmetic
+      const bool warp_live = t * TILE_ROWS + (warp & 3) * 32 < p.Lq;
+      if (mine && !warp_live) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pkp[j] = pks[j] = 0u;
+      }
+      if (mine && warp_live) {
         uint32_t rs[32], rp[32];
         ptx::tmem_ld32(trow + 128u * (uint32_t)set + (uint32_t)(32 * half), rs);
         ptx::tmem_ld32(trow + 128u * (uint32_t)set + 64u + (uint32_t)(32 * half), rp);
