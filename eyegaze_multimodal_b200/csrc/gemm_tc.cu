@@ -524,6 +524,136 @@ __device__ __forceinline__ void epilogue_tile_row(const EpiParams& epi, const CU
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LEAN form of the row-layout epilogue for CTAs with SIXTEEN epilogue warps (four per TMEM lane quadrant, 64 columns of
+// a 256-wide tile each).  ncu on the fc1 + GELU and the EEG ffn1 GEMMs: the two epilogue warps a scheduler gets in the
+// 10-warp CTA issue one instruction per ~4.5 cycles (fixed-latency dependency stalls 28-35 %, issue slots 40-45 % busy,
+// tensor pipe 23-52 %) whatever the instruction-level parallelism of the source -- the drain needs more warps, and 18
+// warps leave 112 registers per thread.  Hence: one accumulator chunk in registers, ONE 2 KB staging tile per warp (the
+// second output of the GELU variant goes through the same tile after the first store has been read out), bias fetched
+// per 8-column run.
+// ------------------------------------------------------------------------------------------------
+// Activation-backward operand of this lane's row, 32 columns (64 bytes) per chunk.  The warp's share is 64 columns = ONE
+// 128-byte line per row: chunk 0's loads are issued before the accumulator is waited for (DRAM latency under the MMAs),
+// chunk 1's right after chunk 0's accumulator values have arrived -- they hit the line chunk 0 brought into L1.
+template <int EF>
+__device__ __forceinline__ void row_lean_load(const EpiParams& epi, int m_warp, int n, int lane, RowOps& o) {
+  if (EF & (EF_RES | EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) {
+    const int m = m_warp + lane;
+    const EpiMat& mat = (EF & EF_RES) ? epi.res : epi.aux;
+    const bf16* row = reinterpret_cast<const bf16*>(mat.ptr) + epi_row_offset(mat, m < epi.M ? m : 0) + n;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (n + 8 * g < epi.N) o.x[g] = __ldg(reinterpret_cast<const uint4*>(row + 8 * g));
+  }
+}
+
+template <int EF, int CHUNK>
+__device__ __forceinline__ void row_chunk_lean(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP,
+                                               unsigned long long seed_eff, unsigned long long row_base, int m_warp, int n,
+                                               const uint32_t (&r)[32], uint8_t* stage, int lane, const RowOps& ops,
+                                               bool row_ok) {
+  constexpr bool TWO = (EF & (EF_PRE | EF_DGELU)) != 0;
+  const uint32_t rowC = ptx::smem_u32(stage) + (uint32_t)(lane * 64);
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+  uint32_t pd[TWO ? 16 : 1];
+  if (lane == 0) ptx::bulk_wait_read<0>();
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8], dv[8], bias[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * g + i]);
+    if ((EF & EF_BIAS) && n + 8 * g < epi.N) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 8 * g));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 8 * g + 4));
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+    EpiPre8 pre;
+    pre.res = (EF & (EF_RES | EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL)) ? ops.x[g] : make_uint4(0u, 0u, 0u, 0u);
+    pre.aux = pre.res;
+    epi_math8<EF>(epi, seed_eff, row_base, n + 8 * g, v, bias, pre, dv);
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = pack2_bf16(v[2 * i], v[2 * i + 1]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowC + (((uint32_t)g ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]),
+                 "r"(pk[2]), "r"(pk[3])
+                 : "memory");
+    if (TWO) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pd[4 * g + i] = pack2_bf16(dv[2 * i], dv[2 * i + 1]);
+    }
+  }
+  if (EF & EF_COLSUM) {
+    // Column sums of the tile AS STORED, read back from the staging tile: lane l walks column l down the 32 rows (one
+    // 2-byte load per row; a row's 32 columns are one conflict-free 64-byte access).  Rows past M hold exact zeros (their
+    // A rows are zero-filled by TMA), so no row mask is needed.  The register butterfly of the 8-warp build needs ~100
+    // live registers; this CTA has 96 per thread.
+    __syncwarp();
+    const uint32_t base = ptx::smem_u32(stage) + (uint32_t)((lane & 7) * 2);
+    float tot = 0.f;
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      unsigned short h;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(base + (uint32_t)(rr * 64) + ((((uint32_t)lane >> 3) ^ (((uint32_t)rr >> 1) & 3u)) << 4)));
+      tot += __uint_as_float((uint32_t)h << 16);
+    }
+    if (n + lane < epi.N) atomicAdd(epi.colsum + n + lane, tot);   // result unused: compiles to RED
+  }
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_2d(tmC, stage, n, m_warp);
+    ptx::bulk_commit();
+  }
+  if (TWO) {
+    if (lane == 0) ptx::bulk_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowC + (((uint32_t)g ^ sw) << 4)), "r"(pd[4 * g]),
+                   "r"(pd[4 * g + 1]), "r"(pd[4 * g + 2]), "r"(pd[4 * g + 3])
+                   : "memory");
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tmP, stage, n, m_warp);
+      ptx::bulk_commit();
+    }
+  }
+}
+
+template <int EF, typename Release>
+__device__ __forceinline__ void epilogue_tile_row_lean(const EpiParams& epi, const CUtensorMap* tmC, const CUtensorMap* tmP,
+                                                       uint32_t taddr, int m_warp, int n_base, int ncol, uint8_t* stage,
+                                                       int lane, const RowOps& ops0, Release release) {
+  int nvalid = epi.N - n_base;
+  if (nvalid > ncol) nvalid = ncol;
+  const int nch = m_warp < epi.M ? (nvalid + 31) / 32 : 0;      // warp-uniform
+  if (nch <= 0) { release(); return; }
+  const unsigned long long seed_eff = epi.drop_thresh != 0u ? egb_mix_seed(epi.seed, epi.epoch) : 0ull;
+  const unsigned long long row_base = (unsigned long long)(m_warp + lane) * (unsigned long long)epi.N;
+  // the warp's share is 64 columns = at most two chunks (compile-time chunk index: the operand registers are indexed by it)
+  const bool row_ok = m_warp + lane < epi.M;
+  RowOps ops1;
+  {
+    uint32_t ra[32];
+    ptx::tmem_ld32(taddr, ra);
+    ptx::tmem_ld_wait();
+    if (nch == 1) release();
+    else row_lean_load<EF>(epi, m_warp, n_base + 32, lane, ops1);
+    row_chunk_lean<EF, 0>(epi, tmC, tmP, seed_eff, row_base, m_warp, n_base, ra, stage, lane, ops0, row_ok);
+  }
+  if (nch > 1) {
+    uint32_t ra[32];
+    ptx::tmem_ld32(taddr + 32u, ra);
+    ptx::tmem_ld_wait();
+    release();
+    row_chunk_lean<EF, 1>(epi, tmC, tmP, seed_eff, row_base, m_warp, n_base + 32, ra, stage, lane, ops1, row_ok);
+  }
+}
+
 // Epilogue variants that run the row-layout path: the ones WITHOUT a row-layout operand.  (Measured with the residual /
 // activation-backward operand read by each lane from its own row -- 32 different 128-byte lines per load instruction --
 // those variants lost 25-80 %: proj + residual 68 -> 121 us, dX-through-GELU' 297 -> 409 us; they keep the transposed
@@ -748,8 +878,8 @@ __device__ __forceinline__ void load_stage_operand_2sm(uint8_t* dst, const CUten
   }
 }
 
-template <int BN, int EF, int BKT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int EF, int BKT, int NEPI = EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NEPI, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const TcParams p) {
   using Cfg = Tc2Config<BN, BKT>;
@@ -781,7 +911,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], 2 * EPI_WARPS);  // epilogue warps of both CTAs (used in the leader only)
+      ptx::mbar_init(&tempty_bar[s], 2 * NEPI);  // epilogue warps of both CTAs (used in the leader only)
     }
     ptx::fence_barrier_init();
   }
@@ -871,8 +1001,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
     const int quad = warp & 3;
-    const int chalf = (warp - 2) >> 2;
-    constexpr int NCOL = BN / 2;
+    const int chalf = (warp - 2) >> 2;          // column share of this warp: NEPI / 4 warps per TMEM lane quadrant
+    constexpr int NCOL = BN / (NEPI / 4);
+    static_assert(NEPI == EPI_WARPS || NCOL == 64, "the lean epilogue drains 64 columns per warp");
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t nstores = 0;
@@ -884,7 +1015,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int mt = mn / p.n_tiles;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       const int m_warp = (mt * 2 + (int)rank) * BM + quad * 32;
-      if (RowEpi<EF>::ok && p.row_epi) {
+      if (NEPI > EPI_WARPS) {
+        // sixteen epilogue warps: always the lean row-layout epilogue (the host launches this variant only for it)
+        RowOps rops;
+        row_lean_load<EF>(p.epi, m_warp, nt * BN + chalf * NCOL, lane, rops);    // row operand: in flight under the MMAs
+        TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
+        ptx::tc_fence_after();
+        const uint32_t tb = acc == 0 ? lead_tempty0 : lead_tempty1;
+        epilogue_tile_row_lean<EF>(p.epi, &tmC, &tmP, taddr + (uint32_t)(chalf * NCOL), m_warp, nt * BN + chalf * NCOL, NCOL,
+                                   reinterpret_cast<uint8_t*>(stage_all) + (warp - 2) * 2048, lane, rops, [&]() {
+                                     ptx::tc_fence_before();
+                                     __syncwarp();
+                                     if (lane == 0) ptx::mbar_arrive_cluster_relaxed(tb);
+                                   });
+      } else if (RowEpi<EF>::ok && p.row_epi) {
         TIMED_WAIT(t_wait0, ptx::mbar_wait(&tfull_bar[acc], acc_phase));
         ptx::tc_fence_after();
         const uint32_t tb = acc == 0 ? lead_tempty0 : lead_tempty1;
@@ -1045,7 +1189,11 @@ int setup_row_epilogue(TcParams* p, CUtensorMap* mc, CUtensorMap* mp) {
   p->row_epi = 0;
   if (!enabled) return 0;
   const int mask = egb_epi_fast_mask(p->epi);
-  if (mask == EF_GENERIC || (mask & (EF_ACC | EF_RES | EF_ABWD_RELU | EF_ABWD_GELU | EF_ABWD_MUL | EF_COLSUM)) || p->N < 32) return 0;
+  // (variants with a row operand or column sums run the row layout only in the 16-epilogue-warp pair kernel; the other
+  //  kernels check RowEpi<EF> and keep the transposed epilogue for them)
+  if (mask == EF_GENERIC || (mask & (EF_ACC | EF_ABWD_GELU)) || p->N < 32) return 0;
+  if (mask & EF_RES) return 0;
+  if ((mask & (EF_ABWD_RELU | EF_ABWD_MUL | EF_COLSUM)) && (p->N % 64) != 0) return 0;
   auto dense = [&](const EpiMat& m) {
     return m.ptr != nullptr && !m.f32 && m.vec_ok && m.rpg >= p->M && m.rs >= p->N;
   };
@@ -1272,9 +1420,48 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
   EGB_EF_SWITCH(launch_tc_ef, BN, true)
 }
 
+// the 16-epilogue-warp build of the pair kernel (lean row-layout epilogue): plain / bias / bias+ReLU / bias+GELU+GELU'
+template <int EF>
+struct Wide16 {
+  static constexpr bool ok = EF == 0 || EF == EF_BIAS || EF == (EF_BIAS | EF_RELU) || EF == (EF_BIAS | EF_GELU | EF_PRE | EF_DGELU) ||
+                             EF == EF_ABWD_MUL || EF == EF_ABWD_RELU ||
+                             EF == (EF_ABWD_MUL | EF_COLSUM) || EF == (EF_ABWD_RELU | EF_COLSUM);
+  // (bias + residual was measured on this path too and lost: proj + residual 69 -> 96 us, fc2 + residual 168 -> 176 us, EEG
+  //  40 -> 53 us; the residual is L2-resident and the transposed epilogue's sector-exact reads serve it better.  The
+  //  activation-backward variants: EEG dX-through-ReLU 145 -> 129 us, ViT dX-through-GELU' 291 -> 289 us.)
+};
+
+template <int BN, int EF, int BKT>
+int launch_tc2_ef_bk16(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
+  using Cfg = Tc2Config<BN, BKT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EF, BKT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  const int pairs = egb_num_sms() / 2;
+  const int grid = 2 * (total < pairs ? total : pairs);
+  const bool prof = egb_prof_enabled() != 0;
+  if (prof) {
+    const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
+    egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
+    egb_prof_tag(p.M, p.N, p.K, 3e6 + BN * 1e4 + EF);
+  }
+  gemm_tc2_kernel<BN, EF, BKT, 16><<<grid, 64 + 32 * 16, Cfg::SMEM_BYTES, stream>>>(ma, mb, mc, mp, p);
+  if (prof) egb_prof_end(stream);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int BN, int EF, int BKT>
 int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcParams& p, cudaStream_t stream) {
   using Cfg = Tc2Config<BN, BKT>;
+  if constexpr (Wide16<EF>::ok && BN == 256) {
+    static const int w16 = getenv("EGB_GEMM_EPI16") ? atoi(getenv("EGB_GEMM_EPI16")) : 1;
+    if (w16 && p.row_epi) return launch_tc2_ef_bk16<BN, EF, BKT>(ma, mb, mc, mp, p, stream);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     EGB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EF, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
