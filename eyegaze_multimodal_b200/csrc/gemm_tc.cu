@@ -25,6 +25,10 @@ void egb_prof_end(cudaStream_t st);
 void egb_prof_tag(double a, double b, double c, double d);
 int egb_fill_epilogue(const egb_gemm_desc* d, EpiParams* e);
 
+#ifndef EGB_LEAN_RES
+#define EGB_LEAN_RES 0      // experiment switch: bias + residual epilogues on the lean 16-warp path as well
+#endif
+
 namespace {
 
 constexpr int BM = 128;
@@ -1192,8 +1196,8 @@ int setup_row_epilogue(TcParams* p, CUtensorMap* mc, CUtensorMap* mp) {
   // (variants with a row operand or column sums run the row layout only in the 16-epilogue-warp pair kernel; the other
   //  kernels check RowEpi<EF> and keep the transposed epilogue for them)
   if (mask == EF_GENERIC || (mask & (EF_ACC | EF_ABWD_GELU)) || p->N < 32) return 0;
-  if (mask & EF_RES) return 0;
-  if ((mask & (EF_ABWD_RELU | EF_ABWD_MUL | EF_COLSUM)) && (p->N % 64) != 0) return 0;
+  if ((mask & EF_RES) && !EGB_LEAN_RES) return 0;
+  if ((mask & (EF_RES | EF_ABWD_RELU | EF_ABWD_MUL | EF_COLSUM)) && (p->N % 64) != 0) return 0;
   auto dense = [&](const EpiMat& m) {
     return m.ptr != nullptr && !m.f32 && m.vec_ok && m.rpg >= p->M && m.rs >= p->N;
   };
@@ -1424,7 +1428,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
 template <int EF>
 struct Wide16 {
   static constexpr bool ok = EF == 0 || EF == EF_BIAS || EF == (EF_BIAS | EF_RELU) || EF == (EF_BIAS | EF_GELU | EF_PRE | EF_DGELU) ||
-                             EF == EF_ABWD_MUL || EF == EF_ABWD_RELU ||
+                             EF == EF_ABWD_MUL || EF == EF_ABWD_RELU || (EF == (EF_BIAS | EF_RES) && EGB_LEAN_RES) ||
                              EF == (EF_ABWD_MUL | EF_COLSUM) || EF == (EF_ABWD_RELU | EF_COLSUM);
   // (bias + residual was measured on this path too and lost: proj + residual 69 -> 96 us, fc2 + residual 168 -> 176 us, EEG
   //  40 -> 53 us; the residual is L2-resident and the transposed epilogue's sector-exact reads serve it better.  The
