@@ -198,7 +198,7 @@ def test_real_size_vit_forward_and_backward(cuda_device, name):
     a, b = gaze_pair_batch(B, seed=32)
     # balanced labels: how well conditioned the batch gradient is depends on them (the same four trials labelled
     # [0, 1, 2, 1] leave a 4x smaller, cancellation-dominated reference gradient and 4x larger relative bf16 errors,
-    # deterministically and in PyTorch's own bf16 path alike -- scratch/vit_s_grad_probe.py)
+    # deterministically and in PyTorch's own bf16 path alike -- tools/vit_s_grad_probe.py)
     labels = torch.arange(B) % 3
     sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     want = V.early_fusion_forward(sdr, a, b, heads, "concat")
