@@ -477,7 +477,8 @@ def run_b200(args):
     eager_step(resident[0])
     torch.cuda.synchronize()
     kernels_per_step = L.launch_count() - n0
-    gpu_launches = kernels_per_step * args.steps if graphed is not None else launches_host
+    captured = getattr(graphed, "captured_launches", None) if graphed is not None else None
+    gpu_launches = (captured or kernels_per_step) * args.steps if graphed is not None else launches_host
 
     # ---- (1b) the un-captured step, for comparison: device time and host enqueue time --------------------------
     eager = None
@@ -488,6 +489,7 @@ def run_b200(args):
         ems, ehost = timed(lambda i: eager_step(resident[i % n_host]), n_eager)
         eager = {"ms_per_step": ems / n_eager, "value": B * world * n_eager / (ems * 1e-3), "unit": UNIT,
                  "host_enqueue_ms_per_step": ehost / n_eager, "kernels_per_step": kernels_per_step,
+                 "kernels_per_graph_replay": captured,
                  "graph_host_enqueue_ms_per_step": host_ms / args.steps}
 
     # ---- (2) end to end: pinned host inputs -> H2D -> step -> loss D2H, every step, double-buffered ----------

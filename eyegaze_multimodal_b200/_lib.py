@@ -81,6 +81,7 @@ _SIGNATURES = {
     "egb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "egb_eeg_window_normalize": [vp, vp, i32, i32, i32, i32, vp],
     "egb_image_u8_normalize": [vp, vp, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp],
+    "egb_multi_tensor_cast_bf16": [vp, vp, i32, vp],
     "egb_multi_tensor_sqnorm": [vp, vp, i32, vp, vp],
     "egb_multi_tensor_adamw": [vp, vp, i32, f32, f32, f32, f32, f32, f32, vp, vp],
     "egb_layernorm_bwd_res": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],

@@ -72,20 +72,25 @@ class GraphedTrainStep:
 
         # ---- capture -------------------------------------------------------------------------------------------------
         self._zero(params)
+        ops.refresh_plain_copies(dev)          # builds the static tables of the one-launch weight re-cast (not capturable)
         ops.bump_param_epoch()                 # derived weight copies are rebuilt INSIDE the graph
         ops.reset_arenas()
         self._defer_prev = trial_parallel.defer_comm if trial_parallel is not None else False
         if multi:
             trial_parallel.defer_comm = True   # hooks pack the buckets; the all-reduces are issued after the replay
         one_graph = optimizer is not None and not multi
+        from . import _lib as _L
+        n0 = _L.launch_count()
         with torch.cuda.graph(self.graph):
             ops.advance_seed_epoch()
+            ops.refresh_plain_copies(dev)      # every bf16 weight copy from its fp32 master: ONE launch per replay
             out = self._fwd_bwd()
             if one_graph:
                 optimizer.step()
                 if schedule is not None:
                     schedule.step()
             self.outputs = {k: v.detach() for k, v in out.items() if isinstance(v, torch.Tensor)}
+        self.captured_launches = _L.launch_count() - n0      # this library's kernels inside one replay
         ops.reset_arenas()
         if trial_parallel is not None:
             trial_parallel.finish()            # (re-arms the buckets; reduces the packed buckets once when sharded)

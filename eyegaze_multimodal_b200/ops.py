@@ -252,12 +252,71 @@ def bump_param_epoch() -> None:
     _param_epoch[0] += 1
 
 
+# bf16 copies of fp32 parameters live in PERSISTENT buffers (one per parameter), so that all of them can be re-derived by
+# one multi-tensor launch (refresh_plain_copies) after an optimizer update instead of one cast launch per parameter.
+_plain_bufs = WeakIdKeyDictionary()          # parameter -> bf16 buffer [N, K]
+_plain_tables = {"sig": None, "cast": None, "chunks": None, "n_chunks": 0, "items": []}
+_PLAIN_CHUNK = 16384
+
+
+def _plain_build(w: torch.Tensor, w2: torch.Tensor, code: int) -> torch.Tensor:
+    if code != BF16 or w2.dtype != torch.float32 or not w2.is_contiguous():
+        return cast(w2, code)
+    buf = _plain_bufs.get(w)
+    if buf is None or buf.shape != w2.shape or buf.device != w2.device:
+        buf = torch.empty(w2.shape, dtype=torch.bfloat16, device=w2.device)
+        _plain_bufs[w] = buf
+    TO.call("cast_from_f32", w2, buf, code, w2.numel())
+    return buf
+
+
 def weight_plain(w: torch.Tensor, code: int) -> torch.Tensor:
     """[N, K...] parameter flattened to [N, K] in the compute dtype (no copy in fp32 mode)."""
     w2 = w.detach().reshape(w.shape[0], -1)
     if code == F32:
         return w2
-    return wcache.get((w,), code, "plain", lambda: cast(w2, code))
+    return wcache.get((w,), code, "plain", lambda: _plain_build(w, w2, code))
+
+
+def refresh_plain_copies(device=None) -> int:
+    """Re-derive EVERY registered bf16 weight copy from its fp32 master with one launch and mark the cache entries valid
+    for the current parameter versions / epoch.  The (static) pointer tables are built on the first call and whenever the
+    set of copies changes -- that upload cannot happen during stream capture, so a captured step calls this once eagerly
+    after its warm-up.  Returns the number of tensors refreshed."""
+    import numpy as np
+    items = []
+    for w, buf in list(_plain_bufs.items()):
+        if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and (device is None or w.device == torch.device(device)):
+            items.append((w, buf))
+    if not items:
+        return 0
+    sig = tuple((w.data_ptr(), buf.data_ptr(), w.numel()) for w, buf in items)
+    T = _plain_tables
+    if T["sig"] != sig:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("refresh_plain_copies: the set of weight copies changed during stream capture")
+        dev = items[0][0].device
+        rec = np.zeros(len(items), dtype=[("src", "<u8"), ("dst", "<u8")])
+        rec["src"] = [w.data_ptr() for w, _ in items]
+        rec["dst"] = [b.data_ptr() for _, b in items]
+        chunks = []
+        for i, (w, _) in enumerate(items):
+            for o in range(0, w.numel(), _PLAIN_CHUNK):
+                chunks.append((i, min(_PLAIN_CHUNK, w.numel() - o), o))
+        ch = np.zeros(len(chunks), dtype=[("tensor", "<i4"), ("n", "<i4"), ("offset", "<i8")])
+        ch["tensor"], ch["n"], ch["offset"] = zip(*chunks)
+        T["cast"] = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
+        T["chunks"] = torch.from_numpy(ch.view(np.uint8).copy()).to(dev)
+        T["n_chunks"] = len(chunks)
+        T["sig"] = sig
+    TO.call("multi_tensor_cast_bf16", T["cast"], T["chunks"], T["n_chunks"])
+    for w, buf in items:
+        slot = wcache._d.get(w)
+        if slot is None:
+            slot = {}
+            wcache._d[w] = slot
+        slot[(BF16, "plain", ())] = ((w._version, w.data_ptr(), _param_epoch[0]), buf)
+    return len(items)
 
 
 def weight_packed(ws, code):

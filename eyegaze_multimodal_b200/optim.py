@@ -221,6 +221,8 @@ class FusedClipAdamW(torch.optim.Optimizer):
                    float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                    float(self.max_grad_norm or 0.0), sq if sq is not None else None, st)
         ops.bump_param_epoch()       # the kernels wrote the parameters behind autograd's version counters
+        if not torch.cuda.is_current_stream_capturing():
+            ops.refresh_plain_copies()   # eager loops: all bf16 weight copies re-derived now, in one launch
         return loss
 
     def _sync_steps(self, only=None):

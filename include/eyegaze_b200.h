@@ -289,6 +289,9 @@ int egb_fill_row0(const float* cls, const float* pos, void* out, int dtype, int 
  * egb_multi_tensor_sqnorm ACCUMULATES sum(g^2) into out_sqnorm (caller zeroes); egb_multi_tensor_adamw reads it on the
  * device (sqnorm NULL or max_norm <= 0: no clipping).
  * ------------------------------------------------------------------------------------------- */
+/* fp32 master parameters -> bf16 compute copies, every tensor of the table in ONE launch.  cast_table: device array of
+   {const float* src, bf16* dst} records; chunk_table: {int32 tensor, int32 n, int64 offset} records, one CTA each. */
+int egb_multi_tensor_cast_bf16(const void* cast_table, const void* chunk_table, int n_chunks, void* stream);
 int egb_multi_tensor_sqnorm(const void* tensor_table, const void* chunk_table, int n_chunks, float* out_sqnorm,
                             void* stream);
 int egb_multi_tensor_adamw(const void* tensor_table, const void* chunk_table, int n_chunks, float lr, float beta1,
