@@ -12,57 +12,6 @@ namespace {
 
 constexpr int LN_MAX_CHUNKS = 4;  // 4 chunks x 32 lanes x 8 elements = D up to 1024
 
-template <typename T>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, T* __restrict__ y,
-                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                            int M, int D, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int chunks = (D + 255) / 256;
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
-    const T* xr = x + (long long)row * D;
-    float v[LN_MAX_CHUNKS][8];
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
-      const int d = c * 256 + lane * 8;
-      if (c < chunks && d < D) {
-        ld8(xr + d, v[c]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[c][j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
-      }
-    }
-    const float mean = warp_sum(s) / (float)D;
-    float q = 0.f;
-#pragma unroll
-    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
-      const int d = c * 256 + lane * 8;
-      if (c < chunks && d < D) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const float t = v[c][j] - mean; q += t * t; }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-#pragma unroll
-    for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
-      const int d = c * 256 + lane * 8;
-      if (c < chunks && d < D) {
-        float g[8], b[8], o[8];
-        ld8(gamma + d, g);
-        ld8(beta + d, b);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
-        st8(y + (long long)row * D + d, o);
-      }
-    }
-    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
-  }
-}
-
 // eight consecutive elements in their storage format (bf16: one 16-byte register quad; fp32: two)
 template <typename T> struct Raw8;
 template <> struct Raw8<bf16> {
@@ -84,6 +33,75 @@ template <> struct Raw8<float> {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 };
+
+// ROWS rows per warp and iteration: their loads are issued back to back before any arithmetic, so a warp keeps ROWS x D
+// elements in flight instead of D (one 1.5 KB row per warp left the ViT-B LayerNorm at 3.4 TB/s).
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int M, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int chunks = (D + 255) / 256;
+  const int stride = gridDim.x * warps_per_block * ROWS;
+  for (int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * ROWS; row0 < M; row0 += stride) {
+    // rows stay in their STORAGE format (bf16: 4 registers per 8 elements) between the passes and are unpacked on use
+    Raw8<T> raw[ROWS][LN_MAX_CHUNKS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = row0 + r;
+#pragma unroll
+      for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+        const int d = c * 256 + lane * 8;
+        if (row < M && c < chunks && d < D) raw[r][c].load(x + (long long)row * D + d);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = row0 + r;
+      if (row >= M) break;
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+        const int d = c * 256 + lane * 8;
+        if (c < chunks && d < D) {
+          float t8[8];
+          raw[r][c].unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += t8[j];
+        }
+      }
+      const float mean = warp_sum(s) / (float)D;
+      float q = 0.f;
+#pragma unroll
+      for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+        const int d = c * 256 + lane * 8;
+        if (c < chunks && d < D) {
+          float t8[8];
+          raw[r][c].unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float t = t8[j] - mean; q += t * t; }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+      for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+        const int d = c * 256 + lane * 8;
+        if (c < chunks && d < D) {
+          float g[8], b[8], o[8], t8[8];
+          raw[r][c].unpack(t8);
+          ld8(gamma + d, g);
+          ld8(beta + d, b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (t8[j] - mean) * rstd * g[j] + b[j];
+          st8(y + (long long)row * D + d, o);
+        }
+      }
+      if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    }
+  }
+}
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum dy*xhat; dbeta += sum dy.
 // One warp per row.  The row's x and dy stay in registers in their STORAGE format between the statistics pass and
@@ -397,13 +415,19 @@ int egb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
   EGB_CHECK(D % 8 == 0 && D <= 256 * LN_MAX_CHUNKS, "layernorm: D=%d must be a multiple of 8 and <= %d", D,
             256 * LN_MAX_CHUNKS);
   EGB_CHECK(M > 0, "layernorm: empty");
-  int blocks = (M + 7) / 8;
+  // two rows per warp in flight measured SLOWER (35.8 vs 33.0 us average over the step's 39 launches): the kernel is not
+  // bound by bytes in flight; one row per warp stays the default
+  static const int rows2 = getenv("EGB_LN_FWD_ROWS") ? atoi(getenv("EGB_LN_FWD_ROWS")) : 1;
+  const int R = (dtype == EGB_BF16 && rows2 == 2) ? 2 : 1;
+  int blocks = (M + 8 * R - 1) / (8 * R);
   const int cap = egb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  if (dtype == EGB_BF16)
-    layernorm_fwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, D, eps);
+  if (dtype == EGB_BF16 && R == 2)
+    layernorm_fwd_kernel<bf16, 2><<<blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, D, eps);
+  else if (dtype == EGB_BF16)
+    layernorm_fwd_kernel<bf16, 1><<<blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, D, eps);
   else
-    layernorm_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, D, eps);
+    layernorm_fwd_kernel<float, 1><<<blocks, 256, 0, st>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, D, eps);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;
