@@ -277,7 +277,7 @@ static int fill_att(const egb_attention_desc* d, AttParams* p) {
   p->S = d->S; p->H = d->H; p->Lq = d->Lq; p->Lk = d->Lk; p->dk_dim = d->head_dim; p->kv_shift = d->kv_shift;
   p->scale = d->scale;
   if (d->dropout_p > 0.f) {
-    p->drop_thresh = drop_threshold16(d->dropout_p);   // 16-bit threshold of the paired decisions
+    p->drop_thresh = drop_threshold(d->dropout_p);
     p->drop_scale = 1.f / (1.f - d->dropout_p);
     p->seed = d->seed;
     p->epoch = egb_seed_epoch_ptr();

@@ -293,12 +293,9 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem) {
 // softmax_bwd_cols32 for the reasoning; both produce the mask of drop_keep_att()).
 template <bool DROP, bool FAST>
 __device__ __forceinline__ float softmax_fwd_cols32(const uint32_t (&raw)[32], float sl2, float mb, int col0, int Lk,
-                                                    unsigned long long seed, unsigned long long row_lin, uint32_t t16,
+                                                    unsigned long long seed, unsigned long long row_lin, uint32_t thresh,
                                                     float drop_scale, uint32_t (&pk)[16]) {
-  const unsigned long long base = row_lin + (unsigned long long)col0;
-  const uint32_t lo0 = (uint32_t)base, seed_lo = (uint32_t)seed;
-  const uint32_t hi_term = ((uint32_t)(base >> 32) ^ (uint32_t)(seed >> 32)) * 0x85EBCA77u;
-  const uint32_t t16s = t16 << 16;
+  const uint32_t s0 = DROP ? drop_att_run_state(seed, row_lin, col0) : 0u;   // col0 is a multiple of 32: one run
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -311,15 +308,9 @@ __device__ __forceinline__ float softmax_fwd_cols32(const uint32_t (&raw)[32], f
     sum0 += e0;
     sum1 += e1;
     if (DROP) {
-      uint32_t h;
-      if (FAST) {
-        h = ((lo0 + (uint32_t)(2 * j)) ^ seed_lo) * 0x9E3779B1u + hi_term;
-        h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;
-      } else {
-        h = drop_hash(seed, base + (unsigned long long)(2 * j));
-      }
-      e0 *= (h << 16) >= t16s ? drop_scale : 0.f;
-      e1 *= h >= t16s ? drop_scale : 0.f;
+      const DropLeap l0 = drop_leap(2 * j), l1 = drop_leap(2 * j + 1);
+      e0 *= (s0 * l0.mul + l0.add) >= thresh ? drop_scale : 0.f;
+      e1 *= (s0 * l1.mul + l1.add) >= thresh ? drop_scale : 0.f;
     }
     pk[j] = pack_bf16(e0, e1);
   }
@@ -455,7 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) att_tc_fwd_kernel(const __grid_
       ptx::tmem_ld32(trow + (uint32_t)(c * 32), raw);
       ptx::tmem_ld_wait();
       const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
-      const bool fast = c * 32 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)(c * 32)) <= 0xFFFFFFFFu - 32u;
+      const bool fast = c * 32 + 32 <= p.Lk;          // all 32 columns are real keys: no per-column predicates
       if (fast) sum += softmax_fwd_cols32<DROP, true>(raw, sl2, mb, c * 32, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pk);
       else sum += softmax_fwd_cols32<DROP, false>(raw, sl2, mb, c * 32, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pk);
     }
@@ -896,8 +887,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) att_tc_bwd_fused_kernel(const A
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float pt2[2], ds2[2];
-            uint32_t hb = 0;                        // one hash decides both columns of the pair (drop_keep_att)
-            if (DROP) hb = drop_hash(seed_eff, (unsigned long long)(row_id * p.Lk + 128 * c + 64 * half + 32 * g + 2 * j));
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int col = 128 * c + 64 * half + 32 * g + 2 * j + u;   // key index
@@ -906,7 +895,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) att_tc_bwd_fused_kernel(const A
               float dp = __uint_as_float(rp[2 * j + u]);
               float pt = pr;
               if (DROP) {
-                const bool keep = (u ? (hb >> 16) : (hb & 0xFFFFu)) >= p.drop_thresh;
+                const bool keep = drop_keep_att(seed_eff, (unsigned long long)(row_id * p.Lk), col, p.drop_thresh);
                 pt = keep ? pr * p.drop_scale : 0.f;
                 dp = keep ? dp * p.drop_scale : 0.f;
               }
@@ -1013,25 +1002,16 @@ constexpr int PIPE_THREADS = TC_THREADS + 64;   // 8 softmax warps + 2 MMA-issui
 template <bool DROP, bool FAST>
 __device__ __forceinline__ void softmax_bwd_cols32(const uint32_t (&rs)[32], const uint32_t (&rp)[32], float sl2, float lse2,
                                                    float dl, int col0, int Lk, unsigned long long seed,
-                                                   unsigned long long row_lin, uint32_t t16, float drop_scale,
+                                                   unsigned long long row_lin, uint32_t thresh, float drop_scale,
                                                    uint32_t (&pkp)[16], uint32_t (&pks)[16]) {
-  const unsigned long long base = row_lin + (unsigned long long)col0;
-  const uint32_t lo0 = (uint32_t)base, seed_lo = (uint32_t)seed;
-  const uint32_t hi_term = ((uint32_t)(base >> 32) ^ (uint32_t)(seed >> 32)) * 0x85EBCA77u;
-  const uint32_t t16s = t16 << 16;
+  const uint32_t s0 = DROP ? drop_att_run_state(seed, row_lin, col0) : 0u;   // col0 is a multiple of 32: one run
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float m0 = 1.f, m1 = 1.f;
     if (DROP) {
-      uint32_t h;
-      if (FAST) {
-        h = ((lo0 + (uint32_t)(2 * j)) ^ seed_lo) * 0x9E3779B1u + hi_term;
-        h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;
-      } else {
-        h = drop_hash(seed, base + (unsigned long long)(2 * j));
-      }
-      m0 = (h << 16) >= t16s ? drop_scale : 0.f;
-      m1 = h >= t16s ? drop_scale : 0.f;
+      const DropLeap l0 = drop_leap(2 * j), l1 = drop_leap(2 * j + 1);
+      m0 = (s0 * l0.mul + l0.add) >= thresh ? drop_scale : 0.f;
+      m1 = (s0 * l1.mul + l1.add) >= thresh ? drop_scale : 0.f;
     }
     float p0 = fast_exp2(fmaf(__uint_as_float(rs[2 * j]), sl2, -lse2));
     float p1 = fast_exp2(fmaf(__uint_as_float(rs[2 * j + 1]), sl2, -lse2));
@@ -1261,7 +1241,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
         ptx::tmem_ld_wait();
         const int col0 = 64 * c + 32 * half;      // first key column of this thread
         const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
-        const bool fast = col0 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)col0) <= 0xFFFFFFFFu - 32u;
+        const bool fast = col0 + 32 <= p.Lk;        // all 32 columns are real keys: no per-column predicates
         if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
         else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
       }
@@ -1582,7 +1562,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
         ptx::tmem_ld_wait();
         const int col0 = 64 * c + 32 * half;      // first key column of this thread
         const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
-        const bool fast = col0 + 32 <= p.Lk && (uint32_t)(row_lin + (unsigned long long)col0) <= 0xFFFFFFFFu - 32u;
+        const bool fast = col0 + 32 <= p.Lk;        // all 32 columns are real keys: no per-column predicates
         if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
         else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
       }
@@ -1700,7 +1680,7 @@ int fill_tc(const egb_attention_desc* d, AttTcParams* p) {
   p->Lk_pad = (d->Lk + 15) / 16 * 16;
   p->scale = d->scale;
   if (d->dropout_p > 0.f) {
-    p->drop_thresh = drop_threshold16(d->dropout_p);   // 16-bit threshold of the paired decisions
+    p->drop_thresh = drop_threshold(d->dropout_p);
     p->drop_scale = 1.f / (1.f - d->dropout_p);
     p->seed = d->seed;
     p->epoch = egb_seed_epoch_ptr();

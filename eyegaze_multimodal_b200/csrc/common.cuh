@@ -239,19 +239,19 @@ __device__ __forceinline__ void drop_apply_run8(uint64_t seed, uint64_t base, ui
     v[i] = s >= thresh ? v[i] * scale : 0.f;
   }
 }
-// Attention-probability dropout: ONE hash decides TWO adjacent key columns (16 random bits each, p resolved to 2^-16).
-// The softmax loops of the tensor-core attention kernels are bound by integer throughput once dropout is on
-// (measured on the EEG encoder: ~2.2 K of 3.1 K cycles per 128 x 64 round); halving the hashes halves that.
-__device__ __forceinline__ bool drop_keep_att(uint64_t seed, uint64_t row_lin, int col, uint32_t thresh16) {
-  const uint32_t h = drop_hash(seed, row_lin + (uint64_t)(col & ~1));
-  return ((col & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16;
+// Attention-probability dropout: the key columns of a query row are grouped into aligned runs of 32; ONE hash of
+// (seed, row, run) seeds the run and column k of the run takes the k-fold LCG step of it (leapfrog constants, i.e. 32
+// independent multiply-adds); keep iff state >= p * 2^32.  The softmax loops of the tensor-core attention kernels are
+// bound by integer throughput once dropout is on: the first scheme (a full multiply-xorshift hash per key) cost the EEG
+// layers 25 % of their time, one hash per PAIR of keys still ~10 integer instructions per pair; this one is one
+// multiply-add and one compare per key.  `row_lin` = row index * Lk (element index of the row's first key).
+__device__ __forceinline__ uint32_t drop_att_run_state(uint64_t seed, uint64_t row_lin, int col0) {
+  return drop_hash(seed, row_lin + (uint64_t)col0);          // col0 = first column of the 32-column run
 }
-static inline uint32_t drop_threshold16(float p) {
-  if (!(p > 0.f)) return 0u;
-  double t = (double)p * 65536.0;
-  if (t < 1.0) t = 1.0;
-  if (t > 65535.0) t = 65535.0;
-  return (uint32_t)t;
+__device__ __forceinline__ bool drop_keep_att(uint64_t seed, uint64_t row_lin, int col, uint32_t thresh) {
+  uint32_t s = drop_att_run_state(seed, row_lin, col & ~31);
+  for (int k = col & 31; k > 0; --k) s = drop_step(s);
+  return s >= thresh;
 }
 static inline uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;
