@@ -440,6 +440,75 @@ def test_mlp2_epilogue_dropout_mask_consistency(cuda_device, mode, act):
         assert _relmax(gp.grad, r.grad) <= tol, (nm, _relmax(gp.grad, r.grad))
 
 
+def test_eeg_encoder_shape_ffn_with_dropout_bf16(cuda_device):
+    """The EEG encoder's FeedForward at the bench's size (71 168 tokens, 256 -> 1024 -> 256, ReLU, dropout on both layers):
+    these launches run the pair kernel with sixteen epilogue warps (bias + ReLU + dropout forward, dX-through-ReLU with
+    column sums backward).  Forward and backward against autograd on the same bf16-rounded operands with the masks the
+    forward kernels applied."""
+    Mr, K, Hd = 71168, 256, 1024
+    p_mid, p_out = 0.1, 0.1
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = (torch.randn(Mr, K, device=DEV, generator=g) * 0.5).bfloat16()
+    w1 = torch.randn(Hd, K, device=DEV, generator=g) / math.sqrt(K)
+    b1 = torch.randn(Hd, device=DEV, generator=g) * 0.1
+    w2 = torch.randn(K, Hd, device=DEV, generator=g) / math.sqrt(Hd)
+    b2 = torch.randn(K, device=DEV, generator=g) * 0.1
+    gy = torch.randn(Mr, K, device=DEV, generator=g).bfloat16()
+    q = lambda t: t.bfloat16().float()   # noqa: E731
+    with precision("bf16"):
+        _replay_seeds()
+        hm = ops.linear(x, torch.nn.Parameter(w1.clone()), torch.nn.Parameter(b1.clone()), act=L.ACT_RELU, p=p_mid)
+        _replay_seeds()
+        xg = x.clone().requires_grad_(True)
+        prm = [torch.nn.Parameter(t.clone()) for t in (w1, b1, w2, b2)]
+        y = ops.mlp2(xg, *prm, L.ACT_RELU, p_mid=p_mid, p_out=p_out)
+        y.backward(gy)
+    # reference on the GPU in fp32 (TF32 off), masks taken from the kernels' outputs
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ps = [t.clone().float().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+        pre = F.relu(F.linear(ps[0], q(ps[1]), ps[2]))
+        mask_mid = ((hm.detach() != 0) | (pre.detach() <= 0)).float()      # relu zeros are not drops
+        h = pre * mask_mid / (1 - p_mid)
+        yr = F.linear(h + (q(h.detach()) - h.detach()), q(ps[3]), ps[4])
+        mask_out = (y.detach() != 0).float()
+        yr = yr * mask_out / (1 - p_out)
+        yr.backward(gy.float())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    drop_mid = 1.0 - ((hm.detach() != 0).float().sum() / (pre.detach() > 0).float().sum()).item()
+    assert abs(drop_mid - p_mid) < 2e-3, drop_mid
+    assert abs(1.0 - mask_out.mean().item() - p_out) < 2e-3
+    assert _relmax(y, yr) <= 2e-2, _relmax(y, yr)
+    assert _relmax(xg.grad, ps[0].grad) <= 3e-2, _relmax(xg.grad, ps[0].grad)
+    for gp, r, nm in zip(prm, ps[1:], ["dw1", "db1", "dw2", "db2"]):
+        assert _relmax(gp.grad, r.grad) <= 3e-2, (nm, _relmax(gp.grad, r.grad))
+
+
+def test_weight_copies_follow_the_master_parameters(cuda_device):
+    """bf16 weight copies live in persistent buffers; ops.refresh_plain_copies() re-derives all of them with one launch
+    after the fp32 masters changed behind autograd's back (fused optimizer, captured step)."""
+    from eyegaze_multimodal_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(3)
+    ws = [torch.nn.Parameter(torch.randn(n, k, device=DEV, generator=g)) for n, k in ((64, 96), (33, 40), (256, 8))]
+    copies = [ops.weight_plain(w, L.BF16) for w in ws]
+    for w, c in zip(ws, copies):
+        assert torch.equal(c, w.detach().bfloat16())
+    with torch.no_grad():
+        for w in ws:
+            w.data.mul_(1.5).add_(0.25)                 # in place through .data: no version bump, as a CUDA optimizer kernel
+    ops.bump_param_epoch()
+    n0 = _lib.launch_count()
+    n = ops.refresh_plain_copies(DEV)
+    assert n >= len(ws) and _lib.launch_count() - n0 == 1          # ONE launch for every registered copy
+    again = [ops.weight_plain(w, L.BF16) for w in ws]
+    assert _lib.launch_count() - n0 == 1                             # ... and the cache serves them without re-casting
+    for w, c, a in zip(ws, copies, again):
+        assert a.data_ptr() == c.data_ptr()                          # same persistent buffer
+        assert torch.equal(a, w.detach().bfloat16())
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # 6. gradients: no aliasing, clip_grad_norm_, accumulation over two backward passes (advisor finding)
 # ---------------------------------------------------------------------------------------------------------------------
