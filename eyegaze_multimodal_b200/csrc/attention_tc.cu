@@ -90,12 +90,12 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // The copies are asynchronous (cp.async / LDGSTS, zero-fill for the padding rows): a thread issues all of its
 // chunks back to back; cp_async_wait_all() + a proxy fence + __syncthreads() publish the tiles to the tensor core.
 __device__ __forceinline__ void load_rows_sw128(uint8_t* dst, const bf16* src, long long rs, int rows_valid,
-                                                int rows_total, int d) {
+                                                int rows_total, int d, int nthreads = 256) {
   const int sh = d == 64 ? 3 : 2;                 // 16-byte chunks per row = d / 8 (head_dim is 32 or 64)
   const int cmask = (1 << sh) - 1;
   const uint32_t dst0 = ptx::smem_u32(dst);
   const int total = rows_total << sh;
-  for (int idx = threadIdx.x; idx < total; idx += TC_THREADS) {
+  for (int idx = threadIdx.x; idx < total; idx += nthreads) {
     const int r = idx >> sh, c = idx & cmask;
     const bool in = r < rows_valid;
     const bf16* g = in ? src + (long long)r * rs + c * 8 : src;
@@ -124,6 +124,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { ptx::tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -999,14 +1015,22 @@ constexpr int PIPE_THREADS = TC_THREADS + 64;   // 8 softmax warps + 2 MMA-issui
 // one hash per column PAIR with the high-word product hoisted, keep-tests on the un-extracted halves
 // (lo16 >= t  <=>  h << 16 >= t << 16;  hi16 >= t  <=>  h >= t << 16).  Rows past the sequence end come in with
 // lse2 = +inf, which makes their P exactly 0 without a predicate.  Both paths produce the mask of drop_keep_att().
-template <bool DROP, bool FAST>
-__device__ __forceinline__ void softmax_bwd_cols32(const uint32_t (&rs)[32], const uint32_t (&rp)[32], float sl2, float lse2,
-                                                   float dl, int col0, int Lk, unsigned long long seed,
-                                                   unsigned long long row_lin, uint32_t thresh, float drop_scale,
-                                                   uint32_t (&pkp)[16], uint32_t (&pks)[16]) {
-  const uint32_t s0 = DROP ? drop_att_run_state(seed, row_lin, col0) : 0u;   // col0 is a multiple of 32: one run
+// NC (32 or 16) key columns starting at col0 (a multiple of NC; the dropout run is the aligned 32-column group)
+template <bool DROP, bool FAST, int NC>
+__device__ __forceinline__ void softmax_bwd_cols(const uint32_t (&rs)[NC], const uint32_t (&rp)[NC], float sl2, float lse2,
+                                                 float dl, int col0, int Lk, unsigned long long seed,
+                                                 unsigned long long row_lin, uint32_t thresh, float drop_scale,
+                                                 uint32_t (&pkp)[NC / 2], uint32_t (&pks)[NC / 2]) {
+  uint32_t s0 = 0u;
+  if (DROP) {
+    s0 = drop_att_run_state(seed, row_lin, col0 & ~31);
+    if (NC == 16 && (col0 & 16)) {                       // second half of the run: 16 steps ahead
+      const DropLeap l16 = drop_leap(16);
+      s0 = s0 * l16.mul + l16.add;
+    }
+  }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < NC / 2; ++j) {
     float m0 = 1.f, m1 = 1.f;
     if (DROP) {
       const DropLeap l0 = drop_leap(2 * j), l1 = drop_leap(2 * j + 1);
@@ -1026,8 +1050,8 @@ __device__ __forceinline__ void softmax_bwd_cols32(const uint32_t (&rs)[32], con
 }
 
 
-template <bool DROP>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
+template <bool DROP, int NSW>
+__global__ void __launch_bounds__(NSW * 32 + 64, 1) att_tc_bwd_pipe_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
   const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
@@ -1050,15 +1074,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
   float* s_cs_all = reinterpret_cast<float*>(slot + 4);
   const bool want_cs = p.dq_cs != nullptr;
   if (want_cs)
-    for (int i = threadIdx.x; i < 8 * 192; i += PIPE_THREADS) s_cs_all[i] = 0.f;   // published by the __syncthreads below
-  float* s_cs = s_cs_all + (threadIdx.x >> 5 & 7) * 192;
+    for (int i = threadIdx.x; i < 8 * 192; i += NSW * 32 + 64) s_cs_all[i] = 0.f;   // published by the __syncthreads below
+  float* s_cs = s_cs_all + (threadIdx.x >> 5 & 7) * 192;   // (private per STORING warp: warps 0..7)
   const int h = blockIdx.x, s = blockIdx.y;
   const int skv = (s + p.kv_shift) % p.S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+  constexpr int SM_THREADS = NSW * 32;            // softmax threads
+  constexpr int CW = 64 / (NSW / 4);              // key columns of a 64-key round per thread (32 or 16)
+  const int quarter = warp >> 2;                  // column share of this warp within a round
+  const int half = quarter & 1, row = (warp & 3) * 32 + lane;   // `half`: column half in the store phases (quarter < 2)
+  const bool storer = quarter < 2;                // warps that read out and store the results
   const int d = p.d;
   const long long row_base = ((long long)s * p.H + h) * p.Lq;
-  const bool softmax_thread = warp < 8;
+  const bool softmax_thread = warp < NSW;
   // TMEM columns: score sets [0,128) [128,256); dV_kc, dK_kc (d columns each per 128-key chunk), dQ
   const uint32_t DV0 = 256, DK0 = 256 + (uint32_t)(d * nk), DQ0 = 256 + (uint32_t)(2 * d * nk);
   const bool dq_alias = DQ0 + (uint32_t)d > 512u;
@@ -1068,11 +1096,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bar_sp[0], 1);
     ptx::mbar_init(&bar_sp[1], 1);
-    ptx::mbar_init(&bar_rd[0], TC_THREADS);
-    ptx::mbar_init(&bar_rd[1], TC_THREADS);
+    ptx::mbar_init(&bar_rd[0], SM_THREADS);
+    ptx::mbar_init(&bar_rd[1], SM_THREADS);
     ptx::mbar_init(bar_acc, 1);
     ptx::mbar_init(bar_dq, 1);
-    ptx::mbar_init(bar_dqrd, TC_THREADS);
+    ptx::mbar_init(bar_dqrd, SM_THREADS);
     ptx::mbar_init(bar_ld, 1);
     ptx::fence_barrier_init();
     if (p.use_tma) {
@@ -1091,13 +1119,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
   const int n16 = d >> 3;
   if (softmax_thread) {
    if (!p.use_tma) {
-    load_rows_sw128(sQ, p.q + s * p.q_bs + h * d, p.q_rs, p.Lq, p.Lq_pad, d);
-    load_rows_sw128(sG, p.d_o + s * p.do_bs + h * d, p.do_rs, p.Lq, p.Lq_pad, d);
-    load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d);
-    load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d);
+    load_rows_sw128(sQ, p.q + s * p.q_bs + h * d, p.q_rs, p.Lq, p.Lq_pad, d, SM_THREADS);
+    load_rows_sw128(sG, p.d_o + s * p.do_bs + h * d, p.do_rs, p.Lq, p.Lq_pad, d, SM_THREADS);
+    load_rows_sw128(sK, p.k + skv * p.k_bs + h * d, p.k_rs, p.Lk, p.Lk_pad, d, SM_THREADS);
+    load_rows_sw128(sV, p.v + skv * p.v_bs + h * d, p.v_rs, p.Lk, p.Lk_pad, d, SM_THREADS);
     // delta_i = dO_i . O_i: O is staged like the other tiles (coalesced; a per-thread read of its own row straight
     // from global memory costs 32 sectors per instruction) into the still idle sP area
-    load_rows_sw128(sP, p.o + s * p.o_bs + h * d, p.o_rs, p.Lq, p.Lq_pad, d);
+    load_rows_sw128(sP, p.o + s * p.o_bs + h * d, p.o_rs, p.Lq, p.Lq_pad, d, SM_THREADS);
    }
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -1107,7 +1135,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
     ATT_STAMP_MID(1);
     cp_async_wait_all();
     ptx::fence_proxy_async_smem();
-  } else if (warp == 8) {
+  } else if (warp == NSW) {
     ptx::tmem_alloc<512>(slot);
   }
   ptx::tc_fence_before();
@@ -1122,7 +1150,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
     // Two issuing threads (each tcgen05.commit tracks its own thread's MMAs): warp 8 feeds the score sets, warp 9
     // the accumulators and dQ -- a single thread's serial instruction stream (~40 cycles per MMA) put the 16
     // accumulating MMAs of a pair in front of the next scores.
-    if (lane == 0 && warp == 8) {
+    if (lane == 0 && warp == NSW) {
       auto issue_scores = [&](int r2) {
         const int t2 = r2 / nc, c2 = r2 - t2 * nc;
         const int w2 = min(64, p.Lk_pad - 64 * c2);
@@ -1140,7 +1168,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
         issue_scores(r + 2);
         if (++c == nc) { c = 0; ++t; }
       }
-    } else if (lane == 0 && warp == 9) {
+    } else if (lane == 0 && warp == NSW + 1) {
       for (int r = 0, t = 0, c = 0; r < R; ++r) {
         const bool last_c = c == nc - 1;
         if ((c & 1) || last_c) {
@@ -1165,7 +1193,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
     // ------------------------------------------------------------------------------------------ softmax threads
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float sl2 = p.scale * LOG2E;
-    uint8_t* stage = sP + warp * 4096;            // warp-private staging rows of the coalesced result stores
+    uint8_t* stage = sP + (warp & 7) * 4096;      // warp-private staging rows of the coalesced result stores (warps 0..7)
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int i = t * TILE_ROWS + row;
@@ -1190,7 +1218,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
         lse_t[t] *= LOG2E;
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // O rows consumed: sP may be written
+    asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");   // O rows consumed: sP may be written
     auto read_dq = [&](int tq) {
       ATT_CLK(c0);
       ptx::mbar_wait(bar_dq, (uint32_t)(tq & 1));
@@ -1201,13 +1229,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
       // sP is idle here (bar_dq covers the accumulating MMAs that read it; this round's tiles are written later)
       const int r0 = tq * TILE_ROWS + (warp & 3) * 32;
       const int cb = d >= 64 ? half * 32 : 0;
-      if (d >= 64 || half == 0)
+      if (storer && (d >= 64 || half == 0))
         store_acc_rows_coalesced(trow + col + (uint32_t)cb, 32, p.scale, stage,
                                  p.dq + s * p.dq_bs + (long long)r0 * p.dq_rs + h * d + cb, p.dq_rs, p.Lq - r0, lane,
                                  want_cs ? s_cs + cb : nullptr);
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_dqrd);
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // every warp's staging rows are free again
+      asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");   // every warp's staging rows are free again
     };
     int pairs = 0;                                // accumulating MMA groups issued so far
     for (int r = 0, t = 0, c = 0; r < R; ++r) {
@@ -1224,26 +1252,26 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
       w_sp += c1 - c0;
       ptx::tc_fence_after();
 
-      // this thread: 32 key columns [32 half, 32 half + 32) of the 64-key round
-      uint32_t pkp[16], pks[16];
-      const bool mine = 32 * half < w;
+      // this thread: CW key columns [CW quarter, CW quarter + CW) of the 64-key round
+      uint32_t pkp[CW / 2], pks[CW / 2];
+      const bool mine = CW * quarter < w;
       // a warp whose 32 query rows all lie past the sequence end (second q-tile: L = 139 leaves 11 live rows, L = 197
       // leaves 69) has P = dS = 0 on all of them: it writes the zeros without the TMEM reads and the softmax arithmetic
       const bool warp_live = t * TILE_ROWS + (warp & 3) * 32 < p.Lq;
       if (mine && !warp_live) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pkp[j] = pks[j] = 0u;
+        for (int j = 0; j < CW / 2; ++j) pkp[j] = pks[j] = 0u;
       }
       if (mine && warp_live) {
-        uint32_t rs[32], rp[32];
-        ptx::tmem_ld32(trow + 128u * (uint32_t)set + (uint32_t)(32 * half), rs);
-        ptx::tmem_ld32(trow + 128u * (uint32_t)set + 64u + (uint32_t)(32 * half), rp);
+        uint32_t rs[CW], rp[CW];
+        tmem_ld_cols<CW>(trow + 128u * (uint32_t)set + (uint32_t)(CW * quarter), rs);
+        tmem_ld_cols<CW>(trow + 128u * (uint32_t)set + 64u + (uint32_t)(CW * quarter), rp);
         ptx::tmem_ld_wait();
-        const int col0 = 64 * c + 32 * half;      // first key column of this thread
+        const int col0 = 64 * c + CW * quarter;   // first key column of this thread
         const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
-        const bool fast = col0 + 32 <= p.Lk;        // all 32 columns are real keys: no per-column predicates
-        if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
-        else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        const bool fast = col0 + CW <= p.Lk;        // all columns are real keys: no per-column predicates
+        if (fast) softmax_bwd_cols<DROP, true, CW>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        else softmax_bwd_cols<DROP, false, CW>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
       }
       // previous q-tile's dQ: read it out behind this round's arithmetic; its barrier also covers the MMAs that read
       // the previous q-tile's sDS, which this q-tile now overwrites
@@ -1259,8 +1287,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
         uint8_t* prow = sP + (c & 1) * (TILE_ROWS * 128) + row * 128;
         uint8_t* srow = sDS + (size_t)c * (TILE_ROWS * 128) + row * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int slot16 = ((half * 4 + q4) ^ (row & 7)) << 4;
+        for (int q4 = 0; q4 < CW / 8; ++q4) {
+          const int slot16 = ((quarter * (CW / 8) + q4) ^ (row & 7)) << 4;
           *reinterpret_cast<uint4*>(prow + slot16) = make_uint4(pkp[4 * q4], pkp[4 * q4 + 1], pkp[4 * q4 + 2], pkp[4 * q4 + 3]);
           *reinterpret_cast<uint4*>(srow + slot16) = make_uint4(pks[4 * q4], pks[4 * q4 + 1], pks[4 * q4 + 2], pks[4 * q4 + 3]);
         }
@@ -1278,7 +1306,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
     // round c = 2) -- store them while the last pair's MMAs and dQ drain.  Staging goes to sV, which only the score
     // MMAs read and those have all been consumed (sP / sDS / sQ / sG / sK are still being read).
     const bool early0 = nk == 2;
-    if (early0) {
+    if (early0 && storer) {
       const int j0 = (warp & 3) * 32;
       uint8_t* st2 = sV + warp * 2048;
       for (int c0 = 0; c0 < d; c0 += 32) {
@@ -1291,7 +1319,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
       }
     }
     read_dq(nq - 1);                              // bar_dq of the last q-tile covers every MMA: dV / dK are final
-    for (int kc = early0 ? 1 : 0; kc < nk; ++kc) {
+    for (int kc = early0 ? 1 : 0; kc < nk && storer; ++kc) {
       const int j0 = kc * TILE_ROWS + (warp & 3) * 32;   // first key row of this warp
       if (half == 0)
         store_acc_rows_coalesced(trow + DV0 + (uint32_t)(d * kc), d, 1.f, stage,
@@ -1310,7 +1338,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
   ptx::tc_fence_before();
   __syncthreads();
   ATT_STAMP_MID(5);
-  if (warp == 8) {
+  if (warp == NSW) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem);
   }
@@ -1329,8 +1357,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pipe_kernel(const 
 // once, and the operand tiles of item i+1 are requested as soon as item i's last MMA has retired, i.e. they arrive
 // while item i's dV / dK rows are still being stored.  O is staged in the (then idle) dS area instead of the P~ area,
 // which doubles as the staging space of those stores.
-template <bool DROP>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
+template <bool DROP, int NSW>
+__global__ void __launch_bounds__(NSW * 32 + 64, 1) att_tc_bwd_pers_kernel(const __grid_constant__ AttTcParams p, const __grid_constant__ AttMaps maps) {
   const unsigned long long seed_eff = egb_mix_seed(p.seed, p.epoch);   // dropout seed of THIS replay
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sQ = align1024(smem_raw);
@@ -1352,11 +1380,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
   // [8 warps][3][64] column sums of this head's dQ | dK | dV rows, one private slot per softmax warp
   float* s_cs_all = reinterpret_cast<float*>(slot + 4);
   const bool want_cs = p.dq_cs != nullptr;
-  float* s_cs = s_cs_all + (threadIdx.x >> 5 & 7) * 192;
+  float* s_cs = s_cs_all + (threadIdx.x >> 5 & 7) * 192;   // (private per STORING warp: warps 0..7)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+  constexpr int SM_THREADS = NSW * 32;            // softmax threads
+  constexpr int CW = 64 / (NSW / 4);              // key columns of a 64-key round per thread (32 or 16)
+  const int quarter = warp >> 2;                  // column share of this warp within a round
+  const int half = quarter & 1, row = (warp & 3) * 32 + lane;   // `half`: column half in the store phases (quarter < 2)
+  const bool storer = quarter < 2;                // warps that read out and store the results
   const int d = p.d;
-  const bool softmax_thread = warp < 8;
+  const bool softmax_thread = warp < NSW;
   // TMEM columns: score sets [0,128) [128,256); dV_kc, dK_kc (d columns each per 128-key chunk), dQ
   const uint32_t DV0 = 256, DK0 = 256 + (uint32_t)(d * nk), DQ0 = 256 + (uint32_t)(2 * d * nk);
   const bool dq_alias = DQ0 + (uint32_t)d > 512u;
@@ -1370,11 +1402,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
     }
     ptx::mbar_init(&bar_sp[0], 1);
     ptx::mbar_init(&bar_sp[1], 1);
-    ptx::mbar_init(&bar_rd[0], TC_THREADS);
-    ptx::mbar_init(&bar_rd[1], TC_THREADS);
+    ptx::mbar_init(&bar_rd[0], SM_THREADS);
+    ptx::mbar_init(&bar_rd[1], SM_THREADS);
     ptx::mbar_init(bar_acc, 1);
     ptx::mbar_init(bar_dq, 1);
-    ptx::mbar_init(bar_dqrd, TC_THREADS);
+    ptx::mbar_init(bar_dqrd, SM_THREADS);
   };
   // operand tiles of one item: Q, dO, K, V and O (O goes to the sDS area, idle between items).  TMA: thread 0 arms the
   // item's load barrier and issues five bulk tensor copies; cp.async: every softmax thread issues its share.
@@ -1392,11 +1424,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
         ptx::tma_load_3d(sDS, &maps.o, bl, hh * d, 0, ss);
       }
     } else if (softmax_thread) {
-      load_rows_sw128(sQ, p.q + ss * p.q_bs + hh * d, p.q_rs, p.Lq, p.Lq_pad, d);
-      load_rows_sw128(sG, p.d_o + ss * p.do_bs + hh * d, p.do_rs, p.Lq, p.Lq_pad, d);
-      load_rows_sw128(sK, p.k + skv2 * p.k_bs + hh * d, p.k_rs, p.Lk, p.Lk_pad, d);
-      load_rows_sw128(sV, p.v + skv2 * p.v_bs + hh * d, p.v_rs, p.Lk, p.Lk_pad, d);
-      load_rows_sw128(sDS, p.o + ss * p.o_bs + hh * d, p.o_rs, p.Lq, p.Lq_pad, d);
+      load_rows_sw128(sQ, p.q + ss * p.q_bs + hh * d, p.q_rs, p.Lq, p.Lq_pad, d, SM_THREADS);
+      load_rows_sw128(sG, p.d_o + ss * p.do_bs + hh * d, p.do_rs, p.Lq, p.Lq_pad, d, SM_THREADS);
+      load_rows_sw128(sK, p.k + skv2 * p.k_bs + hh * d, p.k_rs, p.Lk, p.Lk_pad, d, SM_THREADS);
+      load_rows_sw128(sV, p.v + skv2 * p.v_bs + hh * d, p.v_rs, p.Lk, p.Lk_pad, d, SM_THREADS);
+      load_rows_sw128(sDS, p.o + ss * p.o_bs + hh * d, p.o_rs, p.Lq, p.Lq_pad, d, SM_THREADS);
     }
   };
 
@@ -1406,7 +1438,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
     ptx::mbar_init(&bar_ld[1], 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 8) ptx::tmem_alloc<512>(slot);
+  if (warp == NSW) ptx::tmem_alloc<512>(slot);
   issue_loads(blockIdx.x, 0);                    // (bar_ld is initialised by the issuing thread itself)
   ptx::tc_fence_before();
   __syncthreads();
@@ -1421,7 +1453,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
   const int next_item = item + gridDim.x;
   float dl_t[2] = {0.f, 0.f}, lse_t[2] = {0.f, 0.f};
   if (want_cs)
-    for (int i = threadIdx.x; i < 8 * 192; i += PIPE_THREADS) s_cs_all[i] = 0.f;   // published by the __syncthreads below
+    for (int i = threadIdx.x; i < 8 * 192; i += SM_THREADS + 64) s_cs_all[i] = 0.f;   // published by the __syncthreads below
   if (softmax_thread) {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -1443,7 +1475,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
     // Two issuing threads (each tcgen05.commit tracks its own thread's MMAs): warp 8 feeds the score sets, warp 9
     // the accumulators and dQ -- a single thread's serial instruction stream (~40 cycles per MMA) put the 16
     // accumulating MMAs of a pair in front of the next scores.
-    if (lane == 0 && warp == 8) {
+    if (lane == 0 && warp == NSW) {
       auto issue_scores = [&](int r2) {
         const int t2 = r2 / nc, c2 = r2 - t2 * nc;
         const int w2 = min(64, p.Lk_pad - 64 * c2);
@@ -1461,7 +1493,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
         issue_scores(r + 2);
         if (++c == nc) { c = 0; ++t; }
       }
-    } else if (lane == 0 && warp == 9) {
+    } else if (lane == 0 && warp == NSW + 1) {
       for (int r = 0, t = 0, c = 0; r < R; ++r) {
         const bool last_c = c == nc - 1;
         if ((c & 1) || last_c) {
@@ -1486,7 +1518,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
     // ------------------------------------------------------------------------------------------ softmax threads
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float sl2 = p.scale * LOG2E;
-    uint8_t* stage = sP + warp * 4096;            // warp-private staging rows of the coalesced result stores
+    uint8_t* stage = sP + (warp & 7) * 4096;      // warp-private staging rows of the coalesced result stores (warps 0..7)
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int i = t * TILE_ROWS + row;
@@ -1511,7 +1543,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
         lse_t[t] *= LOG2E;
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // O rows consumed: sDS may be written
+    asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");   // O rows consumed: sDS may be written
     auto read_dq = [&](int tq) {
       ATT_CLK(c0);
       ptx::mbar_wait(bar_dq, (uint32_t)(tq & 1));
@@ -1522,13 +1554,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
       // sP is idle here (bar_dq covers the accumulating MMAs that read it; this round's tiles are written later)
       const int r0 = tq * TILE_ROWS + (warp & 3) * 32;
       const int cb = d >= 64 ? half * 32 : 0;
-      if (d >= 64 || half == 0)
+      if (storer && (d >= 64 || half == 0))
         store_acc_rows_coalesced(trow + col + (uint32_t)cb, 32, p.scale, stage,
                                  p.dq + s * p.dq_bs + (long long)r0 * p.dq_rs + h * d + cb, p.dq_rs, p.Lq - r0, lane,
                                  want_cs ? s_cs + cb : nullptr);
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_dqrd);
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // every warp's staging rows are free again
+      asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");   // every warp's staging rows are free again
     };
     int pairs = 0;                                // accumulating MMA groups issued so far
     for (int r = 0, t = 0, c = 0; r < R; ++r) {
@@ -1545,26 +1577,26 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
       w_sp += c1 - c0;
       ptx::tc_fence_after();
 
-      // this thread: 32 key columns [32 half, 32 half + 32) of the 64-key round
-      uint32_t pkp[16], pks[16];
-      const bool mine = 32 * half < w;
+      // this thread: CW key columns [CW quarter, CW quarter + CW) of the 64-key round
+      uint32_t pkp[CW / 2], pks[CW / 2];
+      const bool mine = CW * quarter < w;
       // a warp whose 32 query rows all lie past the sequence end (second q-tile: L = 139 leaves 11 live rows, L = 197
       // leaves 69) has P = dS = 0 on all of them: it writes the zeros without the TMEM reads and the softmax arithmetic
       const bool warp_live = t * TILE_ROWS + (warp & 3) * 32 < p.Lq;
       if (mine && !warp_live) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pkp[j] = pks[j] = 0u;
+        for (int j = 0; j < CW / 2; ++j) pkp[j] = pks[j] = 0u;
       }
       if (mine && warp_live) {
-        uint32_t rs[32], rp[32];
-        ptx::tmem_ld32(trow + 128u * (uint32_t)set + (uint32_t)(32 * half), rs);
-        ptx::tmem_ld32(trow + 128u * (uint32_t)set + 64u + (uint32_t)(32 * half), rp);
+        uint32_t rs[CW], rp[CW];
+        tmem_ld_cols<CW>(trow + 128u * (uint32_t)set + (uint32_t)(CW * quarter), rs);
+        tmem_ld_cols<CW>(trow + 128u * (uint32_t)set + 64u + (uint32_t)(CW * quarter), rp);
         ptx::tmem_ld_wait();
-        const int col0 = 64 * c + 32 * half;      // first key column of this thread
+        const int col0 = 64 * c + CW * quarter;   // first key column of this thread
         const unsigned long long row_lin = (unsigned long long)(row_id * p.Lk);
-        const bool fast = col0 + 32 <= p.Lk;        // all 32 columns are real keys: no per-column predicates
-        if (fast) softmax_bwd_cols32<DROP, true>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
-        else softmax_bwd_cols32<DROP, false>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        const bool fast = col0 + CW <= p.Lk;        // all columns are real keys: no per-column predicates
+        if (fast) softmax_bwd_cols<DROP, true, CW>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
+        else softmax_bwd_cols<DROP, false, CW>(rs, rp, sl2, lse2, dl, col0, p.Lk, seed_eff, row_lin, p.drop_thresh, p.drop_scale, pkp, pks);
       }
       // previous q-tile's dQ: read it out behind this round's arithmetic; its barrier also covers the MMAs that read
       // the previous q-tile's sDS, which this q-tile now overwrites
@@ -1580,8 +1612,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
         uint8_t* prow = sP + (c & 1) * (TILE_ROWS * 128) + row * 128;
         uint8_t* srow = sDS + (size_t)c * (TILE_ROWS * 128) + row * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int slot16 = ((half * 4 + q4) ^ (row & 7)) << 4;
+        for (int q4 = 0; q4 < CW / 8; ++q4) {
+          const int slot16 = ((quarter * (CW / 8) + q4) ^ (row & 7)) << 4;
           *reinterpret_cast<uint4*>(prow + slot16) = make_uint4(pkp[4 * q4], pkp[4 * q4 + 1], pkp[4 * q4 + 2], pkp[4 * q4 + 3]);
           *reinterpret_cast<uint4*>(srow + slot16) = make_uint4(pks[4 * q4], pks[4 * q4 + 1], pks[4 * q4 + 2], pks[4 * q4 + 3]);
         }
@@ -1598,7 +1630,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
     // round c = 2) -- store them while the last pair's MMAs and dQ drain.  Staging goes to sV, which only the score
     // MMAs read and those have all been consumed (sP / sDS / sQ / sG / sK are still being read).
     const bool early0 = nk == 2;
-    if (early0) {
+    if (early0 && storer) {
       const int j0 = (warp & 3) * 32;
       uint8_t* st2 = sV + warp * 2048;
       for (int c0 = 0; c0 < d; c0 += 32) {
@@ -1616,7 +1648,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
     // column-sum flush and the next item's prologue (measured on the one-item-per-CTA kernel: tile loads 4.8 K and
     // result stores 5 K of a 29 K-cycle CTA ran back to back).
     if (next_item < n_items) issue_loads(next_item, k_item + 1);
-    for (int kc = early0 ? 1 : 0; kc < nk; ++kc) {
+    for (int kc = early0 ? 1 : 0; kc < nk && storer; ++kc) {
       const int j0 = kc * TILE_ROWS + (warp & 3) * 32;   // first key row of this warp
       if (half == 0)
         store_acc_rows_coalesced(trow + DV0 + (uint32_t)(d * kc), d, 1.f, stage,
@@ -1651,7 +1683,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) att_tc_bwd_pers_kernel(const 
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NSW) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem);
   }
@@ -1761,7 +1793,6 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
   if (cs_in_kernel) smem_f += 8 * 192 * 4 + 32;
   if (fused && smem_f <= 227 * 1024) {
     if (set_smem_tc(att_tc_bwd_fused_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_fused_kernel<false>, smem_f)) return 1;
-    if (set_smem_tc(att_tc_bwd_pipe_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_pipe_kernel<false>, smem_f)) return 1;
     dim3 grid(d->H, d->S);
     if (prof) egb_prof_begin(st, 10.0 * d->S * d->H * (double)d->Lq * d->Lk * d->head_dim,
                              2.0 * d->S * d->H * (double)d->head_dim * (4.0 * d->Lq + 4.0 * d->Lk), 3);
@@ -1786,14 +1817,31 @@ int egb_attention_tc_bwd(const egb_attention_desc* d, cudaStream_t st) {
       // (head_dim 64 / TMA tiles only: 408 -> 389 us per ViT-B layer; with cp.async staging (head_dim 32) the prefetch
       //  competes with the result stores for the same LSU queue and the static item split costs more than it saves:
       //  483 -> 499 us per EEG layer)
+      // eight softmax warps (32 key columns of a round per thread) or, EGB_ATT_NSW=16, sixteen (16 columns, 18-warp CTA,
+      // 96 registers per thread).  Unlike the GEMM epilogue the backward does NOT profit from the extra warps: measured
+      // 424 vs 388 us per ViT-B layer and 466 vs 450 us per EEG layer -- a round's critical path is the barrier / MMA
+      // round trip, not the softmax arithmetic, and twice the threads arrive on every barrier.
+      static const int nsw16 = getenv("EGB_ATT_NSW") ? (atoi(getenv("EGB_ATT_NSW")) == 16) : 0;
+#define EGB_ATT_LAUNCH(KERNEL, GRID)                                                                          \
+  do {                                                                                                        \
+    if (nsw16) {                                                                                              \
+      if (set_smem_tc(KERNEL<true, 16>, smem_f) || set_smem_tc(KERNEL<false, 16>, smem_f)) return 1;         \
+      if (drop) KERNEL<true, 16><<<GRID, 16 * 32 + 64, smem_f, st>>>(p, maps);                                \
+      else KERNEL<false, 16><<<GRID, 16 * 32 + 64, smem_f, st>>>(p, maps);                                    \
+    } else {                                                                                                  \
+      if (set_smem_tc(KERNEL<true, 8>, smem_f) || set_smem_tc(KERNEL<false, 8>, smem_f)) return 1;           \
+      if (drop) KERNEL<true, 8><<<GRID, 8 * 32 + 64, smem_f, st>>>(p, maps);                                  \
+      else KERNEL<false, 8><<<GRID, 8 * 32 + 64, smem_f, st>>>(p, maps);                                      \
+    }                                                                                                         \
+  } while (0)
       if (persist && p.use_tma) {
-        if (set_smem_tc(att_tc_bwd_pers_kernel<true>, smem_f) || set_smem_tc(att_tc_bwd_pers_kernel<false>, smem_f)) return 1;
         const int items = d->H * d->S;
         const int ctas = items < egb_num_sms() ? items : egb_num_sms();
-        if (drop) att_tc_bwd_pers_kernel<true><<<ctas, PIPE_THREADS, smem_f, st>>>(p, maps);
-        else att_tc_bwd_pers_kernel<false><<<ctas, PIPE_THREADS, smem_f, st>>>(p, maps);
-      } else if (drop) att_tc_bwd_pipe_kernel<true><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
-      else att_tc_bwd_pipe_kernel<false><<<grid, PIPE_THREADS, smem_f, st>>>(p, maps);
+        EGB_ATT_LAUNCH(att_tc_bwd_pers_kernel, ctas);
+      } else {
+        EGB_ATT_LAUNCH(att_tc_bwd_pipe_kernel, grid);
+      }
+#undef EGB_ATT_LAUNCH
       if (prof) egb_prof_end(st);
       egb_count_launch(1);
       EGB_LAUNCH_CHECK();
