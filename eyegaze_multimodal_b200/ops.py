@@ -284,9 +284,14 @@ def refresh_plain_copies(device=None) -> int:
     set of copies changes -- that upload cannot happen during stream capture, so a captured step calls this once eagerly
     after its warm-up.  Returns the number of tensors refreshed."""
     import numpy as np
+    if not torch.cuda.is_available():
+        return 0
+    dev_want = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev_want.index is None:
+        dev_want = torch.device("cuda", torch.cuda.current_device())
     items = []
     for w, buf in list(_plain_bufs.items()):
-        if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and (device is None or w.device == torch.device(device)):
+        if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.device == dev_want:   # one GPU per process
             items.append((w, buf))
     if not items:
         return 0
