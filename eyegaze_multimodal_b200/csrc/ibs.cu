@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256) ibs_pairs_kernel(const float* __restrict_
       float sn, cs;
       sincosf(ph, &sn, &cs);
       const float pw = x * x;
-      const float vals[IBS_NF] = {ph, valid ? cs : 0.f, valid ? sn : 0.f, pw, valid ? (x - st.x) * st.y : 0.f,
+      // (the power is staged HALVED: the wPLI weight (p1 + p2) / 2 becomes one add in the pair loop, bit-identically)
+      const float vals[IBS_NF] = {ph, valid ? cs : 0.f, valid ? sn : 0.f, 0.5f * pw, valid ? (x - st.x) * st.y : 0.f,
                                   valid ? (pw - st.z) * st.w : 0.f};
 #pragma unroll
       for (int f = 0; f < IBS_NF; ++f) {
@@ -270,12 +271,20 @@ __global__ void __launch_bounds__(256) ibs_pairs_kernel(const float* __restrict_
       const float p1a[4] = {p1.x, p1.y, p1.z, p1.w}, zx1a[4] = {zx1.x, zx1.y, zx1.z, zx1.w}, zp1a[4] = {zp1.x, zp1.y, zp1.z, zp1.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        // The loop is bound by instruction issue (ncu: issue slots 78 % busy, 29 instructions per pair-sample), so every
+        // term is written as the fewest instructions: cos / sin of the phase difference as two fused multiply-adds each,
+        // sign(d) and sign(d) * w by copying d's sign bit onto 1 and w, zeroed by ONE d != 0 predicate (sign(0) = 0 as in
+        // the reference, det:627,655).
         const float d = ph1a[q] - ph2;
-        const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-        l_re[q] += c1a[q] * c2 + s1a[q] * s2;
-        l_im[q] += s1a[q] * c2 - c1a[q] * s2;
+        const bool nz = d != 0.f;
+        const uint32_t sbit = __float_as_uint(d) & 0x80000000u;
+        const float w = p1a[q] + p2;                                  // halves were staged: (p1 + p2) / 2
+        const float sg = nz ? __uint_as_float(0x3f800000u | sbit) : 0.f;
+        const float sgw = nz ? __uint_as_float(__float_as_uint(w) | sbit) : 0.f;   // w >= 0
+        l_re[q] = fmaf(s1a[q], s2, fmaf(c1a[q], c2, l_re[q]));
+        l_im[q] = fmaf(-c1a[q], s2, fmaf(s1a[q], c2, l_im[q]));
         l_sg[q] += sg;
-        l_w[q] += sg * ((p1a[q] + p2) * 0.5f);
+        l_w[q] += sgw;
         l_pd[q] += fabsf(d);
         l_pc[q] = fmaf(zp1a[q], zp2, l_pc[q]);
         l_tc[q] = fmaf(zx1a[q], zx2, l_tc[q]);
