@@ -1384,7 +1384,7 @@ int launch_tc_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensor
   if (prof) {
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
-    egb_prof_tag(p.M, p.N, p.K, 1e6 + BN * 1e4 + EF);
+    egb_prof_tag(p.M, p.N, p.K, 1e10 + BN * 1e7 + EF);      // kernel variant 1 = single CTA
   }
   gemm_tc_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, mc, mp, p);
   if (prof) egb_prof_end(stream);
@@ -1450,7 +1450,7 @@ int launch_tc2_ef_bk16(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   if (prof) {
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
-    egb_prof_tag(p.M, p.N, p.K, 3e6 + BN * 1e4 + EF);
+    egb_prof_tag(p.M, p.N, p.K, 3e10 + BN * 1e7 + EF);      // 3 = CTA pair, 16 epilogue warps
   }
   gemm_tc2_kernel<BN, EF, BKT, 16><<<grid, 64 + 32 * 16, Cfg::SMEM_BYTES, stream>>>(ma, mb, mc, mp, p);
   if (prof) egb_prof_end(stream);
@@ -1478,7 +1478,7 @@ int launch_tc2_ef_bk(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   if (prof) {
     const double out_b = p.epi.c.f32 ? 4.0 : 2.0;
     egb_prof_begin(stream, 2.0 * p.M * (double)p.N * p.K, 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * p.M * p.N, 0);
-    egb_prof_tag(p.M, p.N, p.K, 2e6 + BN * 1e4 + EF);
+    egb_prof_tag(p.M, p.N, p.K, 2e10 + BN * 1e7 + EF);      // 2 = CTA pair, 8 epilogue warps
   }
   gemm_tc2_kernel<BN, EF, BKT><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, mc, mp, p);
   if (prof) egb_prof_end(stream);
