@@ -10,6 +10,8 @@ import ctypes as C
 import math
 import threading
 
+import os
+
 import torch
 from torch.utils.weak import WeakIdKeyDictionary
 
@@ -942,17 +944,26 @@ def _spec_w2_seg(w, code):
     return wcache.get((w,), code, "spec_w2_seg", build)
 
 
+# kw slots per K segment of the conv-2 dX GEMM: 4 = a zero slot pads the segment to 256 (128-wide TMA stages); 3 = no padding,
+# 192-wide segments, but those only fit 64-wide stages -- measured SLOWER (1.98 vs 1.57 ms): the per-instruction cost of TMA
+# outweighs the 25 % of operand bytes saved
+_SPEC_DX_SLOTS = int(os.environ.get("EGB_SPEC_DX_SLOTS", "4"))
+
+
 def _spec_w2_flip(w, code):
-    """dX operand: [32 c, 3 segs(a) x (4 b x 64 o)] = W[o, c, 2-a, 2-b], zero for b = 3."""
+    """dX operand: [32 c, 3 segs(a) x (S b x 64 o)] = W[o, c, 2-a, 2-b]; S = 3 (K segments of 192 = three positions x 64
+    channels, no padding) or 4 (a zero b = 3 slot: 256-wide segments, 25 % of the GEMM spent on zeros)."""
+    S = _SPEC_DX_SLOTS
+
     def build():
         O, Cc = w.shape[0], w.shape[1]
-        out = zeros((Cc, 3 * 4 * O), _TORCH_DT[code], w.device)
+        out = zeros((Cc, 3 * S * O), _TORCH_DT[code], w.device)
         for a in range(3):
             for b in range(3):
-                copy_strided4(w.detach(), out, (1, 1, Cc, O), (0, 0, 9, Cc * 9), (0, 0, 12 * O, 1),
-                              src_offset=(2 - a) * 3 + (2 - b), dst_offset=a * 4 * O + b * O)
+                copy_strided4(w.detach(), out, (1, 1, Cc, O), (0, 0, 9, Cc * 9), (0, 0, 3 * S * O, 1),
+                              src_offset=(2 - a) * 3 + (2 - b), dst_offset=a * S * O + b * O)
         return out
-    return wcache.get((w,), code, "spec_w2_flip", build)
+    return wcache.get((w,), code, "spec_w2_flip%d" % S, build)
 
 
 def _spec_geometry(bins, frames):
@@ -1008,9 +1019,10 @@ def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
         # dP1 (padded layout) = full correlation of dY with the flipped kernel: same implicit GEMM, K = 3 x 256
         w2f = _spec_w2_flip(w2, code)
         dp1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
-        a = TO.Operand(dy2, 0, 0, 64, 0, 256, Wp)
+        Kd = 3 * _SPEC_DX_SLOTS * 64
+        a = TO.Operand(dy2, 0, 0, 64, 0, _SPEC_DX_SLOTS * 64, Wp)
         cm = _dense_matrix(TO.at(dp1, (Wp + 1) * 32), code, 32)
-        gemm(N * RP, 32, 768, code, a, TO.Operand(w2f, 0, 0, 768, 0, 0, 0), cm)
+        gemm(N * RP, 32, Kd, code, a, TO.Operand(w2f, 0, 0, Kd, 0, 0, 0), cm)
         dwb = zeros((320,), torch.float32, dev)
         TO.call("spec_conv1_pool_bwd", img, w1, b1, dp1, code,
                dwb, dwb[288:], N, bins, frames, amax)
