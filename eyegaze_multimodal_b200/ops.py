@@ -948,6 +948,7 @@ def _spec_w2_seg(w, code):
 # 192-wide segments, but those only fit 64-wide stages -- measured SLOWER (1.98 vs 1.57 ms): the per-instruction cost of TMA
 # outweighs the 25 % of operand bytes saved
 _SPEC_DX_SLOTS = int(os.environ.get("EGB_SPEC_DX_SLOTS", "4"))
+_SPEC_DX_DIRECT = int(os.environ.get("EGB_SPEC_DX_DIRECT", "1"))    # 0: the generic GEMM over the overlapping-row view
 
 
 def _spec_w2_flip(w, code):
@@ -1019,10 +1020,14 @@ def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
         # dP1 (padded layout) = full correlation of dY with the flipped kernel: same implicit GEMM, K = 3 x 256
         w2f = _spec_w2_flip(w2, code)
         dp1 = torch.empty((N * RP + slack) * 32, dtype=tdt, device=dev)
-        Kd = 3 * _SPEC_DX_SLOTS * 64
-        a = TO.Operand(dy2, 0, 0, 64, 0, _SPEC_DX_SLOTS * 64, Wp)
-        cm = _dense_matrix(TO.at(dp1, (Wp + 1) * 32), code, 32)
-        gemm(N * RP, 32, Kd, code, a, TO.Operand(w2f, 0, 0, Kd, 0, 0, 0), cm)
+        if code == BF16 and _SPEC_DX_SLOTS == 4 and _SPEC_DX_DIRECT and 128 + 2 * Wp + 2 <= 256:
+            # implicit GEMM that stages each input tile once and issues the nine taps as row-shifted MMA operands
+            TO.call("conv3x3_c64_c32", dy2, dy2.numel() // 64, w2f, dp1, N * RP, Wp + 1, Wp)
+        else:
+            Kd = 3 * _SPEC_DX_SLOTS * 64
+            a = TO.Operand(dy2, 0, 0, 64, 0, _SPEC_DX_SLOTS * 64, Wp)
+            cm = _dense_matrix(TO.at(dp1, (Wp + 1) * 32), code, 32)
+            gemm(N * RP, 32, Kd, code, a, TO.Operand(w2f, 0, 0, Kd, 0, 0, 0), cm)
         dwb = zeros((320,), torch.float32, dev)
         TO.call("spec_conv1_pool_bwd", img, w1, b1, dp1, code,
                dwb, dwb[288:], N, bins, frames, amax)

@@ -227,6 +227,12 @@ int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias,
                             int Ww, int64_t out_elems, uint16_t* amax, void* stream);
 int egb_spec_conv1_pool_bwd(const float* img, const float* w, const float* bias, const void* dout, int dtype, float* dw,
                             float* db, int N, int Hh, int Ww, const uint16_t* amax, void* stream);
+/* 3x3 convolution, 64 -> 32 channels, over zero-bordered channels-last images as an implicit GEMM that stages every input
+   tile once (data gradient of spec_conv[3], dual_eeg_transformer.py:81-86):
+       y[(m + out_shift) * 32 + c] = sum_{a, b < 3, o < 64} x[(m + a * Wp + b) * 64 + o] * w[c * 768 + a * 256 + b * 64 + o]
+   for m in [0, M).  x: bf16 [x_rows, 64]; w: bf16 [32, 768]; y: bf16 rows of 32 channels. */
+int egb_conv3x3_c64_c32(const void* x, long long x_rows, const void* w, void* y, long long M, long long out_shift, int Wp,
+                        void* stream);
 /* ReLU + AdaptiveAvgPool2d(4,4) + flatten over the padded conv-2 output [N, H1+2, W1+2, 64] */
 int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int W1, void* stream);
 int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream);
