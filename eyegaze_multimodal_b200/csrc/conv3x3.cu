@@ -1,5 +1,5 @@
-// 3x3 convolution over zero-bordered channels-last images as a TRUE implicit GEMM on tcgen05 (64 -> 32 channels: the
-// data gradient of the spectrogram CNN's second convolution, dual_eeg_transformer.py:81-86 / its autograd).
+// 3x3 convolution over zero-bordered channels-last images as a TRUE implicit GEMM on tcgen05: the spectrogram CNN's second
+// convolution (32 -> 64 channels, + bias; dual_eeg_transformer.py:81-86) and its data gradient (64 -> 32 channels).
 //
 // The generic GEMM kernel runs this convolution over an overlapping-row VIEW of the image buffer (K = 3 row segments x
 // 4 positions x 64 channels): every input element crosses L2 -> shared memory 12 times, 8.5 GB per launch, and the
@@ -7,7 +7,8 @@
 // ([128 + 2 Wp + 2 positions][64 channels], one TMA box, 128-byte swizzle) and issues the nine taps as MMAs whose A
 // descriptors simply START (a Wp + b) rows further down: the hardware applies the 128-byte swizzle to absolute
 // shared-memory address bits, so a K-major operand may begin at any row of a swizzled tile (verified on the device by
-// csrc/tests/shift_desc_test.cu: exact for every row offset with the descriptor's base-offset field left at 0).
+// csrc/tests/shift_desc_test.cu: exact for every row offset with the descriptor's base-offset field left at 0, for
+// 128-byte rows / SWIZZLE_128B and for 64-byte rows / SWIZZLE_64B alike).
 //
 //   y[p, c] = sum_{a, b < 3} sum_o x[p - (Wp + 1) + a Wp + b, o] * w[c][a][b][o]        p = flat padded position
 //
@@ -22,17 +23,18 @@
 #include "../../include/eyegaze_b200.h"
 
 extern void egb_count_launch(int n);
-int egb_tmap_rows64(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long groups, long long rs,
-                    long long gs, int box_rows);
+int egb_tmap_2d(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long rs, int box_inner, int box_rows);
 
 namespace {
 
 constexpr int CV_THREADS = 192;
 constexpr int CV_M = 128;
-constexpr int CV_XS = 4;        // input-tile ring (a tile is ~20 KB; a TMA round trip outlasts a tile's 36 MMAs)
+constexpr int CV_XS = 3;        // input-tile ring (a tile is ~20 KB; a TMA round trip outlasts a tile's 36 MMAs)
+constexpr int CV_CTAS_PER_SM = 2;   // two CTAs per SM: a tile's MMAs are issued by ONE thread (36-18 small instructions), two issuers keep the tensor pipe fed
 
 struct ConvParams {
-  bf16* y;            // [rows, 32]
+  bf16* y;            // [rows, COUT]
+  const float* bias;  // [COUT] or NULL
   long long M;        // output rows m = 0 .. M-1, written at flat position m + out_shift
   long long out_shift;
   int Wp;             // padded image width (row shift of one kernel row)
@@ -40,14 +42,31 @@ struct ConvParams {
   int tiles;
 };
 
-__global__ void __launch_bounds__(CV_THREADS, 1)
-conv3x3_c64_c32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+// K-major shared-memory operand descriptor for rows of RB bytes (128: SWIZZLE_128B, 64: SWIZZLE_64B); 8-row groups are
+// 8 * RB bytes apart
+template <int RB>
+__device__ __forceinline__ uint64_t conv_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(((8u * RB) >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(RB == 128 ? 2 : 4) << 61;
+  return d;
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(CV_THREADS, CV_CTAS_PER_SM)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  constexpr int RB = CIN * 2;                 // bytes per input row (position)
+  constexpr int WTAP = COUT * RB;             // bytes of one tap's weight tile [COUT rows][CIN]
+  constexpr int WSEG = 4 * CIN;               // columns of one kernel-row segment of the weight matrix (four position slots)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int tile_bytes = ((p.box_rows * 128) + 1023) & ~1023;
+  const int tile_bytes = ((p.box_rows * RB) + 1023) & ~1023;
   uint8_t* sX = smem;                                  // [CV_XS][box_rows][128 B]
-  uint8_t* sW = smem + CV_XS * tile_bytes;             // [9][32 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 9 * 4096);
+  uint8_t* sW = smem + CV_XS * tile_bytes;             // [9][COUT rows][RB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 9 * WTAP);
   uint64_t* full = bars;                     // [CV_XS] input tile landed
   uint64_t* empty = bars + CV_XS;            // [CV_XS] input tile consumed by the MMAs
   uint64_t* tfull = bars + 2 * CV_XS;        // [2] accumulator ready
@@ -70,7 +89,7 @@ conv3x3_c64_c32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     ptx::mbar_init(wbar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<64>(slot);
+  if (warp == 1) ptx::tmem_alloc<2 * COUT>(slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -78,19 +97,19 @@ conv3x3_c64_c32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(wbar, 9 * 4096);
-      for (int t = 0; t < 9; ++t) ptx::tma_load_3d(sW + t * 4096, &tmW, wbar, (t / 3) * 256 + (t % 3) * 64, 0, 0);
+      ptx::mbar_arrive_expect_tx(wbar, 9 * WTAP);
+      for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * WTAP, &tmW, wbar, (t / 3) * WSEG + (t % 3) * CIN, 0);
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
         ptx::mbar_wait(&empty[s], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(p.box_rows * 128));
-        ptx::tma_load_3d(sX + s * tile_bytes, &tmX, &full[s], 0, tile * CV_M, 0);   // rows past the buffer end: zero-filled
+        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(p.box_rows * RB));
+        ptx::tma_load_2d(sX + s * tile_bytes, &tmX, &full[s], 0, tile * CV_M);      // rows past the buffer end: zero-filled
         if (++s == CV_XS) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = ptx::make_idesc_bf16(CV_M, 32, 0, 0);
+    const uint32_t idesc = ptx::make_idesc_bf16(CV_M, COUT, 0, 0);
     ptx::mbar_wait(wbar, 0);
     int s = 0, ts = 0;
     uint32_t ph = 0, tph = 0;
@@ -100,14 +119,14 @@ conv3x3_c64_c32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       ptx::tc_fence_after();
       if (lane == 0) {
         const uint32_t xa = ptx::smem_u32(sX + s * tile_bytes);
-        const uint32_t td = tmem + (uint32_t)(32 * ts);
+        const uint32_t td = tmem + (uint32_t)(COUT * ts);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           // tap (a, b): the A operand starts (a Wp + b) rows into the tile (any row: the swizzle is on absolute address bits)
-          const uint64_t ad = ptx::make_smem_desc(xa + (uint32_t)(((t / 3) * p.Wp + (t % 3)) * 128), 16u, 1024u);
-          const uint64_t bd = ptx::make_smem_desc(ptx::smem_u32(sW + t * 4096), 16u, 1024u);
+          const uint64_t ad = conv_desc<RB>(xa + (uint32_t)(((t / 3) * p.Wp + (t % 3)) * RB));
+          const uint64_t bd = conv_desc<RB>(ptx::smem_u32(sW + t * WTAP));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (t > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < CIN / 16; ++k) ptx::umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (t > 0 || k > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&empty[s]);     // the input tile may be refilled once these MMAs have retired
         ptx::umma_commit(&tfull[ts]);
@@ -123,22 +142,30 @@ conv3x3_c64_c32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tfull[s], ph);
       ptx::tc_fence_after();
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * s), v);
+      uint32_t v[COUT];
+#pragma unroll
+      for (int h = 0; h < COUT / 32; ++h)
+        ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(COUT * s + 32 * h), reinterpret_cast<uint32_t (&)[32]>(v[32 * h]));
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_relaxed(&tempty[s]);
       const long long m = (long long)tile * CV_M + quad * 32 + lane;
       if (m < p.M) {
-        uint4* dst = reinterpret_cast<uint4*>(p.y + (m + p.out_shift) * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.y + (m + p.out_shift) * COUT);   // this lane's row: COUT * 2 contiguous bytes
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < COUT / 8; ++g) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * g + i]);
+          if (p.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + 8 * g));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + 8 * g + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
           uint4 o;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
           o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
           o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
           dst[g] = o;
@@ -151,8 +178,42 @@ conv3x3_c64_c32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<64>(tmem);
+    ptx::tmem_dealloc<2 * COUT>(tmem);
   }
+}
+
+template <int CIN, int COUT>
+int launch_conv(const void* x, long long x_rows, const void* w, const float* bias, void* y, long long M, long long out_shift,
+                int Wp, cudaStream_t st) {
+  EGB_CHECK(M > 0 && Wp >= 3 && 128 + 2 * Wp + 2 <= 256, "conv3x3: unsupported geometry (M=%lld, Wp=%d)", M, Wp);
+  EGB_CHECK(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0 && (out_shift * COUT * 2) % 16 == 0 &&
+                (bias == nullptr || ((uintptr_t)bias % 16) == 0),
+            "conv3x3: misaligned buffers");
+  ConvParams p;
+  p.y = (bf16*)y;
+  p.bias = bias;
+  p.M = M;
+  p.out_shift = out_shift;
+  p.Wp = Wp;
+  p.box_rows = 128 + 2 * Wp + 2;
+  p.tiles = (int)((M + CV_M - 1) / CV_M);
+  CUtensorMap mx, mw;
+  if (egb_tmap_2d(&mx, x, CIN, x_rows, CIN, CIN, p.box_rows)) return 1;
+  if (egb_tmap_2d(&mw, w, 12 * CIN, COUT, 12 * CIN, CIN, COUT)) return 1;
+  const int tile_bytes = ((p.box_rows * CIN * 2) + 1023) & ~1023;
+  const size_t smem = (size_t)CV_XS * tile_bytes + 9 * COUT * CIN * 2 + 256 + 1024;
+  EGB_CHECK(smem <= 112 * 1024, "conv3x3: tile too large for two CTAs per SM (%zu bytes)", smem);
+  static bool attr = false;
+  if (!attr) {
+    EGB_CUDA(cudaFuncSetAttribute(conv3x3_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr = true;
+  }
+  const int cap = CV_CTAS_PER_SM * egb_num_sms();
+  const int grid = p.tiles < cap ? p.tiles : cap;
+  conv3x3_kernel<CIN, COUT><<<grid, CV_THREADS, smem, st>>>(mx, mw, p);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace
@@ -165,32 +226,14 @@ extern "C" {
    64-wide slots, the fourth unused), y: bf16 rows of 32.  Reads x rows up to M + 2 Wp + 2 (rows >= x_rows read as 0). */
 int egb_conv3x3_c64_c32(const void* x, long long x_rows, const void* w, void* y, long long M, long long out_shift, int Wp,
                         void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  EGB_CHECK(M > 0 && Wp >= 3 && 128 + 2 * Wp + 2 <= 256, "conv3x3: unsupported geometry (M=%lld, Wp=%d)", M, Wp);
-  EGB_CHECK(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0 && (out_shift * 64) % 16 == 0,
-            "conv3x3: misaligned buffers");
-  ConvParams p;
-  p.y = (bf16*)y;
-  p.M = M;
-  p.out_shift = out_shift;
-  p.Wp = Wp;
-  p.box_rows = 128 + 2 * Wp + 2;
-  p.tiles = (int)((M + CV_M - 1) / CV_M);
-  CUtensorMap mx, mw;
-  if (egb_tmap_rows64(&mx, x, 64, x_rows, 1, 64, 0, p.box_rows)) return 1;
-  if (egb_tmap_rows64(&mw, w, 768, 32, 1, 768, 0, 32)) return 1;
-  const int tile_bytes = ((p.box_rows * 128) + 1023) & ~1023;
-  const size_t smem = (size_t)CV_XS * tile_bytes + 9 * 4096 + 256 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    EGB_CUDA(cudaFuncSetAttribute(conv3x3_c64_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
-  const int grid = p.tiles < egb_num_sms() ? p.tiles : egb_num_sms();
-  conv3x3_c64_c32_kernel<<<grid, CV_THREADS, smem, st>>>(mx, mw, p);
-  egb_count_launch(1);
-  EGB_LAUNCH_CHECK();
-  return 0;
+  return launch_conv<64, 32>(x, x_rows, w, nullptr, y, M, out_shift, Wp, (cudaStream_t)stream);
+}
+
+/* the forward convolution: y[(m + out_shift) * 64 + o] = bias[o] + sum over taps and 32 input channels c of
+       x[(m + a * Wp + b) * 32 + c] * w[o * 384 + a * 128 + b * 32 + c];  x: bf16 [x_rows, 32], w: bf16 [64, 384], bias fp32 */
+int egb_conv3x3_c32_c64(const void* x, long long x_rows, const void* w, const float* bias, void* y, long long M,
+                        long long out_shift, int Wp, void* stream) {
+  return launch_conv<32, 64>(x, x_rows, w, bias, y, M, out_shift, Wp, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1569,6 +1569,37 @@ int egb_tmap_rows64(CUtensorMap* out, const void* ptr, long long inner, long lon
   return make_map(out, ptr, inner, rows, groups, rs, gs, box_rows, 1);
 }
 
+// 2-D bf16 tensor map {inner elements, rows} (row stride rs elements) with a {box_inner, box_rows} box and a 64- or
+// 128-byte swizzle (box_inner * 2 bytes must equal the swizzle span); cached.  Used by the implicit-GEMM convolution.
+int egb_tmap_2d(CUtensorMap* out, const void* ptr, long long inner, long long rows, long long rs, int box_inner, int box_rows) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = inner; key.rows = rows; key.groups = 1; key.rs = rs; key.gs = -2222;
+  key.b0 = box_inner; key.b1 = box_rows; key.b2 = 1;
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  EGB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  EGB_CHECK(box_inner == 32 || box_inner == 64, "tmap_2d: box of 32 or 64 bf16 elements");
+  EGB_CHECK(((uintptr_t)ptr % 16) == 0 && (rs % 8) == 0 && rs > 0 && box_rows <= 256, "tmap_2d: misaligned operand");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)rs * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (2-D) failed (%d): inner=%lld rows=%lld rs=%lld box=%d,%d", (int)r, inner,
+            rows, rs, box_inner, box_rows);
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps[key] = *out;
+  return 0;
+}
+
 extern "C" int egb_debug_gemm_timing(long long* device_buf) {
   g_gemm_dbg = device_buf;
   return 0;

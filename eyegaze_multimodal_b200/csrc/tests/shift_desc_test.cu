@@ -55,7 +55,94 @@ __global__ void __launch_bounds__(128) shift_kernel(const bf16* __restrict__ A, 
   if (threadIdx.x < 32) ptx::tmem_dealloc<32>(tmem);
 }
 
+// Same question for 64-BYTE rows (32 bf16 = the 32-channel activation of the forward convolution): tile staged with the
+// 64-byte swizzle (16-byte chunk index ^= (row >> 1) & 3), descriptor swizzle mode 4 (SWIZZLE_64B), SBO = 512 B.
+// D[m][c] = sum_{k < 32} A[m + shift][k] * B[c][k], c < 64: two tcgen05.mma (K = 16 each).
+__global__ void __launch_bounds__(128) shift64_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, float* __restrict__ out,
+                                                      int R, int shift) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = sA + ((R * 64 + 1023) & ~1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int idx = threadIdx.x; idx < R * 4; idx += blockDim.x) {
+    const int r = idx >> 2, c = idx & 3;
+    *reinterpret_cast<uint4*>(sA + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(A + r * 32 + c * 8);
+  }
+  for (int idx = threadIdx.x; idx < 64 * 4; idx += blockDim.x) {
+    const int r = idx >> 2, c = idx & 3;
+    *reinterpret_cast<uint4*>(sB + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(B + r * 32 + c * 8);
+  }
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); }
+  if (threadIdx.x < 32) ptx::tmem_alloc<64>(&slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 0, 0);
+    auto desc64 = [](uint32_t addr) {
+      uint64_t d = 0;
+      d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+      d |= (uint64_t)((16u >> 4) & 0x3FFFu) << 16;
+      d |= (uint64_t)((512u >> 4) & 0x3FFFu) << 32;
+      d |= (uint64_t)1 << 46;
+      d |= (uint64_t)4 << 61;   // SWIZZLE_64B
+      return d;
+    };
+    const uint64_t ad = desc64(ptx::smem_u32(sA) + (uint32_t)shift * 64u);
+    const uint64_t bd = desc64(ptx::smem_u32(sB));
+    for (int k = 0; k < 2; ++k) ptx::umma_bf16(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+    ptx::umma_commit(&bar);
+  }
+  ptx::mbar_wait(&bar, 0);
+  ptx::tc_fence_after();
+  for (int h = 0; h < 2; ++h) {
+    uint32_t v[32];
+    ptx::tmem_ld32(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + (uint32_t)(32 * h), v);
+    ptx::tmem_ld_wait();
+    for (int c = 0; c < 32; ++c) out[threadIdx.x * 64 + 32 * h + c] = __uint_as_float(v[c]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc<64>(tmem);
+}
+
+int test64() {
+  const int R = 160;
+  std::vector<bf16> hA(R * 32), hB(64 * 32);
+  std::vector<float> fA(R * 32), fB(64 * 32);
+  srand(2);
+  for (int i = 0; i < R * 32; ++i) { float x = (rand() % 2001 - 1000) / 1000.f; hA[i] = __float2bfloat16(x); fA[i] = __bfloat162float(hA[i]); }
+  for (int i = 0; i < 64 * 32; ++i) { float x = (rand() % 2001 - 1000) / 1000.f; hB[i] = __float2bfloat16(x); fB[i] = __bfloat162float(hB[i]); }
+  bf16 *dA, *dB; float* dO;
+  cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dO, 128 * 64 * 4);
+  cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
+  const size_t smem = ((R * 64 + 1023) & ~1023) + 64 * 64 + 2048;
+  std::vector<float> ho(128 * 64);
+  for (int shift : {0, 8, 16, 1, 2, 3, 5, 7, 10, 11, 21}) {
+    cudaMemset(dO, 0, 128 * 64 * 4);
+    shift64_kernel<<<1, 128, smem>>>(dA, dB, dO, R, shift);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("64B shift %d: CUDA error %s\n", shift, cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(ho.data(), dO, ho.size() * 4, cudaMemcpyDeviceToHost);
+    double worst = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int c = 0; c < 64; ++c) {
+        double ref = 0;
+        for (int k = 0; k < 32; ++k) ref += (double)fA[(m + shift) * 32 + k] * fB[c * 32 + k];
+        worst = fmax(worst, fabs(ref - ho[m * 64 + c]));
+      }
+    printf("64-byte rows, SWIZZLE_64B  shift %2d rows: max abs err %.3e  %s\n", shift, worst, worst < 1e-3 ? "OK" : "WRONG");
+  }
+  return 0;
+}
+
 int main() {
+  if (test64()) return 1;
+
   const int R = 160;
   std::vector<bf16> hA(R * 64), hB(32 * 64);
   std::vector<float> fA(R * 64), fB(32 * 64);

@@ -994,9 +994,13 @@ def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins, 
            frames, p1.numel(), amax)
     y2 = zeros(((N * RP + slack) * 64,), tdt, dev)
     w2s = _spec_w2_seg(w2, code)
-    a = TO.Operand(p1, 0, 0, 32, 0, 128, Wp)
-    cm = _dense_matrix(TO.at(y2, (Wp + 1) * 64), code, 64)
-    gemm(N * RP, 64, 384, code, a, TO.Operand(w2s, 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
+    if code == BF16 and _SPEC_DX_DIRECT and 128 + 2 * Wp + 2 <= 256:
+        # implicit GEMM that stages each input tile once (nine row-shifted MMA operands per tile)
+        TO.call("conv3x3_c32_c64", p1, p1.numel() // 32, w2s, b2.detach(), y2, N * RP, Wp + 1, Wp)
+    else:
+        a = TO.Operand(p1, 0, 0, 32, 0, 128, Wp)
+        cm = _dense_matrix(TO.at(y2, (Wp + 1) * 64), code, 64)
+        gemm(N * RP, 64, 384, code, a, TO.Operand(w2s, 0, 0, 384, 0, 0, 0), cm, bias=b2.detach())
     return img, p1, y2, (code, N, bins, frames, H1, W1, Wp, RP, slack, amax)
 
 

@@ -233,6 +233,11 @@ int egb_spec_conv1_pool_bwd(const float* img, const float* w, const float* bias,
    for m in [0, M).  x: bf16 [x_rows, 64]; w: bf16 [32, 768]; y: bf16 rows of 32 channels. */
 int egb_conv3x3_c64_c32(const void* x, long long x_rows, const void* w, void* y, long long M, long long out_shift, int Wp,
                         void* stream);
+/* the forward convolution spec_conv[3] (32 -> 64 channels, + bias) by the same kernel:
+       y[(m + out_shift) * 64 + o] = bias[o] + sum_{a, b < 3, c < 32} x[(m + a * Wp + b) * 32 + c] * w[o * 384 + a * 128 + b * 32 + c]
+   x: bf16 [x_rows, 32]; w: bf16 [64, 384]; bias: fp32 [64]; y: bf16 rows of 64 channels. */
+int egb_conv3x3_c32_c64(const void* x, long long x_rows, const void* w, const float* bias, void* y, long long M,
+                        long long out_shift, int Wp, void* stream);
 /* ReLU + AdaptiveAvgPool2d(4,4) + flatten over the padded conv-2 output [N, H1+2, W1+2, 64] */
 int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int W1, void* stream);
 int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream);
