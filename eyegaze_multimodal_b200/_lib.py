@@ -94,6 +94,7 @@ _SIGNATURES = {
     "egb_stft_logmag": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "egb_conv3x3_c64_c32": [vp, i64, vp, vp, i64, i64, i32, vp],
     "egb_conv3x3_c32_c64": [vp, i64, vp, vp, vp, i64, i64, i32, vp],
+    "egb_conv3x3_dw_c32_c64": [vp, i64, vp, i64, vp, i64, i64, i32, vp],
     "egb_spec_conv1_pool_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i64, vp, vp],
     "egb_spec_conv1_pool_bwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, vp],
     "egb_relu_avgpool_fwd": [vp, vp, i32, i32, i32, i32, vp],

@@ -216,6 +216,163 @@ int launch_conv(const void* x, long long x_rows, const void* w, const float* bia
   return 0;
 }
 
+// ---- weight gradient --------------------------------------------------------------------------------------------------
+//   dW^T[(a, j, c)][o] = sum over flat positions m of  x[m + a Wp + j][c] * dy[m + dy_shift][o]      a < 3, j < 4 (j = 3 unused)
+// Both operands are MN-major (K = positions = tile rows).  The 32-channel activation tile [128 + 2 Wp + 3 rows][64 B]
+// (SWIZZLE_64B) is read as an M = 128 operand whose four 32-element M atoms are ONE ROW (64 B) apart -- the descriptor's
+// leading-dimension offset is just an address increment, so atom j is the same tile starting one position later: the four
+// horizontal taps of a kernel row come out of ONE MMA (csrc/tests/shift_desc_test.cu, test_dw).  Per 128-position tile:
+// 3 kernel rows x 8 K-steps = 24 MMAs (M = 128, N = 64, K = 16) into three accumulators that stay in TMEM for the whole
+// CTA; every element of x and dy crosses L2 -> shared memory once.  At the end the CTA adds its partial sums to dW^T
+// (fp32, red.global.add.v4).
+struct ConvDwParams {
+  float* dwt;          // [384, 64] fp32, zeroed by the caller
+  long long dy_shift;
+  int Wp;
+  int box_rows;        // activation rows per tile = 128 + 2 Wp + 3
+  int tiles;
+};
+
+constexpr int DW_STAGES = 3;
+
+__device__ __forceinline__ void red_add4(float* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(CV_THREADS, CV_CTAS_PER_SM)
+conv3x3_dw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const ConvDwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int xtile = ((p.box_rows * 64) + 1023) & ~1023;
+  const int stage = xtile + CV_M * 128;               // activation rows, then the 128 gradient rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DW_STAGES * stage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + DW_STAGES;
+  uint64_t* done = bars + 2 * DW_STAGES;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2 * DW_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmX);
+    ptx::prefetch_tmap(&tmD);
+    for (int i = 0; i < DW_STAGES; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<256>(slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(p.box_rows * 64 + CV_M * 128));
+        ptx::tma_load_2d(smem + s * stage, &tmX, &full[s], 0, tile * CV_M);
+        ptx::tma_load_2d(smem + s * stage + xtile, &tmD, &full[s], 0, (int)p.dy_shift + tile * CV_M);   // rows past the end: zeros
+        if (++s == DW_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ptx::make_idesc_bf16(CV_M, 64, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&full[s], ph);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t xa = ptx::smem_u32(smem + s * stage);
+        const uint64_t bd = ptx::make_smem_desc(xa + (uint32_t)xtile, 128u * 128u, 1024u);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          // MN-major, SWIZZLE_64B, M atoms 64 B (one position) apart, 8-position groups 512 B apart
+          const uint32_t addr = xa + (uint32_t)(a * p.Wp * 64);
+          uint64_t ad = (uint64_t)((addr & 0x3FFFFu) >> 4);
+          ad |= (uint64_t)(64u >> 4) << 16;
+          ad |= (uint64_t)(512u >> 4) << 32;
+          ad |= (uint64_t)1 << 46;
+          ad |= (uint64_t)4 << 61;
+#pragma unroll
+          for (int k = 0; k < CV_M / 16; ++k)
+            ptx::umma_bf16(tmem + (uint32_t)(64 * a), ad + (uint64_t)(64 * k), bd + (uint64_t)(128 * k), idesc, (!first || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[s]);
+      }
+      __syncwarp();
+      first = false;
+      if (++s == DW_STAGES) { s = 0; ph ^= 1u; }
+    }
+    if (lane == 0) ptx::umma_commit(done);
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    ptx::mbar_wait(done, 0);
+    ptx::tc_fence_after();
+    if (quad < 3) {                                   // M rows 96..127 are the unused fourth position slot
+      const int row = quad * 32 + lane;
+#pragma unroll 1
+      for (int a = 0; a < 3; ++a) {
+        float* dst = p.dwt + ((size_t)(a * 128 + row)) * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(64 * a + 32 * h), v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) red_add4(dst + 32 * h + 4 * g, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<256>(tmem);
+  }
+}
+
+int launch_conv_dw(const void* x, long long x_rows, const void* dy, long long dy_rows, float* dwt, long long M, long long dy_shift,
+                   int Wp, cudaStream_t st) {
+  EGB_CHECK(M > 0 && Wp >= 3 && 128 + 2 * Wp + 3 <= 256 && dy_shift >= 0 && dy_shift + M < (1ll << 31),
+            "conv3x3_dw: unsupported geometry (M=%lld, Wp=%d)", M, Wp);
+  EGB_CHECK(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dwt % 16) == 0, "conv3x3_dw: misaligned buffers");
+  ConvDwParams p;
+  p.dwt = dwt;
+  p.dy_shift = dy_shift;
+  p.Wp = Wp;
+  p.box_rows = 128 + 2 * Wp + 3;
+  p.tiles = (int)((M + CV_M - 1) / CV_M);
+  CUtensorMap mx, md;
+  if (egb_tmap_2d(&mx, x, 32, x_rows, 32, 32, p.box_rows)) return 1;
+  const long long drows = dy_rows < dy_shift + M ? dy_rows : dy_shift + M;     // positions >= M contribute nothing
+  if (egb_tmap_2d(&md, dy, 64, drows, 64, 64, CV_M)) return 1;
+  const int xtile = ((p.box_rows * 64) + 1023) & ~1023;
+  const size_t smem = (size_t)DW_STAGES * (xtile + CV_M * 128) + 256 + 1024;
+  EGB_CHECK(smem <= 112 * 1024, "conv3x3_dw: tile too large for two CTAs per SM (%zu bytes)", smem);
+  static bool attr = false;
+  if (!attr) {
+    EGB_CUDA(cudaFuncSetAttribute(conv3x3_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr = true;
+  }
+  const int cap = CV_CTAS_PER_SM * egb_num_sms();
+  const int grid = p.tiles < cap ? p.tiles : cap;
+  conv3x3_dw_kernel<<<grid, CV_THREADS, smem, st>>>(mx, md, p);
+  egb_count_launch(1);
+  EGB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -234,6 +391,14 @@ int egb_conv3x3_c64_c32(const void* x, long long x_rows, const void* w, void* y,
 int egb_conv3x3_c32_c64(const void* x, long long x_rows, const void* w, const float* bias, void* y, long long M,
                         long long out_shift, int Wp, void* stream) {
   return launch_conv<32, 64>(x, x_rows, w, bias, y, M, out_shift, Wp, (cudaStream_t)stream);
+}
+
+/* weight gradient of the forward convolution, transposed: dwt[(a * 128 + j * 32 + c) * 64 + o] += sum over m in [0, M) of
+       x[(m + a * Wp + j) * 32 + c] * dy[(m + dy_shift) * 64 + o]      a < 3, j < 3 (rows j = 3 of every 128 are not written)
+   x: bf16 [x_rows, 32], dy: bf16 [dy_rows, 64] (zero at border positions), dwt: fp32 [384, 64], zeroed by the caller. */
+int egb_conv3x3_dw_c32_c64(const void* x, long long x_rows, const void* dy, long long dy_rows, float* dwt, long long M,
+                           long long dy_shift, int Wp, void* stream) {
+  return launch_conv_dw(x, x_rows, dy, dy_rows, dwt, M, dy_shift, Wp, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1016,10 +1016,17 @@ def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
     esz = dy2.element_size()
     if need_w2:
         # dW2[o, (kh, kw4, c)] = sum over flat padded positions of dY[m + Wp + 1, o] * P1[m + kh*Wp, kw4*32 + c]
-        dw = torch.empty(64, 384, dtype=torch.float32, device=dev)
-        gemm(64, 384, N * RP, code, TO.Operand(TO.at(dy2, (Wp + 1) * 64), 1, 0, 64, 0, 0, 0),
-             TO.Operand(p1, 1, 0, 32, 0, 128, Wp), _dense_matrix(dw, F32, 384), accumulate=2)
-        dw2 = dw.view(64, 3, 4, 32)[:, :, :3, :].permute(0, 3, 1, 2)
+        if code == BF16 and _SPEC_DX_DIRECT and 128 + 2 * Wp + 3 <= 256:
+            # both operands staged once per 128-position tile; the four position slots of a kernel row are the M atoms of
+            # one MMA operand (conv3x3.cu); result transposed: [(kh, kw4, c), o]
+            dwt = zeros((384, 64), torch.float32, dev)
+            TO.call("conv3x3_dw_c32_c64", p1, p1.numel() // 32, dy2, dy2.numel() // 64, dwt, N * RP, Wp + 1, Wp)
+            dw2 = dwt.view(3, 4, 32, 64)[:, :3].permute(3, 2, 0, 1)
+        else:
+            dw = torch.empty(64, 384, dtype=torch.float32, device=dev)
+            gemm(64, 384, N * RP, code, TO.Operand(TO.at(dy2, (Wp + 1) * 64), 1, 0, 64, 0, 0, 0),
+                 TO.Operand(p1, 1, 0, 32, 0, 128, Wp), _dense_matrix(dw, F32, 384), accumulate=2)
+            dw2 = dw.view(64, 3, 4, 32)[:, :, :3, :].permute(0, 3, 1, 2)
     if need_w1:
         # dP1 (padded layout) = full correlation of dY with the flipped kernel: same implicit GEMM, K = 3 x 256
         w2f = _spec_w2_flip(w2, code)

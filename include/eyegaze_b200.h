@@ -238,6 +238,12 @@ int egb_conv3x3_c64_c32(const void* x, long long x_rows, const void* w, void* y,
    x: bf16 [x_rows, 32]; w: bf16 [64, 384]; bias: fp32 [64]; y: bf16 rows of 64 channels. */
 int egb_conv3x3_c32_c64(const void* x, long long x_rows, const void* w, const float* bias, void* y, long long M,
                         long long out_shift, int Wp, void* stream);
+/* weight gradient of spec_conv[3], transposed and in the four-slot segment layout of the forward weight matrix:
+       dwt[(a * 128 + j * 32 + c) * 64 + o] += sum_{m < M} x[(m + a * Wp + j) * 32 + c] * dy[(m + dy_shift) * 64 + o]   a, j < 3
+   x: bf16 [x_rows, 32]; dy: bf16 [dy_rows, 64], zero at border positions; dwt: fp32 [384, 64], ZEROED BY THE CALLER (rows
+   j = 3 stay zero).  Both operands cross L2 -> shared memory once; partial sums are added with fp32 atomics. */
+int egb_conv3x3_dw_c32_c64(const void* x, long long x_rows, const void* dy, long long dy_rows, float* dwt, long long M,
+                           long long dy_shift, int Wp, void* stream);
 /* ReLU + AdaptiveAvgPool2d(4,4) + flatten over the padded conv-2 output [N, H1+2, W1+2, 64] */
 int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int W1, void* stream);
 int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream);
