@@ -98,7 +98,7 @@ _SIGNATURES = {
     "egb_spec_conv1_pool_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i64, vp, vp],
     "egb_spec_conv1_pool_bwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, vp],
     "egb_relu_avgpool_fwd": [vp, vp, i32, i32, i32, i32, vp],
-    "egb_relu_avgpool_bwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "egb_relu_avgpool_bwd": [vp, vp, vp, i32, i32, i32, i32, vp, vp],
     "egb_ibs_connectivity": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32),
                              C.POINTER(i32), i32, vp],
     "egb_ibs_scalar_features": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp],

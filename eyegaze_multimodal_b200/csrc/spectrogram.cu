@@ -225,6 +225,19 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __res
     st4(o + ((long long)(ph + 1) * Wp + (pw + 1)) * 32 + cq * 4, res);
     if (amax != nullptr) amax[((long long)n * H1 * W1 + pos) * 8 + cq] = (unsigned short)code;
   }
+  // the zero border of this image (top and bottom rows, first and last column), so that the buffer needs no memset
+  {
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nb = 2 * Wp + 2 * H1;
+    for (int idx = threadIdx.x; idx < nb * 8; idx += blockDim.x) {
+      const int b = idx >> 3;
+      int pos;
+      if (b < Wp) pos = b;
+      else if (b < 2 * Wp) pos = (H1 + 1) * Wp + (b - Wp);
+      else { const int r = (b - 2 * Wp) >> 1; pos = (r + 1) * Wp + (((b - 2 * Wp) & 1) ? Wp - 1 : 0); }
+      st4(o + (long long)pos * 32 + (idx & 7) * 4, z);
+    }
+  }
 }
 
 // dW1[c,kh,kw] += sum dP1 * img(arg-max patch); db1[c] += sum dP1 (only where the pooled relu is active).
@@ -418,11 +431,16 @@ __global__ void __launch_bounds__(256) relu_avgpool_kernel(const T* __restrict__
 // the bin's element count, so the per-position work is one 16-byte load of y, <= 4 x 2 float4 shared loads and one
 // 16-byte store (the first version gathered the 2-byte pooled gradients straight from global memory with a 32-byte
 // stride, eight per bin and thread: 778 us for 1.07 GB).
+template <typename T> __device__ __forceinline__ float round_to(float x);
+template <> __device__ __forceinline__ float round_to<float>(float x) { return x; }
+template <> __device__ __forceinline__ float round_to<bf16>(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
 template <typename T>
 __global__ void __launch_bounds__(256) relu_avgpool_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dpool,
                                                                T* __restrict__ dy, int N, int H1, int W1, int Wp, int Hp,
-                                                               long long img_stride) {
+                                                               long long img_stride, float* __restrict__ db) {
   __shared__ __align__(16) float g_s[16 * 64];   // [ph*4+pw][c], scaled by 1 / bin size
+  __shared__ float cs_s[8][64];                  // per-warp channel sums of the stored gradient (bias gradient of the conv)
   __shared__ int hb[4][2], wb[4][2];
   const int n = blockIdx.x;
   if (threadIdx.x < 4) {
@@ -443,6 +461,9 @@ __global__ void __launch_bounds__(256) relu_avgpool_bwd_kernel(const T* __restri
   }
   __syncthreads();
   const int per_img = Hp * Wp * 8;
+  float cs[8];                                   // a thread's channel group (rem & 7) is fixed: blockDim.x % 8 == 0
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[i] = 0.f;
   for (int rem = threadIdx.x; rem < per_img; rem += blockDim.x) {
     const int cg = rem & 7, pos = rem >> 3;
     const int h = pos / Wp - 1, w = pos % Wp - 1;
@@ -467,9 +488,32 @@ __global__ void __launch_bounds__(256) relu_avgpool_bwd_kernel(const T* __restri
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = v[i] > 0.f ? g[i] : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        g[i] = v[i] > 0.f ? round_to<T>(g[i]) : 0.f;       // the column sums are those of the STORED values
+        cs[i] += g[i];
+      }
     }
     st8(dy + off, g);
+  }
+  if (db != nullptr) {
+    // bias gradient of spec_conv[3] = column sums of dy: lanes with equal (lane & 7) hold the same channel group
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cs_s[warp][lane * 8 + i] = cs[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += cs_s[w][threadIdx.x];
+      atomicAdd(db + threadIdx.x, t);
+    }
   }
 }
 
@@ -517,9 +561,12 @@ int egb_spec_conv1_pool_fwd(const float* img, const float* w, const float* bias,
   const int H1 = Hh / 2, W1 = Ww / 2, Wp = W1 + 2;
   EGB_CHECK(H1 > 0 && W1 > 0, "spec_conv1: image too small");
   const size_t esz = dtype == EGB_BF16 ? 2 : 4;
-  EGB_CUDA(cudaMemsetAsync(out, 0, (size_t)out_elems * esz, st));
   const size_t smem = sizeof(float) * ((size_t)(Hh + 2) * (Ww + 2) + 320);
   const long long istr = (long long)(H1 + 2) * Wp * 32;
+  // the kernel writes every position of every image (borders included); only the slack rows behind the last image are cleared
+  EGB_CHECK(out_elems >= (long long)N * istr, "spec_conv1: output buffer smaller than N padded images");
+  if (out_elems > (long long)N * istr)
+    EGB_CUDA(cudaMemsetAsync((char*)out + (size_t)N * istr * esz, 0, (size_t)(out_elems - (long long)N * istr) * esz, st));
   if (dtype == EGB_BF16)
     spec_conv1_pool_kernel<bf16><<<N, 256, smem, st>>>(img, w, bias, (bf16*)out, Hh, Ww, H1, W1, Wp, istr, amax);
   else
@@ -591,16 +638,16 @@ int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int
   return 0;
 }
 
-int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream) {
+int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, float* db, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int Wp = W1 + 2, Hp = H1 + 2;
   const long long istr = (long long)Hp * Wp * 64;
   const int grid_bwd = N;                          // one CTA per image
   if (dtype == EGB_BF16)
-    relu_avgpool_bwd_kernel<bf16><<<grid_bwd, 256, 0, st>>>((const bf16*)y, (const bf16*)dpool, (bf16*)dy, N, H1, W1, Wp, Hp, istr);
+    relu_avgpool_bwd_kernel<bf16><<<grid_bwd, 256, 0, st>>>((const bf16*)y, (const bf16*)dpool, (bf16*)dy, N, H1, W1, Wp, Hp, istr, db);
   else
     relu_avgpool_bwd_kernel<float><<<grid_bwd, 256, 0, st>>>((const float*)y, (const float*)dpool, (float*)dy, N, H1, W1, Wp, Hp,
-                                                      istr);
+                                                      istr, db);
   egb_count_launch(1);
   EGB_LAUNCH_CHECK();
   return 0;

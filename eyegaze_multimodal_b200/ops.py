@@ -992,7 +992,8 @@ def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins, 
     amax = torch.empty(N * H1 * W1 * 8, dtype=torch.int16, device=dev) if want_amax else None
     TO.call("spec_conv1_pool_fwd", img, w1, b1, p1, code, N, bins,
            frames, p1.numel(), amax)
-    y2 = zeros(((N * RP + slack) * 64,), tdt, dev)
+    # every row the pooling reads (m + Wp + 1, m < N * RP) is written by the convolution: no memset
+    y2 = torch.empty((N * RP + slack) * 64, dtype=tdt, device=dev)
     w2s = _spec_w2_seg(w2, code)
     if code == BF16 and _SPEC_DX_DIRECT and 128 + 2 * Wp + 2 <= 256:
         # implicit GEMM that stages each input tile once (nine row-shifted MMA operands per tile)
@@ -1004,12 +1005,22 @@ def _spec_front_fwd(eeg1, eeg2, window, w1, b1, w2, b2, code, n_fft, hop, bins, 
     return img, p1, y2, (code, N, bins, frames, H1, W1, Wp, RP, slack, amax)
 
 
-def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2):
-    """Gradients of conv2 / conv1 given dY2 in the padded channels-last layout."""
+def _spec_padded_grad_buffer(meta, ch, device):
+    """Uninitialised padded channels-last buffer whose slack rows (behind the last image) are zero: for kernels that write
+    every position of every image themselves."""
+    code, N, RP, slack = meta[0], meta[1], meta[7], meta[8]
+    buf = torch.empty((N * RP + slack) * ch, dtype=_TORCH_DT[code], device=device)
+    tail = buf[N * RP * ch:]
+    TO.call("zero", tail, tail.numel() * tail.element_size())
+    return buf
+
+
+def _spec_front_bwd(dy2, img, p1, w1, b1, w2, meta, need_w1, need_w2, need_b2, db2=None):
+    """Gradients of conv2 / conv1 given dY2 in the padded channels-last layout (db2: already computed by the producer)."""
     code, N, bins, frames, H1, W1, Wp, RP, slack, amax = meta
     dev, tdt = dy2.device, _TORCH_DT[code]
-    dw1 = db1 = dw2 = db2 = None
-    if need_b2:
+    dw1 = db1 = dw2 = None
+    if need_b2 and db2 is None:
         db2 = torch.empty(64, dtype=torch.float32, device=dev)
         m = _dense_matrix(dy2, code, 64)
         TO.call("colsum", m, N * RP, 64, db2, 1)
@@ -1089,10 +1100,11 @@ class SpectrogramCNNFn(torch.autograd.Function):
         dpool = dpool.contiguous()
         if _code(dpool) != code:
             dpool = cast(dpool, code)
-        dy2 = zeros(((N * RP + slack) * 64,), tdt, dev)
-        TO.call("relu_avgpool_bwd", y2, dpool, dy2, code, N, H1, W1)
         need = ctx.needs_input_grad
-        dw1, db1, dw2, db2 = _spec_front_bwd(dy2, img, p1, w1, b1, w2, ctx.meta, need[3] or need[4], need[5], need[6])
+        dy2 = _spec_padded_grad_buffer(ctx.meta, 64, dev)
+        db2 = zeros((64,), torch.float32, dev) if need[6] else None      # column sums of dy2, out of the same kernel
+        TO.call("relu_avgpool_bwd", y2, dpool, dy2, code, N, H1, W1, db2)
+        dw1, db1, dw2, db2 = _spec_front_bwd(dy2, img, p1, w1, b1, w2, ctx.meta, need[3] or need[4], need[5], need[6], db2)
         return None, None, None, dw1, db1, dw2, db2, None, None, None, None
 
 
@@ -1147,8 +1159,8 @@ class SpecPoolFn(torch.autograd.Function):
         dpool = dpool.contiguous()
         if _code(dpool) != code:
             dpool = cast(dpool, code)
-        dy2 = zeros(((N * RP + slack) * 64,), _TORCH_DT[code], dpool.device)
-        TO.call("relu_avgpool_bwd", y2, dpool, dy2, code, N, H1, W1)
+        dy2 = _spec_padded_grad_buffer(ctx.meta, 64, dpool.device)
+        TO.call("relu_avgpool_bwd", y2, dpool, dy2, code, N, H1, W1, None)
         return _spec_padded_to_nchw(dy2, ctx.meta, 64), None, None, None
 
 

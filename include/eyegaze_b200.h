@@ -246,7 +246,9 @@ int egb_conv3x3_dw_c32_c64(const void* x, long long x_rows, const void* dy, long
                            long long dy_shift, int Wp, void* stream);
 /* ReLU + AdaptiveAvgPool2d(4,4) + flatten over the padded conv-2 output [N, H1+2, W1+2, 64] */
 int egb_relu_avgpool_fwd(const void* y, void* out, int dtype, int N, int H1, int W1, void* stream);
-int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, void* stream);
+/* backward: dy (zero on the border and where ReLU is inactive); db, when not NULL, receives (+=, fp32 atomics; zeroed by
+   the caller) the column sums of dy = the bias gradient of spec_conv[3], so dy is not read again for it */
+int egb_relu_avgpool_bwd(const void* y, const void* dpool, void* dy, int dtype, int N, int H1, int W1, float* db, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Inter-brain-synchrony connectivity (dual_eeg_transformer.py:473-819), parameter-free, forward only.
