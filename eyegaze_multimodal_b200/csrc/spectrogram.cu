@@ -186,41 +186,45 @@ __global__ void __launch_bounds__(256) spec_conv1_pool_kernel(const float* __res
   // blockDim is a multiple of 8, so a thread serves the same channel quad for all its positions: its 36 weights and 4
   // biases are read into registers once (with the weights re-read from shared memory for every FMA the kernel was
   // bound by the shared-memory pipe: 355 us for 290 MB)
+  // The 144 FMAs per (position, channel quad) bound the kernel by instruction issue; as packed pairs (two channels per
+  // fma.rn.f32x2, the same fma per lane in the same order: bit-identical) they are 72.
   const int cq = threadIdx.x & 7;
-  float wr[4][9], br[4];
+  float2 wr[2][9], br[2];                        // channel pairs (4 cq, 4 cq + 1), (4 cq + 2, 4 cq + 3)
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    br[cc] = wsm[288 + cq * 4 + cc];
+  for (int cp = 0; cp < 2; ++cp) {
+    br[cp] = make_float2(wsm[288 + cq * 4 + 2 * cp], wsm[288 + cq * 4 + 2 * cp + 1]);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) wr[cc][i] = wsm[(cq * 4 + cc) * 9 + i];
+    for (int i = 0; i < 9; ++i) wr[cp][i] = make_float2(wsm[(cq * 4 + 2 * cp) * 9 + i], wsm[(cq * 4 + 2 * cp + 1) * 9 + i]);
   }
   for (int idx = threadIdx.x; idx < H1 * W1 * 8; idx += blockDim.x) {
     const int pos = idx >> 3;
     const int ph = pos / W1, pw = pos % W1;
-    float patch[4][4];
+    float2 patch[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) patch[a][b] = im[(2 * ph + a) * ldw + 2 * pw + b];
+      for (int b = 0; b < 4; ++b) patch[a][b] = splat2(im[(2 * ph + a) * ldw + 2 * pw + b]);
     float res[4];
     unsigned code = 0;   // per channel 3 bits: 0..3 = which of the 2 x 2 conv outputs won the pool, 4 = relu inactive
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      float best = 0.f;  // relu(max(.)) == max(0, .)
-      unsigned sel = 4u;
+    for (int cp = 0; cp < 2; ++cp) {
+      float best0 = 0.f, best1 = 0.f;  // relu(max(.)) == max(0, .)
+      unsigned sel0 = 4u, sel1 = 4u;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          float a = br[cc];
+          float2 a = br[cp];
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) a = fmaf(wr[cc][kh * 3 + kw], patch[dy + kh][dx + kw], a);
-          if (a > best) { best = a; sel = (unsigned)(dy * 2 + dx); }   // first maximum wins, as in max_pool2d
+            for (int kw = 0; kw < 3; ++kw) a = fma2(wr[cp][kh * 3 + kw], patch[dy + kh][dx + kw], a);
+          if (a.x > best0) { best0 = a.x; sel0 = (unsigned)(dy * 2 + dx); }   // first maximum wins, as in max_pool2d
+          if (a.y > best1) { best1 = a.y; sel1 = (unsigned)(dy * 2 + dx); }
         }
-      res[cc] = best;
-      code |= sel << (3 * cc);
+      res[2 * cp] = best0;
+      res[2 * cp + 1] = best1;
+      code |= (sel0 << (6 * cp)) | (sel1 << (6 * cp + 3));
     }
     st4(o + ((long long)(ph + 1) * Wp + (pw + 1)) * 32 + cq * 4, res);
     if (amax != nullptr) amax[((long long)n * H1 * W1 + pos) * 8 + cq] = (unsigned short)code;

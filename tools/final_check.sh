@@ -9,3 +9,4 @@ d=json.load(open("gpurun_out/r02_bench_cfg2_n1_final.json")); print(d["ms_per_st
 PY
 CMD="python bench.py --graphs 0 --steps 1 --warmup 3 --no-train-step --no-gpu-eager --no-cpu-baseline --no-e2e --no-roofline"
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1800 -c 640 --csv --log-file gpurun_out/r02_launches_cfg2_final3.csv $CMD > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"
+python tools/gemm_table.py > gpurun_out/r02_gemm_table_final.txt 2>/dev/null; head -3 gpurun_out/r02_gemm_table_final.txt

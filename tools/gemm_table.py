@@ -75,6 +75,6 @@ print("%d launches / step, %.2f ms / step, %.0f TFLOP/s average (%.2f of %.0f)" 
 print("%8s %6s %6s  %-22s %4s %8s %8s %7s %6s   (kernel<BN, epilogue mask>)" % ("M", "N", "K", "kernel", "n", "us", "ms/step", "TFLOP/s", "frac"))
 for tag, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     M_, N_, K_, var = tag
-    kind = {1: "single", 2: "pair/8w", 3: "pair/16w"}.get(int(var // 1e10), "?")
+    kind = {1: "single", 2: "pair/8w", 3: "pair/16w", 4: "conv3x3"}.get(int(var // 1e10), "?")
     kern = "%s<%d,%d>" % (kind, int(var % 1e10) // 10000000, int(var % 1e7))
     print("%8d %6d %6d  %-22s %4d %8.1f %8.3f %7.0f %6.2f" % (M_, N_, K_, kern, n // N, ms / n * 1e3, ms / N, fl / ms / 1e9, fl / ms / 1e9 / peak))
