@@ -64,6 +64,8 @@ def test_conv3x3_forward_matches_conv2d(cuda_device, geom):
     y = torch.full(((N * RP + 2 * Wp + 8) * 64,), float("nan"), dtype=torch.bfloat16, device=DEV)
     TO.call("conv3x3_c32_c64", xp, xp.shape[0], wseg, b.to(DEV), y, N * RP, Wp + 1, Wp)
     torch.cuda.synchronize()
+    rows = y.view(-1, 64).float().cpu()
+    assert torch.isnan(rows[: Wp + 1]).all() and torch.isnan(rows[N * RP + Wp + 1:]).all(), "rows outside [shift, shift + M) written"
     got = _interior(y.view(-1, 64), N, 64, H1, W1)
     want = F.conv2d(x, w, b, padding=1)
     _assert_close(got, want, 6e-3, "forward")                     # bf16 rounding of the stored output: 2^-9 relative
@@ -81,6 +83,8 @@ def test_conv3x3_data_gradient_matches_autograd(cuda_device, geom):
     dx = torch.full(((N * RP + 2 * Wp + 8) * 32,), float("nan"), dtype=torch.bfloat16, device=DEV)
     TO.call("conv3x3_c64_c32", dyp, dyp.shape[0], wflip, dx, N * RP, Wp + 1, Wp)
     torch.cuda.synchronize()
+    rows = dx.view(-1, 32).float().cpu()
+    assert torch.isnan(rows[: Wp + 1]).all() and torch.isnan(rows[N * RP + Wp + 1:]).all(), "rows outside [shift, shift + M) written"
     got = _interior(dx.view(-1, 32), N, 32, H1, W1)
     xr = x.clone().requires_grad_(True)
     F.conv2d(xr, w, b, padding=1).backward(dy)
