@@ -8,6 +8,7 @@
 // also routed here (bf16 in, fp32 math); they are the 3-class heads, a few kFLOP each.
 #include <string.h>
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -31,6 +32,7 @@ struct FParams {
   int M, N, K;
   FOperand a, b;
   int split_k, k_per_split;
+  int cluster_k;       // 1: the split_k CTAs of a tile form a thread-block cluster (1, 1, split_k) and reduce through DSMEM
   EpiParams epi;
 };
 
@@ -206,6 +208,7 @@ template <typename T>
 __global__ void __launch_bounds__(FTHREADS) gemm_fma_small_kernel(const FParams p) {
   __shared__ __align__(16) float As[2][FBK][SBM + 4];
   __shared__ __align__(16) float Bs[2][FBK][SBN + 4];
+  __shared__ __align__(16) float red[SBM * SBN];   // partial tile of a cluster rank (cluster split-K)
   const int m0 = blockIdx.y * SBM;
   const int n0 = blockIdx.x * SBN;
   const int kbeg = blockIdx.z * p.k_per_split;
@@ -249,6 +252,32 @@ __global__ void __launch_bounds__(FTHREADS) gemm_fma_small_kernel(const FParams 
       __syncthreads();
       buf ^= 1;
     }
+  }
+  if (p.cluster_k) {
+    // K split over the CTAs of a cluster: ranks > 0 park their partial tile in their own shared memory, rank 0 adds them
+    // in rank order over distributed shared memory and runs the epilogue (bias / activation / dropout need the full sum)
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned rank = cl.block_rank();
+    if (rank != 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(&red[(ty * 4 + i) * SBN + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    cl.sync();
+    if (rank == 0) {
+      const unsigned nb = cl.num_blocks();
+      for (unsigned r = 1; r < nb; ++r) {
+        const float* peer = cl.map_shared_rank(red, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(&peer[(ty * 4 + i) * SBN + tx * 4]);
+          acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+        }
+      }
+    }
+    cl.sync();                                       // peers keep their shared memory alive until rank 0 has read it
+    if (rank != 0) return;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -376,18 +405,46 @@ extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
     split = d->split_k;
     if (split <= 0) {
       split = (2 * egb_num_sms() + mt * nt - 1) / (mt * nt);
-      const int max_split = (d->K + 255) / 256;
+      // the small launches are chains of K steps on a handful of SMs: split down to 64 per CTA
+      const int max_split = small ? (d->K + 63) / 64 : (d->K + 255) / 256;
       if (split > max_split) split = max_split;
       if (split < 1) split = 1;
     }
+  } else if (small) {
+    // no accumulation into C (bias / activation / dropout epilogues): split K over a thread-block cluster instead; the
+    // fp32 heads of a step (M = batch, K <= 768) otherwise run 4-48 CTAs for 20-75 us each at the serial tail of the step
+    static const int cluster_ok = getenv("EGB_GEMM_FMA_CLUSTER") ? atoi(getenv("EGB_GEMM_FMA_CLUSTER")) : 1;
+    if (cluster_ok)
+      while (split < 8 && d->K >= 128 * split && mt * nt * split * 2 <= 2 * egb_num_sms()) split *= 2;
+    p.cluster_k = split > 1;
   }
   int kps = (d->K + split - 1) / split;
   kps = ((kps + FBK - 1) / FBK) * FBK;
   p.k_per_split = kps;
   p.split_k = (d->K + kps - 1) / kps;
+  if (p.cluster_k && p.split_k != split) {            // (K not a multiple of 16 * split: fall back to one CTA per tile)
+    p.cluster_k = 0;
+    p.k_per_split = ((d->K + FBK - 1) / FBK) * FBK;
+    p.split_k = 1;
+  }
   dim3 grid(nt, mt, p.split_k);
   EGB_CHECK(mt <= 65535 && p.split_k <= 65535, "gemm: grid too large");
-  if (small) {
+  if (small && p.cluster_k) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(FTHREADS, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = (unsigned)p.split_k;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (d->in_dtype == EGB_BF16) EGB_CUDA(cudaLaunchKernelEx(&cfg, gemm_fma_small_kernel<bf16>, p));
+    else EGB_CUDA(cudaLaunchKernelEx(&cfg, gemm_fma_small_kernel<float>, p));
+  } else if (small) {
     if (d->in_dtype == EGB_BF16) gemm_fma_small_kernel<bf16><<<grid, FTHREADS, 0, stream>>>(p);
     else gemm_fma_small_kernel<float><<<grid, FTHREADS, 0, stream>>>(p);
   } else if (d->in_dtype == EGB_BF16)
