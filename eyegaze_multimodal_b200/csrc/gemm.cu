@@ -406,7 +406,8 @@ extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
     if (split <= 0) {
       split = (2 * egb_num_sms() + mt * nt - 1) / (mt * nt);
       // the small launches are chains of K steps on a handful of SMs: split down to 64 per CTA
-      const int max_split = small ? (d->K + 63) / 64 : (d->K + 255) / 256;
+      static const int split64 = getenv("EGB_GEMM_FMA_SPLIT64") ? atoi(getenv("EGB_GEMM_FMA_SPLIT64")) : 1;
+      const int max_split = (small && split64) ? (d->K + 63) / 64 : (d->K + 255) / 256;
       if (split > max_split) split = max_split;
       if (split < 1) split = 1;
     }
@@ -414,7 +415,7 @@ extern "C" int egb_gemm(const egb_gemm_desc* d, void* stream_) {
     // no accumulation into C (bias / activation / dropout epilogues): split K over a thread-block cluster instead; the
     // fp32 heads of a step (M = batch, K <= 768) otherwise run 4-48 CTAs for 20-75 us each at the serial tail of the step
     static const int cluster_ok = getenv("EGB_GEMM_FMA_CLUSTER") ? atoi(getenv("EGB_GEMM_FMA_CLUSTER")) : 1;
-    if (cluster_ok)
+    if (cluster_ok && d->split_k == 0)      // split_k = 1 on a non-accumulating launch: one CTA walks K in order (parity mode)
       while (split < 8 && d->K >= 128 * split && mt * nt * split * 2 <= 2 * egb_num_sms()) split *= 2;
     p.cluster_k = split > 1;
   }

@@ -595,7 +595,7 @@ int egb_instnorm_tokens_fwd(const float* x, const float* gamma, const float* bet
 int egb_instnorm_tokens_bwd(const float* x, const void* dy, int dtype, float* dgamma, float* dbeta, int B, int NT, int P,
                             float eps, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((P + 127) / 128, B < 32 ? B : 32);
+  dim3 grid((P + 127) / 128, B < 256 ? B : 256);   // (64 CTAs walked 8 matrices each: 116 us at 0.57 TB/s)
   if (dtype == EGB_BF16)
     instnorm_tokens_bwd_kernel<bf16><<<grid, 128, 0, st>>>(x, (const bf16*)dy, dgamma, dbeta, B, NT, P, eps);
   else

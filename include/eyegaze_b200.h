@@ -106,7 +106,9 @@ typedef struct {
   float dropout_p;     /* applied after activation; 0 disables */
   uint64_t dropout_seed;
   int32_t accumulate;  /* 1: C += result (C must be fp32, split-K with red.global.add); 2: zero C first, then accumulate */
-  int32_t split_k;     /* 0 = auto */
+  int32_t split_k;     /* accumulating launches: number of K splits, 0 = auto.  Non-accumulating fp32 launches of small problems:
+                          0 = the library may split K over a thread-block cluster (sum of the partial sums in rank order),
+                          1 = one CTA walks K in order (the summation order the fp32 parity mode is pinned with) */
   float* c_colsum;     /* optional [N] fp32, ACCUMULATED (caller zeroes): column sums of the stored C -- the bias gradient
                           of the layer whose pre-activation gradient this GEMM produces (F.linear backward), taken in the
                           epilogue instead of a second pass over C */

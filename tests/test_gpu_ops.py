@@ -441,3 +441,33 @@ def test_fuzzy_gating_golden(cuda_device, mode_name):
 def test_library_has_no_cpu_path(cuda_device):
     with pytest.raises(RuntimeError):
         ops.linear(torch.randn(4, 8), torch.nn.Parameter(torch.randn(8, 8)))
+
+
+# The fp32 heads of a step are "small" problems (M = batch rows): their K loop is split over a thread-block cluster
+# (non-accumulating launches, DSMEM reduction) or over atomically accumulating CTAs (weight gradients).
+# Under precision("bf16") (the throughput mode, whose heads stay fp32) the cluster split is on; under precision("fp32")
+# (parity mode) ops.gemm asks for the in-order K loop.
+@pytest.mark.parametrize("dims", [(256, 1024, 512, 256), (256, 768, 256, 3), (100, 300, 200, 40), (256, 128, 128, 64)])
+@pytest.mark.parametrize("act", ["relu", "gelu"])
+@pytest.mark.parametrize("policy", ["fp32", "bf16"])
+def test_mlp2_small_rows_fp32_split_k(cuda_device, dims, act, policy):
+    R, K, Hd, N = dims
+    torch.manual_seed(3)
+    x = torch.randn(R, K)
+    w1, b1 = torch.randn(Hd, K) / math.sqrt(K), torch.randn(Hd) * 0.1
+    w2, b2 = torch.randn(N, Hd) / math.sqrt(Hd), torch.randn(N) * 0.1
+    gy = torch.randn(R, N)
+    ps = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    fn = F.relu if act == "relu" else F.gelu
+    yr = F.linear(fn(F.linear(ps[0], ps[1], ps[2])), ps[3], ps[4])
+    yr.backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    prm = [_param(t) for t in (w1, b1, w2, b2)]
+    with precision(policy):
+        y = ops.mlp2(xg, *prm, L.ACT_RELU if act == "relu" else L.ACT_GELU)
+        y.backward(gy.to(DEV))
+    assert y.dtype == torch.float32
+    _close(y, yr, "fp32", msg="y")
+    _close(xg.grad, ps[0].grad, "fp32", msg="dx")
+    for g, r, nm in zip(prm, ps[1:], ["dw1", "db1", "dw2", "db2"]):
+        _close(g.grad, r.grad, "fp32", msg=nm)
